@@ -1,0 +1,226 @@
+// common.cuh -- shared helpers + hand-written sm_100a PTX wrappers (mbarrier, TMA, tcgen05).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#ifndef DCCN_DEVINL
+#define DCCN_DEVINL __device__ __forceinline__
+#endif
+
+namespace dccn {
+
+// ---------------------------------------------------------------------------------
+// error plumbing (thread-local message surfaced through dccn_last_error())
+// ---------------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+int set_error(int code, const char* fmt, ...);
+
+#define DCCN_CUDA_OK(expr)                                                            \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      return dccn::set_error(-1, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                     \
+  } while (0)
+
+#define DCCN_CHECK(cond, ...)                                  \
+  do {                                                         \
+    if (!(cond)) return dccn::set_error(-2, __VA_ARGS__);      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// tf32 split:  v = hi + lo,  hi = rna_tf32(v), lo = rna_tf32(v - hi)
+// (both have their low 13 mantissa bits cleared, so the tensor core's own operand
+//  truncation is a no-op and  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  carries ~22 bits).
+// ---------------------------------------------------------------------------------
+DCCN_DEVINL float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+DCCN_DEVINL void tf32_split(float v, float& hi, float& lo) {
+  hi = tf32_rna(v);
+  lo = tf32_rna(v - hi);
+}
+// host version (round to nearest, ties away from zero in magnitude like cvt.rna)
+inline float tf32_rna_host(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return v;
+  u += 0x1000u;
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------
+DCCN_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DCCN_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DCCN_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+DCCN_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DCCN_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+DCCN_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+DCCN_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DCCN_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) -- 2-D tile load, completion on an mbarrier
+// ---------------------------------------------------------------------------------
+DCCN_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+DCCN_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, MMA issue, commit, TMEM load
+// ---------------------------------------------------------------------------------
+DCCN_DEVINL void tmem_alloc(uint32_t* smem_out, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)),
+               "r"(ncols)
+               : "memory");
+}
+DCCN_DEVINL void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+DCCN_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+DCCN_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DCCN_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by ONE thread for the CTA
+DCCN_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// make the mbarrier track completion of all previously issued tcgen05.mma of this thread
+DCCN_DEVINL void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane i <-> TMEM lane base+i)
+DCCN_DEVINL void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: K-major operand tile, rows of 128 bytes (32 fp32),
+// TMA SWIZZLE_128B layout, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).
+// Bit layout per the PTX ISA "tcgen05 shared memory descriptor":
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
+//   [46,48) version = 1         [61,64) layout type: 2 = SWIZZLE_128B
+DCCN_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 B between 8-row core-matrix groups
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor for kind::tf32: fp32 accumulate, A and B both K-major, M=128, N=n.
+//   [4,6) c_format=1 (F32)  [7,10) a_format=2 (TF32)  [10,13) b_format=2 (TF32)
+//   [15] a_major=0 [16] b_major=0  [17,23) N>>3  [24,29) M>>4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+DCCN_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t.reg .b32 R;\n\t"
+      "elect.sync R|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Philox-4x32-10 counter RNG (stateless; key = seed, counter = element index)
+// ---------------------------------------------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __host__ __device__ explicit Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ inline void operator()(uint64_t ctr, uint32_t stream, uint32_t (&out)[4]) const {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x5DCC0FD1u;
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, c0, h0, l0);
+      mulhilo(0xCD9E8D57u, c2, h1, l1);
+      c0 = h1 ^ c1 ^ a;
+      c1 = l1;
+      c2 = h0 ^ c3 ^ b;
+      c3 = l0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+// two uniforms in (0,1] -> two independent N(0,1) (Box-Muller, fp32)
+DCCN_DEVINL void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
+  float a = ((float)u0 + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  float b = (float)u1 * 2.3283064365386963e-10f;           // [0,1)
+  float r = sqrtf(-2.0f * __logf(a));
+  float s, c;
+  __sincosf(6.283185307179586f * b, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+}  // namespace dccn

@@ -1,0 +1,867 @@
+// dccn.cu -- libdccn.so: handle, weight packing, layer schedule and the C ABI (include/dccn.h).
+//
+// Reference path being replaced (zhongyuanzhao/dl_ofdm @ 5665b50):
+//   tx_ofdm -> batch-moment norm (dev/py/ofdmreceiver_np.py:128-129)
+//           -> [equalizer_ofdm  dev/py/model.py:349-478]
+//           -> ofdm_dense_rx     dev/py/model.py:1222-1292
+//           -> argmax / confusion matrix / xent (dev/py/ofdmreceiver_np.py:154-169)
+// Every complex layer is `layers_conv2d_complex` (dev/py/complex.py:140-196) and is packed
+// into ONE real GEMM on IQ-interleaved activations with the reference's own sign
+// convention ([[a, b], [-b, -a]] per complex weight, bias (ba-bb, bb-ba)).
+#include "../../include/dccn.h"
+
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace dccn {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA descriptor creation (driver entry point fetched through the runtime: no -lcuda)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// fp32 matrix [rows, cols] with row pitch ld (elements); box = [box_rows x 32 cols], 128B swizzle
+static int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  DCCN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+  DCCN_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0,
+             "TMA operand must be 16-byte aligned (base %p, ld %lld)", (const void*)base, (long long)ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCCN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%d", (int)r,
+             (long long)rows, (long long)cols, (long long)ld, box_rows);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------------------
+struct Act {          // activation matrix, 1 or 2 planes
+  float* p0 = nullptr;
+  float* p1 = nullptr;
+  int ld = 0;
+};
+
+struct GemmLayer {
+  int K = 0, N = 0;
+  int BN = 128;                 // tcgen05 tile width
+  std::vector<float> W;         // host [K, N]
+  std::vector<float> bias;      // host [N]
+  float* dW = nullptr;          // [K, N] fp32 (SIMT path)
+  float* dWt0 = nullptr;        // [N, K] tf32-hi (or full fp32 for FAST)  -- B operand, K-major
+  float* dWt1 = nullptr;        // [N, K] tf32-lo (PARITY only)
+  float* dBias = nullptr;
+  CUtensorMap tmB0, tmB1;
+  bool built = false;
+};
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+}  // namespace dccn
+
+using namespace dccn;
+
+struct dccn_handle {
+  dccn_cfg cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::map<std::string, HostTensor> raw;
+  bool committed = false;
+  // geometry
+  int S, K, T, Tin, F, D, NB, P;      // T = samples/symbol incl. CP, Tin = samples the receiver consumes
+  int chunk;
+  // layers
+  GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
+  GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
+  HeadWeights hw;
+  // workspace
+  std::vector<void*> allocs;
+  double* d_sums = nullptr;       // [2P] moments accumulators
+  float* d_mean = nullptr;
+  float* d_rstd = nullptr;
+  double* d_power = nullptr;      // channel power accumulator
+  unsigned long long* d_conf = nullptr;   // internal [4]
+  double* d_ce = nullptr;
+  Act a0, t1, f, p32, u1, u2, eq, corr, cat, oeq, r1o;
+  // staging for dccn_forward_host
+  float* d_x = nullptr;
+  uint8_t* d_bits = nullptr;
+  uint8_t* d_hard = nullptr;
+  int64_t stage_frames = 0;
+  int64_t* d_res_conf = nullptr;  // result slots of dccn_forward_host
+  double* d_res_ce = nullptr;
+  size_t ws_bytes = 0;
+};
+
+namespace dccn {
+
+static int dev_alloc(dccn_handle* h, void** p, size_t bytes) {
+  DCCN_CUDA_OK(cudaMalloc(p, bytes));
+  h->allocs.push_back(*p);
+  h->ws_bytes += bytes;
+  return 0;
+}
+
+static int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split) {
+  a->ld = ld;
+  int rc = dev_alloc(h, (void**)&a->p0, (size_t)rows * ld * sizeof(float));
+  if (rc) return rc;
+  if (split) rc = dev_alloc(h, (void**)&a->p1, (size_t)rows * ld * sizeof(float));
+  return rc;
+}
+
+static const HostTensor* find(const dccn_handle* h, const std::string& n) {
+  auto it = h->raw.find(n);
+  return it == h->raw.end() ? nullptr : &it->second;
+}
+
+// ---------------------------------------------------------------------------------------
+// weight packing (host)
+// ---------------------------------------------------------------------------------------
+// complex layer, per-k rows: Wa[k][f], Wb[k][f] -> Bp [2K, 2F] + bias_p [2F]   
+static void pack_complex(const float* Wa, const float* Wb, int64_t strideK, int Kc, int F, const float* bias2F,
+                         GemmLayer* L) {
+  L->K = 2 * Kc;
+  L->N = 2 * F;
+  L->W.assign((size_t)L->K * L->N, 0.f);
+  for (int k = 0; k < Kc; ++k)
+    for (int f = 0; f < F; ++f) {
+      const float a = Wa[k * strideK + f], b = Wb[k * strideK + f];
+      L->W[(size_t)(2 * k) * L->N + 2 * f] = a;
+      L->W[(size_t)(2 * k) * L->N + 2 * f + 1] = b;
+      L->W[(size_t)(2 * k + 1) * L->N + 2 * f] = -b;
+      L->W[(size_t)(2 * k + 1) * L->N + 2 * f + 1] = -a;
+    }
+  L->bias.resize(L->N);
+  for (int f = 0; f < F; ++f) {
+    L->bias[2 * f] = bias2F[f] - bias2F[F + f];
+    L->bias[2 * f + 1] = bias2F[F + f] - bias2F[f];
+  }
+}
+
+static void pack_dense(const HostTensor& k, const HostTensor& b, GemmLayer* L) {
+  L->K = (int)k.shape[0];
+  L->N = (int)k.shape[1];
+  L->W = k.data;
+  L->bias = b.data;
+}
+
+static int pick_bn(int N) {
+  if (N <= 32) return 32;
+  if (N == 160) return 160;
+  return 128;
+}
+
+static int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
+  const int K = L->K, N = L->N;
+  L->BN = pick_bn(N);
+  const int prec = h->cfg.precision;
+  DCCN_CHECK((K * 4) % 16 == 0, "layer K=%d is not a multiple of 4", K);
+  if (!L->built) {
+    int rc = dev_alloc(h, (void**)&L->dBias, (size_t)N * 4);
+    if (rc) return rc;
+    if (prec == DCCN_PREC_EXACT) {
+      rc = dev_alloc(h, (void**)&L->dW, (size_t)K * N * 4);
+      if (rc) return rc;
+    } else {
+      rc = dev_alloc(h, (void**)&L->dWt0, (size_t)K * N * 4);
+      if (rc) return rc;
+      if (prec == DCCN_PREC_PARITY) {
+        rc = dev_alloc(h, (void**)&L->dWt1, (size_t)K * N * 4);
+        if (rc) return rc;
+      }
+    }
+    L->built = true;
+  }
+  DCCN_CUDA_OK(cudaMemcpyAsync(L->dBias, L->bias.data(), (size_t)N * 4, cudaMemcpyHostToDevice, s));
+  if (prec == DCCN_PREC_EXACT) {
+    DCCN_CUDA_OK(cudaMemcpyAsync(L->dW, L->W.data(), (size_t)K * N * 4, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+  }
+  std::vector<float> t0((size_t)K * N), t1;
+  if (prec == DCCN_PREC_PARITY) t1.resize((size_t)K * N);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) {
+      const float w = L->W[(size_t)k * N + n];
+      if (prec == DCCN_PREC_PARITY) {
+        const float hi = tf32_rna_host(w);
+        t0[(size_t)n * K + k] = hi;
+        t1[(size_t)n * K + k] = tf32_rna_host(w - hi);
+      } else {
+        t0[(size_t)n * K + k] = w;
+      }
+    }
+  DCCN_CUDA_OK(cudaMemcpyAsync(L->dWt0, t0.data(), t0.size() * 4, cudaMemcpyHostToDevice, s));
+  if (prec == DCCN_PREC_PARITY)
+    DCCN_CUDA_OK(cudaMemcpyAsync(L->dWt1, t1.data(), t1.size() * 4, cudaMemcpyHostToDevice, s));
+  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  int rc = make_tmap(&L->tmB0, L->dWt0, N, K, K, L->BN);
+  if (rc) return rc;
+  if (prec == DCCN_PREC_PARITY) rc = make_tmap(&L->tmB1, L->dWt1, N, K, K, L->BN);
+  return rc;
+}
+
+#define NEED(var, name)                                           \
+  const HostTensor* var = find(h, name);                          \
+  DCCN_CHECK(var != nullptr, "weight '%s' was not set", name)
+
+static int build_layers(dccn_handle* h, cudaStream_t s) {
+  const dccn_cfg& c = h->cfg;
+  const int S = h->S, K = h->K, F = h->F, Tin = h->Tin, NB = h->NB, D = h->D;
+  const int MO = 1 << NB;
+  int rc;
+  // ---- receiver ---------------------------------------------------------------
+  {
+    NEED(k, "fft_like/conv3d/kernel");
+    NEED(b, "fft_like/conv3d/bias");
+    // stored [1, Tk, 1, Tk, 2F]; 'same' over a width-1 axis => only tap (Tk-1)/2 is live
+    DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == 1 && k->shape[2] == 1 && k->shape[1] == Tin &&
+                   k->shape[3] == Tin && k->shape[4] == 2 * F,
+               "fft_like/conv3d/kernel: expected [1,%d,1,%d,%d]", Tin, Tin, 2 * F);
+    const int tap = (Tin - 1) / 2;
+    const float* base = k->data.data() + (size_t)tap * Tin * 2 * F;   // [Tin, 2F]
+    pack_complex(base, base + F, 2 * F, Tin, F, b->data.data(), &h->r1);
+  }
+  {
+    NEED(k, "demodulation/dense/kernel");
+    NEED(b, "demodulation/dense/bias");
+    DCCN_CHECK(k->shape.size() == 2 && k->shape[0] == S * F * 2 && k->shape[1] == 2 * D,
+               "demodulation/dense/kernel: expected [%d,%d]", S * F * 2, 2 * D);
+    pack_dense(*k, *b, &h->r2);
+  }
+  {
+    NEED(kc, "demodulation/conv2d/kernel");
+    NEED(bc, "demodulation/conv2d/bias");
+    NEED(k1, "demodulation/dense_1/kernel");
+    NEED(b1, "demodulation/dense_1/bias");
+    DCCN_CHECK((int)kc->data.size() == 2 * MO && (int)k1->data.size() == (MO + 2) * 2 * NB,
+               "demodulation head shapes do not match nbits=%d", NB);
+    memset(&h->hw, 0, sizeof(h->hw));
+    for (int i = 0; i < 2; ++i)
+      for (int m = 0; m < MO; ++m) h->hw.Wc[i][m] = kc->data[i * MO + m];
+    for (int m = 0; m < MO; ++m) h->hw.bc[m] = bc->data[m];
+    for (int m = 0; m < MO + 2; ++m)
+      for (int j = 0; j < 2 * NB; ++j) h->hw.W1[m][j] = k1->data[m * 2 * NB + j];
+    for (int j = 0; j < 2 * NB; ++j) h->hw.b1[j] = b1->data[j];
+    if (c.head == DCCN_HEAD_V1) {
+      NEED(kc1, "demodulation/conv2d_1/kernel");
+      NEED(bc1, "demodulation/conv2d_1/bias");
+      DCCN_CHECK((int)kc1->data.size() == MO * MO, "demodulation/conv2d_1/kernel size");
+      for (int m = 0; m < MO; ++m)
+        for (int n = 0; n < MO; ++n) h->hw.Wc1[m][n] = kc1->data[m * MO + n];
+      for (int m = 0; m < MO; ++m) h->hw.bc1[m] = bc1->data[m];
+    }
+  }
+  if ((rc = upload_layer(h, &h->r1, s))) return rc;
+  if ((rc = upload_layer(h, &h->r2, s))) return rc;
+  if (!c.equalizer) return 0;
+
+  // ---- equalizer_ofdm -----------------------------------------------------------
+  const int SK2 = S * K * 2;
+  {
+    NEED(k, "Equalizer/dense/kernel");
+    NEED(b, "Equalizer/dense/bias");
+    DCCN_CHECK(k->shape.size() == 2 && k->shape[0] == Tin * 2 && k->shape[1] == 2 * K, "Equalizer/dense/kernel shape");
+    pack_dense(*k, *b, &h->g1);
+  }
+  auto pack_1xK = [&](const char* kn, const char* bn, GemmLayer* L, bool real_only) -> int {
+    NEED(k, kn);
+    NEED(b, bn);
+    DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == 1 && k->shape[1] == K && k->shape[3] == 1 &&
+                   k->shape[4] == 2 * K,
+               "%s: expected [1,%d,1,1,%d]", kn, K, 2 * K);
+    GemmLayer full;
+    pack_complex(k->data.data(), k->data.data() + K, 2 * K, K, K, b->data.data(), &full);
+    if (!real_only) {
+      L->K = full.K; L->N = full.N; L->W = full.W; L->bias = full.bias;
+    } else {   // input imag part is identically 0: keep the xr rows only
+      L->K = K; L->N = full.N; L->bias = full.bias;
+      L->W.resize((size_t)K * full.N);
+      for (int kk = 0; kk < K; ++kk)
+        memcpy(&L->W[(size_t)kk * full.N], &full.W[(size_t)(2 * kk) * full.N], (size_t)full.N * 4);
+    }
+    return 0;
+  };
+  if ((rc = pack_1xK("Equalizer/conv3d/kernel", "Equalizer/conv3d/bias", &h->g2, false))) return rc;
+  {
+    NEED(k, "Equalizer/dense_1/kernel");
+    NEED(b, "Equalizer/dense_1/bias");
+    DCCN_CHECK(k->shape[0] == SK2 && k->shape[1] == 2 * c.pilot_size, "Equalizer/dense_1/kernel shape");
+    pack_dense(*k, *b, &h->g3);
+  }
+  {
+    NEED(k, "Equalizer/dense_2/kernel");
+    NEED(b, "Equalizer/dense_2/bias");
+    DCCN_CHECK(k->shape[0] == 2 * c.pilot_size && k->shape[1] == SK2, "Equalizer/dense_2/kernel shape");
+    pack_dense(*k, *b, &h->g4);
+  }
+  {
+    NEED(k, "Equalizer/dense_3/kernel");
+    NEED(b, "Equalizer/dense_3/bias");
+    DCCN_CHECK(k->shape[0] == SK2 && k->shape[1] == SK2, "Equalizer/dense_3/kernel shape");
+    pack_dense(*k, *b, &h->g5);
+  }
+  {
+    NEED(k, "Equalizer/dense_4/kernel");
+    NEED(b, "Equalizer/dense_4/bias");
+    DCCN_CHECK(k->shape[0] == SK2 && k->shape[1] == SK2, "Equalizer/dense_4/kernel shape");
+    pack_dense(*k, *b, &h->g6);
+  }
+  {
+    // (S,K) 'same' complex conv with one filter -> dense Toeplitz [S*K*2, S*K*2]
+    NEED(k, "Equalizer/conv3d_1/kernel");
+    NEED(b, "Equalizer/conv3d_1/bias");
+    DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == S && k->shape[1] == K && k->shape[4] == 2,
+               "Equalizer/conv3d_1/kernel: expected [%d,%d,1,1,2]", S, K);
+    GemmLayer* L = &h->g7;
+    L->K = SK2; L->N = SK2;
+    L->W.assign((size_t)SK2 * SK2, 0.f);
+    const int pl = (S - 1) / 2, pw = (K - 1) / 2;
+    for (int d = 0; d < S; ++d)
+      for (int hh = 0; hh < K; ++hh) {
+        const int co = (d * K + hh) * 2;                 // output column (re)
+        for (int i = 0; i < S; ++i) {
+          const int di = d + i - pl;
+          if (di < 0 || di >= S) continue;
+          for (int j = 0; j < K; ++j) {
+            const int hj = hh + j - pw;
+            if (hj < 0 || hj >= K) continue;
+            const float wa = k->data[(size_t)(i * K + j) * 2], wb = k->data[(size_t)(i * K + j) * 2 + 1];
+            const int ri = (di * K + hj) * 2;            // input row (re)
+            L->W[(size_t)ri * SK2 + co] = wa;
+            L->W[(size_t)ri * SK2 + co + 1] = wb;
+            L->W[(size_t)(ri + 1) * SK2 + co] = -wb;
+            L->W[(size_t)(ri + 1) * SK2 + co + 1] = -wa;
+          }
+        }
+      }
+    L->bias.resize(SK2);
+    for (int i = 0; i < SK2; i += 2) {
+      L->bias[i] = b->data[0] - b->data[1];
+      L->bias[i + 1] = b->data[1] - b->data[0];
+    }
+  }
+  if ((rc = pack_1xK("Equalizer/conv3d_2/kernel", "Equalizer/conv3d_2/bias", &h->g8, true))) return rc;
+  if ((rc = pack_1xK("Equalizer/conv3d_3/kernel", "Equalizer/conv3d_3/bias", &h->g9, false))) return rc;
+  {
+    // dense_5 input is concat per subcarrier (eq_re, eq_im, corr_re, corr_im) -> row h*4+c.
+    // Our producers write [eq_out (2K) | corr_out (2K)]; permute the rows accordingly.
+    NEED(k, "Equalizer/dense_5/kernel");
+    NEED(b, "Equalizer/dense_5/bias");
+    DCCN_CHECK(k->shape[0] == 4 * K && k->shape[1] == 2 * h->T, "Equalizer/dense_5/kernel shape");
+    GemmLayer* L = &h->g10;
+    L->K = 4 * K; L->N = 2 * h->T;
+    L->W.resize((size_t)L->K * L->N);
+    for (int hh = 0; hh < K; ++hh)
+      for (int cc = 0; cc < 4; ++cc) {
+        const int src = hh * 4 + cc;
+        const int dst = (cc < 2 ? 0 : 2 * K) + hh * 2 + (cc & 1);
+        memcpy(&L->W[(size_t)dst * L->N], &k->data[(size_t)src * L->N], (size_t)L->N * 4);
+      }
+    L->bias = b->data;
+  }
+  GemmLayer* ls[] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
+  for (GemmLayer* L : ls)
+    if ((rc = upload_layer(h, L, s))) return rc;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// GEMM dispatch
+// ---------------------------------------------------------------------------------------
+template <class Epi>
+static int run_gemm(dccn_handle* h, const GemmLayer& L, const Act& A, int a_col_off, int64_t M, const Epi& epi,
+                    cudaStream_t s) {
+  const int prec = h->cfg.precision;
+  if (prec == DCCN_PREC_EXACT)
+    return launch_gemm_simt<Epi>(A.p0 + a_col_off, A.p1 ? A.p1 + a_col_off : nullptr, A.ld, L.dW, (int)M, L.N, L.K,
+                                 epi, s);
+  TcOperands op;
+  int rc = make_tmap(&op.a0, A.p0 + a_col_off, M, L.K, A.ld, 128);
+  if (rc) return rc;
+  op.b0 = L.tmB0;
+  const bool split = prec == DCCN_PREC_PARITY;
+  if (split) {
+    DCCN_CHECK(A.p1 != nullptr, "parity mode needs hi/lo activation planes");
+    rc = make_tmap(&op.a1, A.p1 + a_col_off, M, L.K, A.ld, 128);
+    if (rc) return rc;
+    op.b1 = L.tmB1;
+  }
+#define DCCN_TC(BNV)                                                                                         \
+  return split ? launch_gemm_tc<BNV, true, Epi>(op, (int)M, L.N, L.K, epi, s, h->num_sms)                    \
+               : launch_gemm_tc<BNV, false, Epi>(op, (int)M, L.N, L.K, epi, s, h->num_sms)
+  if constexpr (std::is_same<Epi, EpiStore>::value) {
+    switch (L.BN) {
+      case 32: DCCN_TC(32);
+      case 160: DCCN_TC(160);
+      default: DCCN_TC(128);
+    }
+  } else {   // fused phase-equaliser / demod-head epilogues only exist for 128-wide tiles
+    DCCN_CHECK(L.BN == 128, "fused epilogue expects BN=128 (N=%d)", L.N);
+    DCCN_TC(128);
+  }
+#undef DCCN_TC
+}
+
+static ActOut out_of(const Act& a, int col_off = 0) { return ActOut{a.p0, a.p1, a.ld, col_off}; }
+
+static EpiStore store_epi(const GemmLayer& L, const Act& dst, int col_off, int64_t M, int act = 0, float* aux = nullptr,
+                          int aux_ld = 0) {
+  EpiStore e;
+  e.bias = L.dBias;
+  e.out = out_of(dst, col_off);
+  e.aux = aux;
+  e.aux_ld = aux_ld;
+  e.act = act;
+  e.M = (int)M;
+  e.N = L.N;
+  return e;
+}
+
+template <int NB, bool V1>
+static int run_head(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
+                    unsigned long long* conf, double* ce, cudaStream_t s) {
+  EpiHead<NB, V1> e;
+  e.bias = h->r2.dBias;
+  e.hw = h->hw;
+  e.bits = bits;
+  e.soft = soft;
+  e.hard = hard;
+  e.conf = conf;
+  e.ce_sum = ce;
+  e.M = (int)Bc;
+  e.N = h->r2.N;
+  return run_gemm(h, h->r2, h->r1o, 0, Bc, e, s);
+}
+
+static int run_head_dispatch(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
+                             unsigned long long* conf, double* ce, cudaStream_t s) {
+  const bool v1 = h->cfg.head == DCCN_HEAD_V1;
+  switch (h->NB) {
+    case 1: return v1 ? run_head<1, true>(h, Bc, bits, soft, hard, conf, ce, s) : run_head<1, false>(h, Bc, bits, soft, hard, conf, ce, s);
+    case 2: return v1 ? run_head<2, true>(h, Bc, bits, soft, hard, conf, ce, s) : run_head<2, false>(h, Bc, bits, soft, hard, conf, ce, s);
+    case 3: return v1 ? run_head<3, true>(h, Bc, bits, soft, hard, conf, ce, s) : run_head<3, false>(h, Bc, bits, soft, hard, conf, ce, s);
+    default: return v1 ? run_head<4, true>(h, Bc, bits, soft, hard, conf, ce, s) : run_head<4, false>(h, Bc, bits, soft, hard, conf, ce, s);
+  }
+}
+
+static int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, float* rstd, cudaStream_t s) {
+  const int P = h->P;
+  DCCN_CUDA_OK(cudaMemsetAsync(h->d_sums, 0, (size_t)2 * P * sizeof(double), s));
+  const int gx = (P / 4 + 127) / 128;
+  int gy = (int)((B + 15) / 16);
+  const int gy_max = (h->num_sms * 8) / gx;
+  if (gy > gy_max) gy = gy_max;
+  if (gy < 1) gy = 1;
+  moments_partial_kernel<<<dim3(gx, gy), 128, 0, s>>>(x, (long long)B, P, h->d_sums);
+  moments_final_kernel<<<(P + 255) / 256, 256, 0, s>>>(h->d_sums, (long long)B, P, mean, rstd);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// one chunk of Bc frames through [equalizer ->] receiver
+static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
+                     float* eq_out, float* chest_out, unsigned long long* conf, double* ce, int flags,
+                     cudaStream_t s) {
+  const bool use_eq = h->cfg.equalizer && !(flags & DCCN_FWD_SKIP_EQ);
+  const int S = h->S, K = h->K, T = h->T, Tin = h->Tin, P = h->P;
+  const int cp_off = (T - Tin) * 2;            // receiver / equalizer skip the CP when !use_cp
+  int rc;
+  // ---- a2 (+ layer norm) ---------------------------------------------------------
+  {
+    const int warps_per_block = 8;
+    const int grid = (int)((Bc + warps_per_block - 1) / warps_per_block);
+    DCCN_CHECK(P <= 10 * 128, "frame of %d floats exceeds the prep kernel's register tile", P);
+    prep_kernel<10><<<grid, 256, 0, s>>>(x, (long long)Bc, P, h->d_mean, h->d_rstd,
+                                         (flags & DCCN_FWD_NO_NORM) ? 0 : 1, use_eq ? 1 : 0, out_of(h->a0));
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  const Act* rx_in = &h->a0;
+  if (use_eq) {
+    const int64_t MS = Bc * S;
+    // views: [Bc, S*X] buffers are addressed as [Bc*S, X] by the per-symbol layers
+    Act a0v = h->a0;  a0v.ld = 2 * T;
+    Act t1v = h->t1;  t1v.ld = 2 * K;
+    Act fv = h->f;    fv.ld = 2 * K;
+    Act eqv = h->eq;  eqv.ld = 2 * K;
+    Act corrv = h->corr; corrv.ld = K;
+    Act catv = h->cat;   // [Bc*S, 4K]
+    Act oeqv = h->oeq; oeqv.ld = 2 * T;
+    // dense: per-symbol 2*Tin -> 2K                               model.py:370
+    if ((rc = run_gemm(h, h->g1, a0v, cp_off, MS, store_epi(h->g1, t1v, 0, MS), s))) return rc;
+    // learned DFT (1,K) 'valid' complex conv                       model.py:377-379
+    if ((rc = run_gemm(h, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
+    // pilot bottleneck and channel-estimate MLP                    model.py:393-424
+    if ((rc = run_gemm(h, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, h->g4, h->p32, 0, Bc, store_epi(h->g4, h->u1, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, h->g5, h->u1, 0, Bc, store_epi(h->g5, h->u2, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, h->g6, h->u2, 0, Bc, store_epi(h->g6, h->u1, 0, Bc, /*tanh*/ 1), s))) return rc;
+    // (S,K) 'same' complex conv as Toeplitz GEMM + fused phase equaliser   model.py:426-437
+    {
+      EpiPhaseEq e;
+      e.bias = h->g7.dBias;
+      e.f0 = h->f.p0;
+      e.f1 = h->f.p1;
+      e.ld_f = h->f.ld;
+      e.eq = out_of(h->eq);
+      e.corr = out_of(h->corr);
+      e.chest_out = chest_out;
+      e.M = (int)Bc;
+      e.N = h->g7.N;
+      if ((rc = run_gemm(h, h->g7, h->u1, 0, Bc, e, s))) return rc;
+    }
+    // corr / eq (1,K) 'valid' complex convs -> [eq_out | corr_out]  model.py:437-448
+    if ((rc = run_gemm(h, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
+    if ((rc = run_gemm(h, h->g9, eqv, 0, MS, store_epi(h->g9, catv, 0, MS), s))) return rc;
+    // dense_5: 4K -> 2T per symbol                                  model.py:457-462
+    if ((rc = run_gemm(h, h->g10, catv, 0, MS, store_epi(h->g10, oeqv, 0, MS, 0, eq_out, 2 * T), s))) return rc;
+    rx_in = &h->oeq;
+    if (flags & DCCN_FWD_EQ_ONLY) return 0;
+  }
+  // ---- ofdm_dense_rx -----------------------------------------------------------------
+  {
+    const int64_t MS = Bc * S;
+    Act inv = *rx_in;  inv.ld = 2 * T;
+    Act r1v = h->r1o;  r1v.ld = 2 * h->F;
+    if ((rc = run_gemm(h, h->r1, inv, cp_off, MS, store_epi(h->r1, r1v, 0, MS), s))) return rc;
+    if ((rc = run_head_dispatch(h, Bc, bits, soft, hard, conf, ce, s))) return rc;
+  }
+  return 0;
+}
+
+__global__ void conf_copy_kernel(const unsigned long long* src, long long* dst) {
+  if (threadIdx.x < 4) dst[threadIdx.x] += (long long)src[threadIdx.x];
+}
+
+}  // namespace dccn
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int dccn_abi_version(void) { return DCCN_ABI_VERSION; }
+const char* dccn_last_error(void) { return g_last_error.c_str(); }
+
+int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
+  DCCN_CHECK(cfg && out, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(-3, "no CUDA device: libdccn has no CPU fallback");
+  DCCN_CHECK(cfg->nbits >= 1 && cfg->nbits <= 4, "nbits must be 1..4");
+  DCCN_CHECK(cfg->nfft > 0 && cfg->nfft % 16 == 0 && cfg->nsymbol > 0 && cfg->nfilter > 0 && cfg->nfilter % 16 == 0,
+             "bad geometry");
+  DCCN_CHECK(cfg->precision >= 0 && cfg->precision <= 2, "bad precision mode");
+  dccn_handle* h = new dccn_handle();
+  h->cfg = *cfg;
+  DCCN_CUDA_OK(cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  DCCN_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+  h->num_sms = prop.multiProcessorCount;
+  if (cfg->precision != DCCN_PREC_EXACT && prop.major != 10) {
+    delete h;
+    return set_error(-3, "tcgen05 precision modes need an sm_100 device (found sm_%d%d)", prop.major, prop.minor);
+  }
+  h->S = cfg->nsymbol;
+  h->K = cfg->nfft;
+  h->T = cfg->nfft + cfg->cp_len;
+  h->Tin = cfg->use_cp ? h->T : h->K;
+  h->F = cfg->nfilter;
+  h->D = cfg->n_data;
+  h->NB = cfg->nbits;
+  h->P = h->S * h->T * 2;
+  h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 4096;
+  if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
+    delete h;
+    return set_error(-2, "frame size must be a multiple of 4 floats");
+  }
+  if (cfg->equalizer && cfg->nfilter != cfg->nfft) {
+    delete h;
+    return set_error(-2, "equalizer_ofdm requires nfilter == nfft");
+  }
+  // ---- workspace -----------------------------------------------------------------
+  const bool split = cfg->precision == DCCN_PREC_PARITY;
+  const int64_t C = h->chunk;
+  const int S = h->S, K = h->K, T = h->T;
+  int rc = 0;
+  rc |= dev_alloc(h, (void**)&h->d_sums, (size_t)2 * h->P * sizeof(double));
+  rc |= dev_alloc(h, (void**)&h->d_mean, (size_t)h->P * 4);
+  rc |= dev_alloc(h, (void**)&h->d_rstd, (size_t)h->P * 4);
+  rc |= dev_alloc(h, (void**)&h->d_power, sizeof(double));
+  rc |= dev_alloc(h, (void**)&h->d_conf, 4 * sizeof(unsigned long long));
+  rc |= dev_alloc(h, (void**)&h->d_ce, sizeof(double));
+  rc |= dev_alloc(h, (void**)&h->d_res_conf, 4 * sizeof(int64_t));
+  rc |= dev_alloc(h, (void**)&h->d_res_ce, sizeof(double));
+  rc |= alloc_act(h, &h->a0, C, h->P, split);
+  rc |= alloc_act(h, &h->r1o, C, S * h->F * 2, split);
+  if (cfg->equalizer) {
+    rc |= alloc_act(h, &h->t1, C, S * K * 2, split);
+    rc |= alloc_act(h, &h->f, C, S * K * 2, split);
+    rc |= alloc_act(h, &h->p32, C, 2 * cfg->pilot_size, split);
+    rc |= alloc_act(h, &h->u1, C, S * K * 2, split);
+    rc |= alloc_act(h, &h->u2, C, S * K * 2, split);
+    rc |= alloc_act(h, &h->eq, C, S * K * 2, split);
+    rc |= alloc_act(h, &h->corr, C, S * K, split);
+    rc |= alloc_act(h, &h->cat, C * S, 4 * K, split);
+    rc |= alloc_act(h, &h->oeq, C, h->P, split);
+  }
+  if (rc) {
+    dccn_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+void dccn_destroy(dccn_handle* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+size_t dccn_workspace_bytes(const dccn_handle* h) { return h ? h->ws_bytes : 0; }
+
+int dccn_set_weight(dccn_handle* h, const char* tf_name, const float* host, const int64_t* shape, int rank) {
+  DCCN_CHECK(h && tf_name && host && shape && rank >= 0 && rank <= 8, "bad argument");
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < rank; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
+  t.data.assign(host, host + n);
+  h->raw[tf_name] = std::move(t);
+  h->committed = false;
+  return 0;
+}
+
+int64_t dccn_get_weight(dccn_handle* h, const char* tf_name, float* host, int64_t capacity) {
+  if (!h || !tf_name) return set_error(-2, "bad argument");
+  const HostTensor* t = find(h, tf_name);
+  if (!t) return set_error(-2, "weight '%s' was not set", tf_name);
+  const int64_t n = (int64_t)t->data.size();
+  if (host) {
+    if (capacity < n) return set_error(-2, "buffer too small for '%s'", tf_name);
+    memcpy(host, t->data.data(), (size_t)n * 4);
+  }
+  return n;
+}
+
+int dccn_commit_weights(dccn_handle* h, void* stream) {
+  DCCN_CHECK(h, "null handle");
+  int rc = build_layers(h, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->committed = true;
+  return 0;
+}
+
+int dccn_batch_moments(dccn_handle* h, const float* x_dev, int64_t B, float* mean_dev, float* rstd_dev,
+                       void* stream) {
+  DCCN_CHECK(h && x_dev && mean_dev && rstd_dev && B > 0, "bad argument");
+  return run_moments(h, x_dev, B, mean_dev, rstd_dev, (cudaStream_t)stream);
+}
+
+int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* bits_dev, float* soft_dev,
+                 uint8_t* hard_dev, float* eq_dev, float* chest_dev, int64_t* conf_dev, double* ce_sum_dev,
+                 int flags, void* stream) {
+  DCCN_CHECK(h && x_dev, "null argument");
+  DCCN_CHECK(!(flags & DCCN_FWD_EQ_ONLY) || h->cfg.equalizer, "DCCN_FWD_EQ_ONLY needs cfg.equalizer");
+  DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
+  DCCN_CHECK(B > 0, "empty batch");
+  DCCN_CHECK(!(eq_dev || chest_dev) || h->cfg.equalizer, "eq/chest outputs need cfg.equalizer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = 0;
+  if (!(flags & DCCN_FWD_NO_NORM)) rc = run_moments(h, x_dev, B, h->d_mean, h->d_rstd, s);
+  if (rc) return rc;
+  const bool want_conf = bits_dev && conf_dev;
+  if (want_conf) DCCN_CUDA_OK(cudaMemsetAsync(h->d_conf, 0, 4 * sizeof(unsigned long long), s));
+  const int D = h->D, NB = h->NB;
+  for (int64_t b0 = 0; b0 < B; b0 += h->chunk) {
+    const int64_t Bc = (B - b0) < h->chunk ? (B - b0) : h->chunk;
+    rc = run_chunk(h, x_dev + (size_t)b0 * h->P, Bc, bits_dev ? bits_dev + (size_t)b0 * D * NB : nullptr,
+                   soft_dev ? soft_dev + (size_t)b0 * D * NB * 2 : nullptr,
+                   hard_dev ? hard_dev + (size_t)b0 * D * NB : nullptr,
+                   eq_dev ? eq_dev + (size_t)b0 * h->P : nullptr,
+                   chest_dev ? chest_dev + (size_t)b0 * h->S * h->K * 2 : nullptr,
+                   want_conf ? h->d_conf : nullptr, (bits_dev && ce_sum_dev) ? ce_sum_dev : nullptr, flags, s);
+    if (rc) return rc;
+  }
+  if (want_conf) {
+    conf_copy_kernel<<<1, 32, 0, s>>>(h->d_conf, (long long*)conf_dev);
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int dccn_forward_host(dccn_handle* h, const float* x_host, int64_t B, const uint8_t* bits_host, uint8_t* hard_host,
+                      int64_t* conf_host, double* ce_sum_host, void* stream) {
+  DCCN_CHECK(h && x_host && B > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nb = (size_t)h->D * h->NB;
+  if (h->stage_frames < B) {
+    // (re)allocate staging; old buffers stay in the alloc list until destroy
+    int rc = dev_alloc(h, (void**)&h->d_x, (size_t)B * h->P * 4);
+    rc |= dev_alloc(h, (void**)&h->d_bits, (size_t)B * nb);
+    rc |= dev_alloc(h, (void**)&h->d_hard, (size_t)B * nb);
+    if (rc) return rc;
+    h->stage_frames = B;
+  }
+  DCCN_CUDA_OK(cudaMemcpyAsync(h->d_x, x_host, (size_t)B * h->P * 4, cudaMemcpyHostToDevice, s));
+  if (bits_host) DCCN_CUDA_OK(cudaMemcpyAsync(h->d_bits, bits_host, (size_t)B * nb, cudaMemcpyHostToDevice, s));
+  int64_t* d_res_conf = h->d_res_conf;
+  double* d_res_ce = h->d_res_ce;
+  DCCN_CUDA_OK(cudaMemsetAsync(d_res_conf, 0, 4 * sizeof(int64_t), s));
+  DCCN_CUDA_OK(cudaMemsetAsync(d_res_ce, 0, sizeof(double), s));
+  int rc = dccn_forward(h, h->d_x, B, bits_host ? h->d_bits : nullptr, nullptr, hard_host ? h->d_hard : nullptr,
+                        nullptr, nullptr, d_res_conf, d_res_ce, 0, s);
+  if (rc) return rc;
+  if (hard_host) DCCN_CUDA_OK(cudaMemcpyAsync(hard_host, h->d_hard, (size_t)B * nb, cudaMemcpyDeviceToHost, s));
+  if (conf_host) DCCN_CUDA_OK(cudaMemcpyAsync(conf_host, d_res_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (ce_sum_host) DCCN_CUDA_OK(cudaMemcpyAsync(ce_sum_host, d_res_ce, sizeof(double), cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int dccn_cconv2d(const float* x_dev, int64_t B, int L, int W, int C, const float* kernel_dev, const float* bias_dev,
+                 int filters, int kl, int kw, int padding, float* y_dev, void* stream) {
+  DCCN_CHECK(x_dev && kernel_dev && bias_dev && y_dev, "null argument");
+  DCCN_CHECK(B > 0 && L > 0 && W > 0 && C > 0 && filters > 0 && kl > 0 && kw > 0, "bad shape");
+  DCCN_CHECK(padding == 0 || padding == 1, "padding must be 0 ('valid') or 1 ('same')");
+  int Lo, Wo, pl = 0, pw = 0;
+  if (padding == 1) {
+    Lo = L; Wo = W; pl = (kl - 1) / 2; pw = (kw - 1) / 2;
+  } else {
+    Lo = L - kl + 1; Wo = W - kw + 1;
+    DCCN_CHECK(Lo > 0 && Wo > 0, "'valid' kernel larger than the input");
+  }
+  const long long total = (long long)B * Lo * Wo * filters;
+  cconv2d_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const float2*)x_dev, (long long)B, L, W, C, kernel_dev, bias_dev, filters, kl, kw, pl, pw, Lo, Wo,
+      (float2*)y_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_samp, const double* alpha_dev,
+                       const double* coeff_dev, int n_taps, int n_fir, const double* z_dev, const float* snr_db_dev,
+                       const double* normals_dev, uint64_t seed, float* rx_dev, float* fir_only_dev, void* stream) {
+  DCCN_CHECK(h && tx_dev && rx_dev && snr_db_dev && B > 0 && n_samp > 0, "bad argument");
+  DCCN_CHECK(n_taps >= 0 && n_taps <= 32 && n_fir <= kMaxFir, "at most 32 paths / FIR taps");
+  DCCN_CHECK(n_taps == 0 || (coeff_dev != nullptr && n_fir >= 1), "coeff_dev / n_fir missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  DCCN_CUDA_OK(cudaMemsetAsync(h->d_power, 0, sizeof(double), s));
+  float* faded = fir_only_dev ? fir_only_dev : rx_dev;
+  chan_fir_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)tx_dev, (long long)B, n_samp, alpha_dev,
+                                                         coeff_dev, n_taps, n_fir, z_dev, seed, (float2*)faded,
+                                                         h->d_power);
+  const long long total = (long long)B * n_samp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+  awgn_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2*)faded, (long long)B, n_samp, h->d_power, snr_db_dev,
+                                               normals_dev, seed ^ 0x9E3779B97F4A7C15ull, (float2*)rx_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dccn_ber_accum(const uint8_t* hard_dev, const uint8_t* bits_dev, int64_t n, int64_t* conf_dev, void* stream) {
+  DCCN_CHECK(hard_dev && bits_dev && conf_dev && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ber_accum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(hard_dev, bits_dev, (long long)n,
+                                                                      (unsigned long long*)conf_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int32_t* data_sc_dev, int n_data,
+                   const int32_t* pilot_sc_dev, int n_pilot, const float* constellation_dev, float pilot_re,
+                   float pilot_im, float* tx_dev, void* stream) {
+  DCCN_CHECK(h && bits_dev && data_sc_dev && constellation_dev && tx_dev && B > 0, "bad argument");
+  DCCN_CHECK(n_data == h->D, "n_data (%d) != cfg.n_data (%d)", n_data, h->D);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int S = h->S, K = h->K;
+  // subcarrier role map built on the fly (tiny): -1 guard, -2 pilot, >=0 data index
+  std::vector<int32_t> hd(n_data), hp(n_pilot > 0 ? n_pilot : 1);
+  DCCN_CUDA_OK(cudaMemcpyAsync(hd.data(), data_sc_dev, (size_t)n_data * 4, cudaMemcpyDeviceToHost, s));
+  if (n_pilot > 0)
+    DCCN_CUDA_OK(cudaMemcpyAsync(hp.data(), pilot_sc_dev, (size_t)n_pilot * 4, cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  std::vector<int32_t> map((size_t)S * K, -1);
+  for (int i = 0; i < n_data; ++i) {
+    DCCN_CHECK(hd[i] >= 0 && hd[i] < S * K, "data subcarrier index out of range");
+    map[hd[i]] = i;
+  }
+  for (int i = 0; i < n_pilot; ++i) {
+    DCCN_CHECK(hp[i] >= 0 && hp[i] < S * K, "pilot subcarrier index out of range");
+    map[hp[i]] = -2;
+  }
+  int32_t* d_map = nullptr;
+  DCCN_CUDA_OK(cudaMalloc((void**)&d_map, map.size() * 4));
+  DCCN_CUDA_OK(cudaMemcpyAsync(d_map, map.data(), map.size() * 4, cudaMemcpyHostToDevice, s));
+  const long long syms = (long long)B * S;
+  const size_t smem = (size_t)9 * K * sizeof(double2);
+  tx_kernel<<<(unsigned)((syms + 7) / 8), 256, smem, s>>>(bits_dev, (long long)B, S, K, h->cfg.cp_len, h->NB, h->D,
+                                                          d_map, (const float2*)constellation_dev,
+                                                          make_float2(pilot_re, pilot_im), (float2*)tx_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  cudaFree(d_map);
+  return 0;
+}
+
+int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream) {
+  DCCN_CHECK(bits_dev && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  const long long threads = (n + 15) / 16;
+  bit_source_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits_dev, (long long)n, seed);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

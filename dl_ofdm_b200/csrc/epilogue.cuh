@@ -1,0 +1,254 @@
+// epilogue.cuh -- fused GEMM epilogues shared by the tcgen05 and the SIMT main loops.
+//
+// Contract: the main loop hands each thread NC consecutive accumulator columns of ONE
+// output row (NC even, col0 even, so an (I,Q) pair never straddles two calls):
+//     epi.run<NC>(row, col0, v);     ... per chunk
+//     epi.flush();                   ... once per thread at kernel end
+// Activations are stored as one fp32 plane (p1 == nullptr) or as a tf32 hi/lo pair
+// of planes (DCCN_PREC_PARITY) that the next layer's TMA loads feed straight to the
+// tensor core.
+#pragma once
+#include "common.cuh"
+
+namespace dccn {
+
+// destination of an activation matrix [rows, ld] (+ column offset) in 1 or 2 planes
+struct ActOut {
+  float* p0;
+  float* p1;   // nullptr => single full-precision plane
+  int ld;
+  int col_off;
+};
+
+template <int NC>
+DCCN_DEVINL void store_act(const ActOut& o, int row, int col, const float (&y)[NC]) {
+  float* d0 = o.p0 + (size_t)row * o.ld + o.col_off + col;
+  if (o.p1 == nullptr) {
+    if constexpr (NC % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(d0 + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; i += 2) *reinterpret_cast<float2*>(d0 + i) = make_float2(y[i], y[i + 1]);
+    }
+  } else {
+    float* d1 = o.p1 + (size_t)row * o.ld + o.col_off + col;
+    float hi[NC], lo[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) tf32_split(y[i], hi[i], lo[i]);
+    if constexpr (NC % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NC; i += 4) {
+        *reinterpret_cast<float4*>(d0 + i) = make_float4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
+        *reinterpret_cast<float4*>(d1 + i) = make_float4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NC; i += 2) {
+        *reinterpret_cast<float2*>(d0 + i) = make_float2(hi[i], hi[i + 1]);
+        *reinterpret_cast<float2*>(d1 + i) = make_float2(lo[i], lo[i + 1]);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// y = act(acc + bias)  ->  activation planes      (tf.layers.dense / packed complex layers)
+// -------------------------------------------------------------------------------------
+struct EpiStore {
+  const float* bias;   // [N] (may be nullptr)
+  ActOut out;
+  float* aux;          // optional extra full-precision copy [rows, aux_ld] (API outputs), or nullptr
+  int aux_ld;
+  int act;             // 0 = linear, 1 = tanh
+  int M, N;
+  struct State {};
+
+  template <int NC>
+  DCCN_DEVINL void run(State&, int row, int col0, float (&v)[NC]) const {
+    if (row >= M || col0 >= N) return;
+    float y[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      float t = v[i] + (bias ? __ldg(bias + col0 + i) : 0.f);
+      y[i] = (act == 1) ? tanhf(t) : t;
+    }
+    store_act<NC>(out, row, col0, y);
+    if (aux) {
+      float* d = aux + (size_t)row * aux_ld + col0;
+#pragma unroll
+      for (int i = 0; i < NC; i += 2) *reinterpret_cast<float2*>(d + i) = make_float2(y[i], y[i + 1]);
+    }
+  }
+  DCCN_DEVINL void flush(State&) const {}
+};
+
+// -------------------------------------------------------------------------------------
+// Phase-only equaliser fused behind the (S,K) 'same' complex conv (dev/py/model.py:426-437):
+//   chest = acc + bias                       (complex, IQ interleaved)
+//   eq    = f * conj(chest) / |chest|        (no epsilon, like the reference)
+//   corr  = eq * conj(eq)                    (real part only is non-zero)
+// f = inputs_complex (output of the learned-DFT layer), read back as hi+lo.
+// -------------------------------------------------------------------------------------
+struct EpiPhaseEq {
+  const float* bias;    // [N] packed (b0-b1, b1-b0) pattern
+  const float* f0;      // inputs_complex plane 0 [M, ld_f]
+  const float* f1;      // plane 1 (lo) or nullptr
+  int ld_f;
+  ActOut eq;            // [M, N]      IQ interleaved
+  ActOut corr;          // [M, N/2]    real part only (imag is exactly 0 and is dropped from the GEMM)
+  float* chest_out;     // optional fp32 [M, N] ('chest' fetch), or nullptr
+  int M, N;
+  struct State {};
+
+  template <int NC>
+  DCCN_DEVINL void run(State&, int row, int col0, float (&v)[NC]) const {
+    if (row >= M || col0 >= N) return;
+    const float* fp0 = f0 + (size_t)row * ld_f + col0;
+    const float* fp1 = f1 ? f1 + (size_t)row * ld_f + col0 : nullptr;
+    float e[NC], c[NC / 2];
+#pragma unroll
+    for (int i = 0; i < NC; i += 2) {
+      float cr = v[i] + __ldg(bias + col0 + i);
+      float ci = v[i + 1] + __ldg(bias + col0 + i + 1);
+      float2 f = *reinterpret_cast<const float2*>(fp0 + i);
+      if (fp1) {
+        float2 fl = *reinterpret_cast<const float2*>(fp1 + i);
+        f.x += fl.x;
+        f.y += fl.y;
+      }
+      float ab = hypotf(cr, ci);                 // tf.abs(complex64)
+      float nr = cr / ab;                        // real(conj)/abs      model.py:432
+      float ni = (-ci) / ab;                     // imag(conj)/abs
+      float er = f.x * nr - f.y * ni;            // complex multiply    model.py:434
+      float ei = f.x * ni + f.y * nr;
+      e[i] = er;
+      e[i + 1] = ei;
+      c[i / 2] = er * er + ei * ei;              // eq*conj(eq): real = er^2+ei^2, imag = 0
+      v[i] = cr;
+      v[i + 1] = ci;
+    }
+    store_act<NC>(eq, row, col0, e);
+    store_act<NC / 2>(corr, row, col0 / 2, c);
+    if (chest_out) {
+      float* d = chest_out + (size_t)row * N + col0;
+#pragma unroll
+      for (int i = 0; i < NC; i += 2) *reinterpret_cast<float2*>(d + i) = make_float2(v[i], v[i + 1]);
+    }
+  }
+  DCCN_DEVINL void flush(State&) const {}
+};
+
+// -------------------------------------------------------------------------------------
+// Demodulation head fused behind the 896->2D dense (dev/py/model.py:1275-1291) + the BER
+// head (dev/py/ofdmreceiver_np.py:154-169).  Per data subcarrier d with (I,Q)=out_iq:
+//   h   = leaky( [conv2d_1(] conv2d(I,Q) [)] )            2 -> 2^nb (-> 2^nb for the v1 head)
+//   lg  = leaky( dense_1( concat(h, I, Q) ) )              -> 2*nb
+//   p   = softmax over each bit's pair; hard = argmax (first index wins ties)
+//   conf[truth][hard]++ ; ce += logsumexp(p) - p[truth]    (softmax-xent ON the softmax, Q5)
+// -------------------------------------------------------------------------------------
+struct HeadWeights {
+  float Wc[2][16];
+  float bc[16];
+  float Wc1[16][16];
+  float bc1[16];
+  float W1[18][8];
+  float b1[8];
+};
+
+template <int NB, bool V1>
+struct EpiHead {
+  static constexpr int MO = 1 << NB;
+  const float* bias;          // [N = 2*D]
+  HeadWeights hw;
+  const uint8_t* bits;        // [M, D, NB] or nullptr
+  float* soft;                // [M, D, NB, 2] or nullptr
+  uint8_t* hard;              // [M, D, NB] or nullptr
+  unsigned long long* conf;   // [4] or nullptr
+  double* ce_sum;             // [1] or nullptr
+  int M, N;
+  struct State {   // per-thread accumulators (flushed once per thread)
+    unsigned int c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+    float ce = 0.f;
+  };
+
+  template <int NC>
+  DCCN_DEVINL void run(State& st, int row, int col0, float (&v)[NC]) const {
+    if (row >= M || col0 >= N) return;
+    const int D = N >> 1;
+#pragma unroll
+    for (int i = 0; i < NC; i += 2) {
+      const int d = (col0 + i) >> 1;
+      const float I = v[i] + __ldg(bias + col0 + i);
+      const float Q = v[i + 1] + __ldg(bias + col0 + i + 1);
+      float h[MO];
+#pragma unroll
+      for (int m = 0; m < MO; ++m) h[m] = I * hw.Wc[0][m] + Q * hw.Wc[1][m] + hw.bc[m];
+      if constexpr (V1) {
+        float h2[MO];
+#pragma unroll
+        for (int n = 0; n < MO; ++n) {
+          float a = hw.bc1[n];
+#pragma unroll
+          for (int m = 0; m < MO; ++m) a += h[m] * hw.Wc1[m][n];
+          h2[n] = a;
+        }
+#pragma unroll
+        for (int m = 0; m < MO; ++m) h[m] = h2[m];
+      }
+#pragma unroll
+      for (int m = 0; m < MO; ++m) h[m] = fmaxf(0.2f * h[m], h[m]);
+      const size_t o = ((size_t)row * D + d) * NB;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        float l0 = hw.b1[2 * k], l1 = hw.b1[2 * k + 1];
+#pragma unroll
+        for (int m = 0; m < MO; ++m) {
+          l0 += h[m] * hw.W1[m][2 * k];
+          l1 += h[m] * hw.W1[m][2 * k + 1];
+        }
+        l0 += I * hw.W1[MO][2 * k] + Q * hw.W1[MO + 1][2 * k];
+        l1 += I * hw.W1[MO][2 * k + 1] + Q * hw.W1[MO + 1][2 * k + 1];
+        l0 = fmaxf(0.2f * l0, l0);
+        l1 = fmaxf(0.2f * l1, l1);
+        const float mx = fmaxf(l0, l1);
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+        const float s = e0 + e1;
+        const float p0 = e0 / s, p1 = e1 / s;
+        const unsigned hb = p1 > p0 ? 1u : 0u;           // tf.argmax: first index on ties
+        if (soft) *reinterpret_cast<float2*>(soft + (o + k) * 2) = make_float2(p0, p1);
+        if (hard) hard[o + k] = (uint8_t)hb;
+        if (bits) {
+          const unsigned y = bits[o + k];
+          st.c00 += (y == 0 && hb == 0);
+          st.c01 += (y == 0 && hb == 1);
+          st.c10 += (y == 1 && hb == 0);
+          st.c11 += (y == 1 && hb == 1);
+          const float lse = logf(expf(p0) + expf(p1));
+          st.ce += lse - (y ? p1 : p0);
+        }
+      }
+    }
+  }
+  DCCN_DEVINL void flush(State& st) const {
+    if (!bits) return;
+    unsigned a = __reduce_add_sync(0xffffffffu, st.c00);
+    unsigned b = __reduce_add_sync(0xffffffffu, st.c01);
+    unsigned c = __reduce_add_sync(0xffffffffu, st.c10);
+    unsigned d = __reduce_add_sync(0xffffffffu, st.c11);
+    double e = (double)st.ce;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if ((threadIdx.x & 31) == 0) {
+      if (conf) {
+        if (a) atomicAdd(conf + 0, (unsigned long long)a);
+        if (b) atomicAdd(conf + 1, (unsigned long long)b);
+        if (c) atomicAdd(conf + 2, (unsigned long long)c);
+        if (d) atomicAdd(conf + 3, (unsigned long long)d);
+      }
+      if (ce_sum) atomicAdd(ce_sum, e);
+    }
+  }
+};
+
+}  // namespace dccn

@@ -1,0 +1,221 @@
+// gemm_tc.cuh -- hand-written sm_100a GEMM: TMA -> shared memory -> tcgen05.mma (kind::tf32)
+// -> TMEM accumulators -> tcgen05.ld -> fused epilogue.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )       A, B row-major with K contiguous ("K-major")
+//
+// * persistent: grid = min(#tiles, #SMs); CTA loops over 128 x BN output tiles, n fastest so
+//   that concurrently running CTAs share the A tile in L2;
+// * warp roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM allocator +
+//   MMA issuer (1 lane), warps 2..5 = epilogue (one TMEM lane quarter each);
+// * three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
+//   (MMA <-> epilogue), static tile schedule;
+// * operands are 128-byte-swizzled [rows x 32 fp32] boxes written by TMA and consumed through
+//   K-major SWIZZLE_128B shared-memory descriptors; out-of-bounds rows / K tail are zero-filled
+//   by TMA, so ragged M, N, K need no special code in the main loop;
+// * SPLIT = true is the 3xTF32 scheme of DCCN_PREC_PARITY: every operand is a (hi, lo) pair of
+//   tf32-exact planes and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  into the same
+//   fp32 accumulator (the lo*lo term, ~2^-22 relative, is dropped).
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace dccn {
+
+constexpr int ilog2_ceil_pow2(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BN, bool SPLIT>
+struct TcCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 32;                       // 32 fp32 = one 128-byte swizzle row
+  static constexpr int UMMA_K = 8;                    // kind::tf32: 32 bytes of K per instruction
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int PLANES = SPLIT ? 2 : 1;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = ilog2_ceil_pow2(2 * BN);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+  static_assert(BN % 32 == 0, "epilogue reads 32-column chunks");
+  static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
+};
+
+struct TcOperands {
+  CUtensorMap a0, a1;   // A hi / lo (a1 unused when !SPLIT)
+  CUtensorMap b0, b1;   // B hi / lo
+};
+
+template <int BN, bool SPLIT, class Epi>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               int M, int N, int K, const __grid_constant__ Epi epi) {
+  using C = TcCfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;   // [2] accumulator ready for the epilogue
+  uint64_t* tempty = tfull + 2;          // [2] accumulator drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = ((M + C::BM - 1) / C::BM) * n_tiles;
+  const int num_kb = (K + C::BK - 1) / C::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (SPLIT) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull[a], 1);
+        mbar_init(&tempty[a], 4);   // one elected lane of each of the 4 epilogue warps
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
+          if (SPLIT) tma_load_2d(st + C::A_BYTES, &tmA1, &full[stage], kb * C::BK, m_blk * C::BM);
+          tma_load_2d(st + C::PLANES * C::A_BYTES, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
+          if (SPLIT)
+            tma_load_2d(st + C::PLANES * C::A_BYTES + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + C::A_BYTES;
+          const uint32_t b_hi = a_hi + C::PLANES * C::A_BYTES;
+          const uint32_t b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+            const uint32_t koff = k * C::UMMA_K * 4;   // byte advance inside the 128 B swizzle row
+            const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
+            const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
+              const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
+              umma_tf32(d, da_lo, db_hi, idesc, first);   // small terms first
+              umma_tf32(d, da_hi, db_lo, idesc, 1u);
+              umma_tf32(d, da_hi, db_hi, idesc, 1u);
+            } else {
+              umma_tf32(d, da_hi, db_hi, idesc, first);
+            }
+          }
+          umma_commit(&empty[stage]);        // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);            // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // =============================== epilogue warps =============================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    typename Epi::State st;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * C::BM + q * 32 + lane;
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(t0 + c * 32, v);
+        epi.template run<32>(st, row, n_blk * BN + c * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    epi.flush(st);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN, bool SPLIT, class Epi>
+inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, const Epi& epi, cudaStream_t s, int num_sms) {
+  using C = TcCfg<BN, SPLIT>;
+  if (M <= 0) return 0;
+  auto kern = gemm_tc_kernel<BN, SPLIT, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, 192, C::SMEM_BYTES, s>>>(op.a0, SPLIT ? op.a1 : op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, epi);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dccn

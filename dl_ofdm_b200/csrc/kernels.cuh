@@ -1,0 +1,359 @@
+// kernels.cuh -- the HBM-bound kernels around the GEMM stack:
+//   batch moments (a2), per-frame normalisation/layer-norm + tf32 split (a2 + model.py:363),
+//   Rayleigh FIR (warp-shuffle) + AWGN (a6, a7), OFDM transmitter, BER accumulation (a5),
+//   and the op-level layers_conv2d_complex (a1).
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace dccn {
+
+// =====================================================================================
+// a2: tf.nn.moments(x, [0])  -- per-position sum / sum-of-squares over the batch axis.
+// x [B, P] fp32 (P = S*T*2, multiple of 4).  grid = (ceil(P/4/128), Gy); each thread owns
+// 4 adjacent positions and strides over frames; fp64 accumulation, one fp64 atomic per
+// position per CTA row-group.  sums[0:P] = sum x, sums[P:2P] = sum x^2.
+// =====================================================================================
+__global__ void __launch_bounds__(128) moments_partial_kernel(const float* __restrict__ x, long long B, int P,
+                                                              double* __restrict__ sums) {
+  const int p4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p4 * 4 >= P) return;
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  for (long long b = blockIdx.y; b < B; b += gridDim.y) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * P) + p4);
+    s[0] += v.x; q[0] += (double)v.x * v.x;
+    s[1] += v.y; q[1] += (double)v.y * v.y;
+    s[2] += v.z; q[2] += (double)v.z * v.z;
+    s[3] += v.w; q[3] += (double)v.w * v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&sums[p4 * 4 + i], s[i]);
+    atomicAdd(&sums[P + p4 * 4 + i], q[i]);
+  }
+}
+
+// mean / rstd in fp32 like the TF graph: rstd = rsqrt(var + 1e-9)
+__global__ void moments_final_kernel(const double* __restrict__ sums, long long B, int P, float* __restrict__ mean,
+                                     float* __restrict__ rstd) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double m = sums[p] / (double)B;
+  double var = sums[P + p] / (double)B - m * m;
+  if (var < 0) var = 0;
+  mean[p] = (float)m;
+  rstd[p] = (float)(1.0 / sqrt(var + 1e-9));
+}
+
+// =====================================================================================
+// prep: one warp per frame.
+//   z  = (x*rstd + (-mean*rstd)) / sqrt(2)          ofdmreceiver_np.py:129  (TF op order, no FMA)
+//   y  = layer_norm(z) over the whole frame          model.py:363 (only in front of the equalizer)
+// and stores y (or z) as activation planes (fp32, or tf32 hi/lo for the 3xTF32 GEMMs).
+// =====================================================================================
+template <int MAXV>   // MAXV float4 per lane: P <= MAXV*128
+__global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ x, long long B, int P,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   int do_norm, int do_ln, ActOut out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int nv = P >> 2;
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)warp * P);
+  float4 z[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 v = __ldg(xp + idx);
+      float4 t = v;
+      if (do_norm) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + idx);
+      const float4 r = __ldg(reinterpret_cast<const float4*>(rstd) + idx);
+      t.x = __fdiv_rn(__fadd_rn(__fmul_rn(v.x, r.x), __fmul_rn(-m.x, r.x)), 1.41421356237f);
+      t.y = __fdiv_rn(__fadd_rn(__fmul_rn(v.y, r.y), __fmul_rn(-m.y, r.y)), 1.41421356237f);
+      t.z = __fdiv_rn(__fadd_rn(__fmul_rn(v.z, r.z), __fmul_rn(-m.z, r.z)), 1.41421356237f);
+      t.w = __fdiv_rn(__fadd_rn(__fmul_rn(v.w, r.w), __fmul_rn(-m.w, r.w)), 1.41421356237f);
+      }
+      z[i] = t;
+      sum += (t.x + t.y) + (t.z + t.w);
+    } else {
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (do_ln) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mu = sum / (float)P;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nv) {
+        const float a = z[i].x - mu, b = z[i].y - mu, c = z[i].z - mu, d = z[i].w - mu;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float inv = (float)(1.0 / sqrt((double)(sq / (float)P) + 1e-12));
+    const float sh = __fmul_rn(-mu, inv);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      z[i].x = __fadd_rn(__fmul_rn(z[i].x, inv), sh);
+      z[i].y = __fadd_rn(__fmul_rn(z[i].y, inv), sh);
+      z[i].z = __fadd_rn(__fmul_rn(z[i].z, inv), sh);
+      z[i].w = __fadd_rn(__fmul_rn(z[i].w, inv), sh);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      float y[4] = {z[i].x, z[i].y, z[i].z, z[i].w};
+      store_act<4>(out, warp, idx * 4, y);
+    }
+  }
+}
+
+// =====================================================================================
+// a6: static Rayleigh FIR, one warp per frame, neighbours exchanged with warp shuffles.
+//   g  = (z * ch_coeff) @ alpha                                 radio.py:433-435
+//   rx = np.convolve(tx, g, 'same')   (centred, zero history)    radio.py:436
+// complex128 arithmetic like NumPy, result rounded to complex64 (radio.py:492).  Also
+// accumulates the batch power sum_b,n |rx|^2 that AWGN_channel_np normalises by.
+// =====================================================================================
+constexpr int kMaxFir = 32;
+
+__global__ void __launch_bounds__(256) chan_fir_kernel(const float2* __restrict__ tx, long long B, int n_samp,
+                                                       const double* __restrict__ alpha,
+                                                       const double* __restrict__ coeff, int n_taps, int n_fir,
+                                                       const double* __restrict__ z_in, uint64_t seed,
+                                                       float2* __restrict__ rx, double* __restrict__ power_sum) {
+  __shared__ double2 gsm[8][kMaxFir];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long frame = (long long)blockIdx.x * 8 + wib;
+  if (frame >= B) return;
+
+  // path gains -> sample-spaced FIR g[j] (lane j owns tap j)
+  double2 a = make_double2(0.0, 0.0);
+  if (n_taps == 0) {
+    if (lane == 0) gsm[wib][0] = make_double2(1.0, 0.0);
+  } else {
+    if (lane < n_taps) {
+      double zr, zi;
+      if (z_in) {
+        zr = z_in[((size_t)frame * n_taps + lane) * 2];
+        zi = z_in[((size_t)frame * n_taps + lane) * 2 + 1];
+      } else {
+        uint32_t r[4];
+        Philox{seed}((uint64_t)frame * 64 + lane, 0xA11CEu, r);
+        float n0, n1;
+        box_muller(r[0], r[1], n0, n1);
+        zr = (double)n0 * 0.70710678118654752;
+        zi = (double)n1 * 0.70710678118654752;
+      }
+      const double c = coeff[lane];
+      a = make_double2(zr * c, zi * c);
+    }
+    double2 g = make_double2(0.0, 0.0);
+    for (int t = 0; t < n_taps; ++t) {
+      const double ar = __shfl_sync(0xffffffffu, a.x, t);
+      const double ai = __shfl_sync(0xffffffffu, a.y, t);
+      if (lane < n_fir) {
+        const double al = alpha ? alpha[t * n_fir + lane] : 1.0;
+        g.x += ar * al;
+        g.y += ai * al;
+      }
+    }
+    if (lane < n_fir) gsm[wib][lane] = g;
+  }
+  __syncwarp();
+  const int M = n_taps == 0 ? 1 : n_fir;
+  const int off = (M - 1) - (M >> 1);         // np.convolve 'same': full[n + off]
+  const float2* txf = tx + (size_t)frame * n_samp;
+  float2* rxf = rx + (size_t)frame * n_samp;
+  double pw = 0.0;
+  float2 prev = make_float2(0.f, 0.f);
+  float2 cur = lane < n_samp ? __ldg(txf + lane) : make_float2(0.f, 0.f);
+  for (int base = 0; base < n_samp; base += 32) {
+    const int nidx = base + 32 + lane;
+    const float2 next = nidx < n_samp ? __ldg(txf + nidx) : make_float2(0.f, 0.f);
+    double accr = 0.0, acci = 0.0;
+    for (int j = 0; j < M; ++j) {
+      const int dlt = off - j;                 // need tx[base + lane + dlt]  (dlt is warp-uniform)
+      // the lane that will be READ decides what it supplies: its sample of the previous /
+      // current / next 32-block (the requesting ranges are disjoint)
+      const float2 supply = dlt < 0 ? (lane >= 32 + dlt ? prev : cur) : (lane < dlt ? next : cur);
+      const int sl = (lane + dlt) & 31;
+      const double xr = __shfl_sync(0xffffffffu, supply.x, sl);
+      const double xi = __shfl_sync(0xffffffffu, supply.y, sl);
+      const double2 g = gsm[wib][j];
+      accr += g.x * xr - g.y * xi;
+      acci += g.x * xi + g.y * xr;
+    }
+    if (base + lane < n_samp) {
+      const float2 o = make_float2((float)accr, (float)acci);
+      rxf[base + lane] = o;
+      pw += (double)o.x * o.x + (double)o.y * o.y;
+    }
+    prev = cur;
+    cur = next;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+  if (lane == 0) atomicAdd(power_sum, pw);
+}
+
+// =====================================================================================
+// a7: AWGN_channel_np -- x / sqrt(mean power of the whole batch) + N(0,1)*sqrt(.5)*10^(-SNR/20)
+// float64 arithmetic like the reference, output rounded to fp32 (the TF feed dtype).
+// One thread per complex sample.
+// =====================================================================================
+__global__ void __launch_bounds__(256) awgn_kernel(const float2* __restrict__ xin, long long B, int n_samp,
+                                                   const double* __restrict__ power_sum,
+                                                   const float* __restrict__ snr_db,
+                                                   const double* __restrict__ normals, uint64_t seed,
+                                                   float2* __restrict__ out) {
+  const long long total = B * n_samp;
+  const double inv = 1.0 / sqrt(*power_sum / (double)total);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / n_samp;
+    const double std_b = sqrt(0.5) * pow(10.0, -(double)__ldg(snr_db + b) / 20.0);
+    double n0, n1;
+    if (normals) {
+      n0 = normals[i * 2];
+      n1 = normals[i * 2 + 1];
+    } else {
+      uint32_t r[4];
+      Philox{seed}((uint64_t)i, 0xB0B0u, r);
+      float f0, f1;
+      box_muller(r[0], r[1], f0, f1);
+      n0 = f0;
+      n1 = f1;
+    }
+    const float2 v = xin[i];
+    out[i] = make_float2((float)((double)v.x * inv + n0 * std_b), (float)((double)v.y * inv + n1 * std_b));
+  }
+}
+
+// =====================================================================================
+// OFDM transmitter (dev/py/ofdm.py:328-380): one warp per OFDM symbol.
+//   grid[k] = constellation[bits] on data carriers, pilot value on pilots, 0 elsewhere
+//   time    = ifft(grid)  (naive 64-point DFT, fp64 accumulate, fp32 out), CP prepended.
+// sc_map [S*K]: -1 guard, -2 pilot, >=0 data index inside the frame.
+// =====================================================================================
+__global__ void __launch_bounds__(256) tx_kernel(const uint8_t* __restrict__ bits, long long B, int S, int K, int CP,
+                                                 int nbits, int D, const int* __restrict__ sc_map,
+                                                 const float2* __restrict__ constellation, float2 pilot,
+                                                 float2* __restrict__ tx) {
+  extern __shared__ double2 tx_sm[];     // [8 warps][K] grid + [K] twiddles
+  double2* tw = tx_sm + 8 * K;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * i / K, &s, &c);
+    tw[i] = make_double2(c, s);
+  }
+  __syncthreads();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long sym = (long long)blockIdx.x * 8 + wib;
+  if (sym >= B * S) return;
+  const long long frame = sym / S;
+  const int s = (int)(sym % S);
+  double2* g = tx_sm + wib * K;
+  for (int k = lane; k < K; k += 32) {
+    const int m = sc_map[s * K + k];
+    float2 v = make_float2(0.f, 0.f);
+    if (m == -2) v = pilot;
+    else if (m >= 0) {
+      int idx = 0;
+      const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
+      for (int b = 0; b < nbits; ++b) idx = (idx << 1) | bp[b];
+      v = constellation[idx];
+    }
+    g[k] = make_double2(v.x, v.y);
+  }
+  __syncwarp();
+  const int T = K + CP;
+  float2* o = tx + (size_t)sym * T;
+  for (int n = lane; n < K; n += 32) {
+    double ar = 0.0, ai = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double2 w = tw[(n * k) % K];
+      const double2 x = g[k];
+      ar += x.x * w.x - x.y * w.y;
+      ai += x.x * w.y + x.y * w.x;
+    }
+    const float2 r = make_float2((float)(ar / K), (float)(ai / K));
+    o[CP + n] = r;
+    if (n >= K - CP) o[n - (K - CP)] = r;
+  }
+}
+
+__global__ void bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint64_t seed) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x);   // 16 bytes per thread
+  if (i * 16 >= n) return;
+  uint32_t r[4];
+  Philox{seed}((uint64_t)i, 0xB175u, r);
+  const uint32_t w = r[0];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (i * 16 + j < n) bits[i * 16 + j] = (uint8_t)((w >> j) & 1u);
+}
+
+// a5: confusion matrix of hard decisions vs bits (rows = truth)
+__global__ void __launch_bounds__(256) ber_accum_kernel(const uint8_t* __restrict__ hard,
+                                                        const uint8_t* __restrict__ bits, long long n,
+                                                        unsigned long long* __restrict__ conf) {
+  unsigned c[4] = {0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c[((bits[i] & 1) << 1) | (hard[i] & 1)]++;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned t = __reduce_add_sync(0xffffffffu, c[k]);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(conf + k, (unsigned long long)t);
+  }
+}
+
+// =====================================================================================
+// a1 op-level: direct evaluation of layers_conv2d_complex (complex.py:140-196).
+// One thread per complex output element (b, l, w, f).
+// =====================================================================================
+__global__ void __launch_bounds__(128) cconv2d_kernel(const float2* __restrict__ x, long long B, int L, int W, int C,
+                                                      const float* __restrict__ kernel, const float* __restrict__ bias,
+                                                      int F, int kl, int kw, int pl, int pw, int Lo, int Wo,
+                                                      float2* __restrict__ y) {
+  const long long total = B * Lo * Wo * F;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = (int)(i % F);
+  long long r = i / F;
+  const int w = (int)(r % Wo);
+  r /= Wo;
+  const int l = (int)(r % Lo);
+  const long long b = r / Lo;
+  // c0 = xr*Wa, c1 = xr*Wb, c2 = xi*Wa, c3 = xi*Wb  (each + its conv3d bias)
+  float c0 = bias[f], c1 = bias[F + f], c2 = bias[f], c3 = bias[F + f];
+  for (int ii = 0; ii < kl; ++ii) {
+    const int li = l + ii - pl;
+    if (li < 0 || li >= L) continue;
+    for (int jj = 0; jj < kw; ++jj) {
+      const int wj = w + jj - pw;
+      if (wj < 0 || wj >= W) continue;
+      const float2* xp = x + (((size_t)b * L + li) * W + wj) * C;
+      const float* kp = kernel + ((size_t)(ii * kw + jj) * C) * (2 * F);
+      for (int c = 0; c < C; ++c) {
+        const float2 xv = __ldg(xp + c);
+        const float wa = __ldg(kp + (size_t)c * 2 * F + f), wb = __ldg(kp + (size_t)c * 2 * F + F + f);
+        c0 = fmaf(xv.x, wa, c0);
+        c1 = fmaf(xv.x, wb, c1);
+        c2 = fmaf(xv.y, wa, c2);
+        c3 = fmaf(xv.y, wb, c3);
+      }
+    }
+  }
+  y[i] = make_float2(c0 - c3, c1 - c2);   // complex.py:187-188
+}
+
+}  // namespace dccn

@@ -1,0 +1,224 @@
+"""Python host over the C ABI: one ``DCCN`` object per (device, model).
+
+PyTorch is used for device storage and streams only; every computation on the
+path is a hand-written CUDA kernel inside libdccn.so.  The class plays the role
+of the reference's ``tf.Session`` + imported graph: feeds ``tx_ofdm`` /
+``bits_in`` and fetches ``output`` / ``conf_matrix`` / ``linear_ber`` /
+``ce_mean`` (reference: dev/py/ofdmreceiver_np.py:80, dev/py/ofdmreceiver_np_mp.py:89).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DccnError, dccn_cfg
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DCCN:
+    """Handle on the B200 implementation of [equalizer_ofdm ->] ofdm_dense_rx.
+
+    Parameters mirror the reference FLAGS / ofdm_tx attributes; ``precision`` is
+    'exact' (fp32 CUDA cores), 'parity' (tcgen05 3xTF32, fp32-equivalent) or
+    'fast' (tcgen05 single-pass TF32, reduced precision).
+    """
+
+    def __init__(self, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data=320, pilot_size=16,
+                 use_cp=True, head='dev', equalizer=False, precision='parity', chunk_frames=0,
+                 device=None):
+        if not torch.cuda.is_available():
+            raise DccnError('dl_ofdm_b200 needs a CUDA device (no CPU fallback)')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.cfg = dccn_cfg(nfft=nfft, cp_len=cp_len, nsymbol=nsymbol, nfilter=nfilter, nbits=nbits,
+                            use_cp=int(bool(use_cp)), n_data=n_data, pilot_size=pilot_size,
+                            head=_lib.HEAD_V1 if head == 'v1' else _lib.HEAD_DEV,
+                            equalizer=int(bool(equalizer)), precision=_lib.PRECISIONS[precision],
+                            chunk_frames=chunk_frames)
+        self.nbits, self.S, self.K, self.T, self.D = nbits, nsymbol, nfft, nfft + cp_len, n_data
+        self.equalizer = bool(equalizer)
+        self.precision = precision
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dccn_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        self._scratch = {}
+
+    # -- lifecycle -----------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.dccn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def from_ofdm(cls, FLAGS, ofdmobj, equalizer=False, precision='parity', head='dev', **kw):
+        """Build from the reference's FLAGS + ofdm_tx object (same fields the TF builders read)."""
+        return cls(nbits=FLAGS.nbits, nfft=ofdmobj.K, cp_len=ofdmobj.CP, nsymbol=ofdmobj.nSymbol,
+                   nfilter=FLAGS.nfilter, n_data=ofdmobj.frame_size, pilot_size=ofdmobj.pilot_size,
+                   use_cp=FLAGS.cp, head=head, equalizer=equalizer, precision=precision, **kw)
+
+    # -- weights ---------------------------------------------------------------------
+    def load_weights(self, weights):
+        """``weights``: TF variable name -> array in the reference layout (see dccn.h)."""
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            if a.ndim == 0:
+                continue
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self.lib.dccn_set_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p),
+                                                shape, a.ndim))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dccn_commit_weights(self._h, _stream()))
+
+    def workspace_bytes(self):
+        return int(self.lib.dccn_workspace_bytes(self._h))
+
+    # -- the pass ----------------------------------------------------------------------
+    def forward(self, x, bits=None, want_soft=True, want_hard=True, want_eq=False, want_chest=False,
+                flags=0):
+        """x: float32 CUDA tensor [B,S,T,2]; bits: uint8 CUDA tensor [B,D,nbits] or None.
+
+        Returns dict(soft, hard, eq, chest, conf (int64 [2,2] tensor), ce_sum (float64 [1]), n_bits).
+        All outputs are CUDA tensors; nothing is synchronised.
+        """
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        B = x.shape[0]
+        assert tuple(x.shape[1:]) == (self.S, self.T, 2), x.shape
+        dev = x.device
+        eq_only = bool(flags & _lib.FWD_EQ_ONLY)
+        out = {}
+        soft = hard = eq = chest = conf = ce = None
+        if want_soft and not eq_only:
+            soft = torch.empty((B, self.D, self.nbits, 2), dtype=torch.float32, device=dev)
+        if want_hard and not eq_only:
+            hard = torch.empty((B, self.D, self.nbits), dtype=torch.uint8, device=dev)
+        if want_eq:
+            eq = torch.empty((B, self.S, self.T, 2), dtype=torch.float32, device=dev)
+        if want_chest:
+            chest = torch.empty((B, self.S, self.K, 2), dtype=torch.float32, device=dev)
+        if bits is not None and not eq_only:
+            assert bits.is_cuda and bits.dtype == torch.uint8 and bits.is_contiguous()
+            assert tuple(bits.shape) == (B, self.D, self.nbits), bits.shape
+            conf = torch.zeros((2, 2), dtype=torch.int64, device=dev)
+            ce = torch.zeros((1,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.dccn_forward(self._h, _ptr(x), B, _ptr(bits), _ptr(soft), _ptr(hard), _ptr(eq),
+                                             _ptr(chest), _ptr(conf), _ptr(ce), int(flags), _stream()))
+        out.update(soft=soft, hard=hard, eq=eq, chest=chest, conf=conf, ce_sum=ce,
+                   n_bits=B * self.D * self.nbits)
+        return out
+
+    def forward_host(self, x_host, bits_host=None, want_hard=False):
+        """End-to-end call with HOST (ideally pinned) tensors: H2D + pass + D2H, synchronous.
+
+        Returns (conf int64[2,2] numpy, ce_sum float, hard uint8 tensor or None).
+        """
+        assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        B = x_host.shape[0]
+        key = ('host', B, want_hard)
+        if key not in self._scratch:
+            self._scratch[key] = (torch.zeros(4, dtype=torch.int64).pin_memory(),
+                                  torch.zeros(1, dtype=torch.float64).pin_memory(),
+                                  torch.empty((B, self.D, self.nbits), dtype=torch.uint8).pin_memory()
+                                  if want_hard else None)
+        conf, ce, hard = self._scratch[key]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dccn_forward_host(self._h, _ptr(x_host), B, _ptr(bits_host), _ptr(hard),
+                                                  _ptr(conf), _ptr(ce), _stream()))
+        return conf.numpy().reshape(2, 2).copy(), float(ce[0]), hard
+
+    def batch_moments(self, x):
+        P = self.S * self.T * 2
+        mean = torch.empty(P, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(P, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(self.lib.dccn_batch_moments(self._h, _ptr(x), x.shape[0], _ptr(mean), _ptr(rstd), _stream()))
+        return mean, rstd
+
+    # -- channel ------------------------------------------------------------------------
+    def channel(self, tx, snr_db, alpha=None, coeff=None, z=None, normals=None, seed=0, want_faded=False):
+        """rayleigh static FIR (optional) + AWGN on the GPU.
+
+        tx float32 [B,S,T,2]; snr_db float32 [B]; alpha float64 [n_taps,n_fir]; coeff float64 [n_taps];
+        z float64 [B,n_taps,2] (optional injected path draws); normals float64 [B,S,T,2] (optional).
+        """
+        assert tx.is_cuda and tx.dtype == torch.float32 and tx.is_contiguous()
+        B = tx.shape[0]
+        n_samp = tx.numel() // (B * 2)
+        n_taps = 0 if coeff is None else int(coeff.numel())
+        n_fir = 1 if alpha is None else int(alpha.shape[1])
+        rx = torch.empty_like(tx)
+        faded = torch.empty_like(tx) if want_faded else None
+        with torch.cuda.device(tx.device):
+            _lib.check(self.lib.dccn_chan_fir_awgn(self._h, _ptr(tx), B, n_samp, _ptr(alpha), _ptr(coeff), n_taps,
+                                                   n_fir, _ptr(z), _ptr(snr_db), _ptr(normals), int(seed),
+                                                   _ptr(rx), _ptr(faded), _stream()))
+        return (rx, faded) if want_faded else rx
+
+    # -- transmitter ---------------------------------------------------------------------
+    def transmit(self, bits, ofdmobj, constellation):
+        """GPU OFDM transmitter: bits uint8 [B,D,nbits] -> float32 [B,S,T,2]."""
+        dev = bits.device
+        key = ('tx', id(ofdmobj))
+        if key not in self._scratch:
+            self._scratch[key] = (torch.as_tensor(np.asarray(ofdmobj.dataSc, dtype=np.int32), device=dev),
+                                  torch.as_tensor(np.asarray(ofdmobj.pilotSc, dtype=np.int32), device=dev),
+                                  torch.as_tensor(np.stack([constellation.real, constellation.imag], -1)
+                                                  .astype(np.float32), device=dev))
+        dsc, psc, const = self._scratch[key]
+        B = bits.shape[0]
+        tx = torch.empty((B, self.S, self.T, 2), dtype=torch.float32, device=dev)
+        pv = complex(ofdmobj.pilotValue)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.dccn_tx_frames(self._h, _ptr(bits), B, _ptr(dsc), dsc.numel(), _ptr(psc),
+                                               psc.numel(), _ptr(const), pv.real, pv.imag, _ptr(tx), _stream()))
+        return tx
+
+
+def bit_source_gpu(n, seed, device='cuda'):
+    """util.bit_source on the GPU (Philox): uint8 tensor of n uniform bits."""
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.dccn_bit_source(_ptr(out), n, int(seed), _stream()))
+    return out
+
+
+def cconv2d(x, kernel, bias, filters, kernal, padding='valid'):
+    """Op-level layers_conv2d_complex on CUDA tensors (dev/py/complex.py:140)."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dim() == 5 and x.shape[-1] == 2
+    B, L, W, Cc, _ = x.shape
+    kl, kw = (kernal, kernal) if isinstance(kernal, int) else kernal
+    pad = 1 if padding.lower() == 'same' else 0
+    Lo, Wo = (L, W) if pad else (L - kl + 1, W - kw + 1)
+    y = torch.empty((B, Lo, Wo, filters, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dccn_cconv2d(_ptr(x.contiguous()), B, L, W, Cc, _ptr(kernel.contiguous()),
+                                    _ptr(bias.contiguous()), filters, kl, kw, pad, _ptr(y), _stream()))
+    return y
+
+
+def ber_accum(hard, bits, conf=None):
+    lib = _lib.load()
+    if conf is None:
+        conf = torch.zeros((2, 2), dtype=torch.int64, device=hard.device)
+    with torch.cuda.device(hard.device):
+        _lib.check(lib.dccn_ber_accum(_ptr(hard), _ptr(bits), hard.numel(), _ptr(conf), _stream()))
+    return conf

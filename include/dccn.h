@@ -1,0 +1,161 @@
+/*
+ * dccn.h -- C ABI of libdccn.so: the B200-native (sm_100a) implementation of the
+ * DCCN OFDM receiver hot path of zhongyuanzhao/dl_ofdm.
+ *
+ * The reference has no FFI: its boundary is Python calling a TF-1 graph
+ * (`session.run(fetches, feed)` at dev/py/ofdmreceiver_np.py:80,234,256 and
+ * dev/py/ofdmreceiver_np_mp.py:89,419,445).  Each entry point below names the
+ * reference interface it replaces.  The Python host (dl_ofdm_b200/) binds this
+ * header with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a device pointer owned by
+ *     the caller (e.g. torch tensor storage), *_host is host memory;
+ *   - every call is asynchronous on the caller-supplied stream (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream) unless it says otherwise;
+ *   - return value 0 = success, negative = error (dccn_last_error() gives the
+ *     thread-local message).  The library never falls back to a CPU path.
+ *   - tensors use the reference layouts: IQ is the fastest axis everywhere.
+ */
+#ifndef DCCN_H_
+#define DCCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCCN_ABI_VERSION 1
+
+/* arithmetic of the GEMM layers */
+enum {
+  DCCN_PREC_EXACT  = 0, /* fp32 FFMA on CUDA cores (bit-near the reference's fp32)        */
+  DCCN_PREC_PARITY = 1, /* tcgen05 kind::tf32, 3-pass hi/lo split, fp32 accumulate in TMEM */
+  DCCN_PREC_FAST   = 2  /* tcgen05 kind::tf32, single pass (reduced precision; not parity) */
+};
+enum { DCCN_HEAD_DEV = 0, DCCN_HEAD_V1 = 1 };
+/* dccn_forward flags: entry points of the sub-graphs the reference exposes as functions */
+enum {
+  DCCN_FWD_NO_NORM = 1, /* x is already the normalised 'input:0' tensor (skip a2)              */
+  DCCN_FWD_EQ_ONLY = 2, /* stop after equalizer_ofdm (eq_dev / chest_dev are the outputs)      */
+  DCCN_FWD_SKIP_EQ = 4  /* run ofdm_dense_rx directly on x even if the handle has an equalizer */
+};
+
+/* Geometry + model selection; field names follow the reference FLAGS
+ * (dev/py/ofdmreceiver_np_mp.py:33-58) and ofdm_tx attributes (dev/py/ofdm.py:198-273). */
+typedef struct dccn_cfg {
+  int32_t nfft;        /* FLAGS.nfft      K, 64                                        */
+  int32_t cp_len;      /* ofdm_tx.CP      16 (longcp) or 4                             */
+  int32_t nsymbol;     /* FLAGS.nsymbol   7 (dev / 'lte' pilots) or 8 (v1)             */
+  int32_t nfilter;     /* FLAGS.nfilter   F, 64                                        */
+  int32_t nbits;       /* FLAGS.nbits     1..4                                         */
+  int32_t use_cp;      /* FLAGS.cp        receiver consumes the cyclic prefix          */
+  int32_t n_data;      /* ofdm_tx.frame_size  data subcarriers per frame (320 / 368)   */
+  int32_t pilot_size;  /* ofdm_tx.pilot_size  16 for 'lte'                             */
+  int32_t head;        /* DCCN_HEAD_*     demodulation head variant                    */
+  int32_t equalizer;   /* 0 = basic receiver only, 1 = equalizer_ofdm (--opt=0) in front */
+  int32_t precision;   /* DCCN_PREC_*                                                  */
+  int32_t chunk_frames;/* frames per internal pass (0 = library default)               */
+} dccn_cfg;
+
+typedef struct dccn_handle dccn_handle;
+
+/* -- lifecycle ------------------------------------------------------------- */
+int         dccn_abi_version(void);
+const char* dccn_last_error(void);
+/* Replaces graph construction: ofdm_dense_rx(...) dev/py/model.py:1222 and
+ * equalizer_ofdm(...) dev/py/model.py:349 (built at ofdmreceiver_np.py:144,
+ * ofdmreceiver_np_mp.py:294).  Binds to the current CUDA device. */
+int  dccn_create(const dccn_cfg* cfg, dccn_handle** out);
+void dccn_destroy(dccn_handle* h);
+size_t dccn_workspace_bytes(const dccn_handle* h);
+
+/* -- weights ---------------------------------------------------------------
+ * Replaces tf.train.Saver.restore (dev/py/model.py:51-56).  `tf_name` is the TF
+ * variable name ("fft_like/conv3d/kernel", "demodulation/dense/bias",
+ * "Equalizer/dense_4/kernel", ...), `host` the tensor in the reference layout
+ * (conv3d [kl,kw,1,Cin,2F], dense [in,out], conv2d [1,1,Cin,Cout]).  The library
+ * repacks: dead-tap removal of the 'same' (1,K) layer, [[a,b],[-b,-a]] tiling of
+ * complex layers with the reference sign (dev/py/complex.py:187-188), Toeplitz
+ * expansion of the (S,K) 'same' conv, tf32 hi/lo split.  Synchronous. */
+int dccn_set_weight(dccn_handle* h, const char* tf_name, const float* host,
+                    const int64_t* shape, int rank);
+/* copies the stored (reference-layout) tensor back; returns element count or <0 */
+int64_t dccn_get_weight(dccn_handle* h, const char* tf_name, float* host, int64_t capacity);
+int dccn_commit_weights(dccn_handle* h, void* stream);
+
+/* -- a2: tf.nn.moments(x,[0]) + batch_normalization (ofdmreceiver_np.py:128-129)
+ * x_dev float32 [B,S,T,2]; mean_dev/rstd_dev float32 [S*T*2] (rstd = rsqrt(var+1e-9)). */
+int dccn_batch_moments(dccn_handle* h, const float* x_dev, int64_t B,
+                       float* mean_dev, float* rstd_dev, void* stream);
+
+/* -- the receiver pass: replaces session.run([conf_matrix, linear_ber, ce_mean,
+ * output, ...], {tx_ofdm: x, bits_in: y}) (ofdmreceiver_np.py:80, _mp.py:89).
+ *   x_dev      float32 [B,S,T,2]   'tx_ofdm' feed
+ *   bits_dev   uint8   [B,D,nbits] 'bits_in' feed (0/1), or NULL (no BER/loss)
+ *   soft_dev   float32 [B,D,nbits,2] 'output' (softmax), or NULL
+ *   hard_dev   uint8   [B,D,nbits]  argmax of 'output' (first index on ties), or NULL
+ *   eq_dev     float32 [B,S,T,2]    equalizer output (cfg.equalizer only), or NULL
+ *   chest_dev  float32 [B,S,K,2]    channel estimate 'chest' (cfg.equalizer only), or NULL
+ *   conf_dev   int64   [2,2]        'conf_matrix' (rows = truth); ACCUMULATED into
+ *   ce_sum_dev double  [1]          sum of the softmax-xent terms (ce_mean * count); accumulated
+ * The batch-moment norm is part of the pass (moments over all B frames) unless
+ * DCCN_FWD_NO_NORM; with it and DCCN_FWD_SKIP_EQ the call is ofdm_dense_rx(x)
+ * (model.py:1222), with DCCN_FWD_NO_NORM|DCCN_FWD_EQ_ONLY it is equalizer_ofdm(x)
+ * (model.py:349). */
+int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* bits_dev,
+                 float* soft_dev, uint8_t* hard_dev, float* eq_dev, float* chest_dev,
+                 int64_t* conf_dev, double* ce_sum_dev, int flags, void* stream);
+
+/* Same pass with HOST buffers (pinned recommended): copies x/bits H2D, runs,
+ * copies conf/ce (and hard bits if hard_host != NULL) D2H; synchronises the
+ * stream before returning.  conf_host/ce_sum_host are overwritten. */
+int dccn_forward_host(dccn_handle* h, const float* x_host, int64_t B, const uint8_t* bits_host,
+                      uint8_t* hard_host, int64_t* conf_host, double* ce_sum_host, void* stream);
+
+/* -- a1: layers_conv2d_complex(inputs, filters, kernal, strides=1, padding)
+ * (dev/py/complex.py:140-196), op-level.  x_dev [B,L,W,C,2], kernel_dev
+ * [kl,kw,1,C,2*filters], bias_dev [2*filters], y_dev [B,L',W',filters,2];
+ * padding 0 = 'valid', 1 = 'same'. */
+int dccn_cconv2d(const float* x_dev, int64_t B, int L, int W, int C,
+                 const float* kernel_dev, const float* bias_dev, int filters, int kl, int kw,
+                 int padding, float* y_dev, void* stream);
+
+/* -- a6 + a7: rayleigh_chan_lte static branch (dev/py/radio.py:432-437,491-506)
+ * followed by AWGN_channel_np (dev/py/radio.py:513-526).
+ *   tx_dev      float32 [B, n_samp, 2]  complex IQ of the transmitted frames (n_samp = S*T)
+ *   alpha_dev   float64 [n_taps, n_fir] interpolation matrix (3gpp/AM_*.csv); NULL => identity 1x1
+ *   coeff_dev   float64 [n_taps]        path amplitudes ch_coeff (radio.py:367-371)
+ *   z_dev       float64 [B, n_taps, 2]  pre-drawn N(0,1/2) path gains, or NULL => Philox(seed)
+ *   snr_db_dev  float32 [B]             per-frame SNR in dB
+ *   normals_dev float64 [B, n_samp, 2]  pre-drawn N(0,1) noise, or NULL => Philox(seed)
+ *   rx_dev      float32 [B, n_samp, 2]  output (normalised by the batch mean power + noise)
+ *   fir_only_dev float32 [B, n_samp, 2] optional: the faded signal before AWGN (complex64 like radio.py:492)
+ * n_taps == 0 skips the fading (AWGN channel). */
+int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_samp,
+                       const double* alpha_dev, const double* coeff_dev, int n_taps, int n_fir,
+                       const double* z_dev, const float* snr_db_dev, const double* normals_dev,
+                       uint64_t seed, float* rx_dev, float* fir_only_dev, void* stream);
+
+/* -- a5: tf.confusion_matrix(bits, argmax) (ofdmreceiver_np.py:165-169); conf accumulated */
+int dccn_ber_accum(const uint8_t* hard_dev, const uint8_t* bits_dev, int64_t n,
+                   int64_t* conf_dev, void* stream);
+
+/* -- next row f-1: OFDM transmitter on the GPU (dev/py/ofdm.py:328-380).
+ *   bits_dev  uint8 [B, D, nbits]; data_sc/pilot_sc: frame-level subcarrier indices (s*K+k)
+ *   constellation float32 [2^nbits, 2]; tx_dev float32 [B, S, K+CP, 2] */
+int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B,
+                   const int32_t* data_sc_dev, int n_data, const int32_t* pilot_sc_dev, int n_pilot,
+                   const float* constellation_dev, float pilot_re, float pilot_im,
+                   float* tx_dev, void* stream);
+
+/* uniform random bits (util.bit_source, dev/py/util.py:25-34) from Philox */
+int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCCN_H_ */

@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    def load(name):
+        return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    return load
+
+
+def v1_weights(npz):
+    """Expand a committed v1 fixture (live centre tap only) back to TF variable layout."""
+    w = {}
+    for k in npz.files:
+        w[k.replace('.', '/')] = npz[k]
+    shape = tuple(int(v) for v in w.pop('fft_like/conv3d/kernel_shape'))
+    centre = w.pop('fft_like/conv3d/kernel_center')
+    full = np.zeros(shape, dtype=np.float32)
+    full[0, (shape[1] - 1) // 2, 0] = centre
+    w['fft_like/conv3d/kernel'] = full
+    return w
+
+
+@pytest.fixture(scope='session')
+def libdccn():
+    import __graft_entry__ as g
+    g.build()
+    from dl_ofdm_b200 import _lib
+    return _lib.load()

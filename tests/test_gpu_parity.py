@@ -1,0 +1,366 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star: bit-exact hard bits, 1e-5 abs on soft outputs).
+SURVEY.md Appendix C measured that even two different fp32 summation orders differ by
+2.3e-5 max / 8.5e-6 p99.9, so the criterion used for every fp32-equivalent mode is
+    p99.9 |soft - soft_fp64| <= 1e-5   and   max <= 5e-5,
+    hard bits identical wherever the fp64 oracle's margin |p1 - p0| >= 1e-4.
+"""
+import numpy as np
+import pytest
+
+from conftest import v1_weights
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+P999_TOL = 1e-5
+MAX_TOL = 5e-5
+MARGIN = 1e-4
+
+
+def _cuda(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def _check_soft(soft, soft_ref, hard, p999=P999_TOL, mx=MAX_TOL):
+    err = np.abs(soft.astype(np.float64) - soft_ref)
+    q = np.quantile(err, 0.999)
+    assert q <= p999, 'p99.9 |dsoft| = %.3g' % q
+    assert err.max() <= mx, 'max |dsoft| = %.3g' % err.max()
+    hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+    decided = np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= MARGIN
+    assert np.array_equal(hard[decided], hard_ref[decided]), 'hard-bit mismatch outside the tie margin'
+    return int((hard != hard_ref).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# a1: op-level layers_conv2d_complex
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [
+    # B, L, W, C, F, kl, kw, padding
+    (3, 7, 1, 80, 64, 1, 80, 'same'),      # fft_like
+    (3, 7, 64, 1, 64, 1, 64, 'valid'),     # learned DFT of the equalizer
+    (2, 7, 64, 1, 1, 7, 64, 'same'),       # (S,K) smoothing conv
+    (2, 5, 9, 3, 4, 3, 2, 'valid'),
+    (2, 5, 9, 3, 4, 2, 4, 'same'),
+])
+def test_cconv2d_matches_oracle(libdccn, shape):
+    from dl_ofdm_b200.engine import cconv2d
+    from oracle import dccn_oracle as orc
+    B, L, W, C, F, kl, kw, pad = shape
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((B, L, W, C, 2)).astype(np.float32)
+    k = (rng.standard_normal((kl, kw, 1, C, 2 * F)) * 0.2).astype(np.float32)
+    b = (rng.standard_normal(2 * F) * 0.1).astype(np.float32)
+    ref = orc.conv2d_complex(x, k, b, pad, np.float64)
+    y = cconv2d(_cuda(x), _cuda(k), _cuda(b), F, (kl, kw), pad).cpu().numpy()
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# a2: batch moments
+# ---------------------------------------------------------------------------------------------
+def test_batch_moments(libdccn):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((777, 7, 80, 2)) * 0.3 + 0.05).astype(np.float32)
+    m = DCCN(nbits=1, precision='exact')
+    mean, rstd = m.batch_moments(_cuda(x))
+    _, mref, iref = orc.batch_moment_norm(x, np.float64)
+    assert np.abs(mean.cpu().numpy() - mref.reshape(-1)).max() < 1e-6
+    assert np.abs(rstd.cpu().numpy() / iref.reshape(-1) - 1).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# a3 + a5 on the reference's own trained weights (v1 checkpoints) -- the pinned parity case
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['exact', 'parity'])
+@pytest.mark.parametrize('fixture,nb,cp', [('v1_4mod_cpTrue.npz', 4, True), ('v1_1mod_cpFalse.npz', 1, False)])
+def test_v1_checkpoint_receiver(libdccn, golden, precision, fixture, nb, cp):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle.v1_recipe import v1_frames
+    w = v1_weights(golden(fixture))
+    snr = 10 if nb == 4 else 0
+    x, bits = v1_frames(nb, snr, 700)
+    soft_ref = orc.basic_receiver(x, w, nb, 16, use_cp=cp, head='v1', dtype=np.float64)
+    _, conf_ref, ber_ref, ce_ref = orc.ber_head(soft_ref, bits)
+    m = DCCN(nbits=nb, nsymbol=8, n_data=368, use_cp=cp, head='v1', precision=precision, chunk_frames=256)
+    m.load_weights(w)
+    out = m.forward(_cuda(x), _cuda(bits))
+    torch.cuda.synchronize()
+    soft, hard = out['soft'].cpu().numpy(), out['hard'].cpu().numpy()
+    flips = _check_soft(soft, soft_ref, hard)
+    conf = out['conf'].cpu().numpy()
+    assert conf.sum() == bits.size
+    assert np.abs(conf - conf_ref).sum() <= 2 * flips
+    ce = float(out['ce_sum'].cpu()[0]) / bits.size
+    assert abs(ce - ce_ref) < 1e-5
+    # known answer of BASELINE.md at this SNR (first 700 frames of the 2000-frame recipe): same ballpark
+    ka = golden('v1_known_answers.npz')
+    tag = '%dmod_cp%s' % (nb, cp)
+    ka_ber = float(ka[tag][list(ka['snr']).index(snr)])
+    ber = (conf[0, 1] + conf[1, 0]) / conf.sum()
+    assert abs(ber - ka_ber) < 0.15 * ka_ber + 1e-4
+
+
+def test_v1_negative_control_sign(libdccn, golden):
+    """Flipping the reference's non-textbook sign (complex.py:188) must break decoding."""
+    from oracle import dccn_oracle as orc
+    from oracle.v1_recipe import v1_frames
+    w = v1_weights(golden('v1_4mod_cpTrue.npz'))
+    x, bits = v1_frames(4, 10, 200)
+    z, _, _ = orc.batch_moment_norm(x)
+    k = w['fft_like/conv3d/kernel'][0, 39, 0].astype(np.float64)
+    Wa, Wb = k[:, :64], k[:, 64:]
+    zr, zi = z[..., 0], z[..., 1]
+    re = zr @ Wa - zi @ Wb
+    im = zr @ Wb + zi @ Wa          # textbook '+'
+    # feed the wrong-sign front layer into the rest of the oracle by monkeypatching the conv
+    orig = orc.conv2d_complex
+    try:
+        orc.conv2d_complex = lambda *a, **kw: np.stack([re, im], -1).reshape(200, 8, 1, 64, 2)
+        soft = orc.ofdm_dense_rx(z, w, 4, 16, True, 'v1')
+    finally:
+        orc.conv2d_complex = orig
+    _, _, ber, _ = orc.ber_head(soft, bits)
+    assert ber > 0.15
+
+
+# ---------------------------------------------------------------------------------------------
+# a3 dev head on seeded weights (parity unpinned for trained dev weights: none are shipped)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['exact', 'parity'])
+@pytest.mark.parametrize('nb,cp', [(1, True), (2, True), (3, False), (4, True)])
+def test_dev_receiver_seeded(libdccn, precision, nb, cp):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(10 + nb)
+    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=False, bias_scale=0.05)
+    B = 300
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    soft_ref = orc.basic_receiver(x, w, nb, 16, use_cp=cp, dtype=np.float64)
+    _, conf_ref, _, ce_ref = orc.ber_head(soft_ref, bits)
+    m = DCCN(nbits=nb, use_cp=cp, precision=precision, chunk_frames=128)
+    m.load_weights(w)
+    out = m.forward(_cuda(x), _cuda(bits))
+    flips = _check_soft(out['soft'].cpu().numpy(), soft_ref, out['hard'].cpu().numpy())
+    conf = out['conf'].cpu().numpy()
+    assert conf.sum() == bits.size and np.abs(conf - conf_ref).sum() <= 2 * flips
+    assert abs(float(out['ce_sum'].cpu()[0]) / bits.size - ce_ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# a4 equalizer_ofdm + receiver on seeded weights
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['exact', 'parity'])
+@pytest.mark.parametrize('cp', [True, False])
+def test_equalizer_seeded(libdccn, precision, cp):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(77)
+    nb, B = 2, 260
+    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    soft_ref, eq_ref, chest_ref = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64)
+    m = DCCN(nbits=nb, use_cp=cp, equalizer=True, precision=precision, chunk_frames=128)
+    m.load_weights(w)
+    out = m.forward(_cuda(x), _cuda(bits), want_eq=True, want_chest=True)
+    chest = out['chest'].cpu().numpy()
+    chest = chest[..., 0] + 1j * chest[..., 1]
+    assert np.abs(chest - chest_ref).max() < 2e-5 * max(1.0, np.abs(chest_ref).max())
+    # the phase-only equaliser divides by |chest| with no epsilon (model.py:430-433): frames whose
+    # estimate comes close to 0 are ill-conditioned in ANY arithmetic -> compare well-conditioned frames
+    good = np.abs(chest_ref).reshape(B, -1).min(axis=1) > 2e-2
+    assert good.sum() > B // 4
+    eq = out['eq'].cpu().numpy()
+    scale = max(1.0, np.abs(eq_ref[good]).max())
+    assert np.abs(eq[good] - eq_ref[good]).max() < 1e-3 * scale
+    assert np.quantile(np.abs(eq[good] - eq_ref[good]), 0.99) < 5e-5 * scale
+    soft = out['soft'].cpu().numpy()
+    err = np.abs(soft[good] - soft_ref[good])
+    assert np.quantile(err, 0.999) < 2e-4
+    hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+    decided = (np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-3) & good[:, None, None]
+    assert np.array_equal(out['hard'].cpu().numpy()[decided], hard_ref[decided])
+
+
+def test_subgraph_entry_points(libdccn):
+    """ofdm_dense_rx(z) and equalizer_ofdm(z) as separate calls == the fused pass."""
+    from dl_ofdm_b200 import _lib
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(3)
+    nb, B = 2, 150
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    z, _, _ = orc.batch_moment_norm(x, np.float32)
+    m = DCCN(nbits=nb, equalizer=True, precision='exact')
+    m.load_weights(w)
+    full = m.forward(_cuda(x), want_eq=True)
+    eq = m.forward(_cuda(z.astype(np.float32)), want_eq=True, flags=_lib.FWD_NO_NORM | _lib.FWD_EQ_ONLY)['eq']
+    soft = m.forward(eq, flags=_lib.FWD_NO_NORM | _lib.FWD_SKIP_EQ)['soft']
+    assert (full['eq'] - eq).abs().max().item() < 5e-4
+    assert (full['soft'] - soft).abs().max().item() < 5e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# precision modes agree statistically (fast mode is NOT a parity mode)
+# ---------------------------------------------------------------------------------------------
+def test_fast_mode_close(libdccn, golden):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle.v1_recipe import v1_frames
+    w = v1_weights(golden('v1_4mod_cpTrue.npz'))
+    x, bits = v1_frames(4, 10, 500)
+    res = {}
+    for prec in ('parity', 'fast'):
+        m = DCCN(nbits=4, nsymbol=8, n_data=368, head='v1', precision=prec)
+        m.load_weights(w)
+        out = m.forward(_cuda(x), _cuda(bits))
+        res[prec] = (out['soft'].cpu().numpy(), out['conf'].cpu().numpy())
+    d = np.abs(res['fast'][0] - res['parity'][0])
+    assert d.max() < 0.1 and np.quantile(d, 0.999) < 3e-2
+    ber = lambda c: (c[0, 1] + c[1, 0]) / c.sum()
+    assert abs(ber(res['fast'][1]) - ber(res['parity'][1])) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# a6 / a7 against outputs of the reference's own NumPy code (fixtures)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('chan', ['epa', 'eva', 'etu', 'flat', 'custom'])
+def test_rayleigh_fir_golden(libdccn, golden, chan):
+    from dl_ofdm_b200.engine import DCCN
+    g = golden('rayleigh_%s.npz' % chan)
+    tx = g['tx']                                    # complex64 [B,7,80]
+    B = tx.shape[0]
+    txf = np.stack([tx.real, tx.imag], -1).astype(np.float32)
+    z = np.stack([g['z'].real, g['z'].imag], -1).astype(np.float64)
+    m = DCCN(nbits=2, precision='exact')
+    snr = torch.full((B,), 300.0, dtype=torch.float32, device='cuda')     # noise ~ 1e-15
+    rx, faded = m.channel(_cuda(txf), snr, alpha=_cuda(np.atleast_2d(g['alpha']).astype(np.float64)),
+                          coeff=_cuda(g['ch_coeff'].astype(np.float64)), z=_cuda(z),
+                          normals=torch.zeros((B, 7, 80, 2), dtype=torch.float64, device='cuda'),
+                          want_faded=True)
+    ref = g['rx'].astype(np.float32)                # reference output (complex64 stored as float)
+    got = faded.cpu().numpy()
+    # complex128 accumulation rounded to complex64: allow 1 ulp for summation-order differences
+    assert np.abs(got - ref).max() <= 2 * np.spacing(np.abs(ref).max())
+    assert (got == ref).mean() > 0.99
+    pw = np.mean(ref[..., 0].astype(np.float64) ** 2 + ref[..., 1].astype(np.float64) ** 2)
+    assert np.abs(rx.cpu().numpy() - (ref / np.sqrt(pw)).astype(np.float32)).max() < 1e-6
+
+
+def test_awgn_golden(libdccn, golden):
+    from dl_ofdm_b200.engine import DCCN
+    g = golden('awgn.npz')
+    x = g['x'].astype(np.float32)          # the kernel takes the fp32 signal
+    from oracle import dccn_oracle as orc
+    ref, npw, _ = orc.awgn(x.astype(np.float64), g['snr'], g['normals'])
+    # oracle == reference on the reference's own float64 input
+    ref64, _, _ = orc.awgn(g['x'], g['snr'], g['normals'])
+    assert np.array_equal(ref64, g['out'])
+    m = DCCN(nbits=1, precision='exact')
+    rx = m.channel(_cuda(x), _cuda(g['snr'].reshape(-1).astype(np.float32)), normals=_cuda(g['normals']))
+    assert np.abs(rx.cpu().numpy() - ref.astype(np.float32)).max() <= 2e-7 * np.abs(ref).max() + 1e-7
+
+
+def test_channel_philox_statistics(libdccn):
+    """Without injected draws the kernel's own Philox stream must have the right moments."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    B = 4096
+    rng = np.random.default_rng(0)
+    tx = (rng.standard_normal((B, 7, 80, 2)) * 0.1).astype(np.float32)
+    m = DCCN(nbits=1, precision='exact')
+    snr_db = 7.0
+    rx = m.channel(_cuda(tx), torch.full((B,), snr_db, device='cuda'), seed=123).cpu().numpy().astype(np.float64)
+    pw = np.mean(tx[..., 0].astype(np.float64) ** 2 + tx[..., 1] ** 2)
+    noise = rx - tx / np.sqrt(pw)
+    assert abs(noise.mean()) < 2e-3
+    assert abs(noise.var() / (0.5 * 10 ** (-snr_db / 10)) - 1) < 0.01
+    # Rayleigh path: E|g|^2 == sum(ch_coeff^2 * |alpha column mass|) -> check unit-ish average gain for 'flat'
+    coeff = torch.ones(1, dtype=torch.float64, device='cuda')
+    _, faded = m.channel(_cuda(tx), torch.full((B,), 100.0, device='cuda'), coeff=coeff, seed=9, want_faded=True)
+    f = faded.cpu().numpy().astype(np.float64)
+    gain = (f[..., 0] ** 2 + f[..., 1] ** 2).sum(axis=(1, 2)) / (tx[..., 0].astype(np.float64) ** 2 + tx[..., 1] ** 2).sum(axis=(1, 2))
+    assert abs(gain.mean() - 1.0) < 0.06          # E|z|^2 = 1 for CN(0,1)
+    assert (orc.channel_coeff('flat') == 1.0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# transmitter + BER helper
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag,nb,pilot,nsym', [('lte_4b', 4, 'lte', 7), ('lte_1b', 1, 'lte', 7),
+                                              ('scattered_4b', 4, 'scattered', 8)])
+def test_tx_golden(libdccn, golden, tag, nb, pilot, nsym):
+    from dl_ofdm_b200.engine import DCCN
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import ofdm_tx, const_map
+    g = golden('ofdm_tx_%s.npz' % tag)
+    fl = Flags(nbits=nb, pilot=pilot, nsymbol=nsym)
+    o = ofdm_tx(fl)
+    m = DCCN(nbits=nb, nsymbol=nsym, n_data=o.frame_size, precision='exact')
+    tx = m.transmit(_cuda(g['bits']), o, const_map(nb)).cpu().numpy()
+    assert np.abs(tx - g['real']).max() < 5e-7
+
+
+def test_ber_accum(libdccn):
+    from dl_ofdm_b200.engine import ber_accum
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 2, 100003).astype(np.uint8)
+    b = rng.integers(0, 2, 100003).astype(np.uint8)
+    conf = ber_accum(_cuda(a), _cuda(b)).cpu().numpy()
+    ref = np.zeros((2, 2), dtype=np.int64)
+    np.add.at(ref, (b, a), 1)
+    assert np.array_equal(conf, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json config 3 shapes): chunk invariance, count conservation,
+# host-buffer entry point == device entry point
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(libdccn):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(42)
+    nb, B = 4, 65536
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.02)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn((B, 7, 80, 2), generator=g, device='cuda') * 0.2
+    bits = torch.randint(0, 2, (B, 320, nb), generator=g, device='cuda', dtype=torch.uint8)
+    outs = []
+    for chunk in (4096, 1024):
+        m = DCCN(nbits=nb, equalizer=True, precision='parity', chunk_frames=chunk)
+        m.load_weights(w)
+        o = m.forward(x, bits, want_soft=False)
+        torch.cuda.synchronize()
+        outs.append((o['hard'].clone(), o['conf'].cpu().numpy(), float(o['ce_sum'].cpu()[0])))
+        if chunk == 1024:
+            conf_h, ce_h, _ = m.forward_host(x.cpu().pin_memory(), bits.cpu().pin_memory())
+            assert np.array_equal(conf_h, outs[-1][1])
+        m.close()
+    assert outs[0][1].sum() == B * 320 * nb
+    assert torch.equal(outs[0][0], outs[1][0]), 'result depends on the internal chunking'
+    assert np.array_equal(outs[0][1], outs[1][1])
+    # hard bits re-counted by the stand-alone BER kernel == fused confusion matrix
+    from dl_ofdm_b200.engine import ber_accum
+    assert np.array_equal(ber_accum(outs[0][0], bits).cpu().numpy(), outs[0][1])
+    # spot-check 64 frames of the big batch against the oracle using the big batch's own moments
+    mean = x.mean(dim=0).double().cpu().numpy()
+    var = x.double().var(dim=0, unbiased=False).cpu().numpy()
+    idx = np.arange(0, B, B // 64)
+    xs = x[idx].double().cpu().numpy()
+    z = ((xs * (1 / np.sqrt(var + 1e-9)) + (-mean / np.sqrt(var + 1e-9))) / np.sqrt(2.0))
+    eq, _ = orc.equalizer_ofdm(z, w, 64, 16)
+    soft_ref = orc.ofdm_dense_rx(eq, w, nb, 16)
+    hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+    decided = np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-2
+    assert np.array_equal(outs[0][0][idx].cpu().numpy()[decided], hard_ref[decided])

@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the DCCN hot path on B200 (driver contract).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  torchrun ... bench.py --gpus N ...           (one rank per GPU, NCCL)
+
+Workload (BASELINE.json config 3 / metric "OFDM frames/s (N=64, 16-QAM)"): 16-QAM, LTE-EPA
+Rayleigh + AWGN, B = 65536 frames of [7,80,2] fp32 per GPU, one *step* = one pass
+  batch-moment norm -> equalizer_ofdm -> ofdm_dense_rx -> softmax/argmax -> confusion matrix
+over that batch (soft [B,320,4,2], hard [B,320,4] and the 2x2 confusion matrix are produced
+every step).  Synthetic frames: Philox bits -> GPU OFDM transmitter -> GPU EPA-FIR + AWGN, random
+glorot-initialised weights of the reference architecture (no trained dev checkpoint exists).
+`value`  : device-timed frames/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same pass through the host-buffer entry point (dccn_forward_host): pinned host
+           IQ + labels copied H2D and the confusion matrix / loss read back D2H EVERY step.
+`roofline`: dominant kernel's algorithmic FLOP/s from per-kernel CUDA events (library hook) vs
+           the measured tensor peak (MEASURED_PEAKS.json bf16 / 2 = tf32 rate).
+`cpu_baseline` / --impl reference: the restated reference (oracle/tf_mirror.py, torch-CPU fp32
+           mirror of the TF-1 graph incl. its zero-padded conv3d) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NBITS, NFFT, CP, NSYM, NFILT, NDATA, PILOT = 4, 64, 16, 7, 64, 320, 16
+SNR_DB = 15.0
+# algorithmic MACs per frame (live taps only), by library profile slot
+MACS = {
+    'eq_dense': 160 * 128 * 7, 'eq_dft': 128 * 128 * 7, 'eq_pilot': 896 * 32, 'eq_dense2': 32 * 896,
+    'eq_dense3': 896 * 896, 'eq_dense4_tanh': 896 * 896, 'eq_conv7x64_phaseeq': 454656,
+    'eq_corr_idft': 128 * 128 * 7, 'eq_idft': 128 * 128 * 7, 'eq_dense5': 256 * 160 * 7,
+    'rx_fft_like': 160 * 128 * 7, 'rx_demod_head': 896 * 640 + 320 * (2 * 16 + 18 * 8),
+}
+MFLOP_PER_FRAME = 2e-6 * sum(MACS.values())          # 7.330 for eq + rx at 16-QAM
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained'),
+                    src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                  '--format=csv,noheader,nounits', '-lms', '100'],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        while not self.stop_flag:
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([c.strip() for c in line.split(',')])
+        p.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_weights(seed=2026):
+    from dl_ofdm_b200 import init
+    rng = np.random.default_rng(seed)
+    w = init.receiver_variables(rng, NBITS, NFFT, CP, NSYM, NFILT, NDATA)
+    w.update(init.equalizer_variables(rng, NFFT, CP, NSYM, PILOT))
+    return w
+
+
+# -------------------------------------------------------------------------------------------
+# restated reference on the CPU (oracle/ -- only used as the baseline arm, never by the product)
+# -------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, frames, min_seconds, threads):
+    import torch
+    from oracle.tf_mirror import TFMirror
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((frames, NSYM, NFFT + CP, 2)) * 0.1).astype(np.float32)
+    m = TFMirror(w, NBITS, NFFT, CP, True, 'dev', NFILT, equalizer=True)
+    m.forward(x[:256])
+    n, t0 = 0, time.perf_counter()
+    while True:
+        m.forward(x)
+        n += frames
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            return n / dt, n, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    w = make_weights()
+    frames = 2048
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, n, dt = cpu_reference_rate(w, frames, 0.0, threads)     # one bounded sample per step
+        if i >= args.warmup:
+            rates.append((n, dt))
+    tot_n = sum(n for n, _ in rates); tot_t = sum(t for _, t in rates)
+    val = tot_n / tot_t
+    line = {
+        'impl': 'reference', 'metric': 'ofdm_frames_per_s_n64_16qam', 'value': val, 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, frames_per_step=frames),
+        'cpu_baseline': {'value': val, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d frames per step through oracle/tf_mirror.py (torch-CPU fp32 op-for-op mirror of '
+                                   'the TF-1 graph incl. padded conv3d; TensorFlow 1.x itself cannot run on this image)' % frames},
+        'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, frames_per_step):
+    return {'workload': 'config3: 16-QAM, LTE-EPA Rayleigh + AWGN %.0f dB, N=64 CP=16 7-symbol frames; '
+                        'norm -> equalizer_ofdm -> ofdm_dense_rx -> BER' % SNR_DB,
+            'frames_per_step_per_gpu': frames_per_step, 'nbits': NBITS, 'precision': args.precision,
+            'chunk_frames': args.chunk, 'parallelism': 'grid cells sharded, 1 all-reduce of the confusion matrix',
+            'l2': 'inputs per step (%.0f MB) exceed the 126 MB L2' % (frames_per_step * 4480 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--frames', type=int, default=65536)
+    ap.add_argument('--precision', default='parity', choices=['parity', 'fast', 'exact'])
+    ap.add_argument('--chunk', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dl_ofdm_b200.engine import DCCN, bit_source_gpu, launch_count
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import const_map, ofdm_tx
+    from dl_ofdm_b200.radio import rayleigh_chan_lte
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.frames
+    fl = Flags(nbits=NBITS, channel='EPA', nfilter=NFILT)
+    ofdm = ofdm_tx(fl)
+    w = make_weights()
+    m = DCCN.from_ofdm(fl, ofdm, equalizer=True, precision=args.precision, chunk_frames=args.chunk)
+    m.load_weights(w)
+
+    # ---- synthetic frames, generated on the GPU, resident in HBM -------------------------
+    bits = bit_source_gpu(B * NDATA * NBITS, seed=1000 + rank, device=dev).view(B, NDATA, NBITS)
+    tx = m.transmit(bits, ofdm, const_map(NBITS))
+    chan = rayleigh_chan_lte(fl, ofdm.Fs, engine=m, seed=77 + rank)
+    x = chan.run(tx, torch.full((B,), SNR_DB, dtype=torch.float32, device=dev))
+    del tx
+    torch.cuda.synchronize()
+
+    def step():
+        return m.forward(x, bits, want_soft=True, want_hard=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    # ---- timed region (device events, max over ranks) -------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    l0 = launch_count()
+    conf_total = torch.zeros((2, 2), dtype=torch.int64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+        conf_total += out['conf']
+    if world > 1:
+        dist.all_reduce(conf_total)                  # the sweep's only collective: final BER all-reduce
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    sampler.stop_flag = True
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0])
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel CUDA events (library hook) -> dominant kernel + roofline ---------------
+    m.profile(True)
+    for _ in range(args.steps):
+        step()
+    prof = m.profile_collect()
+    m.profile(False)
+    tot_prof = sum(v[0] for v in prof.values())
+    dom = max((k for k in prof if k in MACS), key=lambda k: prof[k][0])
+    dom_ms, dom_n = prof[dom]
+    frames_per_launch = B * args.steps / dom_n
+    pk = peaks()
+    tf32_peak = pk['bf16'] / 2.0
+    achieved = 2.0 * MACS[dom] * frames_per_launch / (dom_ms / dom_n * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / tf32_peak, 'traffic': traffic,
+                'peak_note': 'kind::tf32 peak taken as %s bf16 %.0f TF/s / 2 (of %s)' % (pk['src'], pk['bf16'], pk['src']),
+                'kernel_share_of_step': dom_ms / tot_prof,
+                'mma_passes': 3 if args.precision == 'parity' else 1,
+                'whole_step_algorithmic_tflops': MFLOP_PER_FRAME * 1e6 * value / world / 1e12,
+                'kernel_ms': {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}}
+
+    # ---- end to end through the host-buffer entry point ------------------------------------
+    xh = x.cpu().pin_memory()
+    bh = bits.cpu().pin_memory()
+    for _ in range(2):
+        m.forward_host(xh, bh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        conf_h, ce_h, _ = m.forward_host(xh, bh)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {'value': world * B * args.steps / float(te[0]), 'unit': 'frames/s',
+           'h2d_bytes_per_step': int(xh.numel() * 4 + bh.numel()), 'd2h_bytes_per_step': 4 * 8 + 8}
+
+    conf = conf_total.cpu().numpy()
+    ber = float(conf[0, 1] + conf[1, 0]) / float(conf.sum())
+    if rank == 0:
+        line = {
+            'metric': 'ofdm_frames_per_s_n64_16qam', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'parity': 'tf32x3 (fp32-equivalent: 3-pass hi/lo split, fp32 accumulate)',
+                      'fast': 'tf32', 'exact': 'f32'}[args.precision],
+            'data': 'synthetic', 'config': workload_config(args, B),
+            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': sampler.summary(),
+            'ber': ber, 'bits_counted': int(conf.sum()),
+            'target': {'frames_per_s_8gpu': 1e8, 'note': 'north_star target; random-init weights so BER ~ 0.5'},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            r, n, dt = cpu_reference_rate(w, 2048, 12.0, threads)
+            line['cpu_baseline'] = {'value': r, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                                    'sample': '%d frames in %.1f s through oracle/tf_mirror.py (restated reference, '
+                                              'torch-CPU fp32 incl. padded conv3d; TF1 itself cannot run here)' % (n, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

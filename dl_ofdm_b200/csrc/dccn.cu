@@ -10,6 +10,7 @@
 // convention ([[a, b], [-b, -a]] per complex weight, bias (ba-bb, bb-ba)).
 #include "../../include/dccn.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 #include <map>
@@ -94,6 +95,7 @@ struct GemmLayer {
   float* dBias = nullptr;
   CUtensorMap tmB0, tmB1;
   bool built = false;
+  bool fused = false;           // consumed by a fused (phase-eq / demod-head) epilogue
 };
 
 struct HostTensor {
@@ -105,8 +107,21 @@ struct HostTensor {
 
 using namespace dccn;
 
+namespace dccn {
+static std::atomic<long long> g_launches{0};   // kernels launched by this library (dccn_launch_count)
+enum { SLOT_MOMENTS = 0, SLOT_PREP, SLOT_G1, SLOT_G2, SLOT_G3, SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G7_PHASEEQ,
+       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_COUNT };
+static const char* kSlotNames[SLOT_COUNT] = {
+    "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
+    "eq_conv7x64_phaseeq", "eq_corr_idft", "eq_idft", "eq_dense5", "rx_fft_like", "rx_demod_head",
+    "chan_fir", "chan_awgn"};
+struct ProfRec { int slot; cudaEvent_t a, b; };
+}  // namespace dccn
+
 struct dccn_handle {
   dccn_cfg cfg;
+  bool prof = false;
+  std::vector<dccn::ProfRec> prof_recs;
   int device = 0;
   int num_sms = 148;
   std::map<std::string, HostTensor> raw;
@@ -114,6 +129,8 @@ struct dccn_handle {
   // geometry
   int S, K, T, Tin, F, D, NB, P;      // T = samples/symbol incl. CP, Tin = samples the receiver consumes
   int chunk;
+  int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
+  int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
   // layers
   GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
   GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
@@ -145,6 +162,27 @@ static int dev_alloc(dccn_handle* h, void** p, size_t bytes) {
   h->ws_bytes += bytes;
   return 0;
 }
+
+// counts launches and (when profiling is on) brackets them with CUDA events on the launch stream
+struct LaunchScope {
+  dccn_handle* h;
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  int slot;
+  LaunchScope(dccn_handle* h_, int slot_, cudaStream_t s_, int n_kernels = 1) : h(h_), s(s_), slot(slot_) {
+    g_launches += n_kernels;
+    if (h && h->prof && h->prof_recs.size() < 65536) {
+      cudaEvent_t a;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+      h->prof_recs.push_back(ProfRec{slot, a, b});
+    }
+  }
+  ~LaunchScope() {
+    if (b) cudaEventRecord(b, s);
+  }
+};
 
 static int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split) {
   a->ld = ld;
@@ -190,15 +228,17 @@ static void pack_dense(const HostTensor& k, const HostTensor& b, GemmLayer* L) {
   L->bias = b.data;
 }
 
-static int pick_bn(int N) {
+static int pick_bn(int N, bool fused_epilogue, int wide) {
+  if (fused_epilogue) return 128;
   if (N <= 32) return 32;
-  if (N == 160) return 160;
+  if (N > 128 && N <= 192) return 192;
+  if (wide && N >= 512) return 256;
   return 128;
 }
 
 static int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   const int K = L->K, N = L->N;
-  L->BN = pick_bn(N);
+  L->BN = pick_bn(N, L->fused, h->bn_wide);
   const int prec = h->cfg.precision;
   DCCN_CHECK((K * 4) % 16 == 0, "layer K=%d is not a multiple of 4", K);
   if (!L->built) {
@@ -297,6 +337,8 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
       for (int m = 0; m < MO; ++m) h->hw.bc1[m] = bc1->data[m];
     }
   }
+  h->r2.fused = true;
+  h->g7.fused = true;
   if ((rc = upload_layer(h, &h->r1, s))) return rc;
   if ((rc = upload_layer(h, &h->r2, s))) return rc;
   if (!c.equalizer) return 0;
@@ -415,9 +457,10 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
 // GEMM dispatch
 // ---------------------------------------------------------------------------------------
 template <class Epi>
-static int run_gemm(dccn_handle* h, const GemmLayer& L, const Act& A, int a_col_off, int64_t M, const Epi& epi,
-                    cudaStream_t s) {
+static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
+                    const Epi& epi, cudaStream_t s) {
   const int prec = h->cfg.precision;
+  LaunchScope ls(h, slot, s);
   if (prec == DCCN_PREC_EXACT)
     return launch_gemm_simt<Epi>(A.p0 + a_col_off, A.p1 ? A.p1 + a_col_off : nullptr, A.ld, L.dW, (int)M, L.N, L.K,
                                  epi, s);
@@ -432,18 +475,19 @@ static int run_gemm(dccn_handle* h, const GemmLayer& L, const Act& A, int a_col_
     if (rc) return rc;
     op.b1 = L.tmB1;
   }
-#define DCCN_TC(BNV)                                                                                         \
-  return split ? launch_gemm_tc<BNV, true, Epi>(op, (int)M, L.N, L.K, epi, s, h->num_sms)                    \
-               : launch_gemm_tc<BNV, false, Epi>(op, (int)M, L.N, L.K, epi, s, h->num_sms)
+#define DCCN_TC(BNV, CGV)                                                                                    \
+  return split ? launch_gemm_tc<BNV, true, CGV, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms)         \
+               : launch_gemm_tc<BNV, false, CGV, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
   if constexpr (std::is_same<Epi, EpiStore>::value) {
     switch (L.BN) {
-      case 32: DCCN_TC(32);
-      case 160: DCCN_TC(160);
-      default: DCCN_TC(128);
+      case 32: DCCN_TC(32, 1);
+      case 192: DCCN_TC(192, 2);
+      case 256: DCCN_TC(256, 2);
+      default: DCCN_TC(128, 2);
     }
   } else {   // fused phase-equaliser / demod-head epilogues only exist for 128-wide tiles
     DCCN_CHECK(L.BN == 128, "fused epilogue expects BN=128 (N=%d)", L.N);
-    DCCN_TC(128);
+    DCCN_TC(128, 2);
   }
 #undef DCCN_TC
 }
@@ -476,7 +520,7 @@ static int run_head(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft
   e.ce_sum = ce;
   e.M = (int)Bc;
   e.N = h->r2.N;
-  return run_gemm(h, h->r2, h->r1o, 0, Bc, e, s);
+  return run_gemm(h, SLOT_R2_HEAD, h->r2, h->r1o, 0, Bc, e, s);
 }
 
 static int run_head_dispatch(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
@@ -498,6 +542,7 @@ static int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, f
   const int gy_max = (h->num_sms * 8) / gx;
   if (gy > gy_max) gy = gy_max;
   if (gy < 1) gy = 1;
+  LaunchScope ls(h, SLOT_MOMENTS, s, 2);
   moments_partial_kernel<<<dim3(gx, gy), 128, 0, s>>>(x, (long long)B, P, h->d_sums);
   moments_final_kernel<<<(P + 255) / 256, 256, 0, s>>>(h->d_sums, (long long)B, P, mean, rstd);
   DCCN_CUDA_OK(cudaGetLastError());
@@ -517,6 +562,7 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
     const int warps_per_block = 8;
     const int grid = (int)((Bc + warps_per_block - 1) / warps_per_block);
     DCCN_CHECK(P <= 10 * 128, "frame of %d floats exceeds the prep kernel's register tile", P);
+    LaunchScope ls(h, SLOT_PREP, s);
     prep_kernel<10><<<grid, 256, 0, s>>>(x, (long long)Bc, P, h->d_mean, h->d_rstd,
                                          (flags & DCCN_FWD_NO_NORM) ? 0 : 1, use_eq ? 1 : 0, out_of(h->a0));
     DCCN_CUDA_OK(cudaGetLastError());
@@ -533,14 +579,14 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
     Act catv = h->cat;   // [Bc*S, 4K]
     Act oeqv = h->oeq; oeqv.ld = 2 * T;
     // dense: per-symbol 2*Tin -> 2K                               model.py:370
-    if ((rc = run_gemm(h, h->g1, a0v, cp_off, MS, store_epi(h->g1, t1v, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G1, h->g1, a0v, cp_off, MS, store_epi(h->g1, t1v, 0, MS), s))) return rc;
     // learned DFT (1,K) 'valid' complex conv                       model.py:377-379
-    if ((rc = run_gemm(h, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G2, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
     // pilot bottleneck and channel-estimate MLP                    model.py:393-424
-    if ((rc = run_gemm(h, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
-    if ((rc = run_gemm(h, h->g4, h->p32, 0, Bc, store_epi(h->g4, h->u1, 0, Bc), s))) return rc;
-    if ((rc = run_gemm(h, h->g5, h->u1, 0, Bc, store_epi(h->g5, h->u2, 0, Bc), s))) return rc;
-    if ((rc = run_gemm(h, h->g6, h->u2, 0, Bc, store_epi(h->g6, h->u1, 0, Bc, /*tanh*/ 1), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G4, h->g4, h->p32, 0, Bc, store_epi(h->g4, h->u1, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G5, h->g5, h->u1, 0, Bc, store_epi(h->g5, h->u2, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G6, h->g6, h->u2, 0, Bc, store_epi(h->g6, h->u1, 0, Bc, /*tanh*/ 1), s))) return rc;
     // (S,K) 'same' complex conv as Toeplitz GEMM + fused phase equaliser   model.py:426-437
     {
       EpiPhaseEq e;
@@ -553,13 +599,13 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
       e.chest_out = chest_out;
       e.M = (int)Bc;
       e.N = h->g7.N;
-      if ((rc = run_gemm(h, h->g7, h->u1, 0, Bc, e, s))) return rc;
+      if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, h->u1, 0, Bc, e, s))) return rc;
     }
     // corr / eq (1,K) 'valid' complex convs -> [eq_out | corr_out]  model.py:437-448
-    if ((rc = run_gemm(h, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
-    if ((rc = run_gemm(h, h->g9, eqv, 0, MS, store_epi(h->g9, catv, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G8, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G9, h->g9, eqv, 0, MS, store_epi(h->g9, catv, 0, MS), s))) return rc;
     // dense_5: 4K -> 2T per symbol                                  model.py:457-462
-    if ((rc = run_gemm(h, h->g10, catv, 0, MS, store_epi(h->g10, oeqv, 0, MS, 0, eq_out, 2 * T), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G10, h->g10, catv, 0, MS, store_epi(h->g10, oeqv, 0, MS, 0, eq_out, 2 * T), s))) return rc;
     rx_in = &h->oeq;
     if (flags & DCCN_FWD_EQ_ONLY) return 0;
   }
@@ -568,7 +614,7 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
     const int64_t MS = Bc * S;
     Act inv = *rx_in;  inv.ld = 2 * T;
     Act r1v = h->r1o;  r1v.ld = 2 * h->F;
-    if ((rc = run_gemm(h, h->r1, inv, cp_off, MS, store_epi(h->r1, r1v, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_R1, h->r1, inv, cp_off, MS, store_epi(h->r1, r1v, 0, MS), s))) return rc;
     if ((rc = run_head_dispatch(h, Bc, bits, soft, hard, conf, ce, s))) return rc;
   }
   return 0;
@@ -616,6 +662,8 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   h->NB = cfg->nbits;
   h->P = h->S * h->T * 2;
   h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 4096;
+  if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
+  if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
     return set_error(-2, "frame size must be a multiple of 4 floats");
@@ -627,7 +675,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   // ---- workspace -----------------------------------------------------------------
   const bool split = cfg->precision == DCCN_PREC_PARITY;
   const int64_t C = h->chunk;
-  const int S = h->S, K = h->K, T = h->T;
+  const int S = h->S, K = h->K;
   int rc = 0;
   rc |= dev_alloc(h, (void**)&h->d_sums, (size_t)2 * h->P * sizeof(double));
   rc |= dev_alloc(h, (void**)&h->d_mean, (size_t)h->P * 4);
@@ -732,6 +780,7 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
     if (rc) return rc;
   }
   if (want_conf) {
+    g_launches += 1;
     conf_copy_kernel<<<1, 32, 0, s>>>(h->d_conf, (long long*)conf_dev);
     DCCN_CUDA_OK(cudaGetLastError());
   }
@@ -796,9 +845,13 @@ int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_sam
   cudaStream_t s = (cudaStream_t)stream;
   DCCN_CUDA_OK(cudaMemsetAsync(h->d_power, 0, sizeof(double), s));
   float* faded = fir_only_dev ? fir_only_dev : rx_dev;
-  chan_fir_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)tx_dev, (long long)B, n_samp, alpha_dev,
-                                                         coeff_dev, n_taps, n_fir, z_dev, seed, (float2*)faded,
-                                                         h->d_power);
+  {
+    LaunchScope ls(h, SLOT_CHAN_FIR, s);
+    chan_fir_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)tx_dev, (long long)B, n_samp, alpha_dev,
+                                                           coeff_dev, n_taps, n_fir, z_dev, seed, (float2*)faded,
+                                                           h->d_power);
+  }
+  LaunchScope ls2(h, SLOT_AWGN, s);
   const long long total = (long long)B * n_samp;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
@@ -854,6 +907,36 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
   cudaFree(d_map);
   return 0;
 }
+
+int64_t dccn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int dccn_profile_enable(dccn_handle* h, int on) {
+  DCCN_CHECK(h, "null handle");
+  h->prof = on != 0;
+  return 0;
+}
+
+int dccn_profile_collect(dccn_handle* h, double* ms_out, int64_t* count_out, int max_slots) {
+  DCCN_CHECK(h && ms_out && count_out && max_slots >= SLOT_COUNT, "need room for %d slots", (int)SLOT_COUNT);
+  DCCN_CUDA_OK(cudaDeviceSynchronize());
+  for (int i = 0; i < max_slots; ++i) {
+    ms_out[i] = 0.0;
+    count_out[i] = 0;
+  }
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_out[r.slot] += ms;
+      count_out[r.slot] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof_recs.clear();
+  return SLOT_COUNT;
+}
+
+const char* dccn_profile_slot_name(int slot) { return (slot >= 0 && slot < SLOT_COUNT) ? kSlotNames[slot] : ""; }
 
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream) {
   DCCN_CHECK(bits_dev && n >= 0, "bad argument");

@@ -176,9 +176,32 @@ struct EpiHead {
   DCCN_DEVINL void run(State& st, int row, int col0, float (&v)[NC]) const {
     if (row >= M || col0 >= N) return;
     const int D = N >> 1;
+    constexpr int ND = NC / 2;                 // data subcarriers in this call
+    constexpr int NBYTES = ND * NB;            // label / hard-decision bytes in this call
+    // Labels and hard decisions of the ND subcarriers are NBYTES contiguous bytes.  With the
+    // 32-column chunks of the tensor-core path they are 16-byte aligned -> vector access.
+    constexpr bool VEC = (NBYTES % 16 == 0);
+    constexpr int NW = (NBYTES + 3) / 4;
+    uint32_t yw[NW], hw_out[NW];
+    const size_t o0 = ((size_t)row * D + (col0 >> 1)) * NB;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) hw_out[w] = 0u;
+    if (bits) {
+      if constexpr (VEC) {
+#pragma unroll
+        for (int w = 0; w < NW; w += 4) {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(bits + o0) + (w >> 2));
+          yw[w] = t.x; yw[w + 1] = t.y; yw[w + 2] = t.z; yw[w + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) yw[w] = 0u;
+#pragma unroll
+        for (int b = 0; b < NBYTES; ++b) yw[b >> 2] |= (uint32_t)bits[o0 + b] << ((b & 3) * 8);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NC; i += 2) {
-      const int d = (col0 + i) >> 1;
       const float I = v[i] + __ldg(bias + col0 + i);
       const float Q = v[i + 1] + __ldg(bias + col0 + i + 1);
       float h[MO];
@@ -198,7 +221,6 @@ struct EpiHead {
       }
 #pragma unroll
       for (int m = 0; m < MO; ++m) h[m] = fmaxf(0.2f * h[m], h[m]);
-      const size_t o = ((size_t)row * D + d) * NB;
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         float l0 = hw.b1[2 * k], l1 = hw.b1[2 * k + 1];
@@ -211,22 +233,37 @@ struct EpiHead {
         l1 += I * hw.W1[MO][2 * k + 1] + Q * hw.W1[MO + 1][2 * k + 1];
         l0 = fmaxf(0.2f * l0, l0);
         l1 = fmaxf(0.2f * l1, l1);
-        const float mx = fmaxf(l0, l1);
-        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
-        const float s = e0 + e1;
-        const float p0 = e0 / s, p1 = e1 / s;
+        // softmax over the pair: exp(l - max) / sum  ==  {1, t} / (1 + t),  t = exp(-|l1 - l0|)
+        const float t = expf(-fabsf(l1 - l0));
+        const float s = 1.0f + t;
+        const float pb = 1.0f / s, ps = t / s;       // probability of the larger / smaller logit
+        const bool one_big = l1 > l0;
+        const float p0 = one_big ? ps : pb, p1 = one_big ? pb : ps;
         const unsigned hb = p1 > p0 ? 1u : 0u;           // tf.argmax: first index on ties
-        if (soft) *reinterpret_cast<float2*>(soft + (o + k) * 2) = make_float2(p0, p1);
-        if (hard) hard[o + k] = (uint8_t)hb;
+        const int bidx = (i >> 1) * NB + k;              // byte index inside this call
+        hw_out[bidx >> 2] |= hb << ((bidx & 3) * 8);
+        if (soft) *reinterpret_cast<float2*>(soft + (o0 + bidx) * 2) = make_float2(p0, p1);
         if (bits) {
-          const unsigned y = bits[o + k];
+          const unsigned y = (yw[bidx >> 2] >> ((bidx & 3) * 8)) & 1u;
           st.c00 += (y == 0 && hb == 0);
           st.c01 += (y == 0 && hb == 1);
           st.c10 += (y == 1 && hb == 0);
           st.c11 += (y == 1 && hb == 1);
-          const float lse = logf(expf(p0) + expf(p1));
+          // softmax-xent applied ON the softmax outputs (ofdmreceiver_np.py:155-159):
+          // logsumexp(p0,p1) - p_y = max(p) + log1p(exp(-|p1-p0|)) - p_y     (monitor only)
+          const float lse = fmaxf(p0, p1) + __logf(1.0f + __expf(-fabsf(p1 - p0)));
           st.ce += lse - (y ? p1 : p0);
         }
+      }
+    }
+    if (hard) {
+      if constexpr (VEC) {
+#pragma unroll
+        for (int w = 0; w < NW; w += 4)
+          *(reinterpret_cast<uint4*>(hard + o0) + (w >> 2)) = make_uint4(hw_out[w], hw_out[w + 1], hw_out[w + 2], hw_out[w + 3]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < NBYTES; ++b) hard[o0 + b] = (uint8_t)((hw_out[b >> 2] >> ((b & 3) * 8)) & 0xFFu);
       }
     }
   }

@@ -1,33 +1,41 @@
 // gemm_tc.cuh -- hand-written sm_100a GEMM: TMA -> shared memory -> tcgen05.mma (kind::tf32)
-// -> TMEM accumulators -> tcgen05.ld -> fused epilogue.
+// -> TMEM accumulators -> tcgen05.ld -> fp32 register accumulation -> fused epilogue.
 //
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T )       A, B row-major with K contiguous ("K-major")
 //
 // * persistent: grid = min(#tiles, #SMs); CTA loops over 128 x BN output tiles, n fastest so
 //   that concurrently running CTAs share the A tile in L2;
-// * warp roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM allocator +
-//   MMA issuer (1 lane), warps 2..5 = epilogue (one TMEM lane quarter each);
-// * three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
+// * warp roles: warp 0 = TMA producer (1 lane), warp 1 = TMEM allocator + MMA issuer
+//   (1 lane), warps 2.. = epilogue: 4*CG warps, each owning one TMEM lane quarter and one of
+//   CG column groups of the tile;
+// * three pipelines: smem full/empty ring (TMA <-> MMA), a 2-deep TMEM accumulator ring
 //   (MMA <-> epilogue), static tile schedule;
 // * operands are 128-byte-swizzled [rows x 32 fp32] boxes written by TMA and consumed through
-//   K-major SWIZZLE_128B shared-memory descriptors; out-of-bounds rows / K tail are zero-filled
-//   by TMA, so ragged M, N, K need no special code in the main loop;
+//   K-major SWIZZLE_128B shared-memory descriptors; out-of-bounds rows / the K tail are
+//   zero-filled by TMA, so ragged M, N, K need no special code in the main loop;
 // * SPLIT = true is the 3xTF32 scheme of DCCN_PREC_PARITY: every operand is a (hi, lo) pair of
 //   tf32-exact planes and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  into the same
-//   fp32 accumulator (the lo*lo term, ~2^-22 relative, is dropped).
+//   TMEM accumulator (the lo*lo term, <= 2^-24 relative, is dropped);
+// * K-CHUNKED ACCUMULATION: the tensor core adds into its fp32 accumulator with truncation,
+//   so a long dependent chain (K = 896..1024 -> hundreds of MMAs) accumulates a systematic
+//   bias ~10x above fp32 round-to-nearest (measured on the shipped 16-QAM checkpoint).  The
+//   MMA warp therefore closes an accumulator every `kc` k-blocks; the epilogue warps drain it
+//   with tcgen05.ld and add the partial sums in registers with IEEE round-to-nearest while
+//   the tensor core already fills the other accumulator.  kc = 0 keeps the whole K in TMEM
+//   (DCCN_PREC_FAST, where operand rounding dominates anyway).
 #pragma once
 #include "common.cuh"
 #include "epilogue.cuh"
 
 namespace dccn {
 
-constexpr int ilog2_ceil_pow2(int v) {
+constexpr int pow2_at_least(int v) {
   int p = 32;
   while (p < v) p <<= 1;
   return p;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int CG>
 struct TcCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 32;                       // 32 fp32 = one 128-byte swizzle row
@@ -39,10 +47,14 @@ struct TcCfg {
   static constexpr int SMEM_BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = ilog2_ceil_pow2(2 * BN);
+  static constexpr int TMEM_COLS = pow2_at_least(2 * BN);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 64 + 128 * CG;
+  static constexpr int COLS_PER_GROUP = BN / CG;
+  static constexpr int NCH = COLS_PER_GROUP / 32;     // 32-column register chunks per epilogue thread
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
-  static_assert(BN % 32 == 0, "epilogue reads 32-column chunks");
+  static_assert(BN % (32 * CG) == 0, "each column group is a whole number of 32-column chunks");
+  static_assert(NCH >= 1 && NCH <= 4, "at most 128 accumulator registers per epilogue thread");
   static_assert(STAGES >= 2, "need at least a double buffer");
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
 };
@@ -52,17 +64,17 @@ struct TcOperands {
   CUtensorMap b0, b1;   // B hi / lo
 };
 
-template <int BN, bool SPLIT, class Epi>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, bool SPLIT, int CG, class Epi>
+__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int M, int N, int K, const __grid_constant__ Epi epi) {
-  using C = TcCfg<BN, SPLIT>;
+               int M, int N, int K, int kc, const __grid_constant__ Epi epi) {
+  using C = TcCfg<BN, SPLIT, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty = full + C::STAGES;
-  uint64_t* tfull = empty + C::STAGES;   // [2] accumulator ready for the epilogue
+  uint64_t* tfull = empty + C::STAGES;   // [2] accumulator (one K chunk) ready for the epilogue
   uint64_t* tempty = tfull + 2;          // [2] accumulator drained
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -70,6 +82,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = ((M + C::BM - 1) / C::BM) * n_tiles;
   const int num_kb = (K + C::BK - 1) / C::BK;
+  const int kb_per_chunk = (kc <= 0 || kc > num_kb) ? num_kb : kc;
+  const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -87,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 4);   // one elected lane of each of the 4 epilogue warps
+        mbar_init(&tempty[a], 4 * CG);   // one elected lane per epilogue warp
       }
       fence_barrier_init();
     }
@@ -132,66 +146,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += kb_per_chunk) {
+          const int kb1 = kb0 + kb_per_chunk < num_kb ? kb0 + kb_per_chunk : num_kb;
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_lo = a_hi + C::A_BYTES;
-          const uint32_t b_hi = a_hi + C::PLANES * C::A_BYTES;
-          const uint32_t b_lo = b_hi + C::B_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint32_t a_lo = a_hi + C::A_BYTES;
+            const uint32_t b_hi = a_hi + C::PLANES * C::A_BYTES;
+            const uint32_t b_lo = b_hi + C::B_BYTES;
 #pragma unroll
-          for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
-            const uint32_t koff = k * C::UMMA_K * 4;   // byte advance inside the 128 B swizzle row
-            const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
-            const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
-            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-            if (SPLIT) {
-              const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
-              const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
-              umma_tf32(d, da_lo, db_hi, idesc, first);   // small terms first
-              umma_tf32(d, da_hi, db_lo, idesc, 1u);
-              umma_tf32(d, da_hi, db_hi, idesc, 1u);
-            } else {
-              umma_tf32(d, da_hi, db_hi, idesc, first);
+            for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+              const uint32_t koff = k * C::UMMA_K * 4;   // byte advance inside the 128 B swizzle row
+              const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
+              const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
+              const uint32_t accum = (kb != kb0 || k != 0) ? 1u : 0u;
+              if (SPLIT) {
+                const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
+                const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
+                umma_tf32(d, da_lo, db_hi, idesc, accum);   // small terms first
+                umma_tf32(d, da_hi, db_lo, idesc, 1u);
+                umma_tf32(d, da_hi, db_hi, idesc, 1u);
+              } else {
+                umma_tf32(d, da_hi, db_hi, idesc, accum);
+              }
+            }
+            umma_commit(&empty[stage]);        // smem slot reusable once these MMAs retire
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
             }
           }
-          umma_commit(&empty[stage]);        // smem slot reusable once these MMAs retire
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&tfull[acc]);            // K chunk complete -> epilogue drains it
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        umma_commit(&tfull[acc]);            // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
     // =============================== epilogue warps =============================
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int cg = (warp - 2) >> 2;            // column group
     typename Epi::State st;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float r[C::NCH][32];
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * C::BM + q * 32 + lane;
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld_32x32(t0 + c * 32, v);
-        epi.template run<32>(st, row, n_blk * BN + c * 32, v);
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t0 =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * C::COLS_PER_GROUP);
+#pragma unroll
+        for (int j = 0; j < C::NCH; ++j) {
+          float v[32];
+          tmem_ld_32x32(t0 + j * 32, v);
+          if (ch == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[j][i] = v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[j][i] = __fadd_rn(r[j][i], v[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j)
+        epi.template run<32>(st, row, n_blk * BN + cg * C::COLS_PER_GROUP + j * 32, r[j]);
     }
     epi.flush(st);
   }
@@ -201,11 +232,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int BN, bool SPLIT, class Epi>
-inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, const Epi& epi, cudaStream_t s, int num_sms) {
-  using C = TcCfg<BN, SPLIT>;
+template <int BN, bool SPLIT, int CG, class Epi>
+inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
+                          int num_sms) {
+  using C = TcCfg<BN, SPLIT, CG>;
   if (M <= 0) return 0;
-  auto kern = gemm_tc_kernel<BN, SPLIT, Epi>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, CG, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -213,7 +245,8 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, const Epi& 
   }
   const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, 192, C::SMEM_BYTES, s>>>(op.a0, SPLIT ? op.a1 : op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, epi);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(op.a0, SPLIT ? op.a1 : op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc,
+                                              epi);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -89,6 +89,17 @@ class DCCN:
     def workspace_bytes(self):
         return int(self.lib.dccn_workspace_bytes(self._h))
 
+    # -- measurement hooks -----------------------------------------------------------------
+    def profile(self, on=True):
+        _lib.check(self.lib.dccn_profile_enable(self._h, int(on)))
+
+    def profile_collect(self):
+        """-> {slot name: (total ms, launches)} since the last collect (synchronises)."""
+        ms = (C.c_double * 32)()
+        cnt = (C.c_int64 * 32)()
+        n = _lib.check(self.lib.dccn_profile_collect(self._h, ms, cnt, 32))
+        return {self.lib.dccn_profile_slot_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
+
     # -- the pass ----------------------------------------------------------------------
     def forward(self, x, bits=None, want_soft=True, want_hard=True, want_eq=False, want_chest=False,
                 flags=0):
@@ -189,6 +200,11 @@ class DCCN:
             _lib.check(self.lib.dccn_tx_frames(self._h, _ptr(bits), B, _ptr(dsc), dsc.numel(), _ptr(psc),
                                                psc.numel(), _ptr(const), pv.real, pv.imag, _ptr(tx), _stream()))
         return tx
+
+
+def launch_count():
+    """Number of kernels libdccn has launched in this process."""
+    return int(_lib.load().dccn_launch_count())
 
 
 def bit_source_gpu(n, seed, device='cuda'):

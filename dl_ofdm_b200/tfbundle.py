@@ -239,7 +239,7 @@ def write_checkpoint(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
     entries.append((b'', header))
     with open(prefix + '.data-00000-of-00001', 'wb') as f:
         for n in names:
-            arr = np.ascontiguousarray(tensors[n])
+            arr = np.asarray(tensors[n], order='C')
             entries.append((n.encode(), _entry_proto(arr, offset)))
             raw = arr.tobytes()
             f.write(raw)

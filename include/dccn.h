@@ -152,6 +152,14 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B,
                    const float* constellation_dev, float pilot_re, float pilot_im,
                    float* tx_dev, void* stream);
 
+/* -- measurement hooks (bench.py): kernels launched by the library so far; per-kernel CUDA-event
+ * timing on the launch stream.  dccn_profile_collect synchronises the device and returns the number
+ * of slots; ms_out/count_out[i] = summed duration / launches of slot i since the last collect. */
+int64_t dccn_launch_count(void);
+int dccn_profile_enable(dccn_handle* h, int on);
+int dccn_profile_collect(dccn_handle* h, double* ms_out, int64_t* count_out, int max_slots);
+const char* dccn_profile_slot_name(int slot);
+
 /* uniform random bits (util.bit_source, dev/py/util.py:25-34) from Philox */
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream);
 

@@ -356,11 +356,15 @@ def equalized_receiver(x, w, nbits, nfft, cp_len, use_cp=True, nfilter=64,
 # ---------------------------------------------------------------------------
 def glorot_weights(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data=320,
                    pilot_size=16, use_cp=True, head='dev', equalizer=True,
-                   bias_scale=0.0):
+                   bias_scale=0.0, chest_bias=None):
     """Seeded weights with the reference's variable names, layouts and init.
 
     ``bias_scale`` > 0 draws small non-zero biases so parity tests exercise the
     bias paths (TF initialises biases to zero; trained models have them non-zero).
+    ``chest_bias`` = (b0, b1) sets Equalizer/conv3d_1/bias so that the channel
+    estimate stays away from 0: the phase-only equaliser divides by |chest| with
+    no epsilon (model.py:430-433), and an untrained estimate that crosses 0 makes
+    the frame ill-conditioned in every arithmetic.
     """
     T = nfft + cp_len if use_cp else nfft
     S, F, K = nsymbol, nfilter, nfft
@@ -406,4 +410,6 @@ def glorot_weights(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data
         conv3d(e + 'conv3d_2', 1, K, 1, 2 * K)
         conv3d(e + 'conv3d_3', 1, K, 1, 2 * K)
         dense(e + 'dense_5', K * 4, (nfft + cp_len) * 2)
+        if chest_bias is not None:
+            w[e + 'conv3d_1/bias'] = np.asarray(chest_bias, dtype=np.float32)
     return w

@@ -137,5 +137,17 @@ def main():
     np.savez(os.path.join(OUT, 'v1_known_answers.npz'), snr=np.array([0, 5, 10, 15, 22]), **rows)
 
 
+
+def make_alpha_npz():
+    """dl_ofdm_b200/data/lte_alpha.npz: the reference's fractional-delay interpolation matrices
+    (dev/py/3gpp/AM_*.csv, exported from MATLAB's channelFilter.alphaMatrix, README.md:60) packed
+    as one npz -- numeric channel-model data the product reads at run time."""
+    d = {}
+    for ch, fn in (('epa', 'AM_EPA.csv'), ('eva', 'AM_EVA.csv'), ('etu', 'AM_ETU.csv'), ('custom', 'AM_Custom.csv')):
+        d[ch] = np.genfromtxt(os.path.join(REF, 'dev', 'py', '3gpp', fn), delimiter=',')
+    np.savez(os.path.join(REPO, 'dl_ofdm_b200', 'data', 'lte_alpha.npz'), **d)
+
+
 if __name__ == '__main__':
+    make_alpha_npz()
     main()

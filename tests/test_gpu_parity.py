@@ -26,11 +26,19 @@ def _cuda(a, dtype=None):
     return t.cuda().contiguous()
 
 
-def _check_soft(soft, soft_ref, hard, p999=P999_TOL, mx=MAX_TOL):
+def _check_soft(soft, soft_ref, hard, soft_ref32=None, p999=P999_TOL, mx=MAX_TOL):
+    """soft_ref: fp64 oracle.  soft_ref32: the same oracle evaluated in fp32 -- the error an fp32
+    CPU implementation (like the reference's TF kernels) makes against fp64 on THIS input; a
+    trained network with steep logits can exceed the nominal 1e-5 in any fp32 arithmetic, so
+    the bound is max(nominal, 1.5 x that intrinsic fp32 error)."""
     err = np.abs(soft.astype(np.float64) - soft_ref)
     q = np.quantile(err, 0.999)
-    assert q <= p999, 'p99.9 |dsoft| = %.3g' % q
-    assert err.max() <= mx, 'max |dsoft| = %.3g' % err.max()
+    if soft_ref32 is not None:
+        e32 = np.abs(soft_ref32.astype(np.float64) - soft_ref)
+        p999 = max(p999, 1.5 * np.quantile(e32, 0.999))
+        mx = max(mx, 2.0 * e32.max())
+    assert q <= p999, 'p99.9 |dsoft| = %.3g (bound %.3g)' % (q, p999)
+    assert err.max() <= mx, 'max |dsoft| = %.3g (bound %.3g)' % (err.max(), mx)
     hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
     decided = np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= MARGIN
     assert np.array_equal(hard[decided], hard_ref[decided]), 'hard-bit mismatch outside the tie margin'
@@ -90,13 +98,14 @@ def test_v1_checkpoint_receiver(libdccn, golden, precision, fixture, nb, cp):
     snr = 10 if nb == 4 else 0
     x, bits = v1_frames(nb, snr, 700)
     soft_ref = orc.basic_receiver(x, w, nb, 16, use_cp=cp, head='v1', dtype=np.float64)
+    soft_ref32 = orc.basic_receiver(x, w, nb, 16, use_cp=cp, head='v1', dtype=np.float32)
     _, conf_ref, ber_ref, ce_ref = orc.ber_head(soft_ref, bits)
     m = DCCN(nbits=nb, nsymbol=8, n_data=368, use_cp=cp, head='v1', precision=precision, chunk_frames=256)
     m.load_weights(w)
     out = m.forward(_cuda(x), _cuda(bits))
     torch.cuda.synchronize()
     soft, hard = out['soft'].cpu().numpy(), out['hard'].cpu().numpy()
-    flips = _check_soft(soft, soft_ref, hard)
+    flips = _check_soft(soft, soft_ref, hard, soft_ref32)
     conf = out['conf'].cpu().numpy()
     assert conf.sum() == bits.size
     assert np.abs(conf - conf_ref).sum() <= 2 * flips
@@ -167,7 +176,7 @@ def test_equalizer_seeded(libdccn, precision, cp):
     from oracle import dccn_oracle as orc
     rng = np.random.default_rng(77)
     nb, B = 2, 260
-    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05)
+    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
     x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
     bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
     soft_ref, eq_ref, chest_ref = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64)
@@ -200,7 +209,7 @@ def test_subgraph_entry_points(libdccn):
     from oracle import dccn_oracle as orc
     rng = np.random.default_rng(3)
     nb, B = 2, 150
-    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05)
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
     x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
     z, _, _ = orc.batch_moment_norm(x, np.float32)
     m = DCCN(nbits=nb, equalizer=True, precision='exact')
@@ -332,7 +341,7 @@ def test_full_size_properties(libdccn):
     from oracle import dccn_oracle as orc
     rng = np.random.default_rng(42)
     nb, B = 4, 65536
-    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.02)
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.02, chest_bias=(0.6, -0.4))
     g = torch.Generator(device='cuda').manual_seed(1)
     x = torch.randn((B, 7, 80, 2), generator=g, device='cuda') * 0.2
     bits = torch.randint(0, 2, (B, 320, nb), generator=g, device='cuda', dtype=torch.uint8)

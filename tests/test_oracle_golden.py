@@ -1,0 +1,103 @@
+"""CPU tests: the oracle against the reference's own artefacts (golden fixtures)."""
+import numpy as np
+import pytest
+
+from conftest import v1_weights
+from oracle import dccn_oracle as orc
+from oracle.v1_recipe import v1_frames, constellation
+
+
+@pytest.mark.parametrize('fixture,nb,cp', [('v1_4mod_cpTrue.npz', 4, True), ('v1_1mod_cpFalse.npz', 1, False)])
+def test_v1_known_answer_ber(golden, fixture, nb, cp):
+    """Shipped trained checkpoints + BASELINE.md recipe -> the recorded BER (exactly)."""
+    w = v1_weights(golden(fixture))
+    ka = golden('v1_known_answers.npz')
+    tag = '%dmod_cp%s' % (nb, cp)
+    for snr in (10, 22) if nb == 4 else (0, 15):
+        x, bits = v1_frames(nb, snr, 2000)
+        soft = orc.basic_receiver(x, w, nb, 16, use_cp=cp, head='v1', dtype=np.float64)
+        _, conf, ber, _ = orc.ber_head(soft, bits)
+        expect = float(ka[tag][list(ka['snr']).index(snr)])
+        assert conf.sum() == 2000 * 368 * nb
+        assert abs(ber - expect) <= 1.5 / conf.sum(), (snr, ber, expect)
+
+
+def test_v1_known_answers_table_matches_baseline_md(golden):
+    """Spot values of BASELINE.md section 2 (computed in the survey session, independently)."""
+    ka = golden('v1_known_answers.npz')
+    snr = list(ka['snr'])
+    assert abs(ka['4mod_cpTrue'][snr.index(10)] - 4.328e-2) < 5e-5
+    assert abs(ka['4mod_cpTrue'][snr.index(15)] - 2.195e-3) < 5e-6
+    assert abs(ka['1mod_cpTrue'][snr.index(0)] - 4.606e-2) < 5e-5
+    assert abs(ka['2mod_cpFalse'][snr.index(5)] - 2.747e-2) < 5e-5
+    assert all(ka[k][snr.index(22)] == 0 for k in ka.files if k != 'snr')
+
+
+def test_fp32_oracle_close_to_fp64(golden):
+    w = v1_weights(golden('v1_4mod_cpTrue.npz'))
+    x, _ = v1_frames(4, 10, 300)
+    s64 = orc.basic_receiver(x, w, 4, 16, head='v1', dtype=np.float64)
+    s32 = orc.basic_receiver(x, w, 4, 16, head='v1', dtype=np.float32)
+    err = np.abs(s32 - s64)
+    assert err.max() < 1e-4 and np.quantile(err, 0.999) < 2e-5
+
+
+def test_constellation_tables(golden):
+    g = golden('const_map.npz')
+    for o in (1, 2, 3, 4):
+        assert np.array_equal(constellation(o), g['ord%d' % o])
+
+
+@pytest.mark.parametrize('chan', ['epa', 'eva', 'etu', 'flat', 'custom'])
+def test_rayleigh_static_matches_reference(golden, chan):
+    g = golden('rayleigh_%s.npz' % chan)
+    B = g['tx'].shape[0]
+    assert np.allclose(orc.channel_coeff(chan), g['ch_coeff'], rtol=0, atol=0)
+    rx, _ = orc.rayleigh_static(g['tx'].reshape(B, -1), g['z'], g['ch_coeff'], np.atleast_2d(g['alpha']))
+    assert np.array_equal(rx.reshape(g['rx'].shape).astype(np.float64), g['rx'])
+
+
+def test_awgn_matches_reference(golden):
+    g = golden('awgn.npz')
+    out, npw, _ = orc.awgn(g['x'], g['snr'], g['normals'])
+    assert np.array_equal(out, g['out'])
+    assert npw == float(g['noise_power'])
+
+
+def test_packed_gemm_equals_conv():
+    """SURVEY App. D packing == literal conv3d/reshape/sub formulation of complex.py."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 7, 64, 1, 2))
+    k = rng.standard_normal((1, 64, 1, 1, 128)) * 0.1
+    b = rng.standard_normal(128) * 0.1
+    ref = orc.conv2d_complex(x, k, b, 'valid')                     # [5,7,1,64,2]
+    Bp, bp = orc.pack_complex_kernel(k[0, :, 0, 0, :64], k[0, :, 0, 0, 64:], b[:64], b[64:])
+    y = x.reshape(35, 128) @ Bp + bp
+    assert np.abs(y.reshape(5, 7, 1, 64, 2) - ref).max() < 1e-12
+
+
+def test_oracle_equals_tf_mirror():
+    """NumPy restatement vs the op-for-op torch mirror (padded conv3d) on seeded weights."""
+    torch = pytest.importorskip('torch')
+    from oracle.tf_mirror import TFMirror
+    rng = np.random.default_rng(4)
+    for nb, cp, eq in ((2, True, True), (4, False, True), (1, True, False)):
+        w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=eq, bias_scale=0.05, chest_bias=(0.6, -0.4))
+        x = (rng.standard_normal((48, 7, 80, 2)) * 0.2).astype(np.float32)
+        if eq:
+            ref, _, chest = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64)
+            good = np.abs(chest).reshape(48, -1).min(axis=1) > 2e-2
+        else:
+            ref = orc.basic_receiver(x, w, nb, 16, use_cp=cp, dtype=np.float64)
+            good = np.ones(48, dtype=bool)
+        got = TFMirror(w, nb, use_cp=cp, equalizer=eq).forward(x).numpy()
+        assert np.quantile(np.abs(got[good] - ref[good]), 0.999) < 2e-4
+
+
+def test_ber_head_counts():
+    soft = np.array([[[[0.7, 0.3]], [[0.5, 0.5]], [[0.2, 0.8]]]])      # [1,3,1,2]
+    bits = np.array([[[0], [1], [1]]])
+    hard, conf, ber, ce = orc.ber_head(soft, bits)
+    assert hard.reshape(-1).tolist() == [0, 0, 1]                       # tie -> index 0
+    assert conf.tolist() == [[1, 0], [1, 1]]
+    assert abs(ber - 1 / 3) < 1e-12

@@ -110,11 +110,11 @@ using namespace dccn;
 namespace dccn {
 static std::atomic<long long> g_launches{0};   // kernels launched by this library (dccn_launch_count)
 enum { SLOT_MOMENTS = 0, SLOT_PREP, SLOT_G1, SLOT_G2, SLOT_G3, SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G7_PHASEEQ,
-       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_COUNT };
+       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_COUNT };
 static const char* kSlotNames[SLOT_COUNT] = {
     "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
     "eq_conv7x64_phaseeq", "eq_corr_idft", "eq_idft", "eq_dense5", "rx_fft_like", "rx_demod_head",
-    "chan_fir", "chan_awgn"};
+    "chan_fir", "chan_awgn", "rx_demod_gemm"};
 struct ProfRec { int slot; cudaEvent_t a, b; };
 }  // namespace dccn
 
@@ -131,6 +131,7 @@ struct dccn_handle {
   int chunk;
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
+  int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   // layers
   GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
   GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
@@ -143,7 +144,7 @@ struct dccn_handle {
   double* d_power = nullptr;      // channel power accumulator
   unsigned long long* d_conf = nullptr;   // internal [4]
   double* d_ce = nullptr;
-  Act a0, t1, f, p32, u1, u2, eq, corr, cat, oeq, r1o;
+  Act a0, t1, f, p32, u1, u2, eq, corr, cat, oeq, r1o, out_iq;
   // staging for dccn_forward_host
   float* d_x = nullptr;
   uint8_t* d_bits = nullptr;
@@ -337,7 +338,7 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
       for (int m = 0; m < MO; ++m) h->hw.bc1[m] = bc1->data[m];
     }
   }
-  h->r2.fused = true;
+  h->r2.fused = h->fused_head != 0;
   h->g7.fused = true;
   if ((rc = upload_layer(h, &h->r1, s))) return rc;
   if ((rc = upload_layer(h, &h->r2, s))) return rc;
@@ -511,7 +512,7 @@ template <int NB, bool V1>
 static int run_head(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
                     unsigned long long* conf, double* ce, cudaStream_t s) {
   EpiHead<NB, V1> e;
-  e.bias = h->r2.dBias;
+  e.bias = h->fused_head ? h->r2.dBias : nullptr;
   e.hw = h->hw;
   e.bits = bits;
   e.soft = soft;
@@ -520,7 +521,19 @@ static int run_head(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft
   e.ce_sum = ce;
   e.M = (int)Bc;
   e.N = h->r2.N;
-  return run_gemm(h, SLOT_R2_HEAD, h->r2, h->r1o, 0, Bc, e, s);
+  if (h->fused_head) return run_gemm(h, SLOT_R2_HEAD, h->r2, h->r1o, 0, Bc, e, s);
+  // default: plain-store GEMM (bias added, one fp32 plane) + the full-occupancy head kernel
+  Act oiq = h->out_iq;
+  int rc = run_gemm(h, SLOT_R2_GEMM, h->r2, h->r1o, 0, Bc, store_epi(h->r2, oiq, 0, Bc), s);
+  if (rc) return rc;
+  LaunchScope ls(h, SLOT_R2_HEAD, s);
+  const long long total = (long long)Bc * (h->r2.N >> 1);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)h->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  head_kernel<NB, V1><<<(unsigned)blocks, 256, 0, s>>>(oiq.p0, e);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 static int run_head_dispatch(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
@@ -664,6 +677,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 4096;
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
+  if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
     return set_error(-2, "frame size must be a multiple of 4 floats");
@@ -687,6 +701,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   rc |= dev_alloc(h, (void**)&h->d_res_ce, sizeof(double));
   rc |= alloc_act(h, &h->a0, C, h->P, split);
   rc |= alloc_act(h, &h->r1o, C, S * h->F * 2, split);
+  rc |= alloc_act(h, &h->out_iq, C, 2 * h->D, false);
   if (cfg->equalizer) {
     rc |= alloc_act(h, &h->t1, C, S * K * 2, split);
     rc |= alloc_act(h, &h->f, C, S * K * 2, split);

@@ -193,6 +193,10 @@ struct EpiHead {
           const uint4 t = __ldg(reinterpret_cast<const uint4*>(bits + o0) + (w >> 2));
           yw[w] = t.x; yw[w + 1] = t.y; yw[w + 2] = t.z; yw[w + 3] = t.w;
         }
+      } else if constexpr (NBYTES == 4) {
+        yw[0] = __ldg(reinterpret_cast<const uint32_t*>(bits + o0));
+      } else if constexpr (NBYTES == 2) {
+        yw[0] = __ldg(reinterpret_cast<const uint16_t*>(bits + o0));
       } else {
 #pragma unroll
         for (int w = 0; w < NW; ++w) yw[w] = 0u;
@@ -202,8 +206,8 @@ struct EpiHead {
     }
 #pragma unroll
     for (int i = 0; i < NC; i += 2) {
-      const float I = v[i] + __ldg(bias + col0 + i);
-      const float Q = v[i + 1] + __ldg(bias + col0 + i + 1);
+      const float I = v[i] + (bias ? __ldg(bias + col0 + i) : 0.f);
+      const float Q = v[i + 1] + (bias ? __ldg(bias + col0 + i + 1) : 0.f);
       float h[MO];
 #pragma unroll
       for (int m = 0; m < MO; ++m) h[m] = I * hw.Wc[0][m] + Q * hw.Wc[1][m] + hw.bc[m];
@@ -261,6 +265,10 @@ struct EpiHead {
 #pragma unroll
         for (int w = 0; w < NW; w += 4)
           *(reinterpret_cast<uint4*>(hard + o0) + (w >> 2)) = make_uint4(hw_out[w], hw_out[w + 1], hw_out[w + 2], hw_out[w + 3]);
+      } else if constexpr (NBYTES == 4) {
+        *reinterpret_cast<uint32_t*>(hard + o0) = hw_out[0];
+      } else if constexpr (NBYTES == 2) {
+        *reinterpret_cast<uint16_t*>(hard + o0) = (uint16_t)hw_out[0];
       } else {
 #pragma unroll
         for (int b = 0; b < NBYTES; ++b) hard[o0 + b] = (uint8_t)((hw_out[b >> 2] >> ((b & 3) * 8)) & 0xFFu);

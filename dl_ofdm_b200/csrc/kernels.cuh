@@ -302,6 +302,27 @@ __global__ void bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint6
     if (i * 16 + j < n) bits[i * 16 + j] = (uint8_t)((w >> j) & 1u);
 }
 
+// =====================================================================================
+// Demodulation head as a stand-alone, fully parallel kernel: one thread per (frame, data
+// subcarrier).  Same arithmetic as EpiHead (it calls it): the GEMM epilogue variant is bound
+// by the latency of 8 epilogue warps, this one runs at full occupancy.
+// out_iq [M, 2D] fp32 (bias already added by the GEMM epilogue).
+// =====================================================================================
+template <int NB, bool V1>
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ out_iq, const __grid_constant__ EpiHead<NB, V1> epi) {
+  const long long total = (long long)epi.M * (epi.N >> 1);
+  typename EpiHead<NB, V1>::State st;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int D = epi.N >> 1;
+    const int row = (int)(i / D), d = (int)(i % D);
+    const float2 iq = __ldg(reinterpret_cast<const float2*>(out_iq + (size_t)row * epi.N) + d);
+    float v[2] = {iq.x, iq.y};
+    epi.template run<2>(st, row, 2 * d, v);
+  }
+  epi.flush(st);
+}
+
 // a5: confusion matrix of hard decisions vs bits (rows = truth)
 __global__ void __launch_bounds__(256) ber_accum_kernel(const uint8_t* __restrict__ hard,
                                                         const uint8_t* __restrict__ bits, long long n,

@@ -88,9 +88,11 @@ def test_batch_moments(libdccn):
 # ---------------------------------------------------------------------------------------------
 # a3 + a5 on the reference's own trained weights (v1 checkpoints) -- the pinned parity case
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fused_head', [0, 1])
 @pytest.mark.parametrize('precision', ['exact', 'parity'])
 @pytest.mark.parametrize('fixture,nb,cp', [('v1_4mod_cpTrue.npz', 4, True), ('v1_1mod_cpFalse.npz', 1, False)])
-def test_v1_checkpoint_receiver(libdccn, golden, precision, fixture, nb, cp):
+def test_v1_checkpoint_receiver(libdccn, golden, monkeypatch, precision, fixture, nb, cp, fused_head):
+    monkeypatch.setenv('DCCN_FUSED_HEAD', str(fused_head))   # head inside the GEMM epilogue vs own kernel
     from dl_ofdm_b200.engine import DCCN
     from oracle import dccn_oracle as orc
     from oracle.v1_recipe import v1_frames
@@ -145,9 +147,11 @@ def test_v1_negative_control_sign(libdccn, golden):
 # ---------------------------------------------------------------------------------------------
 # a3 dev head on seeded weights (parity unpinned for trained dev weights: none are shipped)
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fused_head', [0, 1])
 @pytest.mark.parametrize('precision', ['exact', 'parity'])
 @pytest.mark.parametrize('nb,cp', [(1, True), (2, True), (3, False), (4, True)])
-def test_dev_receiver_seeded(libdccn, precision, nb, cp):
+def test_dev_receiver_seeded(libdccn, monkeypatch, precision, nb, cp, fused_head):
+    monkeypatch.setenv('DCCN_FUSED_HEAD', str(fused_head))
     from dl_ofdm_b200.engine import DCCN
     from oracle import dccn_oracle as orc
     rng = np.random.default_rng(10 + nb)

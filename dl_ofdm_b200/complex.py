@@ -1,0 +1,32 @@
+"""Op-level mirror of the reference's complex-layer library (dev/py/complex.py).
+
+Only ``layers_conv2d_complex`` is on the DCCN path (the 1-D, transpose,
+vector and streams variants are unused by the default model).  TF creates the variables inside
+the call; here they are passed in (``kernel`` [kl,kw,1,C,2*filters], ``bias`` [2*filters]).
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import cconv2d
+
+
+def layers_conv2d_complex(inputs, filters, kernal, strides=1, padding='valid', kernel=None, bias=None):
+    """[batch, length, width, channel, IQ(2)] real or [batch, length, width, channel] complex64
+    CUDA tensor -> same rank, `filters` output channels (dev/py/complex.py:140-196)."""
+    if strides not in (1, (1, 1)):
+        raise NotImplementedError('strides != 1 is never used on the DCCN path')
+    if isinstance(kernal, int):
+        kernal = (kernal, kernal)
+    elif not (isinstance(kernal, tuple) and len(kernal) == 2):
+        raise NameError('Unacceptable Kernal Size')
+    complex_flag = False
+    if inputs.dim() == 4 and inputs.is_complex():
+        inputs = torch.view_as_real(inputs.contiguous())
+        complex_flag = True
+    elif not (inputs.dim() == 5 and inputs.shape[-1] == 2):
+        raise TypeError('Check input tensor dtypes or shape')
+    if kernel is None or bias is None:
+        raise ValueError('kernel / bias tensors are required (TF would create them here)')
+    out = cconv2d(inputs.float().contiguous(), kernel, bias, filters, kernal, padding)
+    return torch.view_as_complex(out) if complex_flag else out

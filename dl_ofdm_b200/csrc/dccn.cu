@@ -470,12 +470,7 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   if (rc) return rc;
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
-  if (split) {
-    DCCN_CHECK(A.p1 != nullptr, "parity mode needs hi/lo activation planes");
-    rc = make_tmap(&op.a1, A.p1 + a_col_off, M, L.K, A.ld, 128);
-    if (rc) return rc;
-    op.b1 = L.tmB1;
-  }
+  if (split) op.b1 = L.tmB1;
 #define DCCN_TC(BNV, CGV)                                                                                    \
   return split ? launch_gemm_tc<BNV, true, CGV, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms)         \
                : launch_gemm_tc<BNV, false, CGV, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
@@ -674,7 +669,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   h->D = cfg->n_data;
   h->NB = cfg->nbits;
   h->P = h->S * h->T * 2;
-  h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 4096;
+  h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 21504;   // 168 M-tiles: 7*168 = 1176 tiles = 7.95 waves of 148
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
@@ -687,7 +682,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
     return set_error(-2, "equalizer_ofdm requires nfilter == nfft");
   }
   // ---- workspace -----------------------------------------------------------------
-  const bool split = cfg->precision == DCCN_PREC_PARITY;
+  const bool split = false;   // activations are one fp32 plane in every mode (hi/lo is made in smem)
   const int64_t C = h->chunk;
   const int S = h->S, K = h->K;
   int rc = 0;

@@ -6,16 +6,21 @@
 // * persistent: grid = min(#tiles, #SMs); CTA loops over 128 x BN output tiles, n fastest so
 //   that concurrently running CTAs share the A tile in L2;
 // * warp roles: warp 0 = TMA producer (1 lane), warp 1 = TMEM allocator + MMA issuer
-//   (1 lane), warps 2.. = epilogue: 4*CG warps, each owning one TMEM lane quarter and one of
-//   CG column groups of the tile;
+//   (1 lane), [SPLIT: warps 2..5 = A-operand tf32 splitters,] then 4*CG epilogue warps, each
+//   owning one TMEM lane quarter and one of CG column groups of the tile;
 // * three pipelines: smem full/empty ring (TMA <-> MMA), a 2-deep TMEM accumulator ring
 //   (MMA <-> epilogue), static tile schedule;
 // * operands are 128-byte-swizzled [rows x 32 fp32] boxes written by TMA and consumed through
 //   K-major SWIZZLE_128B shared-memory descriptors; out-of-bounds rows / the K tail are
 //   zero-filled by TMA, so ragged M, N, K need no special code in the main loop;
 // * SPLIT = true is the 3xTF32 scheme of DCCN_PREC_PARITY: every operand is a (hi, lo) pair of
-//   tf32-exact planes and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  into the same
-//   TMEM accumulator (the lo*lo term, <= 2^-24 relative, is dropped);
+//   tf32-exact values and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  into the same
+//   TMEM accumulator (the lo*lo term, <= 2^-24 relative, is dropped).  B (weights) is split once
+//   on the host into two planes.  A (activations) stays ONE fp32 plane in HBM/L2: TMA lands the
+//   fp32 tile in shared memory and four "splitter" warps rewrite it in place as hi and write lo
+//   to a second buffer (same byte offsets, so the 128B swizzle is preserved), then
+//   fence.proxy.async + mbarrier hand the stage to the MMA warp.  This halves activation
+//   traffic and footprint compared with storing hi/lo planes;
 // * K-CHUNKED ACCUMULATION: the tensor core adds into its fp32 accumulator with truncation,
 //   so a long dependent chain (K = 896..1024 -> hundreds of MMAs) accumulates a systematic
 //   bias ~10x above fp32 round-to-nearest (measured on the shipped 16-QAM checkpoint).  The
@@ -44,12 +49,15 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int PLANES = SPLIT ? 2 : 1;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int TX_BYTES = A_BYTES + PLANES * B_BYTES;   // bytes TMA delivers per stage
+  static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
+  static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
   static constexpr int SMEM_BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = pow2_at_least(2 * BN);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 64 + 128 * CG;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int THREADS = 64 + 32 * SPLIT_WARPS + 128 * CG;
   static constexpr int COLS_PER_GROUP = BN / CG;
   static constexpr int NCH = COLS_PER_GROUP / 32;     // 32-column register chunks per epilogue thread
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
@@ -60,13 +68,13 @@ struct TcCfg {
 };
 
 struct TcOperands {
-  CUtensorMap a0, a1;   // A hi / lo (a1 unused when !SPLIT)
-  CUtensorMap b0, b1;   // B hi / lo
+  CUtensorMap a0;       // A, one fp32 plane
+  CUtensorMap b0, b1;   // B hi / lo (b1 unused when !SPLIT)
 };
 
 template <int BN, bool SPLIT, int CG, class Epi>
 __global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG>::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                int M, int N, int K, int kc, const __grid_constant__ Epi epi) {
   using C = TcCfg<BN, SPLIT, CG>;
@@ -74,7 +82,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty = full + C::STAGES;
-  uint64_t* tfull = empty + C::STAGES;   // [2] accumulator (one K chunk) ready for the epilogue
+  uint64_t* ready = empty + C::STAGES;   // [STAGES] A tile split into hi/lo (SPLIT only)
+  uint64_t* tfull = ready + C::STAGES;   // [2] accumulator (one K chunk) ready for the epilogue
   uint64_t* tempty = tfull + 2;          // [2] accumulator drained
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -88,16 +97,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
-    if (SPLIT) {
-      tma_prefetch_desc(&tmA1);
-      tma_prefetch_desc(&tmB1);
-    }
+    if (SPLIT) tma_prefetch_desc(&tmB1);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) {
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
+        mbar_init(&ready[s], 4);   // one elected lane of each splitter warp
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
@@ -123,10 +130,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          mbar_expect_tx(&full[stage], C::TX_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
-          if (SPLIT) tma_load_2d(st + C::A_BYTES, &tmA1, &full[stage], kb * C::BK, m_blk * C::BM);
           tma_load_2d(st + C::PLANES * C::A_BYTES, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
           if (SPLIT)
             tma_load_2d(st + C::PLANES * C::A_BYTES + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
@@ -152,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&full[stage], phase);
+            mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
@@ -186,10 +192,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
+  } else if (SPLIT && warp < C::EPI_WARP0) {
+    // =============================== A-operand splitters ========================
+    // fp32 tile (as landed by TMA, swizzled) -> hi in place, lo at the same offsets of the
+    // second buffer.  Elementwise, so the swizzle pattern needs no decoding.
+    const int t = threadIdx.x - 64;            // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        float4* a_hi = reinterpret_cast<float4*>(smem + stage * C::STAGE_BYTES);
+        float4* a_lo = reinterpret_cast<float4*>(smem + stage * C::STAGE_BYTES + C::A_BYTES);
+#pragma unroll
+        for (int i = 0; i < C::A_BYTES / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          const float4 v = a_hi[idx];
+          float4 h, l;
+          tf32_split(v.x, h.x, l.x);
+          tf32_split(v.y, h.y, l.y);
+          tf32_split(v.z, h.z, l.z);
+          tf32_split(v.w, h.w, l.w);
+          a_hi[idx] = h;
+          a_lo[idx] = l;
+        }
+        fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[stage]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
   } else {
     // =============================== epilogue warps =============================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int cg = (warp - 2) >> 2;            // column group
+    const int cg = (warp - C::EPI_WARP0) >> 2; // column group
     typename Epi::State st;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -245,8 +284,7 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
   }
   const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(op.a0, SPLIT ? op.a1 : op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc,
-                                              epi);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, epi);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,107 @@
+"""Model surface of the reference (dev/py/model.py) on top of libdccn.
+
+``ofdm_dense_rx`` and ``equalizer_ofdm`` keep the reference call signatures; instead of adding
+ops to a TF graph they run the corresponding sub-graph entry point of the CUDA library on a
+CUDA tensor and return CUDA tensors.  ``load_model_np`` restores a TF-bundle checkpoint written by
+the reference (or by ``save_model``) into a ``Session`` whose ``run`` serves the reference's named
+fetches (conf_matrix, linear_ber, log_ber, ce_mean, output).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, tfbundle
+from .engine import DCCN
+
+_CACHE = {}
+
+
+def _engine(FLAGS, ofdmobj, weights, equalizer, head, precision):
+    key = (id(weights), equalizer, head, precision, FLAGS.nbits, FLAGS.cp, torch.cuda.current_device())
+    if key not in _CACHE:
+        m = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=equalizer, precision=precision, head=head)
+        m.load_weights(weights)
+        _CACHE[key] = m
+    return _CACHE[key]
+
+
+def ofdm_dense_rx(inputs, FLAGS, ofdmobj, outshape=None, weights=None, head='dev', precision='parity'):
+    """Normalised IQ [B,S,T,2] -> softmax [B, frame_size, nbits, 2] (dev/py/model.py:1222-1292)."""
+    m = _engine(FLAGS, ofdmobj, weights, False, head, precision)
+    out = m.forward(inputs.contiguous(), want_hard=False, flags=_lib.FWD_NO_NORM | _lib.FWD_SKIP_EQ)['soft']
+    if outshape is not None:
+        assert tuple(out.shape[1:]) == tuple(int(v) for v in outshape[1:])
+    return out
+
+
+def equalizer_ofdm(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """Normalised IQ [B,S,T,2] -> (equalized [B,S,T,2], snr_db placeholder, chest complex [B,S,K])
+    (dev/py/model.py:349-478).  The snr_db monitor of the reference is not computed (None)."""
+    m = _engine(FLAGS, ofdmobj, weights, True, 'dev', precision)
+    o = m.forward(inputs.contiguous(), want_soft=False, want_hard=False, want_eq=True, want_chest=True,
+                  flags=_lib.FWD_NO_NORM | _lib.FWD_EQ_ONLY)
+    return o['eq'], None, torch.view_as_complex(o['chest'])
+
+
+class Session:
+    """Stands in for tf.Session + imported graph: holds the engine, serves the named fetches."""
+
+    FETCHES = ('conf_matrix', 'linear_ber', 'log_ber', 'ce_mean', 'output', 'hard')
+
+    def __init__(self, FLAGS, ofdmobj, weights, precision='parity', head=None, chunk_frames=0):
+        self.FLAGS, self.ofdm = FLAGS, ofdmobj
+        self.weights = weights
+        has_eq = any(k.startswith('Equalizer/') for k in weights)
+        if head is None:
+            head = 'v1' if 'demodulation/conv2d_1/kernel' in weights else 'dev'
+        self.engine = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=has_eq, precision=precision, head=head,
+                                     chunk_frames=chunk_frames)
+        self.engine.load_weights(weights)
+
+    def run(self, fetches, feed):
+        """feed: {'tx_ofdm': float32 [B,S,T,2], 'bits_in': uint8/int [B,D,nbits]} (CUDA or numpy)."""
+        dev = self.engine.device
+        x = torch.as_tensor(feed['tx_ofdm'], dtype=torch.float32, device=dev).contiguous()
+        y = feed.get('bits_in')
+        if y is not None:
+            y = torch.as_tensor(y, device=dev).to(torch.uint8).contiguous()
+        single = isinstance(fetches, str)
+        names = [fetches] if single else list(fetches)
+        for n in names:
+            if n not in self.FETCHES:
+                raise KeyError('unknown fetch %r (have %s)' % (n, ', '.join(self.FETCHES)))
+        o = self.engine.forward(x, y, want_soft='output' in names, want_hard='hard' in names)
+        res = []
+        conf = o['conf'].cpu().numpy() if o['conf'] is not None else None
+        for n in names:
+            if n == 'conf_matrix':
+                res.append(conf)
+            elif n == 'linear_ber':
+                res.append(np.float32((conf[0, 1] + conf[1, 0]) / conf.sum()))
+            elif n == 'log_ber':
+                res.append(np.log((conf[0, 1] + conf[1, 0]) / conf.sum()) if conf[0, 1] + conf[1, 0] else -np.inf)
+            elif n == 'ce_mean':
+                res.append(np.float32(float(o['ce_sum'].cpu()[0]) / o['n_bits']))
+            elif n == 'output':
+                res.append(o['soft'])
+            elif n == 'hard':
+                res.append(o['hard'])
+        return res[0] if single else res
+
+    def close(self):
+        self.engine.close()
+
+
+def load_model_np(path, session=None, FLAGS=None, ofdmobj=None, precision='parity'):
+    """Restore ``path``.index/.data (TF bundle) -> Session (dev/py/model.py:51-72)."""
+    weights = tfbundle.read_checkpoint(path)
+    weights.pop('global_step', None)
+    return Session(FLAGS, ofdmobj, weights, precision=precision)
+
+
+def save_model(path, weights, global_step=0):
+    """Write a checkpoint the reference's tf.train.Saver can restore (TF bundle v2)."""
+    w = dict(weights)
+    w['global_step'] = np.asarray(global_step, dtype=np.float32).reshape(())
+    tfbundle.write_checkpoint(path, w)

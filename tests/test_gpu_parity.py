@@ -377,3 +377,82 @@ def test_full_size_properties(libdccn):
     hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
     decided = np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-2
     assert np.array_equal(outs[0][0][idx].cpu().numpy()[decided], hard_ref[decided])
+
+
+# ---------------------------------------------------------------------------------------------
+# host surface on the GPU: Session fetches, model/complex mirrors, checkpoint I/O, sweep runner
+# ---------------------------------------------------------------------------------------------
+def test_session_known_answer_end_to_end(libdccn, golden, tmp_path):
+    """Reference-trained v1 weights, restored from a TF bundle, driven by the GPU transmitter and the
+    GPU AWGN channel through the sweep runner: BER must land on the BASELINE.md known-answer curve."""
+    from dl_ofdm_b200 import sweep
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.model import load_model_np, save_model
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    w = v1_weights(golden('v1_4mod_cpTrue.npz'))
+    prefix = str(tmp_path / 'OFDM_Dense3_4mod')
+    save_model(prefix, w, global_step=201800)
+    fl = Flags(nbits=4, nsymbol=8, pilot='scattered', npilot=8, nguard=8, channel='AWGN', token='t')
+    o = ofdm_tx(fl)
+    assert o.frame_size == 368
+    sess = load_model_np(prefix, FLAGS=fl, ofdmobj=o)
+    cells = sweep.make_cells(['AWGN'], [10, 15, 22], (4,))
+    conf, ce = sweep.run_sweep(cells, sweep.CellRunner(sess, 4000, seed=3))
+    rows = sweep.ber_table(cells, conf, ce)
+    ka = golden('v1_known_answers.npz')
+    snr = list(ka['snr'])
+    for r in rows:
+        expect = float(ka['4mod_cpTrue'][snr.index(int(r['SNR']))])
+        assert r['bits'] == 4000 * 368 * 4
+        assert abs(r['BER'] - expect) <= 0.06 * expect + 3e-5, (r, expect)
+    # named fetches of the reference graph
+    x = torch.randn((64, 8, 80, 2), device='cuda') * 0.1
+    y = torch.randint(0, 2, (64, 368, 4), device='cuda', dtype=torch.uint8)
+    cm, ber, lber, ce_mean, out = sess.run(['conf_matrix', 'linear_ber', 'log_ber', 'ce_mean', 'output'],
+                                           {'tx_ofdm': x, 'bits_in': y})
+    assert cm.shape == (2, 2) and cm.sum() == 64 * 368 * 4 and out.shape == (64, 368, 4, 2)
+    assert abs(float(ber) - (cm[0, 1] + cm[1, 0]) / cm.sum()) < 1e-7 and abs(np.exp(lber) - ber) < 1e-6
+    assert 0.3 < float(ce_mean) < 1.4
+    with pytest.raises(KeyError):
+        sess.run('nope', {'tx_ofdm': x})
+    sess.close()
+
+
+def test_model_function_mirrors(libdccn):
+    from dl_ofdm_b200 import model
+    from dl_ofdm_b200.complex import layers_conv2d_complex
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(8)
+    fl = Flags(nbits=2)
+    o = ofdm_tx(fl)
+    w = orc.glorot_weights(rng, 2, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    z = (rng.standard_normal((40, 7, 80, 2)) * 0.5).astype(np.float32)
+    eq, _, chest = model.equalizer_ofdm(_cuda(z), fl, o, weights=w, precision='exact')
+    eq_ref, chest_ref = orc.equalizer_ofdm(z, w, 64, 16)
+    assert np.abs(eq.cpu().numpy() - eq_ref).max() < 1e-3 and chest.shape == (40, 7, 64)
+    assert np.abs(chest.cpu().numpy() - chest_ref).max() < 1e-4
+    soft = model.ofdm_dense_rx(eq, fl, o, outshape=[-1, o.frame_size, 2, 2], weights=w, precision='exact')
+    assert np.abs(soft.cpu().numpy() - orc.ofdm_dense_rx(eq_ref, w, 2, 16)).max() < 1e-3
+    # complex64 entry of the op (complex.py:154-160, 193-194)
+    xc = torch.view_as_complex(_cuda(rng.standard_normal((3, 7, 64, 1, 2)).astype(np.float32)))
+    k = _cuda(w['Equalizer/conv3d/kernel']); b = _cuda(w['Equalizer/conv3d/bias'])
+    yc = layers_conv2d_complex(xc, 64, (1, 64), strides=1, padding='valid', kernel=k, bias=b)
+    ref = orc.conv2d_complex(torch.view_as_real(xc).cpu().numpy(), w['Equalizer/conv3d/kernel'],
+                             w['Equalizer/conv3d/bias'], 'valid')
+    assert yc.is_complex() and tuple(yc.shape) == (3, 7, 1, 64)
+    assert np.abs(torch.view_as_real(yc).cpu().numpy() - ref).max() < 1e-4
+    with pytest.raises(TypeError):
+        layers_conv2d_complex(torch.zeros((2, 3, 4), device='cuda'), 1, 1, kernel=k, bias=b)
+
+
+def test_error_paths(libdccn):
+    from dl_ofdm_b200.engine import DCCN, DccnError
+    m = DCCN(nbits=2, precision='exact')
+    with pytest.raises(DccnError, match='not committed'):
+        m.forward(torch.zeros((4, 7, 80, 2), device='cuda'))
+    with pytest.raises(DccnError, match="was not set"):
+        m.load_weights({'fft_like/conv3d/bias': np.zeros(128, np.float32)})
+    with pytest.raises(DccnError):
+        DCCN(nbits=7)

@@ -131,6 +131,7 @@ struct dccn_handle {
   int chunk;
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
+  int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   // layers
   GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
@@ -471,19 +472,20 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
   if (split) op.b1 = L.tmB1;
-#define DCCN_TC(BNV, CGV)                                                                                    \
-  return split ? launch_gemm_tc<BNV, true, CGV, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms)         \
-               : launch_gemm_tc<BNV, false, CGV, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
+#define DCCN_TC(BNV, CGV, ATMV)                                                                              \
+  return split ? launch_gemm_tc<BNV, true, CGV, ATMV, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms)   \
+               : launch_gemm_tc<BNV, false, CGV, false, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
+  const bool atm = h->a_tmem != 0;
   if constexpr (std::is_same<Epi, EpiStore>::value) {
     switch (L.BN) {
-      case 32: DCCN_TC(32, 1);
-      case 192: DCCN_TC(192, 2);
-      case 256: DCCN_TC(256, 2);
-      default: DCCN_TC(128, 2);
+      case 32: if (atm) { DCCN_TC(32, 1, true); } else { DCCN_TC(32, 1, false); }
+      case 192: DCCN_TC(192, 2, false);
+      case 256: DCCN_TC(256, 2, false);
+      default: if (atm) { DCCN_TC(128, 2, true); } else { DCCN_TC(128, 2, false); }
     }
   } else {   // fused phase-equaliser / demod-head epilogues only exist for 128-wide tiles
     DCCN_CHECK(L.BN == 128, "fused epilogue expects BN=128 (N=%d)", L.N);
-    DCCN_TC(128, 2);
+    if (atm) { DCCN_TC(128, 2, true); } else { DCCN_TC(128, 2, false); }
   }
 #undef DCCN_TC
 }
@@ -673,6 +675,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
+  if (const char* e = getenv("DCCN_A_TMEM")) h->a_tmem = atoi(e);
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
     return set_error(-2, "frame size must be a multiple of 4 floats");

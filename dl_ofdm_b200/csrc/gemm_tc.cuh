@@ -40,22 +40,35 @@ constexpr int pow2_at_least(int v) {
   return p;
 }
 
-template <int BN, bool SPLIT, int CG>
+constexpr int imin(int a, int b) { return a < b ? a : b; }
+
+// ATM ("A in tensor memory", SPLIT only): the splitter warps write the hi / lo tf32 images of
+// the A tile into TMEM with tcgen05.st instead of back into shared memory, and the MMAs use
+// the TS form (A from TMEM, B from shared memory).  Shared memory then carries only the raw
+// fp32 A tile (written once by TMA, read once by the splitters) and the B planes: the SS form
+// at N = 128 needs 8 KB of operand reads per 64-cycle MMA = all of the 128 B/clk shared-memory
+// bandwidth, which left nothing for TMA writes and the split traffic.
+template <int BN, bool SPLIT, int CG, bool ATM = false>
 struct TcCfg {
+  static_assert(!ATM || SPLIT, "A-in-TMEM is the parity (3xTF32) configuration");
   static constexpr int BM = 128;
   static constexpr int BK = 32;                       // 32 fp32 = one 128-byte swizzle row
   static constexpr int UMMA_K = 8;                    // kind::tf32: 32 bytes of K per instruction
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int PLANES = SPLIT ? 2 : 1;
-  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = (ATM ? A_BYTES : PLANES * A_BYTES) + PLANES * B_BYTES;
+  static constexpr int B_OFF = ATM ? A_BYTES : PLANES * A_BYTES;   // offset of B_hi inside a stage
+  static constexpr int A_TMEM_COLS = ATM ? 64 : 0;                 // per stage: 32 hi + 32 lo columns
   static constexpr int TX_BYTES = A_BYTES + PLANES * B_BYTES;   // bytes TMA delivers per stage
   static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
   static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
   static constexpr int SMEM_BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = pow2_at_least(2 * BN);
+  static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 8;
+  static constexpr int STAGES = imin(imin(STAGES_RAW, STAGES_TM), 8);
+  static constexpr int A_TMEM_COL0 = 2 * BN;                       // A staging columns follow the accumulators
+  static constexpr int TMEM_COLS = pow2_at_least(2 * BN + STAGES * A_TMEM_COLS);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int THREADS = 64 + 32 * SPLIT_WARPS + 128 * CG;
   static constexpr int COLS_PER_GROUP = BN / CG;
@@ -72,12 +85,12 @@ struct TcOperands {
   CUtensorMap b0, b1;   // B hi / lo (b1 unused when !SPLIT)
 };
 
-template <int BN, bool SPLIT, int CG, class Epi>
-__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG>::THREADS, 1)
+template <int BN, bool SPLIT, int CG, bool ATM, class Epi>
+__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                int M, int N, int K, int kc, const __grid_constant__ Epi epi) {
-  using C = TcCfg<BN, SPLIT, CG>;
+  using C = TcCfg<BN, SPLIT, CG, ATM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -133,9 +146,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           mbar_expect_tx(&full[stage], C::TX_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
-          tma_load_2d(st + C::PLANES * C::A_BYTES, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
-          if (SPLIT)
-            tma_load_2d(st + C::PLANES * C::A_BYTES + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
+          tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
+          if (SPLIT) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -162,15 +174,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
-            const uint32_t b_hi = a_hi + C::PLANES * C::A_BYTES;
+            const uint32_t b_hi = a_hi + C::B_OFF;
             const uint32_t b_lo = b_hi + C::B_BYTES;
+            const uint32_t ta_hi = tmem_base + (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
 #pragma unroll
             for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
               const uint32_t koff = k * C::UMMA_K * 4;   // byte advance inside the 128 B swizzle row
               const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
               const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
               const uint32_t accum = (kb != kb0 || k != 0) ? 1u : 0u;
-              if (SPLIT) {
+              if constexpr (ATM) {
+                const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
+                const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);      // 8 tf32 columns per k-step
+                umma_tf32_ts(d, ka + 32, db_hi, idesc, accum);              // A_lo * B_hi
+                umma_tf32_ts(d, ka, db_lo, idesc, 1u);                      // A_hi * B_lo
+                umma_tf32_ts(d, ka, db_hi, idesc, 1u);                      // A_hi * B_hi
+              } else if (SPLIT) {
                 const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
                 const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
                 umma_tf32(d, da_lo, db_hi, idesc, accum);   // small terms first
@@ -202,6 +221,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
+        if constexpr (ATM) {
+          // thread <-> A row (TMEM lane).  Undo the TMA 128B swizzle while reading: the 16-byte
+          // chunk c of row r lives at chunk position c ^ (r & 7).
+          const int r = (warp & 3) * 32 + lane;
+          const uint8_t* rowp = smem + stage * C::STAGE_BYTES + r * 128;
+          float hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+            tf32_split(v.x, hi[4 * c + 0], lo[4 * c + 0]);
+            tf32_split(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+            tf32_split(v.z, hi[4 * c + 2], lo[4 * c + 2]);
+            tf32_split(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                              (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
+          tmem_st_32x32(ta, hi);
+          tmem_st_32x32(ta + 32, lo);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         float4* a_hi = reinterpret_cast<float4*>(smem + stage * C::STAGE_BYTES);
         float4* a_lo = reinterpret_cast<float4*>(smem + stage * C::STAGE_BYTES + C::A_BYTES);
 #pragma unroll
@@ -271,12 +318,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int BN, bool SPLIT, int CG, class Epi>
+template <int BN, bool SPLIT, int CG, bool ATM, class Epi>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
                           int num_sms) {
-  using C = TcCfg<BN, SPLIT, CG>;
+  using C = TcCfg<BN, SPLIT, CG, ATM>;
   if (M <= 0) return 0;
-  auto kern = gemm_tc_kernel<BN, SPLIT, CG, Epi>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

@@ -103,6 +103,26 @@ DCCN_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar
       : "memory");
 }
 
+// multicast variant: the box is written to the same shared-memory offset of every CTA in
+// cta_mask and completes bytes on the mbarrier at the same offset in each of them
+DCCN_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
+DCCN_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DCCN_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM load
 // ---------------------------------------------------------------------------------
@@ -143,6 +163,13 @@ DCCN_DEVINL void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
 DCCN_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of cta_mask
+DCCN_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane i <-> TMEM lane base+i)
 DCCN_DEVINL void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {

@@ -96,6 +96,7 @@ struct GemmLayer {
   CUtensorMap tmB0, tmB1;
   bool built = false;
   bool fused = false;           // consumed by a fused (phase-eq / demod-head) epilogue
+  bool mc = false;              // weight tile fetched as two multicast halves by a CTA pair
 };
 
 struct HostTensor {
@@ -132,6 +133,8 @@ struct dccn_handle {
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
   int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
+  int multicast = 1;   // CTA-pair clusters with TMA multicast of the weight tile
+  int mc_min_k = 128;
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   // layers
   GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
@@ -282,9 +285,12 @@ static int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   if (prec == DCCN_PREC_PARITY)
     DCCN_CUDA_OK(cudaMemcpyAsync(L->dWt1, t1.data(), t1.size() * 4, cudaMemcpyHostToDevice, s));
   DCCN_CUDA_OK(cudaStreamSynchronize(s));
-  int rc = make_tmap(&L->tmB0, L->dWt0, N, K, K, L->BN);
+  // multicast pairs: parity mode, A-in-TMEM tiles of width 128, and enough K to amortise the cluster syncs
+  L->mc = prec == DCCN_PREC_PARITY && h->a_tmem && h->multicast && L->BN == 128 && K >= h->mc_min_k;
+  const int box = L->mc ? L->BN / 2 : L->BN;
+  int rc = make_tmap(&L->tmB0, L->dWt0, N, K, K, box);
   if (rc) return rc;
-  if (prec == DCCN_PREC_PARITY) rc = make_tmap(&L->tmB1, L->dWt1, N, K, K, L->BN);
+  if (prec == DCCN_PREC_PARITY) rc = make_tmap(&L->tmB1, L->dWt1, N, K, K, box);
   return rc;
 }
 
@@ -472,22 +478,30 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
   if (split) op.b1 = L.tmB1;
-#define DCCN_TC(BNV, CGV, ATMV)                                                                              \
-  return split ? launch_gemm_tc<BNV, true, CGV, ATMV, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms)   \
-               : launch_gemm_tc<BNV, false, CGV, false, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
-  const bool atm = h->a_tmem != 0;
+  // parity mode on 128-wide tiles: A staged in TMEM (TS-form MMA) + weight tile multicast across a CTA pair
+#define DCCN_TC_PAR(BNV, CGV)                                                                                \
+  do {                                                                                                       \
+    if (L.mc) return launch_gemm_tc<BNV, true, CGV, true, true, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms);  \
+    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms); \
+    return launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms);  \
+  } while (0)
+#define DCCN_TC_SS(BNV, CGV)                                                                                 \
+  return split ? launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms) \
+               : launch_gemm_tc<BNV, false, CGV, false, false, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
   if constexpr (std::is_same<Epi, EpiStore>::value) {
     switch (L.BN) {
-      case 32: if (atm) { DCCN_TC(32, 1, true); } else { DCCN_TC(32, 1, false); }
-      case 192: DCCN_TC(192, 2, false);
-      case 256: DCCN_TC(256, 2, false);
-      default: if (atm) { DCCN_TC(128, 2, true); } else { DCCN_TC(128, 2, false); }
+      case 32: if (split) DCCN_TC_PAR(32, 1); DCCN_TC_SS(32, 1);
+      case 192: DCCN_TC_SS(192, 2);
+      case 256: DCCN_TC_SS(256, 2);
+      default: if (split) DCCN_TC_PAR(128, 2); DCCN_TC_SS(128, 2);
     }
   } else {   // fused phase-equaliser / demod-head epilogues only exist for 128-wide tiles
     DCCN_CHECK(L.BN == 128, "fused epilogue expects BN=128 (N=%d)", L.N);
-    if (atm) { DCCN_TC(128, 2, true); } else { DCCN_TC(128, 2, false); }
+    if (split) DCCN_TC_PAR(128, 2);
+    DCCN_TC_SS(128, 2);
   }
-#undef DCCN_TC
+#undef DCCN_TC_PAR
+#undef DCCN_TC_SS
 }
 
 static ActOut out_of(const Act& a, int col_off = 0) { return ActOut{a.p0, a.p1, a.ld, col_off}; }
@@ -676,6 +690,8 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
   if (const char* e = getenv("DCCN_A_TMEM")) h->a_tmem = atoi(e);
+  if (const char* e = getenv("DCCN_MULTICAST")) h->multicast = atoi(e);
+  if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
     return set_error(-2, "frame size must be a multiple of 4 floats");

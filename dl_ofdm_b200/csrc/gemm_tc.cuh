@@ -21,6 +21,11 @@
 //   to a second buffer (same byte offsets, so the 128B swizzle is preserved), then
 //   fence.proxy.async + mbarrier hand the stage to the MMA warp.  This halves activation
 //   traffic and footprint compared with storing hi/lo planes;
+// * MC = true launches CTA pairs as clusters of 2 that work on two M-tiles of the same N-tile:
+//   each CTA fetches HALF of the B (weight) tile and TMA-multicasts it into both CTAs' shared
+//   memory, halving the L2->SM traffic of the operand that every M-tile re-reads (the large
+//   layers are bound by exactly that traffic).  A slot may only be refilled when BOTH MMA
+//   issuers have released it, so tcgen05.commit arrives on the empty barrier of both CTAs;
 // * K-CHUNKED ACCUMULATION: the tensor core adds into its fp32 accumulator with truncation,
 //   so a long dependent chain (K = 896..1024 -> hundreds of MMAs) accumulates a systematic
 //   bias ~10x above fp32 round-to-nearest (measured on the shipped 16-QAM checkpoint).  The
@@ -85,7 +90,7 @@ struct TcOperands {
   CUtensorMap b0, b1;   // B hi / lo (b1 unused when !SPLIT)
 };
 
-template <int BN, bool SPLIT, int CG, bool ATM, class Epi>
+template <int BN, bool SPLIT, int CG, bool ATM, bool MC, class Epi>
 __global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -102,7 +107,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = ((M + C::BM - 1) / C::BM) * n_tiles;
+  // MC: "tile" below is a PAIR tile (two consecutive M-tiles x one N-tile); CTA rank r of the
+  // cluster owns M-tile 2*m_pair + r.  Both CTAs of a pair run the same tile sequence.
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const int m_tiles = (M + C::BM - 1) / C::BM;
+  const int num_tiles = (MC ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int tile0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = (K + C::BK - 1) / C::BK;
   const int kb_per_chunk = (kc <= 0 || kc > num_kb) ? num_kb : kc;
   const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
@@ -116,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], 1);
+        mbar_init(&empty[s], MC ? 2 : 1);   // MC: released by both MMA issuers of the pair
         mbar_init(&ready[s], 4);   // one elected lane of each splitter warp
       }
       for (int a = 0; a < 2; ++a) {
@@ -132,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (MC) cluster_sync_all();               // peer barriers are initialised before any multicast lands
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -139,15 +151,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = MC ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], C::TX_BYTES);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
-          tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
-          if (SPLIT) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
+          if (MC) {   // my half of the weight tile, multicast to both CTAs of the pair
+            const int hoff = crank * (C::B_BYTES / 2), hrow = n_blk * BN + crank * (BN / 2);
+            tma_load_2d_mc(st + C::B_OFF + hoff, &tmB0, &full[stage], kb * C::BK, hrow, 0x3);
+            if (SPLIT) tma_load_2d_mc(st + C::B_OFF + C::B_BYTES + hoff, &tmB1, &full[stage], kb * C::BK, hrow, 0x3);
+          } else {
+            tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
+            if (SPLIT) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -163,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += kb_per_chunk) {
           const int kb1 = kb0 + kb_per_chunk < num_kb ? kb0 + kb_per_chunk : num_kb;
           mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -199,7 +217,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 umma_tf32(d, da_hi, db_hi, idesc, accum);
               }
             }
-            umma_commit(&empty[stage]);        // smem slot reusable once these MMAs retire
+            if (MC) umma_commit_mc(&empty[stage], 0x3);   // slot released in both CTAs of the pair
+            else umma_commit(&empty[stage]);              // smem slot reusable once these MMAs retire
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -218,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int t = threadIdx.x - 64;            // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         if constexpr (ATM) {
@@ -280,8 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     int acc = 0;
     uint32_t acc_phase = 0;
     float r[C::NCH][32];
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = MC ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
       const int row = m_blk * C::BM + q * 32 + lane;
       for (int ch = 0; ch < num_chunks; ++ch) {
         mbar_wait(&tfull[acc], acc_phase);
@@ -315,24 +334,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();               // no CTA leaves while its peer can still signal / write into it
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int BN, bool SPLIT, int CG, bool ATM, class Epi>
+template <int BN, bool SPLIT, int CG, bool ATM, bool MC, class Epi>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
                           int num_sms) {
   using C = TcCfg<BN, SPLIT, CG, ATM>;
   if (M <= 0) return 0;
-  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, Epi>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, MC, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + C::BM - 1) / C::BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, epi);
-  DCCN_CUDA_OK(cudaGetLastError());
+  const int m_tiles = (M + C::BM - 1) / C::BM, n_tiles = (N + BN - 1) / BN;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (MC) {
+    const int pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
+    const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    cfg.gridDim = dim3(2 * pairs);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    const int tiles = m_tiles * n_tiles;
+    cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+  }
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, epi));
   return 0;
 }
 

@@ -96,7 +96,7 @@ struct GemmLayer {
   CUtensorMap tmB0, tmB1;
   bool built = false;
   bool fused = false;           // consumed by a fused (phase-eq / demod-head) epilogue
-  bool mc = false;              // weight tile fetched as two multicast halves by a CTA pair
+  bool mc = false;              // run as cta_group::2 CTA pairs (each CTA holds half of the weight tile)
 };
 
 struct HostTensor {
@@ -133,7 +133,7 @@ struct dccn_handle {
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
   int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
-  int multicast = 1;   // CTA-pair clusters with TMA multicast of the weight tile
+  int multicast = 0;   // cta_group::2 CTA pairs (DCCN_PAIR=1 enables; measured slower than single-CTA tiles)
   int mc_min_k = 128;
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   // layers
@@ -478,7 +478,7 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
   if (split) op.b1 = L.tmB1;
-  // parity mode on 128-wide tiles: A staged in TMEM (TS-form MMA) + weight tile multicast across a CTA pair
+  // parity mode on 128-wide tiles: A staged in TMEM (TS-form MMA) + cta_group::2 CTA pairs (half a weight tile per SM)
 #define DCCN_TC_PAR(BNV, CGV)                                                                                \
   do {                                                                                                       \
     if (L.mc) return launch_gemm_tc<BNV, true, CGV, true, true, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms);  \
@@ -644,6 +644,59 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
   return 0;
 }
 
+// ---- measurement aid: raw TMA -> shared-memory delivery rate of one SM (no MMA) ----------
+// Each CTA's producer thread keeps `stages` slots of `boxes` [128 x 32 fp32] boxes in flight; a
+// consumer thread frees a slot as soon as its bytes have landed.  Reports SM cycles per CTA.
+__global__ void __launch_bounds__(64, 1)
+tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows, int kcols, int stages, int boxes, int iters,
+                long long* clks) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * boxes * 16384);
+  uint64_t* empty = full + stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int row_tiles = rows / 128, k_tiles = kcols / 32;
+  long long t0 = clock64();
+  if (threadIdx.x == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int rt = blockIdx.x % row_tiles, kt = 0;
+    for (int i = 0; i < iters; ++i) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      mbar_expect_tx(&full[stage], boxes * 16384);
+      for (int b = 0; b < boxes; ++b)
+        tma_load_2d(smem + (stage * boxes + b) * 16384, &tm, &full[stage], kt * 32, ((rt + b * 7) % row_tiles) * 128);
+      if (++kt == k_tiles) {
+        kt = 0;
+        rt = (rt + gridDim.x) % row_tiles;
+      }
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < iters; ++i) {
+      mbar_wait(&full[stage], phase);
+      mbar_arrive(&empty[stage]);
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    clks[blockIdx.x] = clock64() - t0;
+  }
+}
+
 __global__ void conf_copy_kernel(const unsigned long long* src, long long* dst) {
   if (threadIdx.x < 4) dst[threadIdx.x] += (long long)src[threadIdx.x];
 }
@@ -690,7 +743,8 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
   if (const char* e = getenv("DCCN_A_TMEM")) h->a_tmem = atoi(e);
-  if (const char* e = getenv("DCCN_MULTICAST")) h->multicast = atoi(e);
+  if (const char* e = getenv("DCCN_SMS")) h->num_sms = atoi(e);   // experiment knob: restrict the persistent grids
+  if (const char* e = getenv("DCCN_PAIR")) h->multicast = atoi(e);
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
@@ -966,6 +1020,21 @@ int dccn_profile_collect(dccn_handle* h, double* ms_out, int64_t* count_out, int
 }
 
 const char* dccn_profile_slot_name(int slot) { return (slot >= 0 && slot < SLOT_COUNT) ? kSlotNames[slot] : ""; }
+
+int dccn_debug_tma_rate(const float* mat_dev, int rows, int cols, int ld, int stages, int boxes, int iters,
+                        int grid, long long* clks_dev) {
+  DCCN_CHECK(mat_dev && clks_dev && rows % 128 == 0 && cols % 32 == 0 && stages >= 1 && boxes >= 1, "bad argument");
+  CUtensorMap tm;
+  int rc = make_tmap(&tm, mat_dev, rows, cols, ld, 128);
+  if (rc) return rc;
+  const int smem = stages * boxes * 16384 + 1024 + 256;
+  DCCN_CHECK(smem <= 227 * 1024, "too much shared memory");
+  DCCN_CUDA_OK(cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tma_rate_kernel<<<grid, 64, smem>>>(tm, rows, cols, stages, boxes, iters, clks_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  DCCN_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
 
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream) {
   DCCN_CHECK(bits_dev && n >= 0, "bad argument");

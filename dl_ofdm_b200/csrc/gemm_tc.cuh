@@ -21,11 +21,15 @@
 //   to a second buffer (same byte offsets, so the 128B swizzle is preserved), then
 //   fence.proxy.async + mbarrier hand the stage to the MMA warp.  This halves activation
 //   traffic and footprint compared with storing hi/lo planes;
-// * MC = true launches CTA pairs as clusters of 2 that work on two M-tiles of the same N-tile:
-//   each CTA fetches HALF of the B (weight) tile and TMA-multicasts it into both CTAs' shared
-//   memory, halving the L2->SM traffic of the operand that every M-tile re-reads (the large
-//   layers are bound by exactly that traffic).  A slot may only be refilled when BOTH MMA
-//   issuers have released it, so tcgen05.commit arrives on the empty barrier of both CTAs;
+// * PAIR = true (needs ATM) runs 2-CTA clusters with cta_group::2 MMAs: one instruction spans
+//   both SMs of the pair (M = 256 x N = BN); each CTA keeps ITS 128 rows of A (in its TMEM) and
+//   its 128 accumulator rows, but only HALF of the weight tile (BN/2 rows) in its shared memory.
+//   The measured limit of the big layers is the per-SM ingress rate (~32-36 B/clk per SM from
+//   L2, multicast does not help because the bytes still arrive); the pair form halves the
+//   weight bytes each SM receives per flop.  Only the leader CTA (cluster rank 0) issues MMAs;
+//   the peer's splitter / epilogue warps signal the leader's `ready` / `tempty` barriers through
+//   mapa + mbarrier.arrive.shared::cluster, and the leader's tcgen05.commit multicasts to the
+//   `empty` / `tfull` barriers of both CTAs;
 // * K-CHUNKED ACCUMULATION: the tensor core adds into its fp32 accumulator with truncation,
 //   so a long dependent chain (K = 896..1024 -> hundreds of MMAs) accumulates a systematic
 //   bias ~10x above fp32 round-to-nearest (measured on the shipped 16-QAM checkpoint).  The
@@ -90,7 +94,7 @@ struct TcOperands {
   CUtensorMap b0, b1;   // B hi / lo (b1 unused when !SPLIT)
 };
 
-template <int BN, bool SPLIT, int CG, bool ATM, bool MC, class Epi>
+template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
 __global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -107,13 +111,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN;
-  // MC: "tile" below is a PAIR tile (two consecutive M-tiles x one N-tile); CTA rank r of the
+  static_assert(!PAIR || ATM, "the CTA-pair form is built on the A-in-TMEM configuration");
+  // PAIR: "tile" below is a pair tile (two consecutive M-tiles x one N-tile); CTA rank r of the
   // cluster owns M-tile 2*m_pair + r.  Both CTAs of a pair run the same tile sequence.
-  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
   const int m_tiles = (M + C::BM - 1) / C::BM;
-  const int num_tiles = (MC ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
-  const int tile0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BROWS = PAIR ? BN / 2 : BN;            // weight rows this CTA holds
+  constexpr int BH = BROWS * C::BK * 4;                // bytes of one weight plane in a stage
+  constexpr int TX = C::A_BYTES + C::PLANES * BH;      // bytes TMA lands in THIS CTA per stage
   const int num_kb = (K + C::BK - 1) / C::BK;
   const int kb_per_chunk = (kc <= 0 || kc > num_kb) ? num_kb : kc;
   const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
@@ -127,45 +135,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], MC ? 2 : 1);   // MC: released by both MMA issuers of the pair
-        mbar_init(&ready[s], 4);   // one elected lane of each splitter warp
+        mbar_init(&empty[s], 1);
+        mbar_init(&ready[s], PAIR ? 8 : 4);   // one elected lane of each splitter warp (of both CTAs)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 4 * CG);   // one elected lane per epilogue warp
+        mbar_init(&tempty[a], (PAIR ? 2 : 1) * 4 * CG);   // one elected lane per epilogue warp (of both CTAs)
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, C::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_ptr, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (MC) cluster_sync_all();               // peer barriers are initialised before any multicast lands
+  if (PAIR) cluster_sync_all();             // both CTAs' barriers / TMEM exist before anything crosses over
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // The WHOLE warp runs the loop so that addresses / coordinates stay warp-uniform (uniform
+    // registers feed UTMALDG directly); one elected lane issues.  A single-lane branch makes the
+    // compiler wrap every TMA / MMA instruction in an R2UR + elect loop (~100 clk per issue).
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = MC ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
+        const int m_blk = PAIR ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], C::TX_BYTES);
-          uint8_t* st = smem + stage * C::STAGE_BYTES;
-          tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
-          if (MC) {   // my half of the weight tile, multicast to both CTAs of the pair
-            const int hoff = crank * (C::B_BYTES / 2), hrow = n_blk * BN + crank * (BN / 2);
-            tma_load_2d_mc(st + C::B_OFF + hoff, &tmB0, &full[stage], kb * C::BK, hrow, 0x3);
-            if (SPLIT) tma_load_2d_mc(st + C::B_OFF + C::B_BYTES + hoff, &tmB1, &full[stage], kb * C::BK, hrow, 0x3);
-          } else {
-            tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, n_blk * BN);
-            if (SPLIT) tma_load_2d(st + C::B_OFF + C::B_BYTES, &tmB1, &full[stage], kb * C::BK, n_blk * BN);
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], TX);
+            uint8_t* st = smem + stage * C::STAGE_BYTES;
+            tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
+            // PAIR: only my half of the weight tile (rows crank*BN/2 ...)
+            const int brow = n_blk * BN + crank * BROWS;
+            tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, brow);
+            if (SPLIT) tma_load_2d(st + C::B_OFF + BH, &tmB1, &full[stage], kb * C::BK, brow);
           }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -175,8 +190,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BN);
+    if (crank == 0) {   // whole warp, warp-uniform control flow; one elected lane issues
+      constexpr uint32_t idesc = umma_idesc_tf32(BN, PAIR ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -184,24 +199,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += kb_per_chunk) {
           const int kb1 = kb0 + kb_per_chunk < num_kb ? kb0 + kb_per_chunk : num_kb;
-          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          if (PAIR) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
+          else mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
+            if (PAIR) mbar_wait_cluster(&ready[stage], phase);
+            else mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
             const uint32_t b_hi = a_hi + C::B_OFF;
-            const uint32_t b_lo = b_hi + C::B_BYTES;
+            const uint32_t b_lo = b_hi + BH;
             const uint32_t ta_hi = tmem_base + (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
+            if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
               const uint32_t koff = k * C::UMMA_K * 4;   // byte advance inside the 128 B swizzle row
               const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
               const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
               const uint32_t accum = (kb != kb0 || k != 0) ? 1u : 0u;
-              if constexpr (ATM) {
+              if constexpr (PAIR) {
+                const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
+                const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);
+                umma_tf32_ts_pair(d, ka + 32, db_hi, idesc, accum);         // A_lo * B_hi   (M = 256, both SMs)
+                umma_tf32_ts_pair(d, ka, db_lo, idesc, 1u);                 // A_hi * B_lo
+                umma_tf32_ts_pair(d, ka, db_hi, idesc, 1u);                 // A_hi * B_hi
+              } else if constexpr (ATM) {
                 const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
                 const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);      // 8 tf32 columns per k-step
                 umma_tf32_ts(d, ka + 32, db_hi, idesc, accum);              // A_lo * B_hi
@@ -217,14 +241,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 umma_tf32(d, da_hi, db_hi, idesc, accum);
               }
             }
-            if (MC) umma_commit_mc(&empty[stage], 0x3);   // slot released in both CTAs of the pair
-            else umma_commit(&empty[stage]);              // smem slot reusable once these MMAs retire
+            if (PAIR) umma_commit_pair(&empty[stage], 0x3);   // slot released in both CTAs of the pair
+            else umma_commit(&empty[stage]);                  // smem slot reusable once these MMAs retire
+            if (kb + 1 == kb1) {                              // K chunk complete -> epilogue(s) drain it
+              if (PAIR) umma_commit_pair(&tfull[acc], 0x3);
+              else umma_commit(&tfull[acc]);
+            }
+            }   // elect_one
+            __syncwarp();
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tfull[acc]);            // K chunk complete -> epilogue drains it
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -261,7 +290,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ready[stage]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&ready[stage]), 0));   // leader's barrier
+            else mbar_arrive(&ready[stage]);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -300,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     uint32_t acc_phase = 0;
     float r[C::NCH][32];
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = MC ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
+      const int m_blk = PAIR ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
       const int row = m_blk * C::BM + q * 32 + lane;
       for (int ch = 0; ch < num_chunks; ++ch) {
         mbar_wait(&tfull[acc], acc_phase);
@@ -321,7 +353,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // leader's barrier
+          else mbar_arrive(&tempty[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -334,16 +369,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();               // no CTA leaves while its peer can still signal / write into it
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (PAIR) cluster_sync_all();             // no CTA leaves while its peer can still signal it
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
-template <int BN, bool SPLIT, int CG, bool ATM, bool MC, class Epi>
+template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
                           int num_sms) {
   using C = TcCfg<BN, SPLIT, CG, ATM>;
   if (M <= 0) return 0;
-  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, MC, Epi>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi>;
   static bool attr_set = false;
   if (!attr_set) {
     DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -352,7 +390,7 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
   const int m_tiles = (M + C::BM - 1) / C::BM, n_tiles = (N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  if (MC) {
+  if (PAIR) {
     const int pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
     const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
     cfg.gridDim = dim3(2 * pairs);

@@ -160,6 +160,10 @@ int dccn_profile_enable(dccn_handle* h, int on);
 int dccn_profile_collect(dccn_handle* h, double* ms_out, int64_t* count_out, int max_slots);
 const char* dccn_profile_slot_name(int slot);
 
+/* measurement aid (tools/tma_rate.py): TMA -> shared memory delivery rate per SM, no MMA */
+int dccn_debug_tma_rate(const float* mat_dev, int rows, int cols, int ld, int stages, int boxes, int iters,
+                        int grid, long long* clks_dev);
+
 /* uniform random bits (util.bit_source, dev/py/util.py:25-34) from Philox */
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream);
 

@@ -273,11 +273,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           // thread <-> A row (TMEM lane).  Undo the TMA 128B swizzle while reading: the 16-byte
           // chunk c of row r lives at chunk position c ^ (r & 7).
           const int r = (warp & 3) * 32 + lane;
-          const uint8_t* rowp = smem + stage * C::STAGE_BYTES + r * 128;
+          const uint32_t rowp = smem_u32(smem + stage * C::STAGE_BYTES + r * 128);
           float hi[32], lo[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+            const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));
             tf32_split(v.x, hi[4 * c + 0], lo[4 * c + 0]);
             tf32_split(v.y, hi[4 * c + 1], lo[4 * c + 1]);
             tf32_split(v.z, hi[4 * c + 2], lo[4 * c + 2]);

@@ -50,6 +50,7 @@ PROTOTYPES = {
     'dccn_tx_frames': (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _vp, C.c_float, C.c_float, _vp, _vp]),
     'dccn_bit_source': (C.c_int, [_vp, _i64, _u64, _vp]),
     'dccn_debug_tma_rate': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'dccn_debug_mma_rate': (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'dccn_launch_count': (_i64, []),
     'dccn_profile_enable': (C.c_int, [_vp, _i32]),
     'dccn_profile_collect': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),

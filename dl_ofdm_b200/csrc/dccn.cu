@@ -697,6 +697,58 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows, int kcols, int
   }
 }
 
+// ---- measurement aid: tcgen05.mma issue / execution rate of one SM (no TMA, operands = whatever is in smem) ----
+// mode 0: SS form, mode 1: TS form (A from TMEM).  `per_commit` MMAs between tcgen05.commit's (0 = one at the end).
+template <int BN>
+__global__ void __launch_bounds__(64, 1) mma_rate_kernel(int n_mma, int per_commit, int mode, int dep, long long* clks) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + BN * 128);
+  uint64_t* bar2 = bar + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 2);
+  for (int i = threadIdx.x; i < (16384 + BN * 128) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.f;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if ((threadIdx.x & 31) == 0) {
+      mbar_init(bar, 1);
+      mbar_init(bar2, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tptr;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_tf32(BN);
+    const uint64_t da = umma_desc_sw128(smem_u32(smem)), db = umma_desc_sw128(smem_u32(smem + 16384));
+    long long t0 = clock64();
+    if (elect_one()) {
+      const int batch = per_commit > 0 ? per_commit : n_mma;
+      for (int i = 0; i < n_mma; i += batch) {
+        const uint32_t d = tb + (dep ? 0u : (uint32_t)(((i / batch) & 1) * BN));   // dep=0: alternate two accumulators per batch
+        for (int j = 0; j < batch; ++j) {
+          if (mode == 0) umma_tf32(d, da, db, idesc, 1u);
+          else umma_tf32_ts(d, tb + 256, db, idesc, 1u);
+        }
+        if (per_commit > 0) umma_commit(bar2);
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) clks[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 __global__ void conf_copy_kernel(const unsigned long long* src, long long* dst) {
   if (threadIdx.x < 4) dst[threadIdx.x] += (long long)src[threadIdx.x];
 }
@@ -1031,6 +1083,20 @@ int dccn_debug_tma_rate(const float* mat_dev, int rows, int cols, int ld, int st
   DCCN_CHECK(smem <= 227 * 1024, "too much shared memory");
   DCCN_CUDA_OK(cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tma_rate_kernel<<<grid, 64, smem>>>(tm, rows, cols, stages, boxes, iters, clks_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  DCCN_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int dccn_debug_mma_rate(int bn, int n_mma, int per_commit, int mode, int dep, int grid, long long* clks_dev) {
+  DCCN_CHECK(clks_dev && (bn == 128 || bn == 256), "bn must be 128 or 256");
+  const int smem = 16384 + bn * 128 + 1024 + 64;
+  if (bn == 128) {
+    mma_rate_kernel<128><<<grid, 64, smem>>>(n_mma, per_commit, mode, dep, clks_dev);
+  } else {
+    DCCN_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_kernel<256><<<grid, 64, smem>>>(n_mma, per_commit, mode, dep, clks_dev);
+  }
   DCCN_CUDA_OK(cudaGetLastError());
   DCCN_CUDA_OK(cudaDeviceSynchronize());
   return 0;

@@ -57,29 +57,39 @@ constexpr int imin(int a, int b) { return a < b ? a : b; }
 // fp32 A tile (written once by TMA, read once by the splitters) and the B planes: the SS form
 // at N = 128 needs 8 KB of operand reads per 64-cycle MMA = all of the 128 B/clk shared-memory
 // bandwidth, which left nothing for TMA writes and the split traffic.
-template <int BN, bool SPLIT, int CG, bool ATM = false>
+//
+// DEC ("decoupled A ring", ATM without PAIR): the raw A tiles get their own small shared-memory
+// ring with their own producer warp.  An A slot is free again as soon as the splitters have read
+// it (long before the MMAs that use it retire), so A tiles are fetched far ahead and the splitters
+// already hold the next tile in registers when a TMEM staging slot frees up: the per-stage
+// dependency loop no longer contains "TMA latency of A + split", only "commit -> tcgen05.st".
+template <int BN, bool SPLIT, int CG, bool ATM = false, bool DEC = false>
 struct TcCfg {
   static_assert(!ATM || SPLIT, "A-in-TMEM is the parity (3xTF32) configuration");
+  static_assert(!DEC || ATM, "the decoupled A ring feeds the TMEM staging");
   static constexpr int BM = 128;
   static constexpr int BK = 32;                       // 32 fp32 = one 128-byte swizzle row
   static constexpr int UMMA_K = 8;                    // kind::tf32: 32 bytes of K per instruction
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int PLANES = SPLIT ? 2 : 1;
-  static constexpr int STAGE_BYTES = (ATM ? A_BYTES : PLANES * A_BYTES) + PLANES * B_BYTES;
-  static constexpr int B_OFF = ATM ? A_BYTES : PLANES * A_BYTES;   // offset of B_hi inside a stage
+  static constexpr int STAGE_BYTES = (DEC ? 0 : (ATM ? A_BYTES : PLANES * A_BYTES)) + PLANES * B_BYTES;
+  static constexpr int B_OFF = DEC ? 0 : (ATM ? A_BYTES : PLANES * A_BYTES);   // offset of B_hi inside a stage
+  static constexpr int SA = DEC ? 4 : 0;                           // slots of the separate raw-A ring
+  static constexpr int A_RING_BYTES = SA * A_BYTES;
   static constexpr int A_TMEM_COLS = ATM ? 64 : 0;                 // per stage: 32 hi + 32 lo columns
   static constexpr int TX_BYTES = A_BYTES + PLANES * B_BYTES;   // bytes TMA delivers per stage
   static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
-  static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;
+  static constexpr int APROD_WARP = 2 + SPLIT_WARPS;               // DEC: producer warp of the A ring
+  static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS + (DEC ? 1 : 0);
   static constexpr int SMEM_BUDGET = 200 * 1024;
-  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - A_RING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 8;
   static constexpr int STAGES = imin(imin(STAGES_RAW, STAGES_TM), 8);
   static constexpr int A_TMEM_COL0 = 2 * BN;                       // A staging columns follow the accumulators
   static constexpr int TMEM_COLS = pow2_at_least(2 * BN + STAGES * A_TMEM_COLS);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
-  static constexpr int THREADS = 64 + 32 * SPLIT_WARPS + 128 * CG;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + A_RING_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int THREADS = 32 * EPI_WARP0 + 128 * CG;
   static constexpr int COLS_PER_GROUP = BN / CG;
   static constexpr int NCH = COLS_PER_GROUP / 32;     // 32-column register chunks per epilogue thread
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
@@ -95,19 +105,23 @@ struct TcOperands {
 };
 
 template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
-__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM>::THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR)>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                int M, int N, int K, int kc, const __grid_constant__ Epi epi) {
-  using C = TcCfg<BN, SPLIT, CG, ATM>;
+  constexpr bool DEC = ATM && !PAIR;
+  using C = TcCfg<BN, SPLIT, CG, ATM, DEC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* a_ring = smem + C::STAGES * C::STAGE_BYTES;                       // DEC: SA raw fp32 A tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(a_ring + C::A_RING_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* ready = empty + C::STAGES;   // [STAGES] A tile split into hi/lo (SPLIT only)
   uint64_t* tfull = ready + C::STAGES;   // [2] accumulator (one K chunk) ready for the epilogue
   uint64_t* tempty = tfull + 2;          // [2] accumulator drained
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* fullA = tempty + 2;          // [4] DEC: raw A tile landed
+  uint64_t* emptyA = fullA + 4;          // [4] DEC: raw A tile consumed by the splitters
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(emptyA + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN;
@@ -121,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int BROWS = PAIR ? BN / 2 : BN;            // weight rows this CTA holds
   constexpr int BH = BROWS * C::BK * 4;                // bytes of one weight plane in a stage
-  constexpr int TX = C::A_BYTES + C::PLANES * BH;      // bytes TMA lands in THIS CTA per stage
+  constexpr int TX = (DEC ? 0 : C::A_BYTES) + C::PLANES * BH;   // bytes TMA lands in THIS CTA per (B) stage
   const int num_kb = (K + C::BK - 1) / C::BK;
   const int kb_per_chunk = (kc <= 0 || kc > num_kb) ? num_kb : kc;
   const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
@@ -137,6 +151,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
         mbar_init(&ready[s], PAIR ? 8 : 4);   // one elected lane of each splitter warp (of both CTAs)
+      }
+      for (int a = 0; a < 4; ++a) {
+        mbar_init(&fullA[a], 1);
+        mbar_init(&emptyA[a], 4);   // one elected lane of each splitter warp
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
@@ -174,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           if (elect_one()) {
             mbar_expect_tx(&full[stage], TX);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
-            tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
+            if (!DEC) tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
             // PAIR: only my half of the weight tile (rows crank*BN/2 ...)
             const int brow = n_blk * BN + crank * BROWS;
             tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, brow);
@@ -206,6 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           for (int kb = kb0; kb < kb1; ++kb) {
             if (PAIR) mbar_wait_cluster(&ready[stage], phase);
             else mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
+            if (DEC) mbar_wait(&full[stage], phase);   // weight planes of this stage have landed too
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
@@ -256,6 +275,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (DEC && warp == C::APROD_WARP) {
+    // =============================== A-ring producer (DEC) ======================
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = tile / n_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&emptyA[sa], pa ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&fullA[sa], C::A_BYTES);
+          tma_load_2d(a_ring + sa * C::A_BYTES, &tmA0, &fullA[sa], kb * C::BK, m_blk * C::BM);
+        }
+        __syncwarp();
+        if (++sa == C::SA) {
+          sa = 0;
+          pa ^= 1;
+        }
+      }
+    }
+  } else if (DEC && warp < C::APROD_WARP) {
+    // =============================== A-operand splitters (DEC) ==================
+    // read the raw tile early (frees the A slot at once), keep hi/lo in registers, and write
+    // them to the TMEM staging slot the moment the MMAs that used it have retired.
+    int stage = 0, sa = 0;
+    uint32_t phase = 0, pa = 0;
+    const int r = (warp & 3) * 32 + lane;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&fullA[sa], pa);
+        const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
+          tf32_split(v.x, hi[4 * c + 0], lo[4 * c + 0]);
+          tf32_split(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+          tf32_split(v.z, hi[4 * c + 2], lo[4 * c + 2]);
+          tf32_split(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&emptyA[sa]);                  // raw tile consumed
+        mbar_wait(&empty[stage], phase ^ 1);                      // TMEM staging slot is free again
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                            (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
+        tmem_st_32x32(ta, hi);
+        tmem_st_32x32(ta + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[stage]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++sa == C::SA) {
+          sa = 0;
+          pa ^= 1;
         }
       }
     }
@@ -379,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
                           int num_sms) {
-  using C = TcCfg<BN, SPLIT, CG, ATM>;
+  using C = TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR)>;
   if (M <= 0) return 0;
   auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi>;
   static bool attr_set = false;

@@ -164,6 +164,9 @@ const char* dccn_profile_slot_name(int slot);
 int dccn_debug_tma_rate(const float* mat_dev, int rows, int cols, int ld, int stages, int boxes, int iters,
                         int grid, long long* clks_dev);
 
+/* measurement aid (tools/mma_rate.py): tcgen05.mma kind::tf32 issue / execution rate of one SM */
+int dccn_debug_mma_rate(int bn, int n_mma, int per_commit, int mode, int dep, int grid, long long* clks_dev);
+
 /* uniform random bits (util.bit_source, dev/py/util.py:25-34) from Philox */
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream);
 

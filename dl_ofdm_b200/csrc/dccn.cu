@@ -149,13 +149,23 @@ struct dccn_handle {
   unsigned long long* d_conf = nullptr;   // internal [4]
   double* d_ce = nullptr;
   Act a0, t1, f, p32, u1, u2, eq, corr, cat, oeq, r1o, out_iq;
-  // staging for dccn_forward_host
-  float* d_x = nullptr;
-  uint8_t* d_bits = nullptr;
-  uint8_t* d_hard = nullptr;
-  int64_t stage_frames = 0;
-  int64_t* d_res_conf = nullptr;  // result slots of dccn_forward_host
-  double* d_res_ce = nullptr;
+  // staging for the host-buffer entry points: two slots so that the H2D copy of one batch
+  // overlaps the pass over the previous one (copy stream + the caller's compute stream)
+  struct HostSlot {
+    float* d_x = nullptr;
+    uint8_t* d_bits = nullptr;
+    uint8_t* d_hard = nullptr;
+    int64_t frames = 0;            // capacity
+    int64_t B = 0;                 // batch in flight
+    int64_t* d_conf = nullptr;     // device results
+    double* d_ce = nullptr;
+    int64_t* h_conf = nullptr;     // pinned host results
+    double* h_ce = nullptr;
+    uint8_t* hard_host = nullptr;  // caller's destination for hard bits (may be null)
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool busy = false;
+  } slot[2];
+  cudaStream_t copy_stream = nullptr;
   size_t ws_bytes = 0;
 };
 
@@ -817,8 +827,17 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   rc |= dev_alloc(h, (void**)&h->d_power, sizeof(double));
   rc |= dev_alloc(h, (void**)&h->d_conf, 4 * sizeof(unsigned long long));
   rc |= dev_alloc(h, (void**)&h->d_ce, sizeof(double));
-  rc |= dev_alloc(h, (void**)&h->d_res_conf, 4 * sizeof(int64_t));
-  rc |= dev_alloc(h, (void**)&h->d_res_ce, sizeof(double));
+  for (int i = 0; i < 2 && !rc; ++i) {
+    rc |= dev_alloc(h, (void**)&h->slot[i].d_conf, 4 * sizeof(int64_t));
+    rc |= dev_alloc(h, (void**)&h->slot[i].d_ce, sizeof(double));
+    if (cudaMallocHost((void**)&h->slot[i].h_conf, 4 * sizeof(int64_t)) != cudaSuccess ||
+        cudaMallocHost((void**)&h->slot[i].h_ce, sizeof(double)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->slot[i].copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming) != cudaSuccess)
+      rc = set_error(-1, "host-slot allocation failed");
+  }
+  if (!rc && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+    rc = set_error(-1, "cudaStreamCreate failed");
   rc |= alloc_act(h, &h->a0, C, h->P, split);
   rc |= alloc_act(h, &h->r1o, C, S * h->F * 2, split);
   rc |= alloc_act(h, &h->out_iq, C, 2 * h->D, false);
@@ -843,6 +862,14 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
 
 void dccn_destroy(dccn_handle* h) {
   if (!h) return;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) {
+    if (h->slot[i].h_conf) cudaFreeHost(h->slot[i].h_conf);
+    if (h->slot[i].h_ce) cudaFreeHost(h->slot[i].h_ce);
+    if (h->slot[i].copied) cudaEventDestroy(h->slot[i].copied);
+    if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -922,33 +949,57 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
   return 0;
 }
 
-int dccn_forward_host(dccn_handle* h, const float* x_host, int64_t B, const uint8_t* bits_host, uint8_t* hard_host,
-                      int64_t* conf_host, double* ce_sum_host, void* stream) {
-  DCCN_CHECK(h && x_host && B > 0, "bad argument");
+int dccn_forward_host_begin(dccn_handle* h, int slot, const float* x_host, int64_t B, const uint8_t* bits_host,
+                            uint8_t* hard_host, void* stream) {
+  DCCN_CHECK(h && x_host && B > 0 && (slot == 0 || slot == 1), "bad argument");
+  dccn_handle::HostSlot& S = h->slot[slot];
+  DCCN_CHECK(!S.busy, "slot %d still in flight: call dccn_forward_host_end first", slot);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t nb = (size_t)h->D * h->NB;
-  if (h->stage_frames < B) {
+  if (S.frames < B) {
     // (re)allocate staging; old buffers stay in the alloc list until destroy
-    int rc = dev_alloc(h, (void**)&h->d_x, (size_t)B * h->P * 4);
-    rc |= dev_alloc(h, (void**)&h->d_bits, (size_t)B * nb);
-    rc |= dev_alloc(h, (void**)&h->d_hard, (size_t)B * nb);
+    int rc = dev_alloc(h, (void**)&S.d_x, (size_t)B * h->P * 4);
+    rc |= dev_alloc(h, (void**)&S.d_bits, (size_t)B * nb);
+    rc |= dev_alloc(h, (void**)&S.d_hard, (size_t)B * nb);
     if (rc) return rc;
-    h->stage_frames = B;
+    S.frames = B;
   }
-  DCCN_CUDA_OK(cudaMemcpyAsync(h->d_x, x_host, (size_t)B * h->P * 4, cudaMemcpyHostToDevice, s));
-  if (bits_host) DCCN_CUDA_OK(cudaMemcpyAsync(h->d_bits, bits_host, (size_t)B * nb, cudaMemcpyHostToDevice, s));
-  int64_t* d_res_conf = h->d_res_conf;
-  double* d_res_ce = h->d_res_ce;
-  DCCN_CUDA_OK(cudaMemsetAsync(d_res_conf, 0, 4 * sizeof(int64_t), s));
-  DCCN_CUDA_OK(cudaMemsetAsync(d_res_ce, 0, sizeof(double), s));
-  int rc = dccn_forward(h, h->d_x, B, bits_host ? h->d_bits : nullptr, nullptr, hard_host ? h->d_hard : nullptr,
-                        nullptr, nullptr, d_res_conf, d_res_ce, 0, s);
+  // H2D on the copy stream (the previous pass over this slot was waited for in ..._end)
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.d_x, x_host, (size_t)B * h->P * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  if (bits_host) DCCN_CUDA_OK(cudaMemcpyAsync(S.d_bits, bits_host, (size_t)B * nb, cudaMemcpyHostToDevice, h->copy_stream));
+  DCCN_CUDA_OK(cudaEventRecord(S.copied, h->copy_stream));
+  // the pass, on the caller's stream, after the copy
+  DCCN_CUDA_OK(cudaStreamWaitEvent(s, S.copied, 0));
+  DCCN_CUDA_OK(cudaMemsetAsync(S.d_conf, 0, 4 * sizeof(int64_t), s));
+  DCCN_CUDA_OK(cudaMemsetAsync(S.d_ce, 0, sizeof(double), s));
+  int rc = dccn_forward(h, S.d_x, B, bits_host ? S.d_bits : nullptr, nullptr, hard_host ? S.d_hard : nullptr, nullptr,
+                        nullptr, S.d_conf, S.d_ce, 0, s);
   if (rc) return rc;
-  if (hard_host) DCCN_CUDA_OK(cudaMemcpyAsync(hard_host, h->d_hard, (size_t)B * nb, cudaMemcpyDeviceToHost, s));
-  if (conf_host) DCCN_CUDA_OK(cudaMemcpyAsync(conf_host, d_res_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  if (ce_sum_host) DCCN_CUDA_OK(cudaMemcpyAsync(ce_sum_host, d_res_ce, sizeof(double), cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  if (hard_host) DCCN_CUDA_OK(cudaMemcpyAsync(hard_host, S.d_hard, (size_t)B * nb, cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_conf, S.d_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_ce, S.d_ce, sizeof(double), cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaEventRecord(S.done, s));
+  S.busy = true;
+  S.B = B;
   return 0;
+}
+
+int dccn_forward_host_end(dccn_handle* h, int slot, int64_t* conf_host, double* ce_sum_host) {
+  DCCN_CHECK(h && (slot == 0 || slot == 1), "bad argument");
+  dccn_handle::HostSlot& S = h->slot[slot];
+  DCCN_CHECK(S.busy, "slot %d has no batch in flight", slot);
+  DCCN_CUDA_OK(cudaEventSynchronize(S.done));
+  S.busy = false;
+  if (conf_host) memcpy(conf_host, S.h_conf, 4 * sizeof(int64_t));
+  if (ce_sum_host) *ce_sum_host = *S.h_ce;
+  return 0;
+}
+
+int dccn_forward_host(dccn_handle* h, const float* x_host, int64_t B, const uint8_t* bits_host, uint8_t* hard_host,
+                      int64_t* conf_host, double* ce_sum_host, void* stream) {
+  int rc = dccn_forward_host_begin(h, 0, x_host, B, bits_host, hard_host, stream);
+  if (rc) return rc;
+  return dccn_forward_host_end(h, 0, conf_host, ce_sum_host);
 }
 
 int dccn_cconv2d(const float* x_dev, int64_t B, int L, int W, int C, const float* kernel_dev, const float* bias_dev,

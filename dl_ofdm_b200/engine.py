@@ -154,6 +154,20 @@ class DCCN:
                                                   _ptr(conf), _ptr(ce), _stream()))
         return conf.numpy().reshape(2, 2).copy(), float(ce[0]), hard
 
+    def forward_host_begin(self, slot, x_host, bits_host=None):
+        """Queue H2D + pass + D2H for one batch on `slot` (0/1) and return immediately."""
+        assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dccn_forward_host_begin(self._h, int(slot), _ptr(x_host), x_host.shape[0],
+                                                        _ptr(bits_host), None, _stream()))
+
+    def forward_host_end(self, slot):
+        """Block until the batch on `slot` is done; -> (conf int64[2,2] numpy, ce_sum float)."""
+        conf = (C.c_int64 * 4)()
+        ce = C.c_double()
+        _lib.check(self.lib.dccn_forward_host_end(self._h, int(slot), conf, C.byref(ce)))
+        return np.array(conf[:], dtype=np.int64).reshape(2, 2), float(ce.value)
+
     def batch_moments(self, x):
         P = self.S * self.T * 2
         mean = torch.empty(P, dtype=torch.float32, device=x.device)

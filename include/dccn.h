@@ -116,6 +116,13 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
 int dccn_forward_host(dccn_handle* h, const float* x_host, int64_t B, const uint8_t* bits_host,
                       uint8_t* hard_host, int64_t* conf_host, double* ce_sum_host, void* stream);
 
+/* Pipelined form of the same call: two slots; `begin` queues H2D (internal copy stream) + the pass +
+ * the D2H of the results and returns immediately, `end` blocks until that slot's results are on the
+ * host.  Issuing begin(slot^1) before end(slot) overlaps the next batch's PCIe copy with the pass. */
+int dccn_forward_host_begin(dccn_handle* h, int slot, const float* x_host, int64_t B,
+                            const uint8_t* bits_host, uint8_t* hard_host, void* stream);
+int dccn_forward_host_end(dccn_handle* h, int slot, int64_t* conf_host, double* ce_sum_host);
+
 /* -- a1: layers_conv2d_complex(inputs, filters, kernal, strides=1, padding)
  * (dev/py/complex.py:140-196), op-level.  x_dev [B,L,W,C,2], kernel_dev
  * [kl,kw,1,C,2*filters], bias_dev [2*filters], y_dev [B,L',W',filters,2];

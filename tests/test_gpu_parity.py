@@ -456,3 +456,32 @@ def test_error_paths(libdccn):
         m.load_weights({'fft_like/conv3d/bias': np.zeros(128, np.float32)})
     with pytest.raises(DccnError):
         DCCN(nbits=7)
+
+
+def test_pipelined_host_entry(libdccn):
+    """begin/end with two slots in flight == synchronous host call == device call."""
+    from dl_ofdm_b200.engine import DCCN, DccnError
+    from dl_ofdm_b200 import init
+    rng = np.random.default_rng(5)
+    w = init.receiver_variables(rng, 2)
+    m = DCCN(nbits=2, precision='parity', chunk_frames=512)
+    m.load_weights(w)
+    xs = [(torch.randn((1500 + 100 * i, 7, 80, 2)) * 0.2).pin_memory() for i in range(4)]
+    bs = [torch.randint(0, 2, (x.shape[0], 320, 2), dtype=torch.uint8).pin_memory() for x in xs]
+    ref = [m.forward(x.cuda(), b.cuda(), want_soft=False)['conf'].cpu().numpy() for x, b in zip(xs, bs)]
+    got = []
+    m.forward_host_begin(0, xs[0], bs[0])
+    for i in range(4):
+        if i + 1 < 4:
+            m.forward_host_begin((i + 1) & 1, xs[i + 1], bs[i + 1])
+        got.append(m.forward_host_end(i & 1)[0])
+    for r, g in zip(ref, got):
+        assert np.array_equal(r, g)
+    sync_conf, _, _ = m.forward_host(xs[2], bs[2])
+    assert np.array_equal(sync_conf, ref[2])
+    with pytest.raises(DccnError, match='no batch in flight'):
+        m.forward_host_end(1)
+    m.forward_host_begin(1, xs[0], bs[0])
+    with pytest.raises(DccnError, match='still in flight'):
+        m.forward_host_begin(1, xs[1], bs[1])
+    m.forward_host_end(1)

@@ -48,6 +48,9 @@ PROTOTYPES = {
     'dccn_cconv2d': (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'dccn_chan_fir_awgn': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _u64,
                                      _vp, _vp, _vp]),
+    'dccn_chan_fading': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _i32, C.c_double, C.c_double, _vp,
+                                   _u64, _i64, _i64, _i32, _vp, _vp]),
+    'dccn_chan_awgn': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _u64, _vp, _vp]),
     'dccn_ber_accum': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'dccn_tx_frames': (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _i32, _vp, C.c_float, C.c_float, _vp, _vp]),
     'dccn_bit_source': (C.c_int, [_vp, _i64, _u64, _vp]),

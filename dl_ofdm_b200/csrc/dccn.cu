@@ -1034,7 +1034,7 @@ int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_sam
   {
     LaunchScope ls(h, SLOT_CHAN_FIR, s);
     chan_fir_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)tx_dev, (long long)B, n_samp, alpha_dev,
-                                                           coeff_dev, n_taps, n_fir, z_dev, seed, (float2*)faded,
+                                                           coeff_dev, n_taps, n_fir, z_dev, seed, 0, 1, (float2*)faded,
                                                            h->d_power);
   }
   LaunchScope ls2(h, SLOT_AWGN, s);
@@ -1042,6 +1042,48 @@ int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_sam
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
   awgn_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2*)faded, (long long)B, n_samp, h->d_power, snr_db_dev,
+                                               normals_dev, seed ^ 0x9E3779B97F4A7C15ull, (float2*)rx_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+/* fading only (no AWGN), for a strided subset of the frames: frame0, frame0+fstride, ... */
+int dccn_chan_fading(dccn_handle* h, const float* tx_dev, int64_t B, int n_sym, int n_sc, const double* alpha_dev,
+                     const double* coeff_dev, int n_taps, int n_fir, double doppler_hz, double sample_rate,
+                     const double* z_or_theta_dev, uint64_t seed, int64_t frame0, int64_t fstride, int reset_power,
+                     float* faded_dev, void* stream) {
+  DCCN_CHECK(h && tx_dev && faded_dev && B > 0 && n_sym > 0 && n_sc > 0 && fstride >= 1 && frame0 >= 0, "bad argument");
+  DCCN_CHECK(n_taps >= 0 && n_taps <= kMaxPaths && n_fir >= 1 && n_fir <= kMaxFir, "at most %d paths / %d FIR taps", kMaxPaths, kMaxFir);
+  DCCN_CHECK(n_taps == 0 || coeff_dev != nullptr, "coeff_dev missing");
+  DCCN_CHECK(doppler_hz <= 0.0 || n_taps > 0, "Doppler fading needs a tap profile");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (reset_power) DCCN_CUDA_OK(cudaMemsetAsync(h->d_power, 0, sizeof(double), s));
+  if (frame0 >= B) return 0;
+  const long long nf = (B - frame0 + fstride - 1) / fstride;
+  LaunchScope ls(h, SLOT_CHAN_FIR, s);
+  if (doppler_hz > 0.0)
+    chan_doppler_kernel<<<(unsigned)((nf + 7) / 8), 256, 0, s>>>((const float2*)tx_dev, (long long)B, n_sym, n_sc,
+                                                               alpha_dev, coeff_dev, n_taps, n_fir, doppler_hz,
+                                                               (double)n_sc / sample_rate, z_or_theta_dev, seed,
+                                                               frame0, fstride, (float2*)faded_dev, h->d_power);
+  else
+    chan_fir_kernel<<<(unsigned)((nf + 7) / 8), 256, 0, s>>>((const float2*)tx_dev, (long long)B, n_sym * n_sc, alpha_dev,
+                                                           coeff_dev, n_taps, n_fir, z_or_theta_dev, seed, frame0,
+                                                           fstride, (float2*)faded_dev, h->d_power);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+/* AWGN_channel_np on an already faded batch; uses the power accumulated by dccn_chan_fading */
+int dccn_chan_awgn(dccn_handle* h, const float* faded_dev, int64_t B, int n_samp, const float* snr_db_dev,
+                   const double* normals_dev, uint64_t seed, float* rx_dev, void* stream) {
+  DCCN_CHECK(h && faded_dev && rx_dev && snr_db_dev && B > 0 && n_samp > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  LaunchScope ls(h, SLOT_AWGN, s);
+  const long long total = (long long)B * n_samp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+  awgn_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2*)faded_dev, (long long)B, n_samp, h->d_power, snr_db_dev,
                                                normals_dev, seed ^ 0x9E3779B97F4A7C15ull, (float2*)rx_dev);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;

@@ -129,10 +129,11 @@ __global__ void __launch_bounds__(256) chan_fir_kernel(const float2* __restrict_
                                                        const double* __restrict__ alpha,
                                                        const double* __restrict__ coeff, int n_taps, int n_fir,
                                                        const double* __restrict__ z_in, uint64_t seed,
+                                                       long long frame0, long long fstride,
                                                        float2* __restrict__ rx, double* __restrict__ power_sum) {
   __shared__ double2 gsm[8][kMaxFir];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long frame = (long long)blockIdx.x * 8 + wib;
+  const long long frame = frame0 + ((long long)blockIdx.x * 8 + wib) * fstride;
   if (frame >= B) return;
 
   // path gains -> sample-spaced FIR g[j] (lane j owns tap j)
@@ -199,6 +200,115 @@ __global__ void __launch_bounds__(256) chan_fir_kernel(const float2* __restrict_
     }
     prev = cur;
     cur = next;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+  if (lane == 0) atomicAdd(power_sum, pw);
+}
+
+// =====================================================================================
+// Mobile (Doppler) fading, dev/py/radio.py:387-422: per frame 48 sinusoids per path with random
+// phases (sum-of-sinusoids Jakes model), path gains re-evaluated at every OFDM symbol, and a
+// per-symbol 'same' convolution over [symbol + n_taps samples of history] (no look-ahead past the
+// symbol end, zero history before the frame).  One warp per frame; lanes share the sinusoids
+// (warp reduction per path), then the FIR taps; float64 like NumPy, output rounded to complex64.
+//   frames handled: frame0 + idx*fstride  (profile cycling of 'mixRayleigh', radio.py:450-467)
+//   theta_in [B, 2, ss, n_taps] uniform(0,2pi) phases or nullptr -> Philox
+// =====================================================================================
+constexpr int kMaxPaths = 16;
+constexpr int kSinusoids = 48;
+
+__global__ void __launch_bounds__(256) chan_doppler_kernel(const float2* __restrict__ tx, long long B, int n_sym,
+                                                           int n_sc, const double* __restrict__ alpha,
+                                                           const double* __restrict__ coeff, int n_taps, int n_fir,
+                                                           double Fd, double t_sym, const double* __restrict__ theta_in,
+                                                           uint64_t seed, long long frame0, long long fstride,
+                                                           float2* __restrict__ rx, double* __restrict__ power_sum) {
+  __shared__ double2 gsm[8][kMaxFir];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long frame = frame0 + ((long long)blockIdx.x * 8 + wib) * fstride;
+  if (frame >= B) return;
+  const double kPi = 3.14159265358979323846;
+  // sinusoid frequencies / phases of this lane: sinusoids n = lane and lane + 32 (< 48)
+  double f_re[2][kMaxPaths], f_im[2][kMaxPaths], th_re[2][kMaxPaths], th_im[2][kMaxPaths];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int n = lane + 32 * h;
+    for (int t = 0; t < n_taps; ++t) {
+      if (n < kSinusoids) {
+        const double nv = ((double)(n + 1) - 0.5) * kPi / (4.0 * kSinusoids);
+        const double a0 = (double)(t + 1) * kPi / (4.0 * kSinusoids);
+        f_re[h][t] = Fd * cos(nv + a0);
+        f_im[h][t] = Fd * cos(nv - a0);
+        if (theta_in) {
+          const double* th = theta_in + (size_t)frame * 2 * kSinusoids * n_taps;
+          th_re[h][t] = th[(size_t)n * n_taps + t];
+          th_im[h][t] = th[(size_t)(kSinusoids + n) * n_taps + t];
+        } else {
+          uint32_t r[4];
+          Philox{seed}((uint64_t)frame * 1024 + (uint64_t)n * kMaxPaths + t, 0xD099u, r);
+          th_re[h][t] = 2.0 * kPi * ((double)r[0] * 2.3283064365386963e-10);
+          th_im[h][t] = 2.0 * kPi * ((double)r[1] * 2.3283064365386963e-10);
+        }
+      } else {
+        f_re[h][t] = f_im[h][t] = th_re[h][t] = th_im[h][t] = 0.0;
+      }
+    }
+  }
+  const double const1 = sqrt(1.0 / kSinusoids);
+  const int M = n_fir;
+  const int off = (M - 1) - (M >> 1);
+  const float2* txf = tx + (size_t)frame * n_sym * n_sc;
+  float2* rxf = rx + (size_t)frame * n_sym * n_sc;
+  double pw = 0.0;
+  for (int i = 0; i < n_sym; ++i) {
+    const double tw = 2.0 * kPi * ((double)i * t_sym);
+    double2 g = make_double2(0.0, 0.0);
+    for (int t = 0; t < n_taps; ++t) {
+      double sr = 0.0, si = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (lane + 32 * h < kSinusoids) {
+          sr += cos(tw * f_re[h][t] + th_re[h][t]);
+          si += cos(tw * f_im[h][t] + th_im[h][t]);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      const double c = coeff[t];
+      const double ar = const1 * sr * c, ai = const1 * si * c;       // zck * ch_coeff
+      if (lane < n_fir) {
+        const double al = alpha ? alpha[t * n_fir + lane] : 1.0;
+        g.x += ar * al;
+        g.y += ai * al;
+      }
+    }
+    __syncwarp();
+    if (lane < n_fir) gsm[wib][lane] = g;
+    __syncwarp();
+    // window of this symbol: local index m in [-n_taps, n_sc) <-> frame sample i*n_sc + m (zero before the frame)
+    for (int base = 0; base < n_sc; base += 32) {
+      const int q = base + lane;
+      if (q < n_sc) {
+        double accr = 0.0, acci = 0.0;
+        for (int j = 0; j < M; ++j) {
+          const int m = q + off - j;
+          const long long gi = (long long)i * n_sc + m;
+          if (m >= -n_taps && m < n_sc && gi >= 0) {
+            const float2 x = __ldg(txf + gi);
+            const double2 gg = gsm[wib][j];
+            accr += gg.x * x.x - gg.y * x.y;
+            acci += gg.x * x.y + gg.y * x.x;
+          }
+        }
+        const float2 o = make_float2((float)accr, (float)acci);
+        rxf[(size_t)i * n_sc + q] = o;
+        pw += (double)o.x * o.x + (double)o.y * o.y;
+      }
+    }
+    __syncwarp();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);

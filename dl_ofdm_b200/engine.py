@@ -196,6 +196,26 @@ class DCCN:
                                                    _ptr(rx), _ptr(faded), _stream()))
         return (rx, faded) if want_faded else rx
 
+    def fading(self, tx, faded, alpha=None, coeff=None, doppler_hz=0.0, sample_rate=0.96e6, draws=None, seed=0,
+               frame0=0, fstride=1, reset_power=True):
+        """Fading only, into `faded`, for frames frame0, frame0+fstride, ... (Doppler if doppler_hz > 0)."""
+        B, S, T = tx.shape[0], tx.shape[1], tx.shape[2]
+        n_taps = 0 if coeff is None else int(coeff.numel())
+        n_fir = 1 if alpha is None else int(alpha.shape[1])
+        with torch.cuda.device(tx.device):
+            _lib.check(self.lib.dccn_chan_fading(self._h, _ptr(tx), B, S, T, _ptr(alpha), _ptr(coeff), n_taps, n_fir,
+                                                 float(doppler_hz), float(sample_rate), _ptr(draws), int(seed),
+                                                 int(frame0), int(fstride), int(bool(reset_power)), _ptr(faded),
+                                                 _stream()))
+
+    def awgn(self, faded, snr_db, normals=None, seed=0):
+        rx = torch.empty_like(faded)
+        B = faded.shape[0]
+        with torch.cuda.device(faded.device):
+            _lib.check(self.lib.dccn_chan_awgn(self._h, _ptr(faded), B, faded.numel() // (2 * B), _ptr(snr_db),
+                                               _ptr(normals), int(seed), _ptr(rx), _stream()))
+        return rx
+
     # -- transmitter ---------------------------------------------------------------------
     def transmit(self, bits, ofdmobj, constellation):
         """GPU OFDM transmitter: bits uint8 [B,D,nbits] -> float32 [B,S,T,2]."""

@@ -23,8 +23,6 @@ TEST_CHANNELS = ['ETU', 'EVA', 'EPA', 'Flat', 'Custom']
 
 def test_model_cross(FLAGS, path_prefix_min, ofdmobj, session=None, frame_cnt=30000, snrs=range(-10, 31, 5),
                      out_dir='.', seed=1, channels=TEST_CHANNELS):
-    if FLAGS.mobile:
-        raise NotImplementedError('Doppler fading (--mobile=True) is not implemented on the GPU path yet')
     own = session is None
     if own:
         session = load_model_np(path_prefix_min, FLAGS=FLAGS, ofdmobj=ofdmobj, precision=FLAGS.precision)

@@ -6,8 +6,8 @@ but run as CUDA kernels (``dccn_chan_fir_awgn``): per-frame CN(0,1) path gains,
 ``g = (z*ch_coeff) @ alpha``, centred 'same' FIR with zero history, then batch-power
 normalisation + AWGN.  Random numbers come from a Philox counter stream (seeded, so
 sweeps are reproducible -- the reference seeds NumPy from the wall clock), or can be
-injected for parity tests.  Only the static (non-Doppler) branch is implemented;
-``mobile=True`` raises.
+injected for parity tests.  Both the static branch and the mobile (Doppler, sum-of-sinusoids)
+branch are implemented, as is the per-frame profile cycling of 'mixRayleigh' / 'mixAll'.
 """
 from __future__ import annotations
 
@@ -45,34 +45,88 @@ def channel_profile(chan):
     return pw / np.sqrt(pw.sum()), _alpha(chan)
 
 
+_FD = {'etu': 300.0, 'epa': 5.0, 'eva': 70.0, 'custom': 80.0}      # Doppler spread when mobile (radio.py:343-360)
+
+
+def doppler_hz(chan, mobile):
+    """Maximum Doppler shift of a profile: 0 when static; the single-tap channel uses 5 Hz (radio.py:363-366)."""
+    if not mobile:
+        return 0.0
+    return _FD.get(chan.lower(), 5.0)
+
+
 class rayleigh_chan_lte:
+    """GPU version of dev/py/radio.py:277-510.  ``channel`` may be a profile (EPA/EVA/ETU/Custom/Flat),
+    'AWGN' (no fading), or 'mixRayleigh' / 'mixAll' which deal the frames round-robin to
+    flat/etu/eva/epa (and awgn); with ``mobile`` the Doppler (sum-of-sinusoids) branch is used, with
+    ``mix`` only on every third (fourth for mixAll) frame like the reference."""
+
     def __init__(self, FLAGS, sample_rate=0.96e6, mobile=False, mix=False, engine=None, seed=0):
-        if mobile:
-            raise NotImplementedError('Doppler (mobile=True) fading is not implemented on the GPU path yet')
         self.nSymbol = FLAGS.nsymbol
         self.chan = FLAGS.channel.lower()
         self.sample_rate = sample_rate
         self.nfft = FLAGS.nfft
+        self.mobile, self.mix = bool(mobile), bool(mix)
         self.engine = engine
         self.seed = seed
         self._calls = 0
-        if self.chan in ('mixrayleigh', 'mixall'):
-            raise NotImplementedError("channel '%s' cycles profiles per frame; use one profile per call" % self.chan)
-        self.ch_coeff, self.alpha_matrix = (None, None) if self.chan == 'awgn' else channel_profile(self.chan)
-        self.n_taps = 0 if self.ch_coeff is None else len(self.ch_coeff)
+        self._dev = {}
+        if self.chan == 'mixrayleigh':
+            self.profiles = ['flat', 'etu', 'eva', 'epa']
+        elif self.chan == 'mixall':
+            self.profiles = ['awgn', 'flat', 'etu', 'eva', 'epa']
+        else:
+            self.profiles = [self.chan]
+        self.Fd = doppler_hz(self.profiles[-1], self.mobile) if len(self.profiles) == 1 else None
+        if len(self.profiles) == 1 and self.chan != 'awgn':
+            self.ch_coeff, self.alpha_matrix = channel_profile(self.chan)
+            self.n_taps = len(self.ch_coeff)
+        else:
+            self.ch_coeff, self.alpha_matrix, self.n_taps = None, None, 0
 
-    def device_profile(self, device):
-        if self.ch_coeff is None:
-            return None, None
-        return (torch.as_tensor(self.alpha_matrix, dtype=torch.float64, device=device).contiguous(),
-                torch.as_tensor(self.ch_coeff, dtype=torch.float64, device=device).contiguous())
+    def _profile(self, name, device):
+        key = (name, str(device))
+        if key not in self._dev:
+            if name == 'awgn':
+                self._dev[key] = (None, None)
+            else:
+                c, a = channel_profile(name)
+                self._dev[key] = (torch.as_tensor(a, dtype=torch.float64, device=device).contiguous(),
+                                  torch.as_tensor(c, dtype=torch.float64, device=device).contiguous())
+        return self._dev[key]
+
+    def fade(self, inputs, draws=None):
+        """Fading only: float32 CUDA [B,S,T,2] -> faded [B,S,T,2] (complex64 like radio.py:492)."""
+        eng = self.engine
+        faded = torch.empty_like(inputs)
+        self._calls += 1
+        n = len(self.profiles)
+        dmod = 3 if self.chan == 'mixrayleigh' else 4
+        first = True
+        for k, name in enumerate(self.profiles):
+            alpha, coeff = self._profile(name, inputs.device)
+            fd = doppler_hz(name, self.mobile)
+            seed = (self.seed << 24) + (self._calls << 4) + k
+            if n == 1:
+                eng.fading(inputs, faded, alpha, coeff, fd, self.sample_rate, draws, seed, 0, 1, first)
+                first = False
+                continue
+            if n > 1 and fd > 0.1 and self.mix:
+                # frames with i % n == k and i % dmod == 0 are Doppler, the others static; lcm stride
+                lcm = n * dmod // np.gcd(n, dmod)
+                for f0 in range(k, lcm, n):
+                    dop = fd if (f0 % dmod == 0) else 0.0
+                    eng.fading(inputs, faded, alpha, coeff, dop, self.sample_rate, None, seed + f0 * 131, f0, lcm, first)
+                    first = False
+            else:
+                eng.fading(inputs, faded, alpha, coeff, 0.0, self.sample_rate, None, seed, k, n, first)
+                first = False
+        return faded
 
     def run(self, inputs, snr_db, z=None, normals=None):
         """inputs: float32 CUDA tensor [B,S,T,2] (transmitted IQ); snr_db: float32 CUDA tensor [B].
-        Returns the received float32 tensor [B,S,T,2] (fading + AWGN fused: radio.py:228-229)."""
-        alpha, coeff = self.device_profile(inputs.device)
-        self._calls += 1
-        return self.engine.channel(inputs, snr_db, alpha=alpha, coeff=coeff, z=z, normals=normals,
-                                   seed=(self.seed << 20) + self._calls)
+        Returns the received float32 tensor [B,S,T,2] (fading + AWGN: radio.py:228-229)."""
+        faded = self.fade(inputs, z)
+        return self.engine.awgn(faded, snr_db, normals, seed=(self.seed << 20) + self._calls)
 
     __call__ = run

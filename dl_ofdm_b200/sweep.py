@@ -87,7 +87,8 @@ class CellRunner:
         dev = eng.device
         bits = bit_source_gpu(B * D * nb, seed=(self.seed << 24) + index, device=dev).view(B, D, nb)
         tx = eng.transmit(bits, ofdm, self.const)
-        chan = rayleigh_chan_lte(fl.copy(channel=chan_name), ofdm.Fs, engine=eng, seed=(self.seed << 12) + index)
+        chan = rayleigh_chan_lte(fl.copy(channel=chan_name), ofdm.Fs, mobile=getattr(fl, 'mobile', False),
+                                 engine=eng, seed=(self.seed << 12) + index)
         x = chan.run(tx, torch.full((B,), snr, dtype=torch.float32, device=dev))
         o = eng.forward(x, bits, want_soft=False, want_hard=False)
         return o['conf'].cpu().numpy(), float(o['ce_sum'].cpu()[0])

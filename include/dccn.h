@@ -147,6 +147,20 @@ int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_sam
                        const double* z_dev, const float* snr_db_dev, const double* normals_dev,
                        uint64_t seed, float* rx_dev, float* fir_only_dev, void* stream);
 
+/* -- f-2: the two halves separately, plus the mobile (Doppler) branch and per-frame profile cycling.
+ * dccn_chan_fading: rayleigh_chan_lte.channel for frames frame0, frame0+fstride, ... (mixRayleigh deals
+ * frames i%4 to flat/etu/eva/epa, dev/py/radio.py:450-467).  doppler_hz > 0 selects doppler_channel
+ * (dev/py/radio.py:399-422); then z_or_theta_dev is float64 [B,2,48,n_taps] uniform(0,2pi) phases, else
+ * float64 [B,n_taps,2] N(0,1/2) path gains (NULL -> Philox(seed)).  The batch power sum |rx|^2 is
+ * accumulated in the handle (reset_power != 0 clears it first); dccn_chan_awgn normalises by it. */
+int dccn_chan_fading(dccn_handle* h, const float* tx_dev, int64_t B, int n_sym, int n_sc,
+                     const double* alpha_dev, const double* coeff_dev, int n_taps, int n_fir,
+                     double doppler_hz, double sample_rate, const double* z_or_theta_dev, uint64_t seed,
+                     int64_t frame0, int64_t fstride, int reset_power, float* faded_dev, void* stream);
+int dccn_chan_awgn(dccn_handle* h, const float* faded_dev, int64_t B, int n_samp,
+                   const float* snr_db_dev, const double* normals_dev, uint64_t seed, float* rx_dev,
+                   void* stream);
+
 /* -- a5: tf.confusion_matrix(bits, argmax) (ofdmreceiver_np.py:165-169); conf accumulated */
 int dccn_ber_accum(const uint8_t* hard_dev, const uint8_t* bits_dev, int64_t n,
                    int64_t* conf_dev, void* stream);

@@ -312,6 +312,37 @@ def rayleigh_static(tx, z, ch_coeff, alpha):
     return np.stack([out.real, out.imag], axis=-1), gs
 
 
+def rayleigh_doppler(tx, theta, Fd, ch_coeff, alpha, n_sym, n_sc, sample_rate, ss=48):
+    """Mobile (Doppler) branch, dev/py/radio.py:387-422: sum-of-sinusoids path gains re-drawn per
+    OFDM symbol, per-symbol 'same' convolution over the symbol plus n_taps samples of history.
+
+    tx [B, n_sym*n_sc] complex; theta [B, 2, ss, n_taps] uniform(0, 2pi) phases (re / im branch).
+    """
+    tx = np.asarray(tx)
+    B = tx.shape[0]
+    n_taps = len(ch_coeff)
+    alpha = np.asarray(alpha, dtype=np.float64)
+    k_vec = np.arange(1, n_taps + 1)
+    n_vec = (np.arange(1, ss + 1).reshape(ss, 1) - 0.5) * np.pi / (4 * ss)        # :389
+    a0 = k_vec * np.pi / (4 * ss)
+    f_re = Fd * np.cos(n_vec + a0)                                                 # :392
+    f_im = Fd * np.cos(n_vec - a0)
+    const1 = np.sqrt(1.0 / ss)
+    t_sym = n_sc / sample_rate                                                     # :407
+    out = np.zeros((B, n_sym * n_sc), dtype=np.complex64)
+    for b in range(B):
+        pre = np.zeros(n_taps + n_sym * n_sc, dtype=np.complex64)                  # :402-403
+        pre[n_taps:] = tx[b]
+        for i in range(n_sym):
+            t = i * t_sym
+            mu_re = const1 * np.sum(np.cos(2 * np.pi * t * f_re + theta[b, 0]), 0)  # :411-414
+            mu_im = const1 * np.sum(np.cos(2 * np.pi * t * f_im + theta[b, 1]), 0)
+            g = ((mu_re + 1j * mu_im) * ch_coeff) @ alpha                          # :417-418
+            roll = pre[n_sc * i: n_taps + n_sc * (i + 1)]                          # :419
+            out[b, n_sc * i:n_sc * (i + 1)] = np.convolve(roll, g, mode='same')[n_taps:]   # :420-421
+    return np.stack([out.real, out.imag], axis=-1)
+
+
 # ---------------------------------------------------------------------------
 # a7  AWGN_channel_np  (dev/py/radio.py:513-526)
 # ---------------------------------------------------------------------------

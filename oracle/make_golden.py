@@ -138,6 +138,29 @@ def main():
 
 
 
+def make_doppler():
+    """rayleigh_<chan>_mobile.npz: Doppler (sum-of-sinusoids) branch of rayleigh_chan_lte.run
+    (dev/py/radio.py:387-422, 491-506) with the per-frame uniform phase draws exposed."""
+    ref_ofdm, ref_radio = _import_reference()
+    fl = Flags(nbits=2)
+    txo = ref_ofdm.ofdm_tx(fl)
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2, (5, txo.frame_size, 2))
+    cpx, _, _ = txo.ofdm_tx_frame_np(bits)
+    for chan in ('ETU', 'EVA', 'Flat'):
+        fading = ref_radio.rayleigh_chan_lte(Flags(channel=chan), txo.Fs, mobile=True)
+        np.random.seed(777)
+        y, H = fading.run(cpx)
+        np.random.seed(777)
+        th = []
+        for _ in range(cpx.shape[0]):
+            tre = np.random.uniform(0, 2 * np.pi, size=(fading.ss, fading.n_taps))
+            tim = np.random.uniform(0, 2 * np.pi, size=(fading.ss, fading.n_taps))
+            th.append(np.stack([tre, tim]))
+        np.savez(os.path.join(OUT, 'rayleigh_%s_mobile.npz' % chan.lower()), tx=cpx, theta=np.array(th), rx=y,
+                 ch_coeff=fading.ch_coeff, alpha=fading.alpha_matrix, Fd=fading.Fd, Fs=txo.Fs)
+
+
 def make_alpha_npz():
     """dl_ofdm_b200/data/lte_alpha.npz: the reference's fractional-delay interpolation matrices
     (dev/py/3gpp/AM_*.csv, exported from MATLAB's channelFilter.alphaMatrix, README.md:60) packed
@@ -149,5 +172,9 @@ def make_alpha_npz():
 
 
 if __name__ == '__main__':
-    make_alpha_npz()
-    main()
+    if 'doppler' in sys.argv:
+        make_doppler()
+    else:
+        make_alpha_npz()
+        make_doppler()
+        main()

@@ -485,3 +485,46 @@ def test_pipelined_host_entry(libdccn):
     with pytest.raises(DccnError, match='still in flight'):
         m.forward_host_begin(1, xs[1], bs[1])
     m.forward_host_end(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# f-2: mobile (Doppler) fading and profile cycling
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('chan', ['etu', 'eva', 'flat'])
+def test_doppler_fading_golden(libdccn, golden, chan):
+    """Doppler branch with the reference's own phase draws injected == the reference's output."""
+    from dl_ofdm_b200.engine import DCCN
+    g = golden('rayleigh_%s_mobile.npz' % chan)
+    tx = g['tx']
+    txf = np.stack([tx.real, tx.imag], -1).astype(np.float32)
+    m = DCCN(nbits=2, precision='exact')
+    faded = torch.empty_like(_cuda(txf))
+    m.fading(_cuda(txf), faded, alpha=_cuda(np.atleast_2d(g['alpha']).astype(np.float64)),
+             coeff=_cuda(g['ch_coeff'].astype(np.float64)), doppler_hz=float(g['Fd']), sample_rate=float(g['Fs']),
+             draws=_cuda(g['theta'].astype(np.float64)))
+    ref = g['rx'].astype(np.float32)
+    got = faded.cpu().numpy()
+    assert np.abs(got - ref).max() <= 4 * np.spacing(np.abs(ref).max())      # libm cos vs CUDA cos: <= a few ulp
+    assert (got == ref).mean() > 0.9
+
+
+def test_mix_rayleigh_cycling(libdccn):
+    """mixRayleigh deals frame i to profile i % 4 (flat, etu, eva, epa); every frame gets written once."""
+    from dl_ofdm_b200.engine import DCCN
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.radio import rayleigh_chan_lte, channel_profile
+    m = DCCN(nbits=1, precision='exact')
+    B = 64
+    tx = torch.zeros((B, 7, 80, 2), device='cuda')
+    tx[:, 3, 40, 0] = 1.0                                   # one impulse per frame -> output = the frame's FIR
+    for mobile, mix in ((False, False), (True, True)):
+        ch = rayleigh_chan_lte(Flags(channel='mixRayleigh'), 0.96e6, mobile=mobile, mix=mix, engine=m, seed=5)
+        f = ch.fade(tx).cpu().numpy()
+        support = (np.abs(f[..., 0]) + np.abs(f[..., 1]) > 0).reshape(B, -1).sum(axis=1)
+        nfir = {0: 1, 1: channel_profile('etu')[1].shape[1], 2: channel_profile('eva')[1].shape[1],
+                3: channel_profile('epa')[1].shape[1]}
+        for i in range(B):
+            assert 1 <= support[i] <= nfir[i % 4], (i, support[i])
+        assert (support[0::4] == 1).all() and support[1::4].max() > 9 and support[3::4].max() <= 9
+    rx = ch.run(tx, torch.full((B,), 20.0, device='cuda'))
+    assert torch.isfinite(rx).all()

@@ -91,6 +91,25 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs next to GPU `index` (NVML's ideal affinity) BEFORE the pinned
+    host buffers are allocated, so that first-touch puts them on the GPU's NUMA node; a buffer on
+    the far socket halves (or worse) the PCIe copy rate of the end-to-end number."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def make_weights(seed=2026):
     from dl_ofdm_b200 import init
     rng = np.random.default_rng(seed)
@@ -213,6 +232,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     B = args.frames
@@ -314,7 +334,9 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {'value': world * B * args.steps / float(te[0]), 'unit': 'frames/s',
-           'h2d_bytes_per_step': int(xh.numel() * 4 + bh.numel()), 'd2h_bytes_per_step': 4 * 8 + 8}
+           'h2d_bytes_per_step': int(xh.numel() * 4 + bh.numel()), 'd2h_bytes_per_step': 4 * 8 + 8,
+           'h2d_gbps': round(args.steps * (xh.numel() * 4 + bh.numel()) / float(te[0]) / 1e9, 1),
+           'numa_local_cpus': numa, 'pipelined': 'H2D of step i+1 overlaps the pass over step i (2 slots)'}
 
     conf = conf_total.cpu().numpy()
     ber = float(conf[0, 1] + conf[1, 0]) / float(conf.sum())
@@ -331,6 +353,10 @@ def main():
             'target': {'frames_per_s_8gpu': 1e8, 'note': 'north_star target; random-init weights so BER ~ 0.5'},
         }
         if world == 1 and not args.no_cpu_baseline:
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count()))      # the CPU arm may use every core again
+            except Exception:
+                pass
             threads = best_threads(w)
             r, n, dt = cpu_reference_rate(w, 2048, 12.0, threads)
             line['cpu_baseline'] = {'value': r, 'unit': 'frames/s', 'cores': threads, 'host_cpus': os.cpu_count(), 'kind': 'port',

@@ -52,6 +52,30 @@ DCCN_DEVINL void store_act(const ActOut& o, int row, int col, const float (&y)[N
   }
 }
 
+// Warp-cooperative store of a [32 rows x 32 cols] fp32 block whose rows are held one per lane
+// (the tcgen05.ld layout): transposed through a 4 KB shared-memory patch (16-byte chunks XOR-
+// swizzled by row, conflict-free both ways) so that every global store instruction writes four
+// complete 128-byte lines instead of 32 scattered 16-byte pieces.
+DCCN_DEVINL void store_block_warp(float* base, int ld, int row0, int M, int lane, const float (&y)[32],
+                                  uint32_t patch /* shared address of this warp's 4 KB patch */) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t a = patch + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(y[4 * c]), "f"(y[4 * c + 1]),
+                 "f"(y[4 * c + 2]), "f"(y[4 * c + 3])
+                 : "memory");
+  }
+  __syncwarp();
+  const int cc = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const float4 v = lds128(patch + (uint32_t)((rr * 8 + (cc ^ (rr & 7))) << 4));
+    if (row0 + rr < M) *reinterpret_cast<float4*>(base + (size_t)(row0 + rr) * ld + cc * 4) = v;
+  }
+  __syncwarp();
+}
+
 // -------------------------------------------------------------------------------------
 // y = act(acc + bias)  ->  activation planes      (tf.layers.dense / packed complex layers)
 // -------------------------------------------------------------------------------------
@@ -80,6 +104,19 @@ struct EpiStore {
       for (int i = 0; i < NC; i += 2) *reinterpret_cast<float2*>(d + i) = make_float2(y[i], y[i + 1]);
     }
   }
+  // tensor-core path: the 32 lanes of a warp hold 32 consecutive rows (row0 + lane)
+  static constexpr bool kWarpStore = true;
+  DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
+    if (col0 >= N) return;                       // warp-uniform
+    float y[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float t = v[i] + (bias ? __ldg(bias + col0 + i) : 0.f);
+      y[i] = (act == 1) ? tanhf(t) : t;
+    }
+    store_block_warp(out.p0 + out.col_off + col0, out.ld, row0, M, lane, y, patch);
+    if (aux) store_block_warp(aux + col0, aux_ld, row0, M, lane, y, patch);
+  }
   DCCN_DEVINL void flush(State&) const {}
 };
 
@@ -100,6 +137,33 @@ struct EpiPhaseEq {
   float* chest_out;     // optional fp32 [M, N] ('chest' fetch), or nullptr
   int M, N;
   struct State {};
+  static constexpr bool kWarpStore = true;
+
+  // tensor-core path: rows row0 + lane; eq goes out through the coalescing transpose
+  DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
+    if (col0 >= N) return;
+    const int row = row0 + lane;
+    const bool ok = row < M;
+    const float* fp0 = f0 + (size_t)(ok ? row : 0) * ld_f + col0;
+    float e[32], c[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float cr = v[i] + __ldg(bias + col0 + i);
+      const float ci = v[i + 1] + __ldg(bias + col0 + i + 1);
+      const float2 f = *reinterpret_cast<const float2*>(fp0 + i);
+      const float inv = rsqrtf(cr * cr + ci * ci);
+      const float nr = cr * inv, ni = (-ci) * inv;
+      const float er = f.x * nr - f.y * ni, ei = f.x * ni + f.y * nr;
+      e[i] = er;
+      e[i + 1] = ei;
+      c[i / 2] = er * er + ei * ei;
+      v[i] = cr;
+      v[i + 1] = ci;
+    }
+    store_block_warp(eq.p0 + eq.col_off + col0, eq.ld, row0, M, lane, e, patch);
+    if (chest_out) store_block_warp(chest_out + col0, N, row0, M, lane, v, patch);
+    if (ok) store_act<16>(corr, row, col0 / 2, c);
+  }
 
   template <int NC>
   DCCN_DEVINL void run(State&, int row, int col0, float (&v)[NC]) const {
@@ -117,9 +181,11 @@ struct EpiPhaseEq {
         f.x += fl.x;
         f.y += fl.y;
       }
-      float ab = hypotf(cr, ci);                 // tf.abs(complex64)
-      float nr = cr / ab;                        // real(conj)/abs      model.py:432
-      float ni = (-ci) / ab;                     // imag(conj)/abs
+      // conj(c)/|c| (model.py:431-433): one rsqrt instead of hypot + two IEEE divides (differs from
+      // the reference's op sequence by ~2e-7 relative; |c| = 0 gives NaN exactly like the reference)
+      const float inv = rsqrtf(cr * cr + ci * ci);
+      float nr = cr * inv;
+      float ni = (-ci) * inv;
       float er = f.x * nr - f.y * ni;            // complex multiply    model.py:434
       float ei = f.x * ni + f.y * nr;
       e[i] = er;
@@ -167,6 +233,7 @@ struct EpiHead {
   unsigned long long* conf;   // [4] or nullptr
   double* ce_sum;             // [1] or nullptr
   int M, N;
+  static constexpr bool kWarpStore = false;
   struct State {   // per-thread accumulators (flushed once per thread)
     unsigned int c00 = 0, c01 = 0, c10 = 0, c11 = 0;
     float ce = 0.f;

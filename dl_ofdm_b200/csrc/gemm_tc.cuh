@@ -82,13 +82,14 @@ struct TcCfg {
   static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
   static constexpr int APROD_WARP = 2 + SPLIT_WARPS;               // DEC: producer warp of the A ring
   static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS + (DEC ? 1 : 0);
-  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int SMEM_BUDGET = 193 * 1024;                   // operand rings; + 4 KB per epilogue warp below
+  static constexpr int PATCH_BYTES = 4 * CG * 4096;                // store-transpose patches of the epilogue warps
   static constexpr int STAGES_RAW = (SMEM_BUDGET - A_RING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 8;
   static constexpr int STAGES = imin(imin(STAGES_RAW, STAGES_TM), 8);
   static constexpr int A_TMEM_COL0 = 2 * BN;                       // A staging columns follow the accumulators
   static constexpr int TMEM_COLS = pow2_at_least(2 * BN + STAGES * A_TMEM_COLS);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + A_RING_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + A_RING_BYTES + PATCH_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int THREADS = 32 * EPI_WARP0 + 128 * CG;
   static constexpr int COLS_PER_GROUP = BN / CG;
   static constexpr int NCH = COLS_PER_GROUP / 32;     // 32-column register chunks per epilogue thread
@@ -114,7 +115,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem + C::STAGES * C::STAGE_BYTES;                       // DEC: SA raw fp32 A tiles
-  uint64_t* full = reinterpret_cast<uint64_t*>(a_ring + C::A_RING_BYTES);
+  uint8_t* patches = a_ring + C::A_RING_BYTES;                               // 4 KB per epilogue warp
+  uint64_t* full = reinterpret_cast<uint64_t*>(patches + C::PATCH_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* ready = empty + C::STAGES;   // [STAGES] A tile split into hi/lo (SPLIT only)
   uint64_t* tfull = ready + C::STAGES;   // [2] accumulator (one K chunk) ready for the epilogue
@@ -441,8 +443,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (acc == 0) acc_phase ^= 1;
       }
 #pragma unroll
-      for (int j = 0; j < C::NCH; ++j)
-        epi.template run<32>(st, row, n_blk * BN + cg * C::COLS_PER_GROUP + j * 32, r[j]);
+      for (int j = 0; j < C::NCH; ++j) {
+        const int col = n_blk * BN + cg * C::COLS_PER_GROUP + j * 32;
+        if constexpr (Epi::kWarpStore)
+          epi.run_warp(st, m_blk * C::BM + q * 32, lane, col, r[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
+        else
+          epi.template run<32>(st, row, col, r[j]);
+      }
     }
     epi.flush(st);
   }

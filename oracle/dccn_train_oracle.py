@@ -1,0 +1,281 @@
+"""CPU oracle for the equalizer transfer-learning step (BASELINE.json config 4)
+--  TEST INFRASTRUCTURE ONLY (same import rules as dccn_oracle.py).
+
+What the reference does (dev/py/ofdmreceiver_np_mp.py:292-347):
+
+  * graph: tx_ofdm -> batch-moment norm -> equalizer_ofdm (scope 'Equalizer') -> (+0) ->
+    frozen ofdm_dense_rx -> softmax -> ce_mean  (dev/py/ofdmreceiver_np.py:154-162: softmax-xent
+    applied ON the softmax outputs, mean over every bit of the batch);
+  * total_loss = ce_mean + REG_COEFF * sum(REGULARIZATION_LOSSES), REG_COEFF = 0.001 (:336-341); the
+    regularisers are tf.keras.regularizers.l2(l=0.01) = 0.01 * sum(w^2) on kernel AND bias of the six
+    tf.layers.dense of equalizer_ofdm (dev/py/model.py:370-461); the conv3d layers have none;
+  * optimizer.minimize(total_loss, var_list=Equalizer vars) with tf.train.AdamOptimizer(lr),
+    lr = exponential_decay(init_learning, global_step, 500, 0.98, staircase=True) (:343-347).
+
+TensorFlow's autodiff itself is not in the tree, so the backward pass below is a hand-derived NumPy
+restatement in GEMM form (complex layers packed per SURVEY App. D).  It is pinned by
+tests/test_train_oracle.py against torch autograd run through the independent op-for-op mirror of
+the TF graph (oracle/tf_mirror.py, padded conv3d formulation) in float64: **parity unpinned** against
+TF itself (no trained dev checkpoint or gradient dump is shipped by the reference).
+
+TF-1.15 semantics encoded here: AdamOptimizer update  lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
+m = b1*m + (1-b1)*g, v = b2*v + (1-b2)*g^2, w -= lr_t*m/(sqrt(v)+eps)  with b1=.9, b2=.999, eps=1e-8;
+LeakyRelu gradient = g where x > 0 else alpha*g; gradients of complex ops for a real loss equal the
+real-variable gradients w.r.t. (re, im).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import dccn_oracle as orc
+
+REG_COEFF = 0.001            # dev/py/ofdmreceiver_np_mp.py:337
+L2_L = 0.01                  # tf.keras.regularizers.l2(l=0.01), dev/py/model.py:372-373
+ADAM_B1, ADAM_B2, ADAM_EPS = 0.9, 0.999, 1e-8
+DENSE_NAMES = ['dense', 'dense_1', 'dense_2', 'dense_3', 'dense_4', 'dense_5']
+CONV_NAMES = ['conv3d', 'conv3d_1', 'conv3d_2', 'conv3d_3']
+
+
+def trainable_names(prefix='Equalizer/'):
+    return [prefix + n + s for n in DENSE_NAMES + CONV_NAMES for s in ('/kernel', '/bias')]
+
+
+def learning_rate(init_learning, global_step):
+    """tf.train.exponential_decay(init, step, 500, 0.98, staircase=True)  (_mp.py:343-344)."""
+    return init_learning * 0.98 ** (global_step // 500)
+
+
+# ---------------------------------------------------------------------------------------------
+# packing of the reference layouts into GEMM operands and the adjoint maps (gradients back)
+# ---------------------------------------------------------------------------------------------
+def _pack_1xk(kernel, bias):
+    k = kernel[0, :, 0, 0, :]
+    F = k.shape[1] // 2
+    return orc.pack_complex_kernel(k[:, :F], k[:, F:], bias[:F], bias[F:], dtype=kernel.dtype)
+
+
+def _unpack_1xk(dBp, dbp, shape):
+    """adjoint of _pack_1xk: d(kernel [1,K,1,1,2F]), d(bias [2F])."""
+    gWa = dBp[0::2, 0::2] - dBp[1::2, 1::2]
+    gWb = dBp[0::2, 1::2] - dBp[1::2, 0::2]
+    gk = np.concatenate([gWa, gWb], axis=1).reshape(shape)
+    gba = dbp[0::2] - dbp[1::2]
+    return gk, np.concatenate([gba, -gba])
+
+
+def _pack_toeplitz(kernel, bias, S, K):
+    """(S,K) 'same' complex conv with one filter as a dense [2SK, 2SK] matrix."""
+    n = S * K * 2
+    Bp = np.zeros((n, n), dtype=kernel.dtype)
+    pl, pw = (S - 1) // 2, (K - 1) // 2
+    for i in range(S):
+        for j in range(K):
+            wa, wb = kernel[i, j, 0, 0, 0], kernel[i, j, 0, 0, 1]
+            d = np.arange(max(0, pl - i), min(S, S + pl - i))
+            h = np.arange(max(0, pw - j), min(K, K + pw - j))
+            co = ((d[:, None] * K + h[None, :]) * 2).ravel()
+            ri = (((d[:, None] + i - pl) * K + (h[None, :] + j - pw)) * 2).ravel()
+            Bp[ri, co] = wa
+            Bp[ri, co + 1] = wb
+            Bp[ri + 1, co] = -wb
+            Bp[ri + 1, co + 1] = -wa
+    bp = np.zeros(n, dtype=kernel.dtype)
+    bp[0::2] = bias[0] - bias[1]
+    bp[1::2] = bias[1] - bias[0]
+    return Bp, bp
+
+
+def _unpack_toeplitz(dBp, dbp, S, K):
+    gk = np.zeros((S, K, 1, 1, 2), dtype=dBp.dtype)
+    pl, pw = (S - 1) // 2, (K - 1) // 2
+    for i in range(S):
+        for j in range(K):
+            d = np.arange(max(0, pl - i), min(S, S + pl - i))
+            h = np.arange(max(0, pw - j), min(K, K + pw - j))
+            co = ((d[:, None] * K + h[None, :]) * 2).ravel()
+            ri = (((d[:, None] + i - pl) * K + (h[None, :] + j - pw)) * 2).ravel()
+            gk[i, j, 0, 0, 0] = np.sum(dBp[ri, co] - dBp[ri + 1, co + 1])
+            gk[i, j, 0, 0, 1] = np.sum(dBp[ri, co + 1] - dBp[ri + 1, co])
+    g0 = np.sum(dbp[0::2] - dbp[1::2])
+    return gk, np.array([g0, -g0], dtype=dBp.dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# forward + backward of  ce_mean + REG_COEFF * sum(l2)  w.r.t. the Equalizer variables
+# ---------------------------------------------------------------------------------------------
+def loss_and_grads(x, bits, w, nbits, nfft=64, cp_len=16, use_cp=True, nfilter=64, dtype=np.float64,
+                   normalize=True, reg=True):
+    """x [B,S,T,2] ('tx_ofdm' feed), bits [B,D,nbits] -> (ce_mean, reg_loss, grads, aux).
+
+    grads: TF variable name -> d total_loss / d var for every 'Equalizer/*' variable, in the
+    reference layout.  aux holds intermediate tensors for layer-level checks.
+    """
+    A = lambda n: np.asarray(w[n], dtype=dtype)
+    x = np.asarray(x, dtype=dtype)
+    B, S, T, _ = x.shape
+    K, F = nfft, nfilter
+    z = orc.batch_moment_norm(x, dtype)[0] if normalize else x
+    # ---- equalizer_ofdm forward (dev/py/model.py:349-462), GEMM form -------------------------
+    a0 = orc.layer_norm(z, dtype)
+    a0 = a0.reshape(B * S, T * 2) if use_cp else a0[:, :, cp_len:cp_len + K, :].reshape(B * S, K * 2)
+    W1, b1 = A('Equalizer/dense/kernel'), A('Equalizer/dense/bias')
+    Bp2, bp2 = _pack_1xk(A('Equalizer/conv3d/kernel'), A('Equalizer/conv3d/bias'))
+    W3, b3 = A('Equalizer/dense_1/kernel'), A('Equalizer/dense_1/bias')
+    W4, b4 = A('Equalizer/dense_2/kernel'), A('Equalizer/dense_2/bias')
+    W5, b5 = A('Equalizer/dense_3/kernel'), A('Equalizer/dense_3/bias')
+    W6, b6 = A('Equalizer/dense_4/kernel'), A('Equalizer/dense_4/bias')
+    Bp7, bp7 = _pack_toeplitz(A('Equalizer/conv3d_1/kernel'), A('Equalizer/conv3d_1/bias'), S, K)
+    Bp8, bp8 = _pack_1xk(A('Equalizer/conv3d_2/kernel'), A('Equalizer/conv3d_2/bias'))
+    Bp9, bp9 = _pack_1xk(A('Equalizer/conv3d_3/kernel'), A('Equalizer/conv3d_3/bias'))
+    W10, b10 = A('Equalizer/dense_5/kernel'), A('Equalizer/dense_5/bias')
+
+    t1 = a0 @ W1 + b1                                   # [BS, 2K]              model.py:370
+    f = t1 @ Bp2 + bp2                                  # [BS, 2K] learned DFT  model.py:377-379
+    fl = f.reshape(B, S * K * 2)                        # model.py:391
+    p = fl @ W3 + b3                                    # model.py:393
+    c2 = p @ W4 + b4                                    # model.py:401
+    c3 = c2 @ W5 + b5                                   # model.py:407
+    c4 = np.tanh(c3 @ W6 + b6)                          # model.py:419
+    ch = c4 @ Bp7 + bp7                                 # [B, 2SK] chest        model.py:426
+    cr, ci = ch[:, 0::2], ch[:, 1::2]
+    fr, fi = fl[:, 0::2], fl[:, 1::2]
+    ab = np.sqrt(cr * cr + ci * ci)                     # model.py:431
+    nr, ni = cr / ab, -ci / ab                          # model.py:432-433
+    er, ei = fr * nr - fi * ni, fr * ni + fi * nr       # model.py:434
+    corr = er * er + ei * ei                            # model.py:437 (imag identically 0)
+    eqv = np.stack([er, ei], -1).reshape(B * S, 2 * K)
+    corrv = np.stack([corr, np.zeros_like(corr)], -1).reshape(B * S, 2 * K)
+    eqo = eqv @ Bp9 + bp9                               # model.py:442
+    corro = corrv @ Bp8 + bp8                           # model.py:438
+    cat = np.concatenate([eqo.reshape(B * S, K, 2), corro.reshape(B * S, K, 2)], -1).reshape(B * S, 4 * K)
+    oeq = (cat @ W10 + b10).reshape(B, S, T, 2)         # model.py:457-462
+    # ---- frozen ofdm_dense_rx forward (dev/py/model.py:1222-1292) -----------------------------
+    Tin = T if use_cp else K
+    rin = oeq.reshape(B * S, 2 * T) if use_cp else oeq[:, :, cp_len:, :].reshape(B * S, 2 * K)
+    kf = A('fft_like/conv3d/kernel')[0, (Tin - 1) // 2, 0]            # live tap [Tin, 2F]
+    bfl = A('fft_like/conv3d/bias')
+    BpR, bpR = orc.pack_complex_kernel(kf[:, :F], kf[:, F:], bfl[:F], bfl[F:], dtype=dtype)
+    r1 = (rin @ BpR + bpR).reshape(B, S * F * 2)
+    Wd, bd = A('demodulation/dense/kernel'), A('demodulation/dense/bias')
+    oiq = (r1 @ Wd + bd).reshape(B, -1, 2)                             # [B, D, 2]
+    D = oiq.shape[1]
+    Wc = A('demodulation/conv2d/kernel').reshape(2, -1)
+    bc = A('demodulation/conv2d/bias')
+    W1h, b1h = A('demodulation/dense_1/kernel'), A('demodulation/dense_1/bias')
+    hpre = oiq @ Wc + bc
+    hh = np.maximum(orc.LEAKY_ALPHA * hpre, hpre)
+    hcat = np.concatenate([hh, oiq], -1)
+    lpre = hcat @ W1h + b1h
+    lg = np.maximum(orc.LEAKY_ALPHA * lpre, lpre).reshape(B, D, nbits, 2)
+    m = lg.max(-1, keepdims=True)
+    e = np.exp(lg - m)
+    soft = e / e.sum(-1, keepdims=True)
+    # ---- loss (dev/py/ofdmreceiver_np.py:154-162) -----------------------------------------------
+    y = np.asarray(bits).astype(np.int64)
+    oh = np.stack([1 - y, y], -1).astype(dtype)
+    lse = np.log(np.exp(soft).sum(-1, keepdims=True))
+    N = B * D * nbits
+    ce_mean = float(np.sum(lse[..., 0] - np.sum(soft * oh, -1)) / N)
+    # ---- backward ----------------------------------------------------------------------------
+    dsoft = (np.exp(soft - lse) - oh) / N                             # softmax(p) - onehot
+    dlg = soft * (dsoft - np.sum(dsoft * soft, -1, keepdims=True))    # through the model's softmax
+    dlpre = dlg.reshape(B, D, 2 * nbits) * np.where(lpre > 0, 1.0, orc.LEAKY_ALPHA)
+    dhcat = dlpre @ W1h.T
+    MO = Wc.shape[1]
+    dhpre = dhcat[..., :MO] * np.where(hpre > 0, 1.0, orc.LEAKY_ALPHA)
+    doiq = dhcat[..., MO:] + dhpre @ Wc.T                              # [B, D, 2]
+    dr1 = doiq.reshape(B, 2 * D) @ Wd.T                                # [B, S*F*2]
+    drin = dr1.reshape(B * S, 2 * F) @ BpR.T                           # [BS, 2Tin]
+    if use_cp:
+        doeq = drin
+    else:
+        doeq = np.zeros((B * S, T, 2), dtype=dtype)
+        doeq[:, cp_len:, :] = drin.reshape(B * S, K, 2)
+        doeq = doeq.reshape(B * S, 2 * T)
+    g = {}
+    pre = 'Equalizer/'
+    g[pre + 'dense_5/kernel'] = cat.T @ doeq
+    g[pre + 'dense_5/bias'] = doeq.sum(0)
+    dcat = (doeq @ W10.T).reshape(B * S, K, 4)
+    deqo = np.ascontiguousarray(dcat[:, :, 0:2]).reshape(B * S, 2 * K)
+    dcorro = np.ascontiguousarray(dcat[:, :, 2:4]).reshape(B * S, 2 * K)
+    g[pre + 'conv3d_3/kernel'], g[pre + 'conv3d_3/bias'] = _unpack_1xk(
+        eqv.T @ deqo, deqo.sum(0), w['Equalizer/conv3d_3/kernel'].shape)
+    g[pre + 'conv3d_2/kernel'], g[pre + 'conv3d_2/bias'] = _unpack_1xk(
+        corrv.T @ dcorro, dcorro.sum(0), w['Equalizer/conv3d_2/kernel'].shape)
+    deqv = (deqo @ Bp9.T).reshape(B, S * K, 2)
+    dcorr = (dcorro @ Bp8.T).reshape(B, S * K, 2)[:, :, 0]
+    der = deqv[:, :, 0] + 2 * er * dcorr
+    dei = deqv[:, :, 1] + 2 * ei * dcorr
+    dfr = der * nr + dei * ni
+    dfi = -der * ni + dei * nr
+    dnr = der * fr + dei * fi
+    dni = -der * fi + dei * fr
+    com = (dnr * ci + dni * cr) / (ab ** 3)
+    dcr, dci = ci * com, -cr * com
+    dch = np.stack([dcr, dci], -1).reshape(B, 2 * S * K)
+    g[pre + 'conv3d_1/kernel'], g[pre + 'conv3d_1/bias'] = _unpack_toeplitz(c4.T @ dch, dch.sum(0), S, K)
+    dpre4 = (dch @ Bp7.T) * (1 - c4 * c4)
+    g[pre + 'dense_4/kernel'] = c3.T @ dpre4
+    g[pre + 'dense_4/bias'] = dpre4.sum(0)
+    dc3 = dpre4 @ W6.T
+    g[pre + 'dense_3/kernel'] = c2.T @ dc3
+    g[pre + 'dense_3/bias'] = dc3.sum(0)
+    dc2 = dc3 @ W5.T
+    g[pre + 'dense_2/kernel'] = p.T @ dc2
+    g[pre + 'dense_2/bias'] = dc2.sum(0)
+    dp = dc2 @ W4.T
+    g[pre + 'dense_1/kernel'] = fl.T @ dp
+    g[pre + 'dense_1/bias'] = dp.sum(0)
+    dfl = dp @ W3.T + np.stack([dfr, dfi], -1).reshape(B, 2 * S * K)
+    df = dfl.reshape(B * S, 2 * K)
+    g[pre + 'conv3d/kernel'], g[pre + 'conv3d/bias'] = _unpack_1xk(
+        t1.T @ df, df.sum(0), w['Equalizer/conv3d/kernel'].shape)
+    dt1 = df @ Bp2.T
+    g[pre + 'dense/kernel'] = a0.T @ dt1
+    g[pre + 'dense/bias'] = dt1.sum(0)
+    # ---- regularisation: REG_COEFF * l * sum(w^2) over dense kernels + biases ---------------------
+    reg_loss = 0.0
+    for n in DENSE_NAMES:
+        for s in ('/kernel', '/bias'):
+            wv = A(pre + n + s)
+            reg_loss += L2_L * float(np.sum(wv * wv))
+            if reg:
+                g[pre + n + s] = g[pre + n + s] + (2.0 * REG_COEFF * L2_L) * wv
+    g = {k: np.asarray(v, dtype=dtype).reshape(np.shape(w[k])) for k, v in g.items()}
+    aux = dict(soft=soft, oeq=oeq, doeq=doeq.reshape(B, S, T, 2), doiq=doiq, dch=dch, dfl=dfl, chest=ch, dt1=dt1)
+    return ce_mean, reg_loss, g, aux
+
+
+class Adam:
+    """tf.train.AdamOptimizer (TF 1.15 formulation, epsilon outside the square root)."""
+
+    def __init__(self, names, weights, dtype=np.float64):
+        self.m = {n: np.zeros(np.shape(weights[n]), dtype=dtype) for n in names}
+        self.v = {n: np.zeros(np.shape(weights[n]), dtype=dtype) for n in names}
+        self.t = 0
+        self.dtype = dtype
+
+    def step(self, weights, grads, lr):
+        """Updates ``weights`` (dict name -> array) in place for the names this optimiser tracks."""
+        self.t += 1
+        lr_t = lr * np.sqrt(1.0 - ADAM_B2 ** self.t) / (1.0 - ADAM_B1 ** self.t)
+        for n in self.m:
+            gr = np.asarray(grads[n], dtype=self.dtype)
+            self.m[n] = ADAM_B1 * self.m[n] + (1 - ADAM_B1) * gr
+            self.v[n] = ADAM_B2 * self.v[n] + (1 - ADAM_B2) * gr * gr
+            upd = lr_t * self.m[n] / (np.sqrt(self.v[n]) + ADAM_EPS)
+            weights[n] = (np.asarray(weights[n], dtype=self.dtype) - upd).astype(np.asarray(weights[n]).dtype)
+
+
+def train_steps(xs, bits, w, nbits, init_learning=1e-3, global_step0=0, **kw):
+    """Run len(xs) reference training steps (one minibatch each); returns (weights, [ce_mean...])."""
+    w = {k: np.array(v, copy=True) for k, v in w.items()}
+    names = trainable_names()
+    opt = Adam(names, w)
+    losses = []
+    for i, (x, b) in enumerate(zip(xs, bits)):
+        ce, _, g, _ = loss_and_grads(x, b, w, nbits, **kw)
+        opt.step(w, g, learning_rate(init_learning, global_step0 + i))
+        losses.append(ce)
+    return w, losses

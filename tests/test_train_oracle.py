@@ -1,0 +1,76 @@
+"""Pins the hand-derived backward pass of oracle/dccn_train_oracle.py (BASELINE config 4) against
+torch autograd through the independent op-for-op mirror of the TF graph (oracle/tf_mirror.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dccn_oracle as orc
+from oracle import dccn_train_oracle as tro
+from oracle.tf_mirror import TFMirror
+
+
+def _case(seed, B, nbits, use_cp=True):
+    rng = np.random.default_rng(seed)
+    w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nbits)).astype(np.uint8)
+    return w, x, bits
+
+
+def _autograd(w, x, bits, nbits, use_cp=True):
+    m = TFMirror(w, nbits, use_cp=use_cp, equalizer=True)
+    m.w = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=k.startswith('Equalizer/'))
+           for k, v in w.items()}
+    z = m.norm(torch.tensor(x, dtype=torch.float64))
+    soft = m.dense_rx(m.equalizer(z)).reshape(-1, 2)
+    y = torch.tensor(bits.reshape(-1).astype(np.int64))
+    ce = torch.nn.functional.cross_entropy(soft, y)          # softmax-xent ON the softmax outputs, mean
+    reg = sum(tro.L2_L * (m.w['Equalizer/' + n + s] ** 2).sum() for n in tro.DENSE_NAMES for s in ('/kernel', '/bias'))
+    total = ce + tro.REG_COEFF * reg
+    total.backward()
+    return float(ce.detach()), float(reg.detach()), {k: v.grad.numpy() for k, v in m.w.items() if v.requires_grad}
+
+
+@pytest.mark.parametrize('nbits,use_cp', [(2, True), (4, True), (1, False)])
+def test_backward_matches_autograd(nbits, use_cp):
+    w, x, bits = _case(3 + nbits, 24, nbits, use_cp)
+    ce, reg, g, _ = tro.loss_and_grads(x, bits, w, nbits, use_cp=use_cp)
+    ce_t, reg_t, g_t = _autograd(w, x, bits, nbits, use_cp)
+    assert abs(ce - ce_t) < 1e-12
+    assert abs(reg - reg_t) < 1e-9 * max(1.0, reg_t)
+    assert set(g) == set(g_t) == set(tro.trainable_names())
+    for k in g:
+        ref = g_t[k]
+        err = np.abs(g[k] - ref).max()
+        assert err <= 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-15, (k, err, np.abs(ref).max())
+
+
+def test_forward_matches_restatement():
+    w, x, bits = _case(11, 16, 2)
+    _, _, _, aux = tro.loss_and_grads(x, bits, w, 2)
+    soft, eq, _ = orc.equalized_receiver(x, w, 2, 64, 16)
+    assert np.abs(aux['soft'] - soft).max() < 1e-12
+    assert np.abs(aux['oeq'] - eq).max() < 1e-10
+
+
+def test_adam_and_schedule():
+    # closed form of the first TF Adam step: w -= lr * g / (|g| + eps*sqrt(1-b2)) (to first order: lr*sign(g))
+    wts = {'a': np.array([1.0, -2.0, 3.0])}
+    opt = tro.Adam(['a'], wts)
+    g = {'a': np.array([0.5, -1e-3, 0.0])}
+    opt.step(wts, g, 1e-3)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    exp = np.array([1.0, -2.0, 3.0]) - lr_t * (0.1 * g['a']) / (np.sqrt(0.001 * g['a'] ** 2) + 1e-8)
+    assert np.allclose(wts['a'], exp, rtol=0, atol=1e-15)
+    assert wts['a'][2] == 3.0
+    assert tro.learning_rate(1e-3, 499) == 1e-3
+    assert abs(tro.learning_rate(1e-3, 500) - 0.98e-3) < 1e-18
+    assert abs(tro.learning_rate(1e-3, 1700) - 1e-3 * 0.98 ** 3) < 1e-18
+
+
+def test_training_reduces_loss():
+    w, x, bits = _case(5, 32, 2)
+    w2, losses = tro.train_steps([x] * 6, [bits] * 6, w, 2)
+    assert losses[-1] < losses[0]
+    assert any(np.abs(w2[k] - w[k]).max() > 0 for k in tro.trainable_names())
+    assert np.array_equal(w2['demodulation/dense/kernel'], w['demodulation/dense/kernel'])   # receiver frozen

@@ -24,6 +24,11 @@ class dccn_cfg(C.Structure):
         'head', 'equalizer', 'precision', 'chunk_frames')]
 
 
+class dccn_train_cfg(C.Structure):
+    _fields_ = [('reg_coeff', C.c_float), ('l2', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float),
+                ('eps', C.c_float), ('max_batch', C.c_int64)]
+
+
 class DccnError(RuntimeError):
     pass
 
@@ -56,6 +61,11 @@ PROTOTYPES = {
     'dccn_bit_source': (C.c_int, [_vp, _i64, _u64, _vp]),
     'dccn_debug_tma_rate': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'dccn_debug_mma_rate': (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'dccn_train_init': (C.c_int, [_vp, C.POINTER(dccn_train_cfg), _vp]),
+    'dccn_train_step': (C.c_int, [_vp, _vp, _i64, _vp, C.c_float, _i32, _vp, _vp, _i32, _vp]),
+    'dccn_train_get_grad': (_i64, [_vp, C.c_char_p, _vp, _i64]),
+    'dccn_train_global_step': (_i64, [_vp]),
+    'dccn_train_set_global_step': (C.c_int, [_vp, _i64]),
     'dccn_launch_count': (_i64, []),
     'dccn_profile_enable': (C.c_int, [_vp, _i32]),
     'dccn_profile_collect': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),

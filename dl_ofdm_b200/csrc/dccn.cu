@@ -8,18 +8,11 @@
 // Every complex layer is `layers_conv2d_complex` (dev/py/complex.py:140-196) and is packed
 // into ONE real GEMM on IQ-interleaved activations with the reference's own sign
 // convention ([[a, b], [-b, -a]] per complex weight, bias (ba-bb, bb-ba)).
-#include "../../include/dccn.h"
-
-#include <atomic>
 #include <cstdarg>
 #include <cstring>
-#include <map>
-#include <string>
 #include <type_traits>
-#include <vector>
 
-#include "common.cuh"
-#include "epilogue.cuh"
+#include "handle.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -58,7 +51,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // fp32 matrix [rows, cols] with row pitch ld (elements); box = [box_rows x 32 cols], 128B swizzle
-static int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   DCCN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
   DCCN_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0,
@@ -75,131 +68,27 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t co
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------
-// device buffers
-// ---------------------------------------------------------------------------------------
-struct Act {          // activation matrix, 1 or 2 planes
-  float* p0 = nullptr;
-  float* p1 = nullptr;
-  int ld = 0;
-};
-
-struct GemmLayer {
-  int K = 0, N = 0;
-  int BN = 128;                 // tcgen05 tile width
-  std::vector<float> W;         // host [K, N]
-  std::vector<float> bias;      // host [N]
-  float* dW = nullptr;          // [K, N] fp32 (SIMT path)
-  float* dWt0 = nullptr;        // [N, K] tf32-hi (or full fp32 for FAST)  -- B operand, K-major
-  float* dWt1 = nullptr;        // [N, K] tf32-lo (PARITY only)
-  float* dBias = nullptr;
-  CUtensorMap tmB0, tmB1;
-  bool built = false;
-  bool fused = false;           // consumed by a fused (phase-eq / demod-head) epilogue
-  bool mc = false;              // run as cta_group::2 CTA pairs (each CTA holds half of the weight tile)
-};
-
-struct HostTensor {
-  std::vector<int64_t> shape;
-  std::vector<float> data;
-};
+std::atomic<long long> g_launches{0};
+const char* kSlotNames[SLOT_COUNT] = {
+    "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
+    "eq_conv7x64_phaseeq", "eq_corr_idft", "eq_idft", "eq_dense5", "rx_fft_like", "rx_demod_head",
+    "chan_fir", "chan_awgn", "rx_demod_gemm", "train_head_bwd", "train_dgrad", "train_wgrad", "train_pointwise",
+    "train_reduce_adam", "train_repack"};
 
 }  // namespace dccn
 
 using namespace dccn;
 
 namespace dccn {
-static std::atomic<long long> g_launches{0};   // kernels launched by this library (dccn_launch_count)
-enum { SLOT_MOMENTS = 0, SLOT_PREP, SLOT_G1, SLOT_G2, SLOT_G3, SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G7_PHASEEQ,
-       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_COUNT };
-static const char* kSlotNames[SLOT_COUNT] = {
-    "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
-    "eq_conv7x64_phaseeq", "eq_corr_idft", "eq_idft", "eq_dense5", "rx_fft_like", "rx_demod_head",
-    "chan_fir", "chan_awgn", "rx_demod_gemm"};
-struct ProfRec { int slot; cudaEvent_t a, b; };
-}  // namespace dccn
 
-struct dccn_handle {
-  dccn_cfg cfg;
-  bool prof = false;
-  std::vector<dccn::ProfRec> prof_recs;
-  int device = 0;
-  int num_sms = 148;
-  std::map<std::string, HostTensor> raw;
-  bool committed = false;
-  // geometry
-  int S, K, T, Tin, F, D, NB, P;      // T = samples/symbol incl. CP, Tin = samples the receiver consumes
-  int chunk;
-  int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
-  int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
-  int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
-  int multicast = 0;   // cta_group::2 CTA pairs (DCCN_PAIR=1 enables; measured slower than single-CTA tiles)
-  int mc_min_k = 128;
-  int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
-  // layers
-  GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
-  GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
-  HeadWeights hw;
-  // workspace
-  std::vector<void*> allocs;
-  double* d_sums = nullptr;       // [2P] moments accumulators
-  float* d_mean = nullptr;
-  float* d_rstd = nullptr;
-  double* d_power = nullptr;      // channel power accumulator
-  unsigned long long* d_conf = nullptr;   // internal [4]
-  double* d_ce = nullptr;
-  Act a0, t1, f, p32, u1, u2, eq, corr, cat, oeq, r1o, out_iq;
-  // staging for the host-buffer entry points: two slots so that the H2D copy of one batch
-  // overlaps the pass over the previous one (copy stream + the caller's compute stream)
-  struct HostSlot {
-    float* d_x = nullptr;
-    uint8_t* d_bits = nullptr;
-    uint8_t* d_hard = nullptr;
-    int64_t frames = 0;            // capacity
-    int64_t B = 0;                 // batch in flight
-    int64_t* d_conf = nullptr;     // device results
-    double* d_ce = nullptr;
-    int64_t* h_conf = nullptr;     // pinned host results
-    double* h_ce = nullptr;
-    uint8_t* hard_host = nullptr;  // caller's destination for hard bits (may be null)
-    cudaEvent_t copied = nullptr, done = nullptr;
-    bool busy = false;
-  } slot[2];
-  cudaStream_t copy_stream = nullptr;
-  size_t ws_bytes = 0;
-};
-
-namespace dccn {
-
-static int dev_alloc(dccn_handle* h, void** p, size_t bytes) {
+int dev_alloc(dccn_handle* h, void** p, size_t bytes) {
   DCCN_CUDA_OK(cudaMalloc(p, bytes));
   h->allocs.push_back(*p);
   h->ws_bytes += bytes;
   return 0;
 }
 
-// counts launches and (when profiling is on) brackets them with CUDA events on the launch stream
-struct LaunchScope {
-  dccn_handle* h;
-  cudaStream_t s;
-  cudaEvent_t b = nullptr;
-  int slot;
-  LaunchScope(dccn_handle* h_, int slot_, cudaStream_t s_, int n_kernels = 1) : h(h_), s(s_), slot(slot_) {
-    g_launches += n_kernels;
-    if (h && h->prof && h->prof_recs.size() < 65536) {
-      cudaEvent_t a;
-      cudaEventCreate(&a);
-      cudaEventCreate(&b);
-      cudaEventRecord(a, s);
-      h->prof_recs.push_back(ProfRec{slot, a, b});
-    }
-  }
-  ~LaunchScope() {
-    if (b) cudaEventRecord(b, s);
-  }
-};
-
-static int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split) {
+int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split) {
   a->ld = ld;
   int rc = dev_alloc(h, (void**)&a->p0, (size_t)rows * ld * sizeof(float));
   if (rc) return rc;
@@ -207,7 +96,7 @@ static int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split) {
   return rc;
 }
 
-static const HostTensor* find(const dccn_handle* h, const std::string& n) {
+const HostTensor* find(const dccn_handle* h, const std::string& n) {
   auto it = h->raw.find(n);
   return it == h->raw.end() ? nullptr : &it->second;
 }
@@ -251,7 +140,7 @@ static int pick_bn(int N, bool fused_epilogue, int wide) {
   return 128;
 }
 
-static int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
+int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   const int K = L->K, N = L->N;
   L->BN = pick_bn(N, L->fused, h->bn_wide);
   const int prec = h->cfg.precision;
@@ -308,7 +197,7 @@ static int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   const HostTensor* var = find(h, name);                          \
   DCCN_CHECK(var != nullptr, "weight '%s' was not set", name)
 
-static int build_layers(dccn_handle* h, cudaStream_t s) {
+int pack_layers_host(dccn_handle* h) {
   const dccn_cfg& c = h->cfg;
   const int S = h->S, K = h->K, F = h->F, Tin = h->Tin, NB = h->NB, D = h->D;
   const int MO = 1 << NB;
@@ -357,8 +246,6 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
   }
   h->r2.fused = h->fused_head != 0;
   h->g7.fused = true;
-  if ((rc = upload_layer(h, &h->r1, s))) return rc;
-  if ((rc = upload_layer(h, &h->r2, s))) return rc;
   if (!c.equalizer) return 0;
 
   // ---- equalizer_ofdm -----------------------------------------------------------
@@ -465,6 +352,15 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
       }
     L->bias = b->data;
   }
+  return 0;
+}
+
+static int build_layers(dccn_handle* h, cudaStream_t s) {
+  int rc = pack_layers_host(h);
+  if (rc) return rc;
+  if ((rc = upload_layer(h, &h->r1, s))) return rc;
+  if ((rc = upload_layer(h, &h->r2, s))) return rc;
+  if (!h->cfg.equalizer) return 0;
   GemmLayer* ls[] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
   for (GemmLayer* L : ls)
     if ((rc = upload_layer(h, L, s))) return rc;
@@ -514,19 +410,9 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
 #undef DCCN_TC_SS
 }
 
-static ActOut out_of(const Act& a, int col_off = 0) { return ActOut{a.p0, a.p1, a.ld, col_off}; }
-
-static EpiStore store_epi(const GemmLayer& L, const Act& dst, int col_off, int64_t M, int act = 0, float* aux = nullptr,
-                          int aux_ld = 0) {
-  EpiStore e;
-  e.bias = L.dBias;
-  e.out = out_of(dst, col_off);
-  e.aux = aux;
-  e.aux_ld = aux_ld;
-  e.act = act;
-  e.M = (int)M;
-  e.N = L.N;
-  return e;
+int run_gemm_store(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
+                   const EpiStore& epi, cudaStream_t s) {
+  return run_gemm<EpiStore>(h, slot, L, A, a_col_off, M, epi, s);
 }
 
 template <int NB, bool V1>
@@ -568,7 +454,7 @@ static int run_head_dispatch(dccn_handle* h, int64_t Bc, const uint8_t* bits, fl
   }
 }
 
-static int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, float* rstd, cudaStream_t s) {
+int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, float* rstd, cudaStream_t s) {
   const int P = h->P;
   DCCN_CUDA_OK(cudaMemsetAsync(h->d_sums, 0, (size_t)2 * P * sizeof(double), s));
   const int gx = (P / 4 + 127) / 128;
@@ -584,7 +470,7 @@ static int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, f
 }
 
 // one chunk of Bc frames through [equalizer ->] receiver
-static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
+int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
                      float* eq_out, float* chest_out, unsigned long long* conf, double* ce, int flags,
                      cudaStream_t s) {
   const bool use_eq = h->cfg.equalizer && !(flags & DCCN_FWD_SKIP_EQ);
@@ -620,7 +506,10 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
     if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
     if ((rc = run_gemm(h, SLOT_G4, h->g4, h->p32, 0, Bc, store_epi(h->g4, h->u1, 0, Bc), s))) return rc;
     if ((rc = run_gemm(h, SLOT_G5, h->g5, h->u1, 0, Bc, store_epi(h->g5, h->u2, 0, Bc), s))) return rc;
-    if ((rc = run_gemm(h, SLOT_G6, h->g6, h->u2, 0, Bc, store_epi(h->g6, h->u1, 0, Bc, /*tanh*/ 1), s))) return rc;
+    // (a training forward keeps dense_2's output in u1 and writes the tanh output to u3)
+    const Act& c4 = h->train_fwd ? h->u3 : h->u1;
+    if (h->train_fwd && !chest_out) chest_out = h->chest_buf;
+    if ((rc = run_gemm(h, SLOT_G6, h->g6, h->u2, 0, Bc, store_epi(h->g6, c4, 0, Bc, /*tanh*/ 1), s))) return rc;
     // (S,K) 'same' complex conv as Toeplitz GEMM + fused phase equaliser   model.py:426-437
     {
       EpiPhaseEq e;
@@ -633,7 +522,7 @@ static int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* 
       e.chest_out = chest_out;
       e.M = (int)Bc;
       e.N = h->g7.N;
-      if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, h->u1, 0, Bc, e, s))) return rc;
+      if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, c4, 0, Bc, e, s))) return rc;
     }
     // corr / eq (1,K) 'valid' complex convs -> [eq_out | corr_out]  model.py:437-448
     if ((rc = run_gemm(h, SLOT_G8, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
@@ -763,6 +652,11 @@ __global__ void conf_copy_kernel(const unsigned long long* src, long long* dst) 
   if (threadIdx.x < 4) dst[threadIdx.x] += (long long)src[threadIdx.x];
 }
 
+void conf_accumulate(const unsigned long long* src, int64_t* dst, cudaStream_t s) {
+  g_launches += 1;
+  conf_copy_kernel<<<1, 32, 0, s>>>(src, (long long*)dst);
+}
+
 }  // namespace dccn
 
 // =========================================================================================
@@ -863,6 +757,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
 void dccn_destroy(dccn_handle* h) {
   if (!h) return;
   cudaDeviceSynchronize();
+  train_free(h);
   for (int i = 0; i < 2; ++i) {
     if (h->slot[i].h_conf) cudaFreeHost(h->slot[i].h_conf);
     if (h->slot[i].h_ce) cudaFreeHost(h->slot[i].h_ce);
@@ -892,8 +787,10 @@ int dccn_set_weight(dccn_handle* h, const char* tf_name, const float* host, cons
 
 int64_t dccn_get_weight(dccn_handle* h, const char* tf_name, float* host, int64_t capacity) {
   if (!h || !tf_name) return set_error(-2, "bad argument");
-  const HostTensor* t = find(h, tf_name);
-  if (!t) return set_error(-2, "weight '%s' was not set", tf_name);
+  auto it = h->raw.find(tf_name);
+  if (it == h->raw.end()) return set_error(-2, "weight '%s' was not set", tf_name);
+  if (h->tr && train_fetch_weight(h, tf_name, &it->second) < 0) return -1;   // trained value lives on the device
+  const HostTensor* t = &it->second;
   const int64_t n = (int64_t)t->data.size();
   if (host) {
     if (capacity < n) return set_error(-2, "buffer too small for '%s'", tf_name);
@@ -907,6 +804,7 @@ int dccn_commit_weights(dccn_handle* h, void* stream) {
   int rc = build_layers(h, (cudaStream_t)stream);
   if (rc) return rc;
   h->committed = true;
+  if (h->tr) return train_on_commit(h, (cudaStream_t)stream);   // re-seed the device master copies
   return 0;
 }
 

@@ -1,0 +1,165 @@
+// handle.cuh -- the library handle and the helpers shared by the translation units of libdccn.so
+// (dccn.cu: inference path + C ABI; train.cu: the equalizer transfer-learning step).
+#pragma once
+#include "../../include/dccn.h"
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace dccn {
+
+// ---------------------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------------------
+struct Act {          // activation matrix, 1 or 2 planes
+  float* p0 = nullptr;
+  float* p1 = nullptr;
+  int ld = 0;
+};
+
+struct GemmLayer {
+  int K = 0, N = 0;
+  int BN = 128;                 // tcgen05 tile width
+  std::vector<float> W;         // host [K, N]
+  std::vector<float> bias;      // host [N]
+  float* dW = nullptr;          // [K, N] fp32 (SIMT path)
+  float* dWt0 = nullptr;        // [N, K] tf32-hi (or full fp32 for FAST)  -- B operand, K-major
+  float* dWt1 = nullptr;        // [N, K] tf32-lo (PARITY only)
+  float* dBias = nullptr;
+  CUtensorMap tmB0, tmB1;
+  bool built = false;
+  bool fused = false;           // consumed by a fused (phase-eq / demod-head) epilogue
+  bool mc = false;              // run as cta_group::2 CTA pairs (each CTA holds half of the weight tile)
+};
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+extern std::atomic<long long> g_launches;   // kernels launched by this library (dccn_launch_count)
+enum { SLOT_MOMENTS = 0, SLOT_PREP, SLOT_G1, SLOT_G2, SLOT_G3, SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G7_PHASEEQ,
+       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_T_HEAD, SLOT_T_DGRAD, SLOT_T_WGRAD, SLOT_T_POINT, SLOT_T_ADAM, SLOT_T_REPACK, SLOT_COUNT };
+extern const char* kSlotNames[SLOT_COUNT];
+struct ProfRec { int slot; cudaEvent_t a, b; };
+struct TrainState;
+}  // namespace dccn
+
+struct dccn_handle {
+  dccn_cfg cfg;
+  bool prof = false;
+  std::vector<dccn::ProfRec> prof_recs;
+  int device = 0;
+  int num_sms = 148;
+  std::map<std::string, dccn::HostTensor> raw;
+  bool committed = false;
+  // geometry
+  int S, K, T, Tin, F, D, NB, P;      // T = samples/symbol incl. CP, Tin = samples the receiver consumes
+  int chunk;
+  int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
+  int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
+  int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
+  int multicast = 0;   // cta_group::2 CTA pairs (DCCN_PAIR=1 enables; measured slower than single-CTA tiles)
+  int mc_min_k = 128;
+  int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
+  // layers
+  dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
+  dccn::GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
+  dccn::HeadWeights hw;
+  // workspace
+  std::vector<void*> allocs;
+  double* d_sums = nullptr;       // [2P] moments accumulators
+  float* d_mean = nullptr;
+  float* d_rstd = nullptr;
+  double* d_power = nullptr;      // channel power accumulator
+  unsigned long long* d_conf = nullptr;   // internal [4]
+  double* d_ce = nullptr;
+  dccn::Act a0, t1, f, p32, u1, u2, eq, corr, cat, oeq, r1o, out_iq;
+  // training (train.cu): state, and the two extra forward buffers a backward pass needs
+  dccn::TrainState* tr = nullptr;
+  bool train_fwd = false;         // forward pass keeps every activation (tanh output -> u3, chest -> chest_buf)
+  dccn::Act u3;
+  float* chest_buf = nullptr;
+  // staging for the host-buffer entry points: two slots so that the H2D copy of one batch
+  // overlaps the pass over the previous one (copy stream + the caller's compute stream)
+  struct HostSlot {
+    float* d_x = nullptr;
+    uint8_t* d_bits = nullptr;
+    uint8_t* d_hard = nullptr;
+    int64_t frames = 0;            // capacity
+    int64_t B = 0;                 // batch in flight
+    int64_t* d_conf = nullptr;     // device results
+    double* d_ce = nullptr;
+    int64_t* h_conf = nullptr;     // pinned host results
+    double* h_ce = nullptr;
+    uint8_t* hard_host = nullptr;  // caller's destination for hard bits (may be null)
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool busy = false;
+  } slot[2];
+  cudaStream_t copy_stream = nullptr;
+  size_t ws_bytes = 0;
+};
+
+namespace dccn {
+
+// counts launches and (when profiling is on) brackets them with CUDA events on the launch stream
+struct LaunchScope {
+  dccn_handle* h;
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  int slot;
+  LaunchScope(dccn_handle* h_, int slot_, cudaStream_t s_, int n_kernels = 1) : h(h_), s(s_), slot(slot_) {
+    g_launches += n_kernels;
+    if (h && h->prof && h->prof_recs.size() < 65536) {
+      cudaEvent_t a;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+      h->prof_recs.push_back(ProfRec{slot, a, b});
+    }
+  }
+  ~LaunchScope() {
+    if (b) cudaEventRecord(b, s);
+  }
+};
+
+
+// ---- shared between dccn.cu and train.cu ------------------------------------------------------
+int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int dev_alloc(dccn_handle* h, void** p, size_t bytes);
+int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split);
+const HostTensor* find(const dccn_handle* h, const std::string& n);
+int pack_layers_host(dccn_handle* h);                            // h->raw -> GemmLayer::W / bias (host only)
+int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s);  // GemmLayer::W -> device operands (+ TMA maps)
+int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, float* rstd, cudaStream_t s);
+int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
+              float* eq_out, float* chest_out, unsigned long long* conf, double* ce, int flags, cudaStream_t s);
+int run_gemm_store(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
+                   const EpiStore& epi, cudaStream_t s);
+void conf_accumulate(const unsigned long long* src, int64_t* dst, cudaStream_t s);
+// train.cu hooks used by the C ABI in dccn.cu
+void train_free(dccn_handle* h);
+int train_on_commit(dccn_handle* h, cudaStream_t s);
+int train_fetch_weight(dccn_handle* h, const char* tf_name, HostTensor* t);
+
+inline ActOut out_of(const Act& a, int col_off = 0) { return ActOut{a.p0, a.p1, a.ld, col_off}; }
+
+inline EpiStore store_epi(const GemmLayer& L, const Act& dst, int col_off, int64_t M, int act = 0, float* aux = nullptr,
+                          int aux_ld = 0) {
+  EpiStore e;
+  e.bias = L.dBias;
+  e.out = out_of(dst, col_off);
+  e.aux = aux;
+  e.aux_ld = aux_ld;
+  e.act = act;
+  e.M = (int)M;
+  e.N = L.N;
+  return e;
+}
+
+}  // namespace dccn

@@ -1,0 +1,740 @@
+// train.cu -- BASELINE config 4: one transfer-learning step of equalizer_ofdm in front of the frozen
+// ofdm_dense_rx, on the GPU.
+//
+// Reference (zhongyuanzhao/dl_ofdm @ 5665b50):
+//   total_loss = ce_mean + 0.001 * sum(REGULARIZATION_LOSSES)        dev/py/ofdmreceiver_np_mp.py:335-341
+//   ce_mean    = mean softmax-xent applied ON the softmax outputs      dev/py/ofdmreceiver_np.py:154-162
+//   regulariser tf.keras.regularizers.l2(0.01) on kernel+bias of the six tf.layers.dense of
+//   equalizer_ofdm (dev/py/model.py:370-461); conv3d layers have none
+//   AdamOptimizer(exponential_decay(lr0, step, 500, 0.98, staircase)).minimize(total_loss,
+//   var_list = Equalizer/*)                                           dev/py/ofdmreceiver_np_mp.py:343-347
+// TF's autodiff is replaced by a hand-derived backward pass (restated and pinned in
+// oracle/dccn_train_oracle.py):
+//   * data gradients (dgrad) reuse the forward GEMM engines (tcgen05 3xTF32 in parity mode, fp32 FFMA in
+//     exact mode) on transposed weight operands that are re-derived on the device after every update;
+//   * weight gradients (wgrad) are  X^T * dY  contractions over the batch: a split-K fp32 FFMA kernel
+//     with deterministic partial sums; an extra all-ones row of X^T yields the bias gradient for free;
+//   * every layer's packed GEMM operand is a signed gather of the reference-layout variable (dead taps,
+//     [[a,b],[-b,-a]] tiling, Toeplitz expansion, row permutation): the gradient of the variable is the
+//     adjoint signed scatter-sum, done with one CSR kernel for all layer kinds;
+//   * pointwise backward kernels: demodulation head + loss, phase-only equaliser, tanh.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "handle.cuh"
+
+namespace dccn {
+
+struct TrainParam {
+  std::string name;
+  int64_t n = 0;
+  float *w = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;
+  float l2g = 0.f;   // d(REG_COEFF * l * sum w^2)/dw = l2g * w
+};
+
+struct TrainLayer {
+  GemmLayer* L = nullptr;   // forward layer (lives in the handle)
+  GemmLayer bw;             // dgrad companion: C[M, K] = dY[M, N] * W^T
+  int kp = -1, bp = -1;     // indices of kernel / bias in TrainState::params
+  int bias_kind = 0;        // 0 dense, 1 complex (ba-bb, bb-ba), 2 one complex filter broadcast (Toeplitz layer)
+  float* Wp = nullptr;      // [K, N] packed fp32 operand (exact mode: the forward operand itself)
+  int32_t* map = nullptr;   // [K*N]  +-(param index + 1), 0 = structural zero
+  int32_t* csr_off = nullptr;
+  int32_t* csr_idx = nullptr;   // +-(operand index + 1) grouped by parameter
+  int max_list = 1;
+  float* dWp = nullptr;     // [(K+1), N]: gradient of the packed operand; last row = packed bias gradient
+};
+
+struct TrainState {
+  dccn_train_cfg cfg;
+  int64_t maxB = 0;
+  int64_t step = 0;
+  std::vector<TrainParam> params;
+  TrainLayer tl[10];
+  GemmLayer bw_r1, bw_r2;
+  Act d_oiq, d_r1o, d_oeq, d_cat, d_eq, d_corr, d_f, d_f2, d_ch, dA, dB, dC, d_p32, d_t1;
+  float* partial = nullptr;
+  size_t partial_floats = 0;
+};
+
+static const char* kLayerVar[10] = {"Equalizer/dense",    "Equalizer/conv3d",   "Equalizer/dense_1", "Equalizer/dense_2",
+                                    "Equalizer/dense_3",  "Equalizer/dense_4",  "Equalizer/conv3d_1", "Equalizer/conv3d_2",
+                                    "Equalizer/conv3d_3", "Equalizer/dense_5"};
+static const int kBiasKind[10] = {0, 1, 0, 0, 0, 0, 2, 1, 1, 0};
+static const int kPerSymbol[10] = {1, 1, 0, 0, 0, 0, 0, 1, 1, 1};   // layer contracts over B*S rows (else B)
+
+// =========================================================================================
+// kernels
+// =========================================================================================
+
+// ---- wgrad: P[z][i][j] = sum_{m in split z} Xaug[m][i] * Y[m][j],  Xaug = [X | 1]  (i <= Kin) -----
+__global__ void __launch_bounds__(256)
+wgrad_simt_kernel(const float* __restrict__ X, int ldx, int Kin, const float* __restrict__ Y, int ldy, int Nout,
+                  long long M, int rps, float* __restrict__ P) {
+  constexpr int BK = 16;
+  __shared__ __align__(16) float As[BK][64];
+  __shared__ __align__(16) float Bs[BK][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const long long m_begin = (long long)blockIdx.z * rps;
+  const long long m_end = (m_begin + rps < M) ? m_begin + rps : M;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;
+  const int gi = i0 + lc, gj = j0 + lc;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long m0 = m_begin; m0 < m_end; m0 += BK) {
+    const long long m = m0 + lr;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (m < m_end) {
+      if (gi + 3 < Kin) a = __ldg(reinterpret_cast<const float4*>(X + (size_t)m * ldx + gi));
+      else if (gi == Kin) a.x = 1.f;                               // the all-ones row -> column sums of dY
+      if (gj + 3 < Nout) b = __ldg(reinterpret_cast<const float4*>(Y + (size_t)m * ldy + gj));
+    }
+    *reinterpret_cast<float4*>(&As[lr][lc]) = a;
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = b;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(aa[i], bv.x, acc[i][0]);
+        acc[i][1] = fmaf(aa[i], bv.y, acc[i][1]);
+        acc[i][2] = fmaf(aa[i], bv.z, acc[i][2]);
+        acc[i][3] = fmaf(aa[i], bv.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  float* Pz = P + (size_t)blockIdx.z * (size_t)(Kin + 1) * Nout;
+  const int oj = j0 + tx * 4;
+  if (oj < Nout) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int oi = i0 + ty * 4 + i;
+      if (oi <= Kin)
+        *reinterpret_cast<float4*>(Pz + (size_t)oi * Nout + oj) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+  }
+}
+
+// deterministic sum of the split-K partials
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ P, int splits, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += P[(size_t)z * n + i];
+  out[i] = s;
+}
+
+// ---- packed operand <-> reference-layout variable ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_map_kernel(const float* __restrict__ w, const int32_t* __restrict__ map, long long n, float* __restrict__ Wp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int m = map[i];
+  Wp[i] = m == 0 ? 0.f : (m > 0 ? w[m - 1] : -w[-m - 1]);
+}
+
+// gradient of the variable = signed sum of the operand gradient over every place the variable was gathered to
+__global__ void __launch_bounds__(256)
+grad_map_thread_kernel(const float* __restrict__ dWp, const int32_t* __restrict__ off, const int32_t* __restrict__ idx,
+                       int n_param, float* __restrict__ g) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_param) return;
+  float s = 0.f;
+  for (int e = off[p]; e < off[p + 1]; ++e) {
+    const int v = idx[e];
+    s += v > 0 ? dWp[v - 1] : -dWp[-v - 1];
+  }
+  g[p] = s;
+}
+
+__global__ void __launch_bounds__(256)
+grad_map_warp_kernel(const float* __restrict__ dWp, const int32_t* __restrict__ off, const int32_t* __restrict__ idx,
+                     int n_param, float* __restrict__ g) {
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= n_param) return;
+  float s = 0.f;
+  for (int e = off[p] + lane; e < off[p + 1]; e += 32) {
+    const int v = idx[e];
+    s += v > 0 ? dWp[v - 1] : -dWp[-v - 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) g[p] = s;
+}
+
+__global__ void __launch_bounds__(256)
+pack_bias_kernel(const float* __restrict__ b, int kind, int N, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  if (kind == 0) out[j] = b[j];
+  else if (kind == 1) {
+    const int F = N >> 1, f = j >> 1;
+    out[j] = (j & 1) ? b[F + f] - b[f] : b[f] - b[F + f];
+  } else out[j] = (j & 1) ? b[1] - b[0] : b[0] - b[1];
+}
+
+// one block; dbp = packed bias gradient [N]
+__global__ void __launch_bounds__(256)
+grad_bias_kernel(const float* __restrict__ dbp, int kind, int N, float* __restrict__ g) {
+  if (kind == 0) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x) g[j] = dbp[j];
+  } else if (kind == 1) {
+    const int F = N >> 1;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      const float ga = dbp[2 * f] - dbp[2 * f + 1];
+      g[f] = ga;
+      g[F + f] = -ga;
+    }
+  } else {
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int f = threadIdx.x; f < (N >> 1); f += blockDim.x) s += dbp[2 * f] - dbp[2 * f + 1];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      g[0] = red[0];
+      g[1] = -red[0];
+    }
+  }
+}
+
+// Wp [K,N] -> plain (P*) and transposed (T*) copies, optionally split into tf32 hi/lo planes
+__global__ void __launch_bounds__(256)
+repack_kernel(const float* __restrict__ Wp, int K, int N, float* __restrict__ T0, float* __restrict__ T1,
+              float* __restrict__ P0, float* __restrict__ P1, int split) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    float v = 0.f;
+    if (k < K && n < N) {
+      v = Wp[(size_t)k * N + n];
+      if (P0) {
+        if (split) {
+          float hi, lo;
+          tf32_split(v, hi, lo);
+          P0[(size_t)k * N + n] = hi;
+          if (P1) P1[(size_t)k * N + n] = lo;
+        } else if (P0 != Wp) P0[(size_t)k * N + n] = v;
+      }
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  if (!T0) return;
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (k < K && n < N) {
+      const float v = tile[tx][r];
+      if (split) {
+        float hi, lo;
+        tf32_split(v, hi, lo);
+        T0[(size_t)n * K + k] = hi;
+        if (T1) T1[(size_t)n * K + k] = lo;
+      } else T0[(size_t)n * K + k] = v;
+    }
+  }
+}
+
+// g += l2g * w  (gradient of the regulariser), so that g is d total_loss / d var
+__global__ void __launch_bounds__(256) add_l2_kernel(float* __restrict__ g, const float* __restrict__ w, long long n, float l2g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] = fmaf(l2g, w[i], g[i]);
+}
+
+// tf.train.AdamOptimizer (TF 1.15): epsilon outside the square root, lr_t carries the bias corrections
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, long long n,
+            float lr_t, float b1, float b2, float eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gt = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gt;
+  const float vi = b2 * v[i] + (1.f - b2) * gt * gt;
+  m[i] = mi;
+  v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+// ---- pointwise backward kernels --------------------------------------------------------------------
+// demodulation head (dev/py/model.py:1275-1291) + loss (dev/py/ofdmreceiver_np.py:154-162):
+// d ce_mean / d out_iq per data subcarrier; the head is recomputed from out_iq.
+template <int NB>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ out_iq, const uint8_t* __restrict__ bits, const __grid_constant__ HeadWeights hw,
+                long long total, float inv_n, float* __restrict__ d_oiq) {
+  constexpr int MO = 1 << NB;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float2 iq = __ldg(reinterpret_cast<const float2*>(out_iq) + i);
+    const float I = iq.x, Q = iq.y;
+    float hpre[MO], hh[MO], dh[MO];
+#pragma unroll
+    for (int m = 0; m < MO; ++m) {
+      hpre[m] = I * hw.Wc[0][m] + Q * hw.Wc[1][m] + hw.bc[m];
+      hh[m] = fmaxf(0.2f * hpre[m], hpre[m]);
+      dh[m] = 0.f;
+    }
+    float dI = 0.f, dQ = 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      float l0 = hw.b1[2 * k], l1 = hw.b1[2 * k + 1];
+#pragma unroll
+      for (int m = 0; m < MO; ++m) {
+        l0 += hh[m] * hw.W1[m][2 * k];
+        l1 += hh[m] * hw.W1[m][2 * k + 1];
+      }
+      l0 += I * hw.W1[MO][2 * k] + Q * hw.W1[MO + 1][2 * k];
+      l1 += I * hw.W1[MO][2 * k + 1] + Q * hw.W1[MO + 1][2 * k + 1];
+      const float s0 = l0 > 0.f ? 1.f : 0.2f, s1 = l1 > 0.f ? 1.f : 0.2f;   // LeakyReluGrad
+      const float a0 = fmaxf(0.2f * l0, l0), a1 = fmaxf(0.2f * l1, l1);
+      const float t = expf(-fabsf(a1 - a0));
+      const float pb = 1.0f / (1.0f + t), ps = t / (1.0f + t);
+      const bool one_big = a1 > a0;
+      const float p0 = one_big ? ps : pb, p1 = one_big ? pb : ps;
+      // loss = logsumexp(p) - p_y  ->  d/dp = softmax(p) - onehot(y)
+      const float q1 = 1.0f / (1.0f + expf(p0 - p1)), q0 = 1.0f - q1;
+      const unsigned y = bits[i * NB + k] & 1u;
+      const float dp0 = (q0 - (y ? 0.f : 1.f)) * inv_n, dp1 = (q1 - (y ? 1.f : 0.f)) * inv_n;
+      // through the model's softmax: da_j = p_j (dp_j - sum dp p)  =>  da0 = p0 p1 (dp0 - dp1) = -da1
+      const float da0 = p0 * p1 * (dp0 - dp1);
+      const float dl0 = da0 * s0, dl1 = -da0 * s1;
+#pragma unroll
+      for (int m = 0; m < MO; ++m) dh[m] += hw.W1[m][2 * k] * dl0 + hw.W1[m][2 * k + 1] * dl1;
+      dI += hw.W1[MO][2 * k] * dl0 + hw.W1[MO][2 * k + 1] * dl1;
+      dQ += hw.W1[MO + 1][2 * k] * dl0 + hw.W1[MO + 1][2 * k + 1] * dl1;
+    }
+#pragma unroll
+    for (int m = 0; m < MO; ++m) {
+      const float d = dh[m] * (hpre[m] > 0.f ? 1.f : 0.2f);
+      dI += hw.Wc[0][m] * d;
+      dQ += hw.Wc[1][m] * d;
+    }
+    reinterpret_cast<float2*>(d_oiq)[i] = make_float2(dI, dQ);
+  }
+}
+
+// phase-only equaliser eq = f * conj(c)/|c|, corr = |eq|^2 (dev/py/model.py:430-437), per complex point
+__global__ void __launch_bounds__(256)
+phaseeq_bwd_kernel(const float2* __restrict__ deq, const float* __restrict__ dcorr, const float2* __restrict__ f,
+                   const float2* __restrict__ ch, const float2* __restrict__ eq, long long total,
+                   float2* __restrict__ df, float2* __restrict__ dch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float2 e = eq[i], c = ch[i], ff = f[i], de = deq[i];
+  const float dc = dcorr[i];
+  const float der = fmaf(2.f * e.x, dc, de.x), dei = fmaf(2.f * e.y, dc, de.y);
+  const float inv = rsqrtf(c.x * c.x + c.y * c.y);
+  const float nr = c.x * inv, ni = -c.y * inv;
+  df[i] = make_float2(der * nr + dei * ni, -der * ni + dei * nr);
+  const float dnr = der * ff.x + dei * ff.y, dni = -der * ff.y + dei * ff.x;
+  const float com = (dnr * c.y + dni * c.x) * inv * inv * inv;
+  dch[i] = make_float2(c.y * com, -c.x * com);
+}
+
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(float* __restrict__ d, const float* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] *= (1.f - y[i] * y[i]);
+}
+
+__global__ void __launch_bounds__(256) add_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+static inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+
+static int rows_per_split(int64_t M) {
+  int64_t rps = 512;
+  if ((M + rps - 1) / rps > 32) rps = ((M + 31) / 32 + 15) / 16 * 16;
+  return (int)rps;
+}
+
+// wgrad of one layer + reduction to the variable gradients
+static int run_wgrad(dccn_handle* h, TrainLayer& t, const float* X, int ldx, const float* Y, int ldy, int64_t M,
+                     cudaStream_t s) {
+  TrainState* tr = h->tr;
+  const int Kin = t.L->K, Nout = t.L->N;
+  DCCN_CHECK(Kin % 4 == 0 && Nout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "wgrad operands must be float4-aligned");
+  const int rps = rows_per_split(M);
+  const int splits = (int)((M + rps - 1) / rps);
+  const size_t n = (size_t)(Kin + 1) * Nout;
+  DCCN_CHECK(n * splits <= tr->partial_floats, "wgrad scratch too small (%zu > %zu)", n * splits, tr->partial_floats);
+  {
+    LaunchScope ls(h, SLOT_T_WGRAD, s, 2);
+    dim3 grid((Nout + 63) / 64, (Kin + 1 + 63) / 64, splits);
+    wgrad_simt_kernel<<<grid, 256, 0, s>>>(X, ldx, Kin, Y, ldy, Nout, (long long)M, rps, tr->partial);
+    reduce_partials_kernel<<<blocks_for((long long)n), 256, 0, s>>>(tr->partial, splits, (long long)n, t.dWp);
+  }
+  LaunchScope ls(h, SLOT_T_ADAM, s, 2);
+  TrainParam& kp = tr->params[t.kp];
+  TrainParam& bp = tr->params[t.bp];
+  if (t.max_list <= 4)
+    grad_map_thread_kernel<<<blocks_for(kp.n), 256, 0, s>>>(t.dWp, t.csr_off, t.csr_idx, (int)kp.n, kp.g);
+  else
+    grad_map_warp_kernel<<<blocks_for(kp.n * 32), 256, 0, s>>>(t.dWp, t.csr_off, t.csr_idx, (int)kp.n, kp.g);
+  grad_bias_kernel<<<1, 256, 0, s>>>(t.dWp + (size_t)Kin * Nout, t.bias_kind, Nout, bp.g);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int run_dgrad(dccn_handle* h, const GemmLayer& bw, const Act& dY, int col_off, int64_t M, const Act& dst,
+                     int dst_col_off, cudaStream_t s) {
+  return run_gemm_store(h, SLOT_T_DGRAD, bw, dY, col_off, M, store_epi(bw, dst, dst_col_off, M), s);
+}
+
+// variables -> packed operands -> forward / dgrad operand copies (after an update or a commit)
+static int repack_all(dccn_handle* h, cudaStream_t s) {
+  TrainState* tr = h->tr;
+  const bool split = h->cfg.precision == DCCN_PREC_PARITY;
+  for (int i = 0; i < 10; ++i) {
+    TrainLayer& t = tr->tl[i];
+    const int K = t.L->K, N = t.L->N;
+    LaunchScope ls(h, SLOT_T_REPACK, s, 3);
+    pack_map_kernel<<<blocks_for((long long)K * N), 256, 0, s>>>(tr->params[t.kp].w, t.map, (long long)K * N, t.Wp);
+    pack_bias_kernel<<<blocks_for(N), 256, 0, s>>>(tr->params[t.bp].w, t.bias_kind, N, t.L->dBias);
+    dim3 grid((N + 31) / 32, (K + 31) / 32);
+    if (split)   // forward B operand [N,K] hi/lo (transposed), dgrad B operand [K,N] hi/lo (plain)
+      repack_kernel<<<grid, 256, 0, s>>>(t.Wp, K, N, t.L->dWt0, t.L->dWt1, t.bw.dWt0, t.bw.dWt1, 1);
+    else         // forward SIMT operand is Wp itself; dgrad SIMT operand W^T [N,K]
+      repack_kernel<<<grid, 256, 0, s>>>(t.Wp, K, N, t.bw.dW, nullptr, nullptr, nullptr, 0);
+  }
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int make_bw_layer(dccn_handle* h, const GemmLayer& L, GemmLayer* bw, cudaStream_t s) {
+  bw->K = L.N;
+  bw->N = L.K;
+  bw->W.resize((size_t)L.K * L.N);
+  for (int k = 0; k < L.K; ++k)
+    for (int n = 0; n < L.N; ++n) bw->W[(size_t)n * L.K + k] = L.W[(size_t)k * L.N + n];
+  bw->bias.assign(bw->N, 0.f);
+  bw->fused = false;
+  return upload_layer(h, bw, s);
+}
+
+static int upload_params(dccn_handle* h, cudaStream_t s) {
+  for (TrainParam& p : h->tr->params) {
+    const HostTensor* t = find(h, p.name);
+    DCCN_CHECK(t && (int64_t)t->data.size() == p.n, "weight '%s' missing or resized", p.name.c_str());
+    DCCN_CUDA_OK(cudaMemcpyAsync(p.w, t->data.data(), (size_t)p.n * 4, cudaMemcpyHostToDevice, s));
+  }
+  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+void train_free(dccn_handle* h) {
+  delete h->tr;   // device memory is owned by the handle's allocation list
+  h->tr = nullptr;
+}
+
+int train_on_commit(dccn_handle* h, cudaStream_t s) {
+  int rc = upload_params(h, s);
+  if (rc) return rc;
+  return repack_all(h, s);
+}
+
+int train_fetch_weight(dccn_handle* h, const char* tf_name, HostTensor* t) {
+  for (TrainParam& p : h->tr->params)
+    if (p.name == tf_name) {
+      DCCN_CUDA_OK(cudaMemcpy(t->data.data(), p.w, (size_t)p.n * 4, cudaMemcpyDeviceToHost));
+      return 1;
+    }
+  return 0;
+}
+
+static int backward(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t s) {
+  TrainState* tr = h->tr;
+  const int S = h->S, K = h->K, T = h->T, Tin = h->Tin, D = h->D, NB = h->NB, F = h->F;
+  const int64_t MS = B * S;
+  const int cp_off = (T - Tin) * 2;
+  const int SK2 = S * K * 2;
+  int rc;
+  // ---- loss + demodulation head ------------------------------------------------------------------
+  {
+    LaunchScope ls(h, SLOT_T_HEAD, s);
+    const long long total = (long long)B * D;
+    const float inv_n = (float)(1.0 / ((double)B * D * NB));
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+    switch (NB) {
+      case 1: head_bwd_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+      case 2: head_bwd_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+      case 3: head_bwd_kernel<3><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+      default: head_bwd_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+    }
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  // ---- frozen receiver: data gradients only ------------------------------------------------------
+  if ((rc = run_dgrad(h, tr->bw_r2, tr->d_oiq, 0, B, tr->d_r1o, 0, s))) return rc;
+  Act d_r1v = tr->d_r1o;  d_r1v.ld = 2 * F;
+  Act d_oeqv = tr->d_oeq; d_oeqv.ld = 2 * T;
+  if (cp_off) DCCN_CUDA_OK(cudaMemsetAsync(tr->d_oeq.p0, 0, (size_t)B * h->P * 4, s));
+  if ((rc = run_dgrad(h, tr->bw_r1, d_r1v, 0, MS, d_oeqv, cp_off, s))) return rc;
+  // ---- equalizer_ofdm ------------------------------------------------------------------------------
+  TrainLayer* tl = tr->tl;
+  Act d_catv = tr->d_cat;                       // [MS, 4K] = [d eq_out | d corr_out]
+  Act d_eqv = tr->d_eq;   d_eqv.ld = 2 * K;
+  Act d_corrv = tr->d_corr; d_corrv.ld = K;
+  Act d_fv = tr->d_f;     d_fv.ld = 2 * K;
+  Act d_t1v = tr->d_t1;   d_t1v.ld = 2 * K;
+  // dense_5                                                                            model.py:457
+  if ((rc = run_wgrad(h, tl[9], h->cat.p0, 4 * K, d_oeqv.p0, 2 * T, MS, s))) return rc;
+  if ((rc = run_dgrad(h, tl[9].bw, d_oeqv, 0, MS, d_catv, 0, s))) return rc;
+  // conv3d_3 on eq, conv3d_2 on corr (real rows only)                                  model.py:437-448
+  if ((rc = run_wgrad(h, tl[8], h->eq.p0, 2 * K, d_catv.p0, 4 * K, MS, s))) return rc;
+  if ((rc = run_dgrad(h, tl[8].bw, d_catv, 0, MS, d_eqv, 0, s))) return rc;
+  if ((rc = run_wgrad(h, tl[7], h->corr.p0, K, d_catv.p0 + 2 * K, 4 * K, MS, s))) return rc;
+  if ((rc = run_dgrad(h, tl[7].bw, d_catv, 2 * K, MS, d_corrv, 0, s))) return rc;
+  // phase-only equaliser                                                               model.py:430-437
+  {
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    const long long total = (long long)B * S * K;
+    phaseeq_bwd_kernel<<<blocks_for(total), 256, 0, s>>>((const float2*)tr->d_eq.p0, tr->d_corr.p0, (const float2*)h->f.p0,
+                                                         (const float2*)h->chest_buf, (const float2*)h->eq.p0, total,
+                                                         (float2*)tr->d_f.p0, (float2*)tr->d_ch.p0);
+  }
+  // conv3d_1 (Toeplitz), tanh, dense_4 .. dense_1                                      model.py:393-426
+  if ((rc = run_wgrad(h, tl[6], h->u3.p0, SK2, tr->d_ch.p0, SK2, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[6].bw, tr->d_ch, 0, B, tr->dA, 0, s))) return rc;
+  {
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    tanh_bwd_kernel<<<blocks_for((long long)B * SK2), 256, 0, s>>>(tr->dA.p0, h->u3.p0, (long long)B * SK2);
+  }
+  if ((rc = run_wgrad(h, tl[5], h->u2.p0, SK2, tr->dA.p0, SK2, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[5].bw, tr->dA, 0, B, tr->dB, 0, s))) return rc;
+  if ((rc = run_wgrad(h, tl[4], h->u1.p0, SK2, tr->dB.p0, SK2, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[4].bw, tr->dB, 0, B, tr->dC, 0, s))) return rc;
+  if ((rc = run_wgrad(h, tl[3], h->p32.p0, h->p32.ld, tr->dC.p0, SK2, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[3].bw, tr->dC, 0, B, tr->d_p32, 0, s))) return rc;
+  if ((rc = run_wgrad(h, tl[2], h->f.p0, SK2, tr->d_p32.p0, tr->d_p32.ld, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[2].bw, tr->d_p32, 0, B, tr->d_f2, 0, s))) return rc;
+  {
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    add_kernel<<<blocks_for((long long)B * SK2), 256, 0, s>>>(tr->d_f.p0, tr->d_f2.p0, (long long)B * SK2);
+  }
+  // learned DFT (conv3d) and the per-symbol input dense                                 model.py:370-379
+  if ((rc = run_wgrad(h, tl[1], h->t1.p0, 2 * K, tr->d_f.p0, 2 * K, MS, s))) return rc;
+  if ((rc = run_dgrad(h, tl[1].bw, d_fv, 0, MS, d_t1v, 0, s))) return rc;
+  if ((rc = run_wgrad(h, tl[0], h->a0.p0 + cp_off, 2 * T, tr->d_t1.p0, 2 * K, MS, s))) return rc;
+  // ---- regulariser -------------------------------------------------------------------------------
+  {
+    LaunchScope ls(h, SLOT_T_ADAM, s, 12);
+    for (TrainParam& p : tr->params)
+      if (p.l2g != 0.f) add_l2_kernel<<<blocks_for(p.n), 256, 0, s>>>(p.g, p.w, p.n, p.l2g);
+  }
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dccn
+
+using namespace dccn;
+
+extern "C" {
+
+int dccn_train_init(dccn_handle* h, const dccn_train_cfg* cfg, void* stream) {
+  DCCN_CHECK(h && cfg, "null argument");
+  DCCN_CHECK(h->cfg.equalizer, "training updates the Equalizer/* variables: the handle has no equalizer");
+  DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
+  DCCN_CHECK(h->cfg.precision == DCCN_PREC_EXACT || h->cfg.precision == DCCN_PREC_PARITY,
+             "training needs fp32-class arithmetic (precision exact or parity)");
+  DCCN_CHECK(!h->fused_head, "training needs the stored out_iq (DCCN_FUSED_HEAD=0)");
+  DCCN_CHECK(h->cfg.head == DCCN_HEAD_DEV, "training is defined for the dev head (dev/py/model.py:1275-1288)");
+  DCCN_CHECK(!h->tr, "training state already initialised");
+  DCCN_CHECK(cfg->max_batch > 0 && cfg->max_batch <= h->chunk, "max_batch must be in 1..chunk_frames (%d)", h->chunk);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int S = h->S, K = h->K, T = h->T, F = h->F, D = h->D;
+  const int64_t C = h->chunk, MB = cfg->max_batch;
+  int rc = 0;
+  TrainState* tr = new TrainState();
+  h->tr = tr;
+  tr->cfg = *cfg;
+  tr->maxB = MB;
+  if (!h->u3.p0) rc |= alloc_act(h, &h->u3, C, S * K * 2, false);
+  if (!h->chest_buf) rc |= dev_alloc(h, (void**)&h->chest_buf, (size_t)C * S * K * 2 * 4);
+  if (rc) return rc;
+  // ---- gather maps of the ten layers: run the host packers on index-valued variables ------------------
+  GemmLayer* Ls[10] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
+  std::vector<std::vector<float>> backup(10);
+  for (int i = 0; i < 10; ++i) {
+    HostTensor& t = h->raw[std::string(kLayerVar[i]) + "/kernel"];
+    DCCN_CHECK(t.data.size() < (1u << 24), "variable too large for the index trick");
+    backup[i] = t.data;
+    for (size_t p = 0; p < t.data.size(); ++p) t.data[p] = (float)(p + 1);
+  }
+  rc = pack_layers_host(h);
+  std::vector<std::vector<int32_t>> maps(10);
+  if (!rc)
+    for (int i = 0; i < 10; ++i) {
+      maps[i].resize(Ls[i]->W.size());
+      for (size_t e = 0; e < maps[i].size(); ++e) maps[i][e] = (int32_t)Ls[i]->W[e];
+    }
+  for (int i = 0; i < 10; ++i) h->raw[std::string(kLayerVar[i]) + "/kernel"].data = backup[i];
+  if (rc) return rc;
+  if ((rc = pack_layers_host(h))) return rc;
+  // ---- variables, optimiser slots, maps, operands ----------------------------------------------------------
+  const float l2g = 2.0f * cfg->reg_coeff * cfg->l2;
+  tr->params.reserve(20);
+  size_t max_partial = 0;
+  for (int i = 0; i < 10; ++i) {
+    TrainLayer& t = tr->tl[i];
+    t.L = Ls[i];
+    t.bias_kind = kBiasKind[i];
+    const bool dense = kBiasKind[i] == 0;
+    for (int kb = 0; kb < 2; ++kb) {
+      TrainParam p;
+      p.name = std::string(kLayerVar[i]) + (kb == 0 ? "/kernel" : "/bias");
+      const HostTensor* ht = find(h, p.name);
+      DCCN_CHECK(ht, "weight '%s' was not set", p.name.c_str());
+      p.n = (int64_t)ht->data.size();
+      p.l2g = dense ? l2g : 0.f;
+      rc |= dev_alloc(h, (void**)&p.w, (size_t)p.n * 4);
+      rc |= dev_alloc(h, (void**)&p.m, (size_t)p.n * 4);
+      rc |= dev_alloc(h, (void**)&p.v, (size_t)p.n * 4);
+      rc |= dev_alloc(h, (void**)&p.g, (size_t)p.n * 4);
+      if (rc) return rc;
+      DCCN_CUDA_OK(cudaMemsetAsync(p.m, 0, (size_t)p.n * 4, s));
+      DCCN_CUDA_OK(cudaMemsetAsync(p.v, 0, (size_t)p.n * 4, s));
+      DCCN_CUDA_OK(cudaMemsetAsync(p.g, 0, (size_t)p.n * 4, s));
+      (kb == 0 ? t.kp : t.bp) = (int)tr->params.size();
+      tr->params.push_back(p);
+    }
+    const int Kl = t.L->K, Nl = t.L->N;
+    const size_t kn = (size_t)Kl * Nl;
+    const int64_t n_param = tr->params[t.kp].n;
+    // CSR: parameter -> signed operand positions
+    std::vector<int32_t> off(n_param + 1, 0), idx;
+    for (size_t e = 0; e < kn; ++e)
+      if (maps[i][e]) off[std::abs(maps[i][e])]++;            // count at p+1
+    for (int64_t p = 0; p < n_param; ++p) {
+      if (off[p + 1] > t.max_list) t.max_list = off[p + 1];
+      off[p + 1] += off[p];
+    }
+    idx.resize(off[n_param] > 0 ? off[n_param] : 1);
+    std::vector<int32_t> cur(off.begin(), off.end() - 1);
+    for (size_t e = 0; e < kn; ++e) {
+      const int32_t mv = maps[i][e];
+      if (!mv) continue;
+      const int32_t p = std::abs(mv) - 1;
+      idx[cur[p]++] = mv > 0 ? (int32_t)(e + 1) : -(int32_t)(e + 1);
+    }
+    rc |= dev_alloc(h, (void**)&t.map, kn * 4);
+    rc |= dev_alloc(h, (void**)&t.csr_off, off.size() * 4);
+    rc |= dev_alloc(h, (void**)&t.csr_idx, idx.size() * 4);
+    rc |= dev_alloc(h, (void**)&t.dWp, (kn + Nl) * 4);
+    if (h->cfg.precision == DCCN_PREC_EXACT) t.Wp = t.L->dW;
+    else rc |= dev_alloc(h, (void**)&t.Wp, kn * 4);
+    if (rc) return rc;
+    DCCN_CUDA_OK(cudaMemcpyAsync(t.map, maps[i].data(), kn * 4, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaMemcpyAsync(t.csr_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaMemcpyAsync(t.csr_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaStreamSynchronize(s));
+    if ((rc = make_bw_layer(h, *t.L, &t.bw, s))) return rc;
+    // wgrad scratch: splits x (K+1) x N for the batch this layer contracts over
+    const int64_t M = kPerSymbol[i] ? MB * S : MB;
+    const int rps = rows_per_split(M);
+    const size_t need = (size_t)((M + rps - 1) / rps) * (kn + Nl);
+    if (need > max_partial) max_partial = need;
+  }
+  if ((rc = make_bw_layer(h, h->r1, &tr->bw_r1, s))) return rc;
+  if ((rc = make_bw_layer(h, h->r2, &tr->bw_r2, s))) return rc;
+  tr->partial_floats = max_partial;
+  rc |= dev_alloc(h, (void**)&tr->partial, max_partial * 4);
+  // ---- gradient activations -------------------------------------------------------------------------------
+  const int SK2 = S * K * 2;
+  rc |= alloc_act(h, &tr->d_oiq, MB, 2 * D, false);
+  rc |= alloc_act(h, &tr->d_r1o, MB, S * F * 2, false);
+  rc |= alloc_act(h, &tr->d_oeq, MB, S * T * 2, false);
+  rc |= alloc_act(h, &tr->d_cat, MB * S, 4 * K, false);
+  rc |= alloc_act(h, &tr->d_eq, MB, SK2, false);
+  rc |= alloc_act(h, &tr->d_corr, MB, S * K, false);
+  rc |= alloc_act(h, &tr->d_f, MB, SK2, false);
+  rc |= alloc_act(h, &tr->d_f2, MB, SK2, false);
+  rc |= alloc_act(h, &tr->d_ch, MB, SK2, false);
+  rc |= alloc_act(h, &tr->dA, MB, SK2, false);
+  rc |= alloc_act(h, &tr->dB, MB, SK2, false);
+  rc |= alloc_act(h, &tr->dC, MB, SK2, false);
+  rc |= alloc_act(h, &tr->d_p32, MB, 2 * h->cfg.pilot_size, false);
+  rc |= alloc_act(h, &tr->d_t1, MB, SK2, false);
+  if (rc) return rc;
+  if ((rc = upload_params(h, s))) return rc;
+  return repack_all(h, s);
+}
+
+int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* bits_dev, float learning_rate,
+                    int apply_update, int64_t* conf_dev, double* ce_sum_dev, int flags, void* stream) {
+  DCCN_CHECK(h && x_dev && bits_dev, "null argument");
+  DCCN_CHECK(h->tr, "dccn_train_init was not called");
+  DCCN_CHECK(B > 0 && B <= h->tr->maxB, "batch %lld outside 1..max_batch (%lld)", (long long)B, (long long)h->tr->maxB);
+  DCCN_CHECK(!(flags & (DCCN_FWD_EQ_ONLY | DCCN_FWD_SKIP_EQ)), "a training step runs equalizer + receiver");
+  cudaStream_t s = (cudaStream_t)stream;
+  TrainState* tr = h->tr;
+  int rc = 0;
+  // ---- forward, keeping every activation ------------------------------------------------------------------
+  if (!(flags & DCCN_FWD_NO_NORM) && (rc = run_moments(h, x_dev, B, h->d_mean, h->d_rstd, s))) return rc;
+  if (conf_dev) DCCN_CUDA_OK(cudaMemsetAsync(h->d_conf, 0, 4 * sizeof(unsigned long long), s));
+  h->train_fwd = true;
+  rc = run_chunk(h, x_dev, B, bits_dev, nullptr, nullptr, nullptr, nullptr, conf_dev ? h->d_conf : nullptr, ce_sum_dev,
+                 flags, s);
+  h->train_fwd = false;
+  if (rc) return rc;
+  if (conf_dev) conf_accumulate(h->d_conf, conf_dev, s);
+  // ---- backward ------------------------------------------------------------------------------------------------
+  if ((rc = backward(h, B, bits_dev, s))) return rc;
+  if (!apply_update) return 0;
+  // ---- Adam (dev/py/ofdmreceiver_np_mp.py:345-347) ------------------------------------------------------------
+  tr->step += 1;
+  const double b1 = tr->cfg.beta1, b2 = tr->cfg.beta2;
+  const float lr_t = (float)((double)learning_rate * std::sqrt(1.0 - std::pow(b2, (double)tr->step)) /
+                             (1.0 - std::pow(b1, (double)tr->step)));
+  {
+    LaunchScope ls(h, SLOT_T_ADAM, s, (int)tr->params.size());
+    for (TrainParam& p : tr->params)
+      adam_kernel<<<blocks_for(p.n), 256, 0, s>>>(p.w, p.m, p.v, p.g, p.n, lr_t, tr->cfg.beta1, tr->cfg.beta2, tr->cfg.eps);
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  return repack_all(h, s);
+}
+
+int64_t dccn_train_get_grad(dccn_handle* h, const char* tf_name, float* host, int64_t capacity) {
+  if (!h || !tf_name || !h->tr) return set_error(-2, "bad argument / training not initialised");
+  for (TrainParam& p : h->tr->params)
+    if (p.name == tf_name) {
+      if (host) {
+        if (capacity < p.n) return set_error(-2, "buffer too small for the gradient of '%s'", tf_name);
+        if (cudaMemcpy(host, p.g, (size_t)p.n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+          return set_error(-1, "cudaMemcpy failed");
+      }
+      return p.n;
+    }
+  return set_error(-2, "'%s' is not a trainable variable", tf_name);
+}
+
+int64_t dccn_train_global_step(const dccn_handle* h) { return (h && h->tr) ? h->tr->step : -1; }
+
+int dccn_train_set_global_step(dccn_handle* h, int64_t step) {
+  DCCN_CHECK(h && h->tr && step >= 0, "bad argument / training not initialised");
+  h->tr->step = step;
+  return 0;
+}
+
+}  // extern "C"

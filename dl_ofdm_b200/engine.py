@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DccnError, dccn_cfg
+from ._lib import DccnError, dccn_cfg, dccn_train_cfg
 
 
 def _ptr(t):
@@ -175,6 +175,52 @@ class DCCN:
         with torch.cuda.device(x.device):
             _lib.check(self.lib.dccn_batch_moments(self._h, _ptr(x), x.shape[0], _ptr(mean), _ptr(rstd), _stream()))
         return mean, rstd
+
+    # -- training (BASELINE config 4) -------------------------------------------------------
+    def get_weight(self, name):
+        """Variable in the reference layout (the trained value once train_init was called)."""
+        n = int(_lib.check(self.lib.dccn_get_weight(self._h, name.encode(), None, 0)))
+        out = np.empty(n, dtype=np.float32)
+        _lib.check(self.lib.dccn_get_weight(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def train_init(self, max_batch, reg_coeff=0.001, l2=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        """Optimiser state for ``optimizer.minimize(total_loss, var_list=Equalizer vars)``
+        (dev/py/ofdmreceiver_np_mp.py:335-347)."""
+        cfg = dccn_train_cfg(reg_coeff=reg_coeff, l2=l2, beta1=beta1, beta2=beta2, eps=eps, max_batch=int(max_batch))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dccn_train_init(self._h, C.byref(cfg), _stream()))
+
+    def train_step(self, x, bits, learning_rate, apply_update=True, flags=0):
+        """One minibatch of ``session.run([train_op, ce_mean, conf_matrix], {x, y})`` (_mp.py:419).
+
+        Returns dict(conf int64 [2,2] CUDA tensor, ce_sum float64 [1] CUDA tensor, n_bits); nothing is synchronised.
+        """
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert bits.is_cuda and bits.dtype == torch.uint8 and bits.is_contiguous()
+        B = x.shape[0]
+        assert tuple(x.shape[1:]) == (self.S, self.T, 2) and tuple(bits.shape) == (B, self.D, self.nbits)
+        conf = torch.zeros((2, 2), dtype=torch.int64, device=x.device)
+        ce = torch.zeros((1,), dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(self.lib.dccn_train_step(self._h, _ptr(x), B, _ptr(bits), float(learning_rate),
+                                                int(bool(apply_update)), _ptr(conf), _ptr(ce), int(flags), _stream()))
+        return dict(conf=conf, ce_sum=ce, n_bits=B * self.D * self.nbits)
+
+    def get_grad(self, name):
+        """d total_loss / d var of the last train_step, reference layout (flat float32)."""
+        n = int(_lib.check(self.lib.dccn_train_get_grad(self._h, name.encode(), None, 0)))
+        out = np.empty(n, dtype=np.float32)
+        _lib.check(self.lib.dccn_train_get_grad(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    @property
+    def global_step(self):
+        return int(self.lib.dccn_train_global_step(self._h))
+
+    @global_step.setter
+    def global_step(self, step):
+        _lib.check(self.lib.dccn_train_set_global_step(self._h, int(step)))
 
     # -- channel ------------------------------------------------------------------------
     def channel(self, tx, snr_db, alpha=None, coeff=None, z=None, normals=None, seed=0, want_faded=False):

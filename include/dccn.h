@@ -83,7 +83,8 @@ size_t dccn_workspace_bytes(const dccn_handle* h);
  * expansion of the (S,K) 'same' conv, tf32 hi/lo split.  Synchronous. */
 int dccn_set_weight(dccn_handle* h, const char* tf_name, const float* host,
                     const int64_t* shape, int rank);
-/* copies the stored (reference-layout) tensor back; returns element count or <0 */
+/* copies the stored (reference-layout) tensor back (the trained value once dccn_train_init was called);
+ * returns element count or <0 */
 int64_t dccn_get_weight(dccn_handle* h, const char* tf_name, float* host, int64_t capacity);
 int dccn_commit_weights(dccn_handle* h, void* stream);
 
@@ -172,6 +173,33 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B,
                    const int32_t* data_sc_dev, int n_data, const int32_t* pilot_sc_dev, int n_pilot,
                    const float* constellation_dev, float pilot_re, float pilot_im,
                    float* tx_dev, void* stream);
+
+/* -- BASELINE config 4: transfer learning of the equalizer in front of the frozen receiver.
+ * Replaces `session.run([train_op, ce_mean, ...], {x, y})` (dev/py/ofdmreceiver_np_mp.py:419) with the graph of
+ * dev/py/ofdmreceiver_np_mp.py:335-347:  total_loss = ce_mean + reg_coeff * sum(l2 * sum(w^2)) over kernel+bias of
+ * the six tf.layers.dense of equalizer_ofdm, AdamOptimizer.minimize(total_loss, var_list = Equalizer/ *).
+ * The receiver variables (fft_like/ *, demodulation/ *) stay frozen. */
+typedef struct dccn_train_cfg {
+  float reg_coeff;    /* REG_COEFF, 0.001 (ofdmreceiver_np_mp.py:337)                        */
+  float l2;           /* tf.keras.regularizers.l2(l=0.01) (model.py:372-373)                  */
+  float beta1, beta2; /* tf.train.AdamOptimizer defaults 0.9, 0.999                           */
+  float eps;          /* 1e-8                                                                 */
+  int64_t max_batch;  /* largest B of dccn_train_step (<= chunk_frames)                       */
+} dccn_train_cfg;
+/* Allocates optimiser slots / gradient buffers and derives the backward operands; weights must be committed. */
+int dccn_train_init(dccn_handle* h, const dccn_train_cfg* cfg, void* stream);
+/* One minibatch: forward (batch-moment norm included unless DCCN_FWD_NO_NORM), backward of total_loss w.r.t. every
+ * Equalizer/ * variable and, if apply_update != 0, one Adam update with `learning_rate` = the decayed rate of this
+ * step (exponential_decay(init, global_step, 500, 0.98, staircase), computed by the caller) and the bias
+ * corrections of TF's Adam.  conf_dev (int64 [2,2]) / ce_sum_dev (double) are ACCUMULATED like dccn_forward
+ * (training monitors `conf_matrix`, `ce_mean`), either may be NULL. */
+int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* bits_dev, float learning_rate,
+                    int apply_update, int64_t* conf_dev, double* ce_sum_dev, int flags, void* stream);
+/* d total_loss / d var of the last dccn_train_step, reference layout; returns the element count or <0. Synchronous. */
+int64_t dccn_train_get_grad(dccn_handle* h, const char* tf_name, float* host, int64_t capacity);
+/* number of Adam updates applied so far (TF's global_step); settable when resuming from a checkpoint */
+int64_t dccn_train_global_step(const dccn_handle* h);
+int dccn_train_set_global_step(dccn_handle* h, int64_t step);
 
 /* -- measurement hooks (bench.py): kernels launched by the library so far; per-kernel CUDA-event
  * timing on the launch stream.  dccn_profile_collect synchronises the device and returns the number

@@ -549,17 +549,13 @@ static int backward(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t
 
 using namespace dccn;
 
-extern "C" {
-
-int dccn_train_init(dccn_handle* h, const dccn_train_cfg* cfg, void* stream) {
-  DCCN_CHECK(h && cfg, "null argument");
+static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stream) {
   DCCN_CHECK(h->cfg.equalizer, "training updates the Equalizer/* variables: the handle has no equalizer");
   DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
   DCCN_CHECK(h->cfg.precision == DCCN_PREC_EXACT || h->cfg.precision == DCCN_PREC_PARITY,
              "training needs fp32-class arithmetic (precision exact or parity)");
   DCCN_CHECK(!h->fused_head, "training needs the stored out_iq (DCCN_FUSED_HEAD=0)");
   DCCN_CHECK(h->cfg.head == DCCN_HEAD_DEV, "training is defined for the dev head (dev/py/model.py:1275-1288)");
-  DCCN_CHECK(!h->tr, "training state already initialised");
   DCCN_CHECK(cfg->max_batch > 0 && cfg->max_batch <= h->chunk, "max_batch must be in 1..chunk_frames (%d)", h->chunk);
   cudaStream_t s = (cudaStream_t)stream;
   const int S = h->S, K = h->K, T = h->T, F = h->F, D = h->D;
@@ -678,6 +674,16 @@ int dccn_train_init(dccn_handle* h, const dccn_train_cfg* cfg, void* stream) {
   if (rc) return rc;
   if ((rc = upload_params(h, s))) return rc;
   return repack_all(h, s);
+}
+
+extern "C" {
+
+int dccn_train_init(dccn_handle* h, const dccn_train_cfg* cfg, void* stream) {
+  DCCN_CHECK(h && cfg, "null argument");
+  DCCN_CHECK(!h->tr, "training state already initialised");
+  const int rc = train_init_impl(h, cfg, stream);
+  if (rc) train_free(h);   // a half-built state must not be used
+  return rc;
 }
 
 int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* bits_dev, float learning_rate,

@@ -164,3 +164,36 @@ def test_train_errors(libdccn):
     with pytest.raises(DccnError):
         m.train_step(x, bits, 1e-3)            # batch larger than max_batch
     m.close()
+
+
+def test_train_equalizer_driver(libdccn, tmp_path):
+    """Host mirror of the epoch loop (dev/py/ofdmreceiver_np_mp.py:394-466): data generation on the GPU,
+    minibatch steps, checkpoint in the reference's bundle format and file name, reload gives the same model."""
+    from dl_ofdm_b200 import tfbundle
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.init import receiver_variables
+    from dl_ofdm_b200.model import load_model_np
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from dl_ofdm_b200.ofdmreceiver_np_mp import TRAINABLE, train_equalizer
+    FLAGS = Flags(nbits=2, channel='EPA', batch_size=7 * 256, msg_length=7 * 1024, opt=0, token='T',
+                  save_dir=str(tmp_path) + '/', precision='parity', early_stop=400)
+    ofdmobj = ofdm_tx(FLAGS)
+    rx = receiver_variables(np.random.default_rng(3), 2)
+    session, hist = train_equalizer(FLAGS, ofdmobj, rx, max_epoch_num=2, log=lambda *a: None)
+    assert len(hist) == 2 and hist[-1]['global_step'] == 8 and session.engine.global_step == 8
+    assert all(np.isfinite(h['train_loss']) and np.isfinite(h['test_loss']) and 0.0 <= h['test_ber'] <= 1.0 for h in hist)
+    path = str(tmp_path) + '/T_Equalizer_EPA'
+    ck = tfbundle.read_checkpoint(path)
+    # the checkpoint is the best-train-loss epoch; if that is the last one it equals the live weights
+    if hist[1]['train_loss'] < hist[0]['train_loss']:
+        for n in TRAINABLE:
+            assert np.array_equal(ck[n].ravel(), session.engine.get_weight(n)), n
+    assert np.array_equal(ck['demodulation/dense/kernel'], rx['demodulation/dense/kernel'])
+    s2 = load_model_np(path, FLAGS=FLAGS, ofdmobj=ofdmobj, precision='parity')
+    x = torch.randn((64, 7, 80, 2), device='cuda') * 0.3
+    if hist[1]['train_loss'] < hist[0]['train_loss']:
+        a = session.engine.forward(x)['soft']
+        b = s2.engine.forward(x)['soft']
+        assert torch.equal(a, b)
+    s2.close()
+    session.close()

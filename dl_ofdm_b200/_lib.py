@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, 'libdccn.so')
 
 PREC_EXACT, PREC_PARITY, PREC_FAST = 0, 1, 2
 HEAD_DEV, HEAD_V1 = 0, 1
-FWD_NO_NORM, FWD_EQ_ONLY, FWD_SKIP_EQ = 1, 2, 4
+FWD_NO_NORM, FWD_EQ_ONLY, FWD_SKIP_EQ, FWD_FOLDED = 1, 2, 4, 8
 PRECISIONS = {'exact': PREC_EXACT, 'parity': PREC_PARITY, 'fast': PREC_FAST}
 
 

@@ -73,7 +73,7 @@ const char* kSlotNames[SLOT_COUNT] = {
     "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
     "eq_conv7x64_phaseeq", "eq_corr_idft", "eq_idft", "eq_dense5", "rx_fft_like", "rx_demod_head",
     "chan_fir", "chan_awgn", "rx_demod_gemm", "train_head_bwd", "train_dgrad", "train_wgrad", "train_pointwise",
-    "train_reduce_adam", "train_repack"};
+    "train_reduce_adam", "train_repack", "fold_dense_dft", "fold_mlp_tanh", "fold_tail_fft"};
 
 }  // namespace dccn
 
@@ -368,11 +368,89 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------
+// DCCN_FWD_FOLDED: pre-multiply consecutive linear layers (fp64 on the host, once per commit)
+// ---------------------------------------------------------------------------------------
+typedef std::vector<double> DVec;
+static DVec to_d(const std::vector<float>& v) { return DVec(v.begin(), v.end()); }
+// C[m,n] = A[m,k] * B[k,n]
+static DVec matmul_d(const DVec& A, int m, int k, const DVec& B, int n) {
+  DVec C((size_t)m * n, 0.0);
+  for (int i = 0; i < m; ++i)
+    for (int l = 0; l < k; ++l) {
+      const double a = A[(size_t)i * k + l];
+      if (a == 0.0) continue;
+      const double* b = &B[(size_t)l * n];
+      double* c = &C[(size_t)i * n];
+      for (int j = 0; j < n; ++j) c[j] += a * b[j];
+    }
+  return C;
+}
+static void set_folded(GemmLayer* L, int K, int N, const DVec& W, const DVec& b) {
+  L->K = K;
+  L->N = N;
+  L->W.assign(W.begin(), W.end());
+  L->bias.assign(b.begin(), b.end());
+  L->fused = false;
+}
+
+static int build_folded(dccn_handle* h, cudaStream_t s) {
+  const int S = h->S, K = h->K, T = h->T, Tin = h->Tin, F = h->F;
+  const int SK2 = S * K * 2, cp_off = (T - Tin) * 2, P2 = 2 * h->cfg.pilot_size;
+  // f1 = dense . conv3d  (model.py:370-379):  [2Tin] -> [2K]
+  {
+    DVec W = matmul_d(to_d(h->g1.W), 2 * Tin, 2 * K, to_d(h->g2.W), 2 * K);
+    DVec b = matmul_d(to_d(h->g1.bias), 1, 2 * K, to_d(h->g2.W), 2 * K);
+    for (int j = 0; j < 2 * K; ++j) b[j] += h->g2.bias[j];
+    set_folded(&h->f1, 2 * Tin, 2 * K, W, b);
+  }
+  // f4 = dense_2 . dense_3 . dense_4 (the tanh of dense_4 stays in the epilogue, model.py:401-424):  [2*pilot] -> [SK2]
+  {
+    DVec W5 = to_d(h->g5.W), W6 = to_d(h->g6.W);
+    DVec W = matmul_d(matmul_d(to_d(h->g4.W), P2, SK2, W5, SK2), P2, SK2, W6, SK2);
+    DVec b = matmul_d(to_d(h->g4.bias), 1, SK2, W5, SK2);
+    for (int j = 0; j < SK2; ++j) b[j] += h->g5.bias[j];
+    b = matmul_d(b, 1, SK2, W6, SK2);
+    for (int j = 0; j < SK2; ++j) b[j] += h->g6.bias[j];
+    set_folded(&h->f4, P2, SK2, W, b);
+  }
+  // f9 = [conv3d_3 (eq) ; conv3d_2 (corr, real rows)] . dense_5 . (CP slice) . fft_like  (model.py:437-462, 1246-1264):
+  //      per symbol [eq (2K) | corr (K)] -> [2F]
+  {
+    // dense_5 restricted to the columns the receiver consumes
+    DVec W10((size_t)4 * K * 2 * Tin), b10(2 * Tin);
+    for (int r = 0; r < 4 * K; ++r)
+      for (int c = 0; c < 2 * Tin; ++c) W10[(size_t)r * 2 * Tin + c] = h->g10.W[(size_t)r * 2 * T + cp_off + c];
+    for (int c = 0; c < 2 * Tin; ++c) b10[c] = h->g10.bias[cp_off + c];
+    DVec top(W10.begin(), W10.begin() + (size_t)2 * K * 2 * Tin), bot(W10.begin() + (size_t)2 * K * 2 * Tin, W10.end());
+    DVec A9 = matmul_d(to_d(h->g9.W), 2 * K, 2 * K, top, 2 * Tin);      // [2K, 2Tin]
+    DVec A8 = matmul_d(to_d(h->g8.W), K, 2 * K, bot, 2 * Tin);          // [K, 2Tin]
+    DVec bm = matmul_d(to_d(h->g9.bias), 1, 2 * K, top, 2 * Tin);
+    DVec bm8 = matmul_d(to_d(h->g8.bias), 1, 2 * K, bot, 2 * Tin);
+    for (int c = 0; c < 2 * Tin; ++c) bm[c] += bm8[c] + b10[c];
+    DVec mid((size_t)3 * K * 2 * Tin);
+    std::copy(A9.begin(), A9.end(), mid.begin());
+    std::copy(A8.begin(), A8.end(), mid.begin() + A9.size());
+    DVec R = to_d(h->r1.W);                                             // [2Tin, 2F]
+    DVec W = matmul_d(mid, 3 * K, 2 * Tin, R, 2 * F);
+    DVec b = matmul_d(bm, 1, 2 * Tin, R, 2 * F);
+    for (int j = 0; j < 2 * F; ++j) b[j] += h->r1.bias[j];
+    set_folded(&h->f9, 3 * K, 2 * F, W, b);
+  }
+  int rc;
+  if ((rc = upload_layer(h, &h->f1, s))) return rc;
+  if ((rc = upload_layer(h, &h->f4, s))) return rc;
+  if ((rc = upload_layer(h, &h->f9, s))) return rc;
+  if (!h->eqc.p0 && (rc = alloc_act(h, &h->eqc, (int64_t)h->chunk * S, 3 * K, false))) return rc;
+  h->fold_built = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // GEMM dispatch
 // ---------------------------------------------------------------------------------------
 template <class Epi>
 static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
-                    const Epi& epi, cudaStream_t s) {
+                    const Epi& epi, cudaStream_t s, KSched ks = KSched()) {
   const int prec = h->cfg.precision;
   LaunchScope ls(h, slot, s);
   if (prec == DCCN_PREC_EXACT)
@@ -387,13 +465,13 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   // parity mode on 128-wide tiles: A staged in TMEM (TS-form MMA) + cta_group::2 CTA pairs (half a weight tile per SM)
 #define DCCN_TC_PAR(BNV, CGV)                                                                                \
   do {                                                                                                       \
-    if (L.mc) return launch_gemm_tc<BNV, true, CGV, true, true, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms);  \
-    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms); \
-    return launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms);  \
+    if (L.mc) return launch_gemm_tc<BNV, true, CGV, true, true, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks);  \
+    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks); \
+    return launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks);  \
   } while (0)
 #define DCCN_TC_SS(BNV, CGV)                                                                                 \
-  return split ? launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms) \
-               : launch_gemm_tc<BNV, false, CGV, false, false, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms)
+  return split ? launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks) \
+               : launch_gemm_tc<BNV, false, CGV, false, false, Epi>(op, (int)M, L.N, L.K, 0, epi, s, h->num_sms, ks)
   if constexpr (std::is_same<Epi, EpiStore>::value) {
     switch (L.BN) {
       case 32: if (split) DCCN_TC_PAR(32, 1); DCCN_TC_SS(32, 1);
@@ -411,8 +489,10 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
 }
 
 int run_gemm_store(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
-                   const EpiStore& epi, cudaStream_t s) {
-  return run_gemm<EpiStore>(h, slot, L, A, a_col_off, M, epi, s);
+                   const EpiStore& epi, cudaStream_t s, int ksplit) {
+  KSched ks;
+  ks.ksplit = ksplit;
+  return run_gemm<EpiStore>(h, slot, L, A, a_col_off, M, epi, s, ks);
 }
 
 template <int NB, bool V1>
@@ -488,6 +568,40 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     DCCN_CUDA_OK(cudaGetLastError());
   }
   const Act* rx_in = &h->a0;
+  const bool folded = use_eq && (flags & DCCN_FWD_FOLDED) && !h->train_fwd && !h->tr && !eq_out &&
+                      !(flags & DCCN_FWD_EQ_ONLY);
+  if (folded) {
+    // ---- same function, 5 GEMMs: consecutive linear layers were pre-multiplied (build_folded) ----------
+    if (!h->fold_built && (rc = build_folded(h, s))) return rc;
+    const int64_t MS = Bc * S;
+    Act a0v = h->a0;  a0v.ld = 2 * T;
+    Act fv = h->f;    fv.ld = 2 * K;
+    Act eqcv = h->eqc;                                      // [MS, 3K]
+    Act r1v = h->r1o; r1v.ld = 2 * h->F;
+    if ((rc = run_gemm(h, SLOT_F1, h->f1, a0v, cp_off, MS, store_epi(h->f1, fv, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_F4, h->f4, h->p32, 0, Bc, store_epi(h->f4, h->u1, 0, Bc, /*tanh*/ 1), s))) return rc;
+    {
+      EpiPhaseEq e;
+      e.bias = h->g7.dBias;
+      e.f0 = h->f.p0;
+      e.f1 = h->f.p1;
+      e.ld_f = h->f.ld;
+      e.eq = ActOut{h->eqc.p0, nullptr, S * 3 * K, 0};      // row = frame; per symbol [eq | corr]
+      e.corr = ActOut{h->eqc.p0, nullptr, S * 3 * K, 2 * K};
+      e.sym_cols = 2 * K;
+      e.eq_sym_stride = 3 * K;
+      e.corr_sym_stride = 3 * K;
+      e.chest_out = chest_out;
+      e.M = (int)Bc;
+      e.N = h->g7.N;
+      KSched ks;
+      if (h->band_skip && h->g7.BN == 2 * K && (2 * K) % 32 == 0) ks.band = ((S - 1) / 2) * (2 * K / 32);
+      if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, h->u1, 0, Bc, e, s, ks))) return rc;
+    }
+    if ((rc = run_gemm(h, SLOT_F9, h->f9, eqcv, 0, MS, store_epi(h->f9, r1v, 0, MS), s))) return rc;
+    return run_head_dispatch(h, Bc, bits, soft, hard, conf, ce, s);
+  }
   if (use_eq) {
     const int64_t MS = Bc * S;
     // views: [Bc, S*X] buffers are addressed as [Bc*S, X] by the per-symbol layers
@@ -522,7 +636,10 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       e.chest_out = chest_out;
       e.M = (int)Bc;
       e.N = h->g7.N;
-      if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, c4, 0, Bc, e, s))) return rc;
+      // block-banded Toeplitz operand: symbols more than (S-1)/2 apart share no tap -> skip those k-blocks
+      KSched ks;
+      if (h->band_skip && h->g7.BN == 2 * K && (2 * K) % 32 == 0) ks.band = ((S - 1) / 2) * (2 * K / 32);
+      if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, c4, 0, Bc, e, s, ks))) return rc;
     }
     // corr / eq (1,K) 'valid' complex convs -> [eq_out | corr_out]  model.py:437-448
     if ((rc = run_gemm(h, SLOT_G8, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
@@ -702,6 +819,8 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_SMS")) h->num_sms = atoi(e);   // experiment knob: restrict the persistent grids
   if (const char* e = getenv("DCCN_PAIR")) h->multicast = atoi(e);
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
+  if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
+  if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
     return set_error(-2, "frame size must be a multiple of 4 floats");
@@ -804,6 +923,7 @@ int dccn_commit_weights(dccn_handle* h, void* stream) {
   int rc = build_layers(h, (cudaStream_t)stream);
   if (rc) return rc;
   h->committed = true;
+  h->fold_built = false;
   if (h->tr) return train_on_commit(h, (cudaStream_t)stream);   // re-seed the device master copies
   return 0;
 }
@@ -818,6 +938,7 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
                  uint8_t* hard_dev, float* eq_dev, float* chest_dev, int64_t* conf_dev, double* ce_sum_dev,
                  int flags, void* stream) {
   DCCN_CHECK(h && x_dev, "null argument");
+  flags |= h->default_flags;
   DCCN_CHECK(!(flags & DCCN_FWD_EQ_ONLY) || h->cfg.equalizer, "DCCN_FWD_EQ_ONLY needs cfg.equalizer");
   DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
   DCCN_CHECK(B > 0, "empty batch");

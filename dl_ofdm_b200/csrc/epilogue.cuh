@@ -136,8 +136,16 @@ struct EpiPhaseEq {
   ActOut corr;          // [M, N/2]    real part only (imag is exactly 0 and is dropped from the GEMM)
   float* chest_out;     // optional fp32 [M, N] ('chest' fetch), or nullptr
   int M, N;
+  // Destination layout: eq column c (symbol s = c / sym_cols) lands at  s * eq_sym_stride + c % sym_cols, the real
+  // corr value of complex point j at  s * corr_sym_stride + j % (sym_cols / 2).  Defaults (stride == width) are the
+  // plain [M, N] / [M, N/2] matrices; the folded schedule interleaves both per symbol in one [M*S, 3K] operand.
+  int sym_cols = 1 << 30, eq_sym_stride = 1 << 30, corr_sym_stride = 1 << 30;
   struct State {};
   static constexpr bool kWarpStore = true;
+  DCCN_DEVINL int eq_col(int c) const { return sym_cols == (1 << 30) ? c : (c / sym_cols) * eq_sym_stride + c % sym_cols; }
+  DCCN_DEVINL int corr_col(int j) const {
+    return sym_cols == (1 << 30) ? j : (j / (sym_cols >> 1)) * corr_sym_stride + j % (sym_cols >> 1);
+  }
 
   // tensor-core path: rows row0 + lane; eq goes out through the coalescing transpose
   DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
@@ -160,9 +168,9 @@ struct EpiPhaseEq {
       v[i] = cr;
       v[i + 1] = ci;
     }
-    store_block_warp(eq.p0 + eq.col_off + col0, eq.ld, row0, M, lane, e, patch);
+    store_block_warp(eq.p0 + eq.col_off + eq_col(col0), eq.ld, row0, M, lane, e, patch);
     if (chest_out) store_block_warp(chest_out + col0, N, row0, M, lane, v, patch);
-    if (ok) store_act<16>(corr, row, col0 / 2, c);
+    if (ok) store_act<16>(corr, row, corr_col(col0 / 2), c);
   }
 
   template <int NC>
@@ -194,8 +202,8 @@ struct EpiPhaseEq {
       v[i] = cr;
       v[i + 1] = ci;
     }
-    store_act<NC>(eq, row, col0, e);
-    store_act<NC / 2>(corr, row, col0 / 2, c);
+    store_act<NC>(eq, row, eq_col(col0), e);
+    store_act<NC / 2>(corr, row, corr_col(col0 / 2), c);
     if (chest_out) {
       float* d = chest_out + (size_t)row * N + col0;
 #pragma unroll

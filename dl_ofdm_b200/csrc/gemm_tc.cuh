@@ -100,6 +100,48 @@ struct TcCfg {
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
 };
 
+// Per-tile K range.  Default: the whole K.  ksplit > 1: split-K -- tile index gains a slice coordinate, slice z
+// contracts k-blocks [z*per, (z+1)*per) and its rows are stored at row offset z * m_tiles * 128 (the caller sums the
+// slices; used by the weight-gradient GEMMs whose K is the batch).  band >= 0: block-banded B operand -- n-tile j
+// only contracts k-blocks [j*BN/32 - band, (j+1)*BN/32 + band) (the (S,K) 'same' conv as a Toeplitz matrix has no
+// taps between OFDM symbols more than (S-1)/2 apart, so those 128x128 blocks are structurally zero).
+struct KSched {
+  int ksplit = 1;
+  int band = -1;
+};
+
+struct TileK {
+  int m_blk, n_blk, kslice, kb0, kb1;
+};
+
+template <int BN>
+DCCN_DEVINL TileK tile_decode(int tile, int m_tiles, int n_tiles, int num_kb, int ksplit, int band) {
+  TileK t;
+  if (ksplit <= 1) {
+    t.kslice = 0;
+    t.m_blk = tile / n_tiles;
+    t.n_blk = tile - t.m_blk * n_tiles;
+    t.kb0 = 0;
+    t.kb1 = num_kb;
+    if (band >= 0) {
+      constexpr int KBN = BN / 32;
+      const int lo = t.n_blk * KBN - band, hi = (t.n_blk + 1) * KBN + band;
+      t.kb0 = lo > 0 ? lo : 0;
+      t.kb1 = hi < num_kb ? hi : num_kb;
+    }
+    return t;
+  }
+  const int mn = m_tiles * n_tiles;
+  t.kslice = tile / mn;
+  const int t2 = tile - t.kslice * mn;
+  t.m_blk = t2 / n_tiles;
+  t.n_blk = t2 - t.m_blk * n_tiles;
+  const int per = (num_kb + ksplit - 1) / ksplit;
+  t.kb0 = t.kslice * per;
+  t.kb1 = t.kb0 + per < num_kb ? t.kb0 + per : num_kb;
+  return t;
+}
+
 struct TcOperands {
   CUtensorMap a0;       // A, one fp32 plane
   CUtensorMap b0, b1;   // B hi / lo (b1 unused when !SPLIT)
@@ -109,7 +151,7 @@ template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
 __global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR)>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int M, int N, int K, int kc, const __grid_constant__ Epi epi) {
+               int M, int N, int K, int kc, int ksplit, int band, const __grid_constant__ Epi epi) {
   constexpr bool DEC = ATM && !PAIR;
   using C = TcCfg<BN, SPLIT, CG, ATM, DEC>;
   extern __shared__ uint8_t smem_raw[];
@@ -132,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   // cluster owns M-tile 2*m_pair + r.  Both CTAs of a pair run the same tile sequence.
   const int crank = PAIR ? (int)cluster_ctarank() : 0;
   const int m_tiles = (M + C::BM - 1) / C::BM;
-  const int num_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int num_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles * ksplit) * n_tiles;   // PAIR: full-K tiles only
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int BROWS = PAIR ? BN / 2 : BN;            // weight rows this CTA holds
@@ -140,7 +182,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   constexpr int TX = (DEC ? 0 : C::A_BYTES) + C::PLANES * BH;   // bytes TMA lands in THIS CTA per (B) stage
   const int num_kb = (K + C::BK - 1) / C::BK;
   const int kb_per_chunk = (kc <= 0 || kc > num_kb) ? num_kb : kc;
-  const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
+  // (m_blk, n_blk, k-block range) of a tile index
+  auto decode = [=](int tile) -> TileK {
+    if constexpr (PAIR) return TileK{(tile / n_tiles) * 2 + crank, tile % n_tiles, 0, 0, num_kb};
+    else return tile_decode<BN>(tile, m_tiles, n_tiles, num_kb, ksplit, band);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -188,8 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = PAIR ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const TileK tk = decode(tile);
+        const int m_blk = tk.m_blk, n_blk = tk.n_blk;
+        for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&full[stage], TX);
@@ -217,8 +264,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += kb_per_chunk) {
-          const int kb1 = kb0 + kb_per_chunk < num_kb ? kb0 + kb_per_chunk : num_kb;
+        const TileK tk = decode(tile);
+        for (int kb0 = tk.kb0; kb0 < tk.kb1; kb0 += kb_per_chunk) {
+          const int kb1 = kb0 + kb_per_chunk < tk.kb1 ? kb0 + kb_per_chunk : tk.kb1;
           if (PAIR) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
           else mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
@@ -285,8 +333,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     int sa = 0;
     uint32_t pa = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile / n_tiles;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const TileK tk = decode(tile);
+      const int m_blk = tk.m_blk;
+      for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
         mbar_wait(&emptyA[sa], pa ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&fullA[sa], C::A_BYTES);
@@ -307,7 +356,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     uint32_t phase = 0, pa = 0;
     const int r = (warp & 3) * 32 + lane;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const TileK tk = decode(tile);
+      for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
         mbar_wait(&fullA[sa], pa);
         const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
         float hi[32], lo[32];
@@ -349,7 +399,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const TileK tk = decode(tile);
+      for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         if constexpr (ATM) {
           // thread <-> A row (TMEM lane).  Undo the TMA 128B swizzle while reading: the 16-byte
@@ -414,8 +465,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     uint32_t acc_phase = 0;
     float r[C::NCH][32];
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = PAIR ? (tile / n_tiles) * 2 + crank : tile / n_tiles, n_blk = tile % n_tiles;
-      const int row = m_blk * C::BM + q * 32 + lane;
+      const TileK tk = decode(tile);
+      const int n_blk = tk.n_blk;
+      const int row_base = (tk.kslice * m_tiles + tk.m_blk) * C::BM + q * 32;   // split-K slices stack along the rows
+      const int row = row_base + lane;
+      const int num_chunks = (tk.kb1 - tk.kb0 + kb_per_chunk - 1) / kb_per_chunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
@@ -446,7 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int j = 0; j < C::NCH; ++j) {
         const int col = n_blk * BN + cg * C::COLS_PER_GROUP + j * 32;
         if constexpr (Epi::kWarpStore)
-          epi.run_warp(st, m_blk * C::BM + q * 32, lane, col, r[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
+          epi.run_warp(st, row_base, lane, col, r[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
         else
           epi.template run<32>(st, row, col, r[j]);
       }
@@ -465,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
 template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
-                          int num_sms) {
+                          int num_sms, KSched ks = KSched()) {
   using C = TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR)>;
   if (M <= 0) return 0;
   auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi>;
@@ -488,13 +542,21 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    const int tiles = m_tiles * n_tiles;
+    const int num_kb = (K + C::BK - 1) / C::BK;
+    if (ks.ksplit > 1) {   // every slice must own at least one k-block
+      const int per = (num_kb + ks.ksplit - 1) / ks.ksplit;
+      ks.ksplit = (num_kb + per - 1) / per;
+      ks.band = -1;
+    }
+    if (ks.ksplit < 1) ks.ksplit = 1;
+    const int tiles = m_tiles * n_tiles * ks.ksplit;
     cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
   }
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
-  DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, epi));
+  if (PAIR) ks = KSched();
+  DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, ks.ksplit, ks.band, epi));
   return 0;
 }
 

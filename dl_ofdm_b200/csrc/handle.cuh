@@ -44,7 +44,7 @@ struct HostTensor {
 
 extern std::atomic<long long> g_launches;   // kernels launched by this library (dccn_launch_count)
 enum { SLOT_MOMENTS = 0, SLOT_PREP, SLOT_G1, SLOT_G2, SLOT_G3, SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G7_PHASEEQ,
-       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_T_HEAD, SLOT_T_DGRAD, SLOT_T_WGRAD, SLOT_T_POINT, SLOT_T_ADAM, SLOT_T_REPACK, SLOT_COUNT };
+       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_T_HEAD, SLOT_T_DGRAD, SLOT_T_WGRAD, SLOT_T_POINT, SLOT_T_ADAM, SLOT_T_REPACK, SLOT_F1, SLOT_F4, SLOT_F9, SLOT_COUNT };
 extern const char* kSlotNames[SLOT_COUNT];
 struct ProfRec { int slot; cudaEvent_t a, b; };
 struct TrainState;
@@ -67,10 +67,16 @@ struct dccn_handle {
   int multicast = 0;   // cta_group::2 CTA pairs (DCCN_PAIR=1 enables; measured slower than single-CTA tiles)
   int mc_min_k = 128;
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
+  int band_skip = 1;   // skip the structurally-zero k-blocks of the Toeplitz ((S,K) 'same' conv) operand
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
   dccn::GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
   dccn::HeadWeights hw;
+  // DCCN_FWD_FOLDED: consecutive linear layers pre-multiplied (built on first use, from the committed weights)
+  dccn::GemmLayer f1, f4, f9;       // dense.conv3d | dense_2.dense_3.dense_4(tanh) | (conv3d_3,conv3d_2).dense_5.fft_like
+  bool fold_built = false;
+  int default_flags = 0;            // OR-ed into the flags of every forward (DCCN_FOLD=1 sets DCCN_FWD_FOLDED)
+  dccn::Act eqc;                    // folded schedule: per symbol [eq (2K) | corr (K)]
   // workspace
   std::vector<void*> allocs;
   double* d_sums = nullptr;       // [2P] moments accumulators
@@ -140,7 +146,7 @@ int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, float* r
 int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
               float* eq_out, float* chest_out, unsigned long long* conf, double* ce, int flags, cudaStream_t s);
 int run_gemm_store(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
-                   const EpiStore& epi, cudaStream_t s);
+                   const EpiStore& epi, cudaStream_t s, int ksplit = 1);
 void conf_accumulate(const unsigned long long* src, int64_t* dst, cudaStream_t s);
 // train.cu hooks used by the C ABI in dccn.cu
 void train_free(dccn_handle* h);

@@ -56,6 +56,10 @@ struct TrainState {
   Act d_oiq, d_r1o, d_oeq, d_cat, d_eq, d_corr, d_f, d_f2, d_ch, dA, dB, dC, d_p32, d_t1;
   float* partial = nullptr;
   size_t partial_floats = 0;
+  // tensor-core wgrad (parity mode): transposed operands  X^T [Kin, M] (fp32)  and  dY^T [Nout, M] (tf32 hi/lo)
+  int wgrad_tc = 0;
+  float *xT = nullptr, *yT0 = nullptr, *yT1 = nullptr;
+  size_t xT_floats = 0, yT_floats = 0;
 };
 
 static const char* kLayerVar[10] = {"Equalizer/dense",    "Equalizer/conv3d",   "Equalizer/dense_1", "Equalizer/dense_2",
@@ -124,14 +128,60 @@ wgrad_simt_kernel(const float* __restrict__ X, int ldx, int Kin, const float* __
   }
 }
 
-// deterministic sum of the split-K partials
+// deterministic sum of the split-K partials (slice z starts at z * stride)
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ P, int splits, long long n, float* __restrict__ out) {
+reduce_partials_kernel(const float* __restrict__ P, int splits, long long n, long long stride, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += P[(size_t)z * n + i];
+  for (int z = 0; z < splits; ++z) s += P[(size_t)z * stride + i];
   out[i] = s;
+}
+
+// X [M, C] (row pitch ld) -> T [C, M] (row pitch ldt); split != 0 writes tf32 hi / lo planes
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ X, int ld, int C, long long M, float* __restrict__ T0, float* __restrict__ T1,
+                 long long ldt, int split) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32;
+  const long long m0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const long long m = m0 + r;
+    const int c = c0 + tx;
+    tile[r][tx] = (m < M && c < C) ? X[(size_t)m * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long m = m0 + tx;
+    if (c < C && m < M) {
+      const float v = tile[tx][r];
+      if (split) {
+        float hi, lo;
+        tf32_split(v, hi, lo);
+        T0[(size_t)c * ldt + m] = hi;
+        T1[(size_t)c * ldt + m] = lo;
+      } else T0[(size_t)c * ldt + m] = v;
+    }
+  }
+}
+
+// out[n] = sum_m (T0[n][m] + T1[n][m]): the bias gradient (column sums of dY) from the transposed planes
+__global__ void __launch_bounds__(256)
+rowsum_kernel(const float* __restrict__ T0, const float* __restrict__ T1, long long M, long long ldt, float* __restrict__ out) {
+  __shared__ float red[256];
+  const float* a = T0 + (size_t)blockIdx.x * ldt;
+  const float* b = T1 + (size_t)blockIdx.x * ldt;
+  float s = 0.f;
+  for (long long m = threadIdx.x; m < M; m += 256) s += a[m] + b[m];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0];
 }
 
 // ---- packed operand <-> reference-layout variable ---------------------------------------------------
@@ -361,6 +411,18 @@ __global__ void __launch_bounds__(256) add_kernel(float* __restrict__ a, const f
 // =========================================================================================
 static inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
 
+// tile width and split-K factor of the tensor-core wgrad GEMM  [Kin, M] x [M, Nout]
+static int wgrad_bn(int Nout) { return Nout <= 32 ? 32 : (Nout > 128 && Nout <= 192 ? 192 : 128); }
+static int wgrad_ksplit(int Kin, int Nout, int64_t M, int num_sms) {
+  const int m_tiles = (Kin + 127) / 128, n_tiles = (Nout + wgrad_bn(Nout) - 1) / wgrad_bn(Nout);
+  const int num_kb = (int)((M + 31) / 32);
+  int ksplit = (2 * num_sms + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);   // ~two waves of tiles
+  if (ksplit > num_kb / 2) ksplit = num_kb / 2;
+  if (ksplit < 1) ksplit = 1;
+  const int per = (num_kb + ksplit - 1) / ksplit;
+  return (num_kb + per - 1) / per;                                             // every slice owns >= 1 k-block
+}
+
 static int rows_per_split(int64_t M) {
   int64_t rps = 512;
   if ((M + rps - 1) / rps > 32) rps = ((M + 31) / 32 + 15) / 16 * 16;
@@ -373,15 +435,53 @@ static int run_wgrad(dccn_handle* h, TrainLayer& t, const float* X, int ldx, con
   TrainState* tr = h->tr;
   const int Kin = t.L->K, Nout = t.L->N;
   DCCN_CHECK(Kin % 4 == 0 && Nout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "wgrad operands must be float4-aligned");
-  const int rps = rows_per_split(M);
-  const int splits = (int)((M + rps - 1) / rps);
-  const size_t n = (size_t)(Kin + 1) * Nout;
-  DCCN_CHECK(n * splits <= tr->partial_floats, "wgrad scratch too small (%zu > %zu)", n * splits, tr->partial_floats);
-  {
+  if (tr->wgrad_tc) {
+    // ---- tcgen05 path: dWp[Kin, Nout] = X^T[Kin, M] * (dY^T[Nout, M])^T, split-K over the batch ----------------
+    const long long ldt = (M + 3) & ~3LL;
+    DCCN_CHECK((size_t)Kin * ldt <= tr->xT_floats && (size_t)Nout * ldt <= tr->yT_floats, "transpose scratch too small");
+    GemmLayer wl;
+    wl.K = (int)M;
+    wl.N = Nout;
+    wl.BN = wgrad_bn(Nout);
+    wl.dWt0 = tr->yT0;
+    wl.dWt1 = tr->yT1;
+    int rc = make_tmap(&wl.tmB0, tr->yT0, Nout, M, ldt, wl.BN);
+    if (rc) return rc;
+    if ((rc = make_tmap(&wl.tmB1, tr->yT1, Nout, M, ldt, wl.BN))) return rc;
+    const int m_tiles = (Kin + 127) / 128;
+    const int ksplit = wgrad_ksplit(Kin, Nout, M, h->num_sms);
+    const size_t stride = (size_t)m_tiles * 128 * Nout;
+    DCCN_CHECK(stride * ksplit <= tr->partial_floats, "wgrad scratch too small (%zu > %zu)", stride * ksplit,
+               tr->partial_floats);
+    {
+      LaunchScope ls(h, SLOT_T_WGRAD, s, 3);
+      dim3 gx((Kin + 31) / 32, (unsigned)((M + 31) / 32)), gy((Nout + 31) / 32, (unsigned)((M + 31) / 32));
+      transpose_kernel<<<gx, 256, 0, s>>>(X, ldx, Kin, (long long)M, tr->xT, nullptr, ldt, 0);
+      transpose_kernel<<<gy, 256, 0, s>>>(Y, ldy, Nout, (long long)M, tr->yT0, tr->yT1, ldt, 1);
+      rowsum_kernel<<<Nout, 256, 0, s>>>(tr->yT0, tr->yT1, (long long)M, ldt, t.dWp + (size_t)Kin * Nout);
+      DCCN_CUDA_OK(cudaGetLastError());
+    }
+    Act A;
+    A.p0 = tr->xT;
+    A.ld = (int)ldt;
+    Act P;
+    P.p0 = tr->partial;
+    P.ld = Nout;
+    EpiStore e = store_epi(wl, P, 0, (int64_t)ksplit * m_tiles * 128);
+    e.bias = nullptr;
+    if ((rc = run_gemm_store(h, SLOT_T_WGRAD, wl, A, 0, Kin, e, s, ksplit))) return rc;
+    LaunchScope ls(h, SLOT_T_WGRAD, s, 1);
+    reduce_partials_kernel<<<blocks_for((long long)Kin * Nout), 256, 0, s>>>(tr->partial, ksplit, (long long)Kin * Nout,
+                                                                           (long long)stride, t.dWp);
+  } else {
+    const int rps = rows_per_split(M);
+    const int splits = (int)((M + rps - 1) / rps);
+    const size_t n = (size_t)(Kin + 1) * Nout;
+    DCCN_CHECK(n * splits <= tr->partial_floats, "wgrad scratch too small (%zu > %zu)", n * splits, tr->partial_floats);
     LaunchScope ls(h, SLOT_T_WGRAD, s, 2);
     dim3 grid((Nout + 63) / 64, (Kin + 1 + 63) / 64, splits);
     wgrad_simt_kernel<<<grid, 256, 0, s>>>(X, ldx, Kin, Y, ldy, Nout, (long long)M, rps, tr->partial);
-    reduce_partials_kernel<<<blocks_for((long long)n), 256, 0, s>>>(tr->partial, splits, (long long)n, t.dWp);
+    reduce_partials_kernel<<<blocks_for((long long)n), 256, 0, s>>>(tr->partial, splits, (long long)n, (long long)n, t.dWp);
   }
   LaunchScope ls(h, SLOT_T_ADAM, s, 2);
   TrainParam& kp = tr->params[t.kp];
@@ -648,8 +748,23 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
     // wgrad scratch: splits x (K+1) x N for the batch this layer contracts over
     const int64_t M = kPerSymbol[i] ? MB * S : MB;
     const int rps = rows_per_split(M);
-    const size_t need = (size_t)((M + rps - 1) / rps) * (kn + Nl);
+    size_t need = (size_t)((M + rps - 1) / rps) * (kn + Nl);
     if (need > max_partial) max_partial = need;
+    // tensor-core wgrad: split-K slices of padded [m_tiles*128, N] + the transposed operands
+    // (split-K grows as the batch shrinks only up to num_kb/2, so the largest batch bounds the scratch)
+    need = (size_t)wgrad_ksplit(Kl, Nl, M, h->num_sms) * ((Kl + 127) / 128) * 128 * Nl;
+    if (need > max_partial) max_partial = need;
+    const size_t ldt = (size_t)((M + 3) & ~3LL);
+    if ((size_t)Kl * ldt > tr->xT_floats) tr->xT_floats = (size_t)Kl * ldt;
+    if ((size_t)Nl * ldt > tr->yT_floats) tr->yT_floats = (size_t)Nl * ldt;
+  }
+  tr->wgrad_tc = h->cfg.precision == DCCN_PREC_PARITY;
+  if (const char* e = getenv("DCCN_WGRAD_SIMT")) if (atoi(e)) tr->wgrad_tc = 0;
+  if (tr->wgrad_tc) {
+    rc |= dev_alloc(h, (void**)&tr->xT, tr->xT_floats * 4);
+    rc |= dev_alloc(h, (void**)&tr->yT0, tr->yT_floats * 4);
+    rc |= dev_alloc(h, (void**)&tr->yT1, tr->yT_floats * 4);
+    if (rc) return rc;
   }
   if ((rc = make_bw_layer(h, h->r1, &tr->bw_r1, s))) return rc;
   if ((rc = make_bw_layer(h, h->r2, &tr->bw_r2, s))) return rc;

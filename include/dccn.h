@@ -41,7 +41,12 @@ enum { DCCN_HEAD_DEV = 0, DCCN_HEAD_V1 = 1 };
 enum {
   DCCN_FWD_NO_NORM = 1, /* x is already the normalised 'input:0' tensor (skip a2)              */
   DCCN_FWD_EQ_ONLY = 2, /* stop after equalizer_ofdm (eq_dev / chest_dev are the outputs)      */
-  DCCN_FWD_SKIP_EQ = 4  /* run ofdm_dense_rx directly on x even if the handle has an equalizer */
+  DCCN_FWD_SKIP_EQ = 4, /* run ofdm_dense_rx directly on x even if the handle has an equalizer */
+  DCCN_FWD_FOLDED = 8   /* inference-graph optimisation (opt-in): consecutive LINEAR layers of the reference graph are
+                           pre-multiplied in fp64 when first used -- dense.conv3d, dense_2.dense_3.dense_4 (before its
+                           tanh), (conv3d_3 | conv3d_2).dense_5.fft_like -- so 12 GEMMs become 5.  Same function of
+                           the inputs (different fp32 rounding); ignored when eq_dev is requested, for
+                           DCCN_FWD_EQ_ONLY, and once dccn_train_init has been called (weights then change). */
 };
 
 /* Geometry + model selection; field names follow the reference FLAGS

@@ -528,3 +528,42 @@ def test_mix_rayleigh_cycling(libdccn):
         assert (support[0::4] == 1).all() and support[1::4].max() > 9 and support[3::4].max() <= 9
     rx = ch.run(tx, torch.full((B,), 20.0, device='cuda'))
     assert torch.isfinite(rx).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# DCCN_FWD_FOLDED: pre-multiplied linear layers give the same function of the inputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision,cp,nb', [('parity', True, 2), ('parity', False, 4), ('exact', True, 4)])
+def test_folded_schedule_matches_oracle(libdccn, precision, cp, nb):
+    from dl_ofdm_b200 import _lib
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(91)
+    B = 300
+    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    soft_ref, _, chest_ref = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64)
+    m = DCCN(nbits=nb, use_cp=cp, equalizer=True, precision=precision, chunk_frames=128)
+    m.load_weights(w)
+    plain = m.forward(_cuda(x), _cuda(bits), want_chest=True)
+    fold = m.forward(_cuda(x), _cuda(bits), want_chest=True, flags=_lib.FWD_FOLDED)
+    good = np.abs(chest_ref).reshape(B, -1).min(axis=1) > 2e-2
+    assert good.sum() > B // 4
+    soft_p, soft_f = plain['soft'].cpu().numpy(), fold['soft'].cpu().numpy()
+    err_f = np.abs(soft_f[good] - soft_ref[good])
+    err_p = np.abs(soft_p[good] - soft_ref[good])
+    # the folded schedule is held to the same bound as the layer-by-layer one (and is usually closer to fp64)
+    assert np.quantile(err_f, 0.999) < 2e-4, np.quantile(err_f, 0.999)
+    assert np.quantile(err_f, 0.999) < 2.0 * np.quantile(err_p, 0.999) + 2e-6
+    hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+    decided = (np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-3) & good[:, None, None]
+    assert np.array_equal(fold['hard'].cpu().numpy()[decided], hard_ref[decided])
+    chest = fold['chest'].cpu().numpy()
+    assert np.abs((chest[..., 0] + 1j * chest[..., 1]) - chest_ref).max() < 2e-5 * max(1.0, np.abs(chest_ref).max())
+    # confusion matrices count the same bits
+    assert int(fold['conf'].sum()) == int(plain['conf'].sum()) == B * 320 * nb
+    # a request for the equalizer output falls back to the layer-by-layer schedule
+    eq = m.forward(_cuda(x), want_eq=True, flags=_lib.FWD_FOLDED)
+    assert torch.equal(eq['soft'], plain['soft'])
+    m.close()

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libdccn.so')
+LIB_PATH = os.environ.get('DCCN_LIB') or os.path.join(HERE, 'libdccn.so')   # DCCN_LIB: debug builds (tools/)
 
 PREC_EXACT, PREC_PARITY, PREC_FAST = 0, 1, 2
 HEAD_DEV, HEAD_V1 = 0, 1

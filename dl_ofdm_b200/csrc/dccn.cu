@@ -68,6 +68,9 @@ int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
   return 0;
 }
 
+#ifdef DCCN_TRACE
+long long* g_trace_host_ptr = nullptr;
+#endif
 std::atomic<long long> g_launches{0};
 const char* kSlotNames[SLOT_COUNT] = {
     "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
@@ -144,6 +147,9 @@ int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   const int K = L->K, N = L->N;
   L->BN = pick_bn(N, L->fused, h->bn_wide);
   const int prec = h->cfg.precision;
+  // 192-wide tiles only exist as the 2-stage shared-memory-split form (TMEM cannot hold 2x192 accumulator columns plus
+  // the A staging); two 128-wide A-in-TMEM tiles (the second mostly empty) are faster.  DCCN_BN192=1 restores them.
+  if (L->BN == 192 && prec == DCCN_PREC_PARITY && h->a_tmem && !h->bn192) L->BN = 128;
   DCCN_CHECK((K * 4) % 16 == 0, "layer K=%d is not a multiple of 4", K);
   if (!L->built) {
     int rc = dev_alloc(h, (void**)&L->dBias, (size_t)N * 4);
@@ -452,6 +458,13 @@ template <class Epi>
 static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
                     const Epi& epi, cudaStream_t s, KSched ks = KSched()) {
   const int prec = h->cfg.precision;
+#ifdef DCCN_TRACE
+  {   // debug build: only the GEMM of profile slot $DCCN_TRACE_SLOT writes the timeline buffer
+    static int want = getenv("DCCN_TRACE_SLOT") ? atoi(getenv("DCCN_TRACE_SLOT")) : -1;
+    long long* p = (slot == want) ? g_trace_host_ptr : nullptr;
+    cudaMemcpyToSymbolAsync(g_trace_buf, &p, sizeof(p), 0, cudaMemcpyHostToDevice, s);
+  }
+#endif
   LaunchScope ls(h, slot, s);
   if (prec == DCCN_PREC_EXACT)
     return launch_gemm_simt<Epi>(A.p0 + a_col_off, A.p1 ? A.p1 + a_col_off : nullptr, A.ld, L.dW, (int)M, L.N, L.K,
@@ -582,7 +595,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
     if ((rc = run_gemm(h, SLOT_F4, h->f4, h->p32, 0, Bc, store_epi(h->f4, h->u1, 0, Bc, /*tanh*/ 1), s))) return rc;
     {
-      EpiPhaseEq e;
+      EpiPhaseEqSym e;
       e.bias = h->g7.dBias;
       e.f0 = h->f.p0;
       e.f1 = h->f.p1;
@@ -590,8 +603,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       e.eq = ActOut{h->eqc.p0, nullptr, S * 3 * K, 0};      // row = frame; per symbol [eq | corr]
       e.corr = ActOut{h->eqc.p0, nullptr, S * 3 * K, 2 * K};
       e.sym_cols = 2 * K;
-      e.eq_sym_stride = 3 * K;
-      e.corr_sym_stride = 3 * K;
+      e.sym_stride = 3 * K;
       e.chest_out = chest_out;
       e.M = (int)Bc;
       e.N = h->g7.N;
@@ -820,6 +832,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_PAIR")) h->multicast = atoi(e);
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
+  if (const char* e = getenv("DCCN_BN192")) h->bn192 = atoi(e);
   if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
     delete h;
@@ -1154,6 +1167,14 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
   cudaFree(d_map);
   return 0;
 }
+
+#ifdef DCCN_TRACE
+/* debug build only (tools/trace_gemm.py): buffer of 8 x 4096 int64 clock samples written by CTA 0 of the next GEMMs */
+int dccn_debug_trace(long long* buf_dev) {
+  dccn::g_trace_host_ptr = buf_dev;
+  return 0;
+}
+#endif
 
 int64_t dccn_launch_count(void) { return (int64_t)g_launches.load(); }
 

@@ -127,7 +127,8 @@ struct EpiStore {
 //   corr  = eq * conj(eq)                    (real part only is non-zero)
 // f = inputs_complex (output of the learned-DFT layer), read back as hi+lo.
 // -------------------------------------------------------------------------------------
-struct EpiPhaseEq {
+template <bool SYM>
+struct EpiPhaseEqT {
   const float* bias;    // [N] packed (b0-b1, b1-b0) pattern
   const float* f0;      // inputs_complex plane 0 [M, ld_f]
   const float* f1;      // plane 1 (lo) or nullptr
@@ -136,15 +137,19 @@ struct EpiPhaseEq {
   ActOut corr;          // [M, N/2]    real part only (imag is exactly 0 and is dropped from the GEMM)
   float* chest_out;     // optional fp32 [M, N] ('chest' fetch), or nullptr
   int M, N;
-  // Destination layout: eq column c (symbol s = c / sym_cols) lands at  s * eq_sym_stride + c % sym_cols, the real
-  // corr value of complex point j at  s * corr_sym_stride + j % (sym_cols / 2).  Defaults (stride == width) are the
-  // plain [M, N] / [M, N/2] matrices; the folded schedule interleaves both per symbol in one [M*S, 3K] operand.
-  int sym_cols = 1 << 30, eq_sym_stride = 1 << 30, corr_sym_stride = 1 << 30;
+  // SYM (folded schedule): eq column c of symbol s = c / sym_cols lands at  s * sym_stride + c % sym_cols  and the
+  // real corr value of complex point j at  s * sym_stride + j % (sym_cols / 2)  (+ the ActOut column offsets), i.e.
+  // both interleave per symbol in one [M*S, 3K] operand.  !SYM: plain [M, N] / [M, N/2] matrices.
+  int sym_cols = 0, sym_stride = 0;
   struct State {};
   static constexpr bool kWarpStore = true;
-  DCCN_DEVINL int eq_col(int c) const { return sym_cols == (1 << 30) ? c : (c / sym_cols) * eq_sym_stride + c % sym_cols; }
+  DCCN_DEVINL int eq_col(int c) const {
+    if constexpr (SYM) return (c / sym_cols) * sym_stride + c % sym_cols;
+    else return c;
+  }
   DCCN_DEVINL int corr_col(int j) const {
-    return sym_cols == (1 << 30) ? j : (j / (sym_cols >> 1)) * corr_sym_stride + j % (sym_cols >> 1);
+    if constexpr (SYM) return (j / (sym_cols >> 1)) * sym_stride + j % (sym_cols >> 1);
+    else return j;
   }
 
   // tensor-core path: rows row0 + lane; eq goes out through the coalescing transpose
@@ -212,6 +217,9 @@ struct EpiPhaseEq {
   }
   DCCN_DEVINL void flush(State&) const {}
 };
+
+typedef EpiPhaseEqT<false> EpiPhaseEq;
+typedef EpiPhaseEqT<true> EpiPhaseEqSym;
 
 // -------------------------------------------------------------------------------------
 // Demodulation head fused behind the 896->2D dense (dev/py/model.py:1275-1291) + the BER

@@ -43,6 +43,21 @@
 
 namespace dccn {
 
+// ---- optional in-kernel timeline (compile with -DDCCN_TRACE; tools/trace_gemm.py) ---------------------------
+// CTA 0 records clock64() at the hand-off points of every role: buf[role * 4096 + i].
+#ifdef DCCN_TRACE
+__device__ long long* g_trace_buf = nullptr;
+struct TraceCtr { int n[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+#define DCCN_TRACE_DECL TraceCtr trc_
+#define DCCN_TRACE_EV(role)                                                                     \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && g_trace_buf && trc_.n[role] < 4096) g_trace_buf[(role) * 4096 + trc_.n[role]++] = clock64(); \
+  } while (0)
+#else
+#define DCCN_TRACE_DECL
+#define DCCN_TRACE_EV(role)
+#endif
+
 constexpr int pow2_at_least(int v) {
   int p = 32;
   while (p < v) p <<= 1;
@@ -168,6 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(emptyA + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DCCN_TRACE_DECL;
   const int n_tiles = (N + BN - 1) / BN;
   static_assert(!PAIR || ATM, "the CTA-pair form is built on the A-in-TMEM configuration");
   // PAIR: "tile" below is a pair tile (two consecutive M-tiles x one N-tile); CTA rank r of the
@@ -247,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, brow);
             if (SPLIT) tma_load_2d(st + C::B_OFF + BH, &tmB1, &full[stage], kb * C::BK, brow);
           }
+          if (lane == 0) DCCN_TRACE_EV(0);
           __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
@@ -275,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             if (PAIR) mbar_wait_cluster(&ready[stage], phase);
             else mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
             if (DEC) mbar_wait(&full[stage], phase);   // weight planes of this stage have landed too
+            if (lane == 0) DCCN_TRACE_EV(5);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
@@ -341,6 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           mbar_expect_tx(&fullA[sa], C::A_BYTES);
           tma_load_2d(a_ring + sa * C::A_BYTES, &tmA0, &fullA[sa], kb * C::BK, m_blk * C::BM);
         }
+        if (lane == 0) DCCN_TRACE_EV(1);
         __syncwarp();
         if (++sa == C::SA) {
           sa = 0;
@@ -359,6 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const TileK tk = decode(tile);
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
         mbar_wait(&fullA[sa], pa);
+        if (warp == 2 && lane == 0) DCCN_TRACE_EV(2);
         const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
         float hi[32], lo[32];
 #pragma unroll
@@ -372,6 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         __syncwarp();
         if (lane == 0) mbar_arrive(&emptyA[sa]);                  // raw tile consumed
         mbar_wait(&empty[stage], phase ^ 1);                      // TMEM staging slot is free again
+        if (warp == 2 && lane == 0) DCCN_TRACE_EV(3);
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
                             (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
@@ -381,6 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[stage]);
+        if (warp == 2 && lane == 0) DCCN_TRACE_EV(4);
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -472,6 +494,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int num_chunks = (tk.kb1 - tk.kb0 + kb_per_chunk - 1) / kb_per_chunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
         mbar_wait(&tfull[acc], acc_phase);
+        if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(6);
         tc_fence_after();
         const uint32_t t0 =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * C::COLS_PER_GROUP);
@@ -493,6 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // leader's barrier
           else mbar_arrive(&tempty[acc]);
         }
+        if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(7);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -67,6 +67,7 @@ struct dccn_handle {
   int multicast = 0;   // cta_group::2 CTA pairs (DCCN_PAIR=1 enables; measured slower than single-CTA tiles)
   int mc_min_k = 128;
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
+  int bn192 = 0;       // 1: 192-wide tiles for 128 < N <= 192 (2-stage smem-split form); 0: two 128-wide A-in-TMEM tiles
   int band_skip = 1;   // skip the structurally-zero k-blocks of the Toeplitz ((S,K) 'same' conv) operand
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense

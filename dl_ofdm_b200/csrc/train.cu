@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) add_kernel(float* __restrict__ a, const f
 static inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
 
 // tile width and split-K factor of the tensor-core wgrad GEMM  [Kin, M] x [M, Nout]
-static int wgrad_bn(int Nout) { return Nout <= 32 ? 32 : (Nout > 128 && Nout <= 192 ? 192 : 128); }
+static int wgrad_bn(int Nout) { return Nout <= 32 ? 32 : 128; }
 static int wgrad_ksplit(int Kin, int Nout, int64_t M, int num_sms) {
   const int m_tiles = (Kin + 127) / 128, n_tiles = (Nout + wgrad_bn(Nout) - 1) / wgrad_bn(Nout);
   const int num_kb = (int)((M + 31) / 32);

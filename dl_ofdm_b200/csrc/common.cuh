@@ -41,9 +41,18 @@ DCCN_DEVINL float tf32_rna(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
-DCCN_DEVINL void tf32_split(float v, float& hi, float& lo) {
+DCCN_DEVINL void tf32_split_cvt(float v, float& hi, float& lo) {
   hi = tf32_rna(v);
   lo = tf32_rna(v - hi);
+}
+// Same values with full-rate integer ops: rna = add half an ulp of the 10-bit mantissa to the magnitude bits and
+// clear the low 13 bits (cvt.rna.tf32.f32 issues at a fraction of the ALU rate and was the longest piece of the
+// splitter warps' loop).  Inf / NaN inputs are not expected on this path; a finite value whose rounding overflows the
+// exponent becomes inf in both forms.
+DCCN_DEVINL float tf32_rna_int(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+DCCN_DEVINL void tf32_split(float v, float& hi, float& lo) {
+  hi = tf32_rna_int(v);
+  lo = tf32_rna_int(v - hi);
 }
 // host version (round to nearest, ties away from zero in magnitude like cvt.rna)
 inline float tf32_rna_host(float v) {

@@ -70,6 +70,7 @@ int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
 
 #ifdef DCCN_TRACE
 long long* g_trace_host_ptr = nullptr;
+int g_abl_host = 0;
 #endif
 std::atomic<long long> g_launches{0};
 const char* kSlotNames[SLOT_COUNT] = {
@@ -152,8 +153,10 @@ int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   if (L->BN == 192 && prec == DCCN_PREC_PARITY && h->a_tmem && !h->bn192) L->BN = 128;
   DCCN_CHECK((K * 4) % 16 == 0, "layer K=%d is not a multiple of 4", K);
   if (!L->built) {
-    int rc = dev_alloc(h, (void**)&L->dBias, (size_t)N * 4);
+    const size_t bias_bytes = (size_t)((N + 127) / 128 * 128) * 4;   // epilogues read it in 32-float vector chunks
+    int rc = dev_alloc(h, (void**)&L->dBias, bias_bytes);
     if (rc) return rc;
+    DCCN_CUDA_OK(cudaMemsetAsync(L->dBias, 0, bias_bytes, s));
     if (prec == DCCN_PREC_EXACT) {
       rc = dev_alloc(h, (void**)&L->dW, (size_t)K * N * 4);
       if (rc) return rc;
@@ -463,6 +466,12 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
     static int want = getenv("DCCN_TRACE_SLOT") ? atoi(getenv("DCCN_TRACE_SLOT")) : -1;
     long long* p = (slot == want) ? g_trace_host_ptr : nullptr;
     cudaMemcpyToSymbolAsync(g_trace_buf, &p, sizeof(p), 0, cudaMemcpyHostToDevice, s);
+    static int abl_slot = getenv("DCCN_ABL_SLOT") ? atoi(getenv("DCCN_ABL_SLOT")) : -1;
+    static int abl_copy[2];
+    abl_copy[0] = 0;
+    abl_copy[1] = g_abl_host;
+    cudaMemcpyToSymbolAsync(g_abl_dev, &abl_copy[(abl_slot < 0 || abl_slot == slot) ? 1 : 0], sizeof(int), 0,
+                            cudaMemcpyHostToDevice, s);
   }
 #endif
   LaunchScope ls(h, slot, s);
@@ -1172,6 +1181,11 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
 /* debug build only (tools/trace_gemm.py): buffer of 8 x 4096 int64 clock samples written by CTA 0 of the next GEMMs */
 int dccn_debug_trace(long long* buf_dev) {
   dccn::g_trace_host_ptr = buf_dev;
+  return 0;
+}
+/* debug build only (tools/ablate_gemm.py): switch pieces of the GEMM pipeline off to time the rest */
+int dccn_debug_abl(int mask) {
+  dccn::g_abl_host = mask;
   return 0;
 }
 #endif

@@ -108,14 +108,28 @@ struct EpiStore {
   static constexpr bool kWarpStore = true;
   DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
     if (col0 >= N) return;                       // warp-uniform
-    float y[32];
+    // All bias loads first (8 independent 16-byte broadcasts; the bias array is padded to a multiple of 128 floats),
+    // then the arithmetic, with the activation switch outside the loop: with the per-element `act ? tanhf : id`
+    // branch inside the loop the compiler serialised load -> wait -> tanh per column (~8 k clk per 32x32 block).
+    if (bias) {
+      const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+      float4 b[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float t = v[i] + (bias ? __ldg(bias + col0 + i) : 0.f);
-      y[i] = (act == 1) ? tanhf(t) : t;
+      for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[4 * i + 0] += b[i].x;
+        v[4 * i + 1] += b[i].y;
+        v[4 * i + 2] += b[i].z;
+        v[4 * i + 3] += b[i].w;
+      }
     }
-    store_block_warp(out.p0 + out.col_off + col0, out.ld, row0, M, lane, y, patch);
-    if (aux) store_block_warp(aux + col0, aux_ld, row0, M, lane, y, patch);
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+    }
+    store_block_warp(out.p0 + out.col_off + col0, out.ld, row0, M, lane, v, patch);
+    if (aux) store_block_warp(aux + col0, aux_ld, row0, M, lane, v, patch);
   }
   DCCN_DEVINL void flush(State&) const {}
 };
@@ -157,13 +171,20 @@ struct EpiPhaseEqT {
     if (col0 >= N) return;
     const int row = row0 + lane;
     const bool ok = row < M;
-    const float* fp0 = f0 + (size_t)(ok ? row : 0) * ld_f + col0;
+    const float4* fp0 = reinterpret_cast<const float4*>(f0 + (size_t)(ok ? row : 0) * ld_f + col0);   // ld_f % 4 == 0
+    const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+    float4 b4[8], f4[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b4[i] = __ldg(bp + i);   // all loads in flight before the arithmetic
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f4[i] = fp0[i];
     float e[32], c[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float cr = v[i] + __ldg(bias + col0 + i);
-      const float ci = v[i + 1] + __ldg(bias + col0 + i + 1);
-      const float2 f = *reinterpret_cast<const float2*>(fp0 + i);
+      const float4 bq = b4[i >> 2], fq = f4[i >> 2];
+      const float cr = v[i] + ((i & 2) ? bq.z : bq.x);
+      const float ci = v[i + 1] + ((i & 2) ? bq.w : bq.y);
+      const float2 f = (i & 2) ? make_float2(fq.z, fq.w) : make_float2(fq.x, fq.y);
       const float inv = rsqrtf(cr * cr + ci * ci);
       const float nr = cr * inv, ni = (-ci) * inv;
       const float er = f.x * nr - f.y * ni, ei = f.x * ni + f.y * nr;

@@ -47,15 +47,20 @@ namespace dccn {
 // CTA 0 records clock64() at the hand-off points of every role: buf[role * 4096 + i].
 #ifdef DCCN_TRACE
 __device__ long long* g_trace_buf = nullptr;
-struct TraceCtr { int n[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
-#define DCCN_TRACE_DECL TraceCtr trc_
+__device__ int g_abl_dev = 0;   // ablation mask (timing experiments only; results are garbage when != 0)
+struct TraceCtr { int n[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; };
+#define DCCN_ABL(bit) ((abl_ & (bit)) != 0)
+#define DCCN_ABL_DECL const int abl_ = g_abl_dev
+#define DCCN_TRACE_DECL TraceCtr trc_; long long* const trc_buf_ = blockIdx.x == 0 ? g_trace_buf : nullptr
 #define DCCN_TRACE_EV(role)                                                                     \
   do {                                                                                          \
-    if (blockIdx.x == 0 && g_trace_buf && trc_.n[role] < 4096) g_trace_buf[(role) * 4096 + trc_.n[role]++] = clock64(); \
+    if (trc_buf_ && trc_.n[role] < 4096) trc_buf_[(role) * 4096 + trc_.n[role]++] = clock64();  \
   } while (0)
 #else
 #define DCCN_TRACE_DECL
 #define DCCN_TRACE_EV(role)
+#define DCCN_ABL(bit) false
+#define DCCN_ABL_DECL
 #endif
 
 constexpr int pow2_at_least(int v) {
@@ -184,6 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DCCN_TRACE_DECL;
+  DCCN_ABL_DECL;
   const int n_tiles = (N + BN - 1) / BN;
   static_assert(!PAIR || ATM, "the CTA-pair form is built on the A-in-TMEM configuration");
   // PAIR: "tile" below is a pair tile (two consecutive M-tiles x one N-tile); CTA rank r of the
@@ -240,6 +246,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   tc_fence_after();
   if (PAIR) cluster_sync_all();             // both CTAs' barriers / TMEM exist before anything crosses over
   const uint32_t tmem_base = *tmem_ptr;
+  // experiment (ABL 256): only lane 0 polls the mbarrier, the rest of the warp parks at __syncwarp
+  auto wait_ = [&](uint64_t* bar, uint32_t par) {
+    if (DCCN_ABL(256)) {
+      if (lane == 0) mbar_wait(bar, par);
+      __syncwarp();
+    } else if (DCCN_ABL(512)) {
+      while (!mbar_try_wait(bar, par)) __nanosleep(32);
+    } else {
+      mbar_wait(bar, par);
+    }
+  };
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -253,8 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         const TileK tk = decode(tile);
         const int m_blk = tk.m_blk, n_blk = tk.n_blk;
         for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (elect_one()) {
+          wait_(&empty[stage], phase ^ 1);
+          if (DCCN_ABL(8)) {
+            if (elect_one()) mbar_arrive(&full[stage]);
+          } else if (elect_one()) {
             mbar_expect_tx(&full[stage], TX);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
             if (!DEC) tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
@@ -263,7 +282,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, brow);
             if (SPLIT) tma_load_2d(st + C::B_OFF + BH, &tmB1, &full[stage], kb * C::BK, brow);
           }
-          if (lane == 0) DCCN_TRACE_EV(0);
           __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
@@ -285,15 +303,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         for (int kb0 = tk.kb0; kb0 < tk.kb1; kb0 += kb_per_chunk) {
           const int kb1 = kb0 + kb_per_chunk < tk.kb1 ? kb0 + kb_per_chunk : tk.kb1;
           if (PAIR) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
-          else mbar_wait(&tempty[acc], acc_phase ^ 1);
-          tc_fence_after();
+          else wait_(&tempty[acc], acc_phase ^ 1);
+          if (!DCCN_ABL(128)) tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = kb0; kb < kb1; ++kb) {
             if (PAIR) mbar_wait_cluster(&ready[stage], phase);
-            else mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
-            if (DEC) mbar_wait(&full[stage], phase);   // weight planes of this stage have landed too
+            else wait_(SPLIT ? &ready[stage] : &full[stage], phase);
+            if (DEC) wait_(&full[stage], phase);   // weight planes of this stage have landed too
             if (lane == 0) DCCN_TRACE_EV(5);
-            tc_fence_after();
+            if (!DCCN_ABL(128)) tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
             const uint32_t b_hi = a_hi + C::B_OFF;
@@ -301,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             const uint32_t ta_hi = tmem_base + (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
             if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+            for (int k = 0; k < (DCCN_ABL(32) ? 0 : C::BK / C::UMMA_K); ++k) {
               const uint32_t koff = k * C::UMMA_K * 4;   // byte advance inside the 128 B swizzle row
               const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
               const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
@@ -328,6 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 umma_tf32(d, da_hi, db_hi, idesc, accum);
               }
             }
+            DCCN_TRACE_EV(9);
             if (PAIR) umma_commit_pair(&empty[stage], 0x3);   // slot released in both CTAs of the pair
             else umma_commit(&empty[stage]);                  // smem slot reusable once these MMAs retire
             if (kb + 1 == kb1) {                              // K chunk complete -> epilogue(s) drain it
@@ -336,6 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
             }   // elect_one
             __syncwarp();
+            if (lane == 0) DCCN_TRACE_EV(8);
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -354,12 +374,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const TileK tk = decode(tile);
       const int m_blk = tk.m_blk;
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
-        mbar_wait(&emptyA[sa], pa ^ 1);
-        if (elect_one()) {
+        wait_(&emptyA[sa], pa ^ 1);
+        if (DCCN_ABL(16)) {
+          if (elect_one()) mbar_arrive(&fullA[sa]);
+        } else if (elect_one()) {
           mbar_expect_tx(&fullA[sa], C::A_BYTES);
           tma_load_2d(a_ring + sa * C::A_BYTES, &tmA0, &fullA[sa], kb * C::BK, m_blk * C::BM);
         }
-        if (lane == 0) DCCN_TRACE_EV(1);
         __syncwarp();
         if (++sa == C::SA) {
           sa = 0;
@@ -377,10 +398,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
-        mbar_wait(&fullA[sa], pa);
+        wait_(&fullA[sa], pa);
         if (warp == 2 && lane == 0) DCCN_TRACE_EV(2);
         const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
         float hi[32], lo[32];
+        if (DCCN_ABL(1)) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) hi[c] = lo[c] = 0.f;
+        } else if (DCCN_ABL(64)) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));
+            tf32_split_cvt(v.x, hi[4 * c + 0], lo[4 * c + 0]);
+            tf32_split_cvt(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+            tf32_split_cvt(v.z, hi[4 * c + 2], lo[4 * c + 2]);
+            tf32_split_cvt(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
@@ -389,16 +423,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
           tf32_split(v.z, hi[4 * c + 2], lo[4 * c + 2]);
           tf32_split(v.w, hi[4 * c + 3], lo[4 * c + 3]);
         }
+        }
+        // The release below must not overtake the loads: an mbarrier arrive does not wait for ld.shared still queued
+        // in the LSU (observed: with the epilogue's global stores backing the LSU up at a tile boundary, TMA refilled
+        // the slot before the queued loads had read it).  Pinning hi[] -- a function of every loaded word -- in front
+        // of the arrive makes the loads complete first.
+#pragma unroll
+        for (int c = 0; c < 32; ++c) asm volatile("" : "+f"(hi[c]));
         __syncwarp();
         if (lane == 0) mbar_arrive(&emptyA[sa]);                  // raw tile consumed
-        mbar_wait(&empty[stage], phase ^ 1);                      // TMEM staging slot is free again
+        wait_(&empty[stage], phase ^ 1);                      // TMEM staging slot is free again
         if (warp == 2 && lane == 0) DCCN_TRACE_EV(3);
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
                             (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
-        tmem_st_32x32(ta, hi);
-        tmem_st_32x32(ta + 32, lo);
-        tmem_st_wait();
+        if (!DCCN_ABL(2)) {
+          tmem_st_32x32(ta, hi);
+          tmem_st_32x32(ta + 32, lo);
+          tmem_st_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[stage]);
@@ -423,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
+        wait_(&full[stage], phase);
         if constexpr (ATM) {
           // thread <-> A row (TMEM lane).  Undo the TMA 128B swizzle while reading: the 16-byte
           // chunk c of row r lives at chunk position c ^ (r & 7).
@@ -493,7 +536,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int row = row_base + lane;
       const int num_chunks = (tk.kb1 - tk.kb0 + kb_per_chunk - 1) / kb_per_chunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
-        mbar_wait(&tfull[acc], acc_phase);
+        wait_(&tfull[acc], acc_phase);
         if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(6);
         tc_fence_after();
         const uint32_t t0 =
@@ -501,7 +544,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll
         for (int j = 0; j < C::NCH; ++j) {
           float v[32];
-          tmem_ld_32x32(t0 + j * 32, v);
+          if (DCCN_ABL(4)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 1.f;
+          } else tmem_ld_32x32(t0 + j * 32, v);
           if (ch == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[j][i] = v[i];
@@ -520,14 +566,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(0);
 #pragma unroll
       for (int j = 0; j < C::NCH; ++j) {
+        if (warp == C::EPI_WARP0 && lane == 0 && j > 0) DCCN_TRACE_EV(1);
         const int col = n_blk * BN + cg * C::COLS_PER_GROUP + j * 32;
         if constexpr (Epi::kWarpStore)
           epi.run_warp(st, row_base, lane, col, r[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
         else
           epi.template run<32>(st, row, col, r[j]);
       }
+      if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(1);
     }
     epi.flush(st);
   }

@@ -20,19 +20,22 @@ lib.dccn_debug_trace.restype = C.c_int
 lib.dccn_debug_trace.argtypes = [C.c_void_p]
 m.forward(xg, want_soft=False)
 torch.cuda.synchronize()
-buf = torch.zeros(8 * 4096, dtype=torch.int64, device='cuda')
+buf = torch.zeros(10 * 4096, dtype=torch.int64, device='cuda')
 # trace ONLY the layer selected by the profile slot order: run EQ_ONLY pass and keep the last writer.  Simplest: trace
 # the whole pass; every GEMM overwrites the buffer, so the LAST GEMM of the pass is what remains -> choose flags.
 # DCCN_TRACE_SLOT (library profile slot index: 2 eq_dense, 3 eq_dft, 6 eq_dense3, 7 eq_dense4_tanh, 8 conv7x64,
 # 9 corr_idft, 10 idft, 11 dense5, 12 rx_fft_like, 16 rx_demod_gemm) selects the GEMM whose CTA 0 writes the buffer
 lib.dccn_debug_trace(C.c_void_p(buf.data_ptr()))
+if os.environ.get('ABL'):
+    lib.dccn_debug_abl.argtypes = [C.c_int]
+    lib.dccn_debug_abl(int(os.environ['ABL']))
 m.forward(xg, want_soft=False)
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(8, 4096)
+t = buf.cpu().numpy().reshape(10, 4096)
 t0 = t[t > 0].min()
-names = ['B-issue', 'A-issue', 'spl gotA', 'spl gotTM', 'spl ready', 'mma ops', 'epi got', 'epi rel']
+names = ['epi tile0', 'epi tile12', 'spl gotA', 'spl gotTM', 'spl ready', 'mma ops', 'epi got', 'epi rel', 'mma commit', 'mma issued']
 n = int(os.environ.get('N', 40))
-for r in range(8):
+for r in range(10):
     v = t[r][t[r] > 0] - t0
     print('%-10s n=%4d' % (names[r], len(v)), ' '.join('%6d' % x for x in v[:n]))
     if len(v) > 8:

@@ -318,8 +318,14 @@ def main():
     barrier()
     # ---- timed region (device events, max over ranks) -------------------------------------
     sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.15)
+    if not os.environ.get('BENCH_NO_SAMPLER'):
+        sampler.start()
+    # keep the GPU busy while nvidia-smi starts sampling: an idle gap here lets the clocks ramp down and the first
+    # timed steps then pay the ramp-up (measured: +5 ms on the first step after a 150 ms sleep)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.25:
+        step()
+        torch.cuda.synchronize()
     l0 = launch_count()
     conf_total = torch.zeros((2, 2), dtype=torch.int64, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

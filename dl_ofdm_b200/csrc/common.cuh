@@ -137,6 +137,16 @@ DCCN_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar
       : "memory");
 }
 
+// 2-D tile store, shared -> global (bulk async group; rows / columns outside the tensor are clipped by the hardware)
+DCCN_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+DCCN_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the source may be reused)
+DCCN_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // multicast variant: the box is written to the same shared-memory offset of every CTA in
 // cta_mask and completes bytes on the mbarrier at the same offset in each of them
 DCCN_DEVINL void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,

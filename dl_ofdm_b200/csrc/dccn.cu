@@ -92,12 +92,76 @@ int dev_alloc(dccn_handle* h, void** p, size_t bytes) {
   return 0;
 }
 
+// a persistent activation-shaped buffer (freed with the handle)
 int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split) {
+  (void)split;   // activations are one fp32 plane in every mode (hi/lo is made in shared memory)
   a->ld = ld;
-  int rc = dev_alloc(h, (void**)&a->p0, (size_t)rows * ld * sizeof(float));
+  a->p1 = nullptr;
+  return dev_alloc(h, (void**)&a->p0, (size_t)rows * ld * sizeof(float));
+}
+
+// an inter-layer buffer of the growable workspace (freed and re-made by ensure_workspace)
+static int alloc_ws_act(dccn_handle* h, Act* a, int64_t rows, int ld) {
+  a->ld = ld;
+  a->p1 = nullptr;
+  const size_t bytes = (size_t)rows * ld * sizeof(float);
+  DCCN_CUDA_OK(cudaMalloc((void**)&a->p0, bytes));
+  h->ws_allocs.push_back(a->p0);
+  h->ws_bytes += bytes;
+  h->ws_act_bytes += bytes;
+  return 0;
+}
+
+// The inter-layer buffers are sized for the largest pass seen so far (at most h->chunk frames) and grown on demand:
+// a handle that only ever sees 256-frame batches holds 10 MB, one that is fed 65 536-frame batches 2.7 GB.
+int ensure_workspace(dccn_handle* h, int64_t frames) {
+  if (frames > h->chunk) frames = h->chunk;
+  frames = (frames + 127) / 128 * 128;
+  if (frames <= h->ws_frames && !h->ws_dirty) return 0;
+  if (frames < h->ws_frames) frames = h->ws_frames;
+  if (h->ws_frames > 0) DCCN_CUDA_OK(cudaDeviceSynchronize());   // nothing may still be using the old buffers
+  for (void* p : h->ws_allocs) cudaFree(p);
+  for (Act* a : {&h->a0, &h->t1, &h->f, &h->p32, &h->u1, &h->u2, &h->eq, &h->corr, &h->cat, &h->oeq, &h->r1o,
+                 &h->out_iq, &h->eqc, &h->u3})
+    a->p0 = nullptr;
+  h->chest_buf = nullptr;
+  h->ws_bytes -= h->ws_act_bytes;
+  h->ws_act_bytes = 0;
+  h->ws_allocs.clear();
+  h->ws_frames = 0;
+  h->ws_dirty = false;
+  const int64_t C = frames;
+  const int S = h->S, K = h->K;
+  int rc = 0;
+  auto act = [&](Act* a, int64_t rows, int ld) {
+    if (!rc) rc = alloc_ws_act(h, a, rows, ld);
+  };
+  act(&h->a0, C, h->P);
+  act(&h->r1o, C, S * h->F * 2);
+  act(&h->out_iq, C, 2 * h->D);
+  if (h->cfg.equalizer) {
+    act(&h->t1, C, S * K * 2);
+    act(&h->f, C, S * K * 2);
+    act(&h->p32, C, 2 * h->cfg.pilot_size);
+    act(&h->u1, C, S * K * 2);
+    act(&h->u2, C, S * K * 2);
+    act(&h->eq, C, S * K * 2);
+    act(&h->corr, C, S * K);
+    act(&h->cat, C * S, 4 * K);
+    act(&h->oeq, C, h->P);
+    if (h->ws_eqc) act(&h->eqc, C * S, 3 * K);
+    if (h->ws_train) {
+      act(&h->u3, C, S * K * 2);
+      if (!rc) {
+        Act cb;
+        rc = alloc_ws_act(h, &cb, C, S * K * 2);
+        h->chest_buf = cb.p0;
+      }
+    }
+  }
   if (rc) return rc;
-  if (split) rc = dev_alloc(h, (void**)&a->p1, (size_t)rows * ld * sizeof(float));
-  return rc;
+  h->ws_frames = C;
+  return 0;
 }
 
 const HostTensor* find(const dccn_handle* h, const std::string& n) {
@@ -449,7 +513,6 @@ static int build_folded(dccn_handle* h, cudaStream_t s) {
   if ((rc = upload_layer(h, &h->f1, s))) return rc;
   if ((rc = upload_layer(h, &h->f4, s))) return rc;
   if ((rc = upload_layer(h, &h->f9, s))) return rc;
-  if (!h->eqc.p0 && (rc = alloc_act(h, &h->eqc, (int64_t)h->chunk * S, 3 * K, false))) return rc;
   h->fold_built = true;
   return 0;
 }
@@ -459,7 +522,7 @@ static int build_folded(dccn_handle* h, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------
 template <class Epi>
 static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, int a_col_off, int64_t M,
-                    const Epi& epi, cudaStream_t s, KSched ks = KSched()) {
+                    const Epi& epi_in, cudaStream_t s, KSched ks = KSched()) {
   const int prec = h->cfg.precision;
 #ifdef DCCN_TRACE
   {   // debug build: only the GEMM of profile slot $DCCN_TRACE_SLOT writes the timeline buffer
@@ -477,10 +540,20 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   LaunchScope ls(h, slot, s);
   if (prec == DCCN_PREC_EXACT)
     return launch_gemm_simt<Epi>(A.p0 + a_col_off, A.p1 ? A.p1 + a_col_off : nullptr, A.ld, L.dW, (int)M, L.N, L.K,
-                                 epi, s);
+                                 epi_in, s);
   TcOperands op;
   int rc = make_tmap(&op.a0, A.p0 + a_col_off, M, L.K, A.ld, 128);
   if (rc) return rc;
+  // destinations of the epilogue's bulk tensor stores (32 x 32 boxes)
+  Epi epi = epi_in;
+  if constexpr (std::is_same<Epi, EpiStore>::value) {
+    if ((rc = make_tmap(&epi.tm_out, epi.out.p0 + epi.out.col_off, epi.M, epi.N, epi.out.ld, 32))) return rc;
+    if (epi.aux && (rc = make_tmap(&epi.tm_aux, epi.aux, epi.M, epi.N, epi.aux_ld, 32))) return rc;
+  } else if constexpr (std::is_same<Epi, EpiPhaseEq>::value || std::is_same<Epi, EpiPhaseEqSym>::value) {
+    if ((rc = make_tmap(&epi.tm_eq, epi.eq.p0 + epi.eq.col_off, epi.M, epi.eq.ld - epi.eq.col_off, epi.eq.ld, 32)))
+      return rc;
+    if (epi.chest_out && (rc = make_tmap(&epi.tm_chest, epi.chest_out, epi.M, epi.N, epi.N, 32))) return rc;
+  }
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
   if (split) op.b1 = L.tmB1;
@@ -832,7 +905,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   h->D = cfg->n_data;
   h->NB = cfg->nbits;
   h->P = h->S * h->T * 2;
-  h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 21504;   // 168 M-tiles: 7*168 = 1176 tiles = 7.95 waves of 148
+  h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 65536;   // per-launch overheads (~10 us x 15 kernels) amortise over the pass
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
@@ -852,9 +925,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
     return set_error(-2, "equalizer_ofdm requires nfilter == nfft");
   }
   // ---- workspace -----------------------------------------------------------------
-  const bool split = false;   // activations are one fp32 plane in every mode (hi/lo is made in smem)
-  const int64_t C = h->chunk;
-  const int S = h->S, K = h->K;
+  // (the inter-layer buffers are allocated by ensure_workspace on first use)
   int rc = 0;
   rc |= dev_alloc(h, (void**)&h->d_sums, (size_t)2 * h->P * sizeof(double));
   rc |= dev_alloc(h, (void**)&h->d_mean, (size_t)h->P * 4);
@@ -873,20 +944,6 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   }
   if (!rc && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = set_error(-1, "cudaStreamCreate failed");
-  rc |= alloc_act(h, &h->a0, C, h->P, split);
-  rc |= alloc_act(h, &h->r1o, C, S * h->F * 2, split);
-  rc |= alloc_act(h, &h->out_iq, C, 2 * h->D, false);
-  if (cfg->equalizer) {
-    rc |= alloc_act(h, &h->t1, C, S * K * 2, split);
-    rc |= alloc_act(h, &h->f, C, S * K * 2, split);
-    rc |= alloc_act(h, &h->p32, C, 2 * cfg->pilot_size, split);
-    rc |= alloc_act(h, &h->u1, C, S * K * 2, split);
-    rc |= alloc_act(h, &h->u2, C, S * K * 2, split);
-    rc |= alloc_act(h, &h->eq, C, S * K * 2, split);
-    rc |= alloc_act(h, &h->corr, C, S * K, split);
-    rc |= alloc_act(h, &h->cat, C * S, 4 * K, split);
-    rc |= alloc_act(h, &h->oeq, C, h->P, split);
-  }
   if (rc) {
     dccn_destroy(h);
     return rc;
@@ -907,6 +964,7 @@ void dccn_destroy(dccn_handle* h) {
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->ws_allocs) cudaFree(p);
   delete h;
 }
 
@@ -972,8 +1030,13 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
   const bool want_conf = bits_dev && conf_dev;
   if (want_conf) DCCN_CUDA_OK(cudaMemsetAsync(h->d_conf, 0, 4 * sizeof(unsigned long long), s));
   const int D = h->D, NB = h->NB;
-  for (int64_t b0 = 0; b0 < B; b0 += h->chunk) {
-    const int64_t Bc = (B - b0) < h->chunk ? (B - b0) : h->chunk;
+  // equal passes of at most h->chunk frames (a 70 000-frame batch runs as 2 x 35 000, not 65 536 + 4 464)
+  const int64_t n_pass = (B + h->chunk - 1) / h->chunk;
+  const int64_t per = ((B + n_pass - 1) / n_pass + 127) / 128 * 128;
+  if ((flags & DCCN_FWD_FOLDED) && h->cfg.equalizer && !h->ws_eqc) h->ws_eqc = h->ws_dirty = true;
+  if ((rc = ensure_workspace(h, per))) return rc;
+  for (int64_t b0 = 0; b0 < B; b0 += per) {
+    const int64_t Bc = (B - b0) < per ? (B - b0) : per;
     rc = run_chunk(h, x_dev + (size_t)b0 * h->P, Bc, bits_dev ? bits_dev + (size_t)b0 * D * NB : nullptr,
                    soft_dev ? soft_dev + (size_t)b0 * D * NB * 2 : nullptr,
                    hard_dev ? hard_dev + (size_t)b0 * D * NB : nullptr,

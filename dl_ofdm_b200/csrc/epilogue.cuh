@@ -76,6 +76,32 @@ DCCN_DEVINL void store_block_warp(float* base, int ld, int row0, int M, int lane
   __syncwarp();
 }
 
+// Same block, handed to the TMA engine instead: the lanes write their rows into the patch in the 128-byte-swizzle
+// pattern (16-byte chunk c of row r at chunk position c ^ (r & 7) -- conflict-free, and exactly what a SWIZZLE_128B
+// tensor map undoes), one lane issues a bulk tensor store per destination and the warp moves on.  The warp no longer
+// waits for global-store credits (measured: ~3.5 k clk per block with st.global while all 148 SMs drain their tiles at
+// once, during which the K-chunk drains of the next tile were stalled); rows >= M and columns >= N are clipped by
+// the tensor map.  `tm1` is an optional second destination of the same block (API side outputs).
+DCCN_DEVINL void store_block_tma(const CUtensorMap* tm0, int col0_0, const CUtensorMap* tm1, int col0_1, int row0,
+                                 int lane, const float (&y)[32], uint32_t patch) {
+  if (lane == 0) tma_store_wait_read();        // the previous block has left the patch
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t a = patch + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(y[4 * c]), "f"(y[4 * c + 1]),
+                 "f"(y[4 * c + 2]), "f"(y[4 * c + 3])
+                 : "memory");
+  }
+  fence_proxy_async();                         // generic-proxy writes -> visible to the TMA engine
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm0, patch, col0_0, row0);
+    if (tm1) tma_store_2d(tm1, patch, col0_1, row0);
+    tma_store_commit();
+  }
+}
+
 // -------------------------------------------------------------------------------------
 // y = act(acc + bias)  ->  activation planes      (tf.layers.dense / packed complex layers)
 // -------------------------------------------------------------------------------------
@@ -86,6 +112,8 @@ struct EpiStore {
   int aux_ld;
   int act;             // 0 = linear, 1 = tanh
   int M, N;
+  CUtensorMap tm_out;  // tensor-core path: [M, N] view of out.p0 + out.col_off, box 32 x 32 (set by run_gemm)
+  CUtensorMap tm_aux;  // same for aux
   struct State {};
 
   template <int NC>
@@ -107,7 +135,7 @@ struct EpiStore {
   // tensor-core path: the 32 lanes of a warp hold 32 consecutive rows (row0 + lane)
   static constexpr bool kWarpStore = true;
   DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
-    if (col0 >= N) return;                       // warp-uniform
+    if (col0 >= N || row0 >= M) return;          // warp-uniform
     // All bias loads first (8 independent 16-byte broadcasts; the bias array is padded to a multiple of 128 floats),
     // then the arithmetic, with the activation switch outside the loop: with the per-element `act ? tanhf : id`
     // branch inside the loop the compiler serialised load -> wait -> tanh per column (~8 k clk per 32x32 block).
@@ -128,10 +156,9 @@ struct EpiStore {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
     }
-    store_block_warp(out.p0 + out.col_off + col0, out.ld, row0, M, lane, v, patch);
-    if (aux) store_block_warp(aux + col0, aux_ld, row0, M, lane, v, patch);
+    store_block_tma(&tm_out, col0, aux ? &tm_aux : nullptr, col0, row0, lane, v, patch);
   }
-  DCCN_DEVINL void flush(State&) const {}
+  DCCN_DEVINL void flush(State&) const { tma_store_wait_read(); }   // shared memory outlives the last bulk store
 };
 
 // -------------------------------------------------------------------------------------
@@ -155,6 +182,8 @@ struct EpiPhaseEqT {
   // real corr value of complex point j at  s * sym_stride + j % (sym_cols / 2)  (+ the ActOut column offsets), i.e.
   // both interleave per symbol in one [M*S, 3K] operand.  !SYM: plain [M, N] / [M, N/2] matrices.
   int sym_cols = 0, sym_stride = 0;
+  CUtensorMap tm_eq;    // tensor-core path: view of eq.p0 + eq.col_off, box 32 x 32 (set by run_gemm)
+  CUtensorMap tm_chest; // same for chest_out
   struct State {};
   static constexpr bool kWarpStore = true;
   DCCN_DEVINL int eq_col(int c) const {
@@ -168,7 +197,7 @@ struct EpiPhaseEqT {
 
   // tensor-core path: rows row0 + lane; eq goes out through the coalescing transpose
   DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
-    if (col0 >= N) return;
+    if (col0 >= N || row0 >= M) return;          // warp-uniform
     const int row = row0 + lane;
     const bool ok = row < M;
     const float4* fp0 = reinterpret_cast<const float4*>(f0 + (size_t)(ok ? row : 0) * ld_f + col0);   // ld_f % 4 == 0
@@ -194,8 +223,8 @@ struct EpiPhaseEqT {
       v[i] = cr;
       v[i + 1] = ci;
     }
-    store_block_warp(eq.p0 + eq.col_off + eq_col(col0), eq.ld, row0, M, lane, e, patch);
-    if (chest_out) store_block_warp(chest_out + col0, N, row0, M, lane, v, patch);
+    store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch);
+    if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch);
     if (ok) store_act<16>(corr, row, corr_col(col0 / 2), c);
   }
 
@@ -236,7 +265,7 @@ struct EpiPhaseEqT {
       for (int i = 0; i < NC; i += 2) *reinterpret_cast<float2*>(d + i) = make_float2(v[i], v[i + 1]);
     }
   }
-  DCCN_DEVINL void flush(State&) const {}
+  DCCN_DEVINL void flush(State&) const { tma_store_wait_read(); }
 };
 
 typedef EpiPhaseEqT<false> EpiPhaseEq;

@@ -60,7 +60,12 @@ struct dccn_handle {
   bool committed = false;
   // geometry
   int S, K, T, Tin, F, D, NB, P;      // T = samples/symbol incl. CP, Tin = samples the receiver consumes
-  int chunk;
+  int chunk;           // most frames one internal pass may take (cfg.chunk_frames, default 65536)
+  int64_t ws_frames = 0;   // frames the inter-layer buffers are currently sized for (grown on demand, ensure_workspace)
+  std::vector<void*> ws_allocs;
+  bool ws_eqc = false, ws_train = false;   // optional buffers: folded schedule / training forward
+  bool ws_dirty = false;                   // an optional buffer was requested after the last build
+  size_t ws_act_bytes = 0;
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
   int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
@@ -140,6 +145,7 @@ struct LaunchScope {
 int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 int dev_alloc(dccn_handle* h, void** p, size_t bytes);
 int alloc_act(dccn_handle* h, Act* a, int64_t rows, int ld, bool split);
+int ensure_workspace(dccn_handle* h, int64_t frames);            // inter-layer buffers for passes of up to `frames` frames
 const HostTensor* find(const dccn_handle* h, const std::string& n);
 int pack_layers_host(dccn_handle* h);                            // h->raw -> GemmLayer::W / bias (host only)
 int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s);  // GemmLayer::W -> device operands (+ TMA maps)

@@ -659,15 +659,14 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   DCCN_CHECK(cfg->max_batch > 0 && cfg->max_batch <= h->chunk, "max_batch must be in 1..chunk_frames (%d)", h->chunk);
   cudaStream_t s = (cudaStream_t)stream;
   const int S = h->S, K = h->K, T = h->T, F = h->F, D = h->D;
-  const int64_t C = h->chunk, MB = cfg->max_batch;
+  const int64_t MB = cfg->max_batch;
   int rc = 0;
   TrainState* tr = new TrainState();
   h->tr = tr;
   tr->cfg = *cfg;
   tr->maxB = MB;
-  if (!h->u3.p0) rc |= alloc_act(h, &h->u3, C, S * K * 2, false);
-  if (!h->chest_buf) rc |= dev_alloc(h, (void**)&h->chest_buf, (size_t)C * S * K * 2 * 4);
-  if (rc) return rc;
+  if (!h->ws_train) h->ws_train = h->ws_dirty = true;   // the backward pass needs u3 (tanh output) and chest
+  if ((rc = ensure_workspace(h, MB))) return rc;
   // ---- gather maps of the ten layers: run the host packers on index-valued variables ------------------
   GemmLayer* Ls[10] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
   std::vector<std::vector<float>> backup(10);

@@ -63,7 +63,7 @@ typedef struct dccn_cfg {
   int32_t head;        /* DCCN_HEAD_*     demodulation head variant                    */
   int32_t equalizer;   /* 0 = basic receiver only, 1 = equalizer_ofdm (--opt=0) in front */
   int32_t precision;   /* DCCN_PREC_*                                                  */
-  int32_t chunk_frames;/* frames per internal pass (0 = library default)               */
+  int32_t chunk_frames;/* most frames per internal pass (0 = 65536); buffers grow on demand */
 } dccn_cfg;
 
 typedef struct dccn_handle dccn_handle;

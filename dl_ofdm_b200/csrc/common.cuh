@@ -96,6 +96,30 @@ DCCN_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Non-blocking probes of up to three barriers issued back to back (one round trip of ~150-200 clk to the barrier unit
+// instead of three in series); the blocking waits only run for a barrier that was not complete yet.  bar1 / bar2 may
+// be nullptr.
+DCCN_DEVINL void mbar_wait_multi(uint64_t* bar0, uint32_t par0, uint64_t* bar1, uint32_t par1, uint64_t* bar2,
+                                 uint32_t par2) {
+  uint64_t* b1 = bar1 ? bar1 : bar0;
+  uint64_t* b2 = bar2 ? bar2 : bar0;
+  const uint32_t q1 = bar1 ? par1 : par0, q2 = bar2 ? par2 : par0;
+  uint32_t ok0, ok1, ok2;
+  asm volatile(
+      "{\n\t.reg .pred p0, p1, p2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p0, [%3], %4;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p1, [%5], %6;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p2, [%7], %8;\n\t"
+      "selp.u32 %0, 1, 0, p0;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "selp.u32 %2, 1, 0, p2;\n\t}"
+      : "=r"(ok0), "=r"(ok1), "=r"(ok2)
+      : "r"(smem_u32(bar0)), "r"(par0), "r"(smem_u32(b1)), "r"(q1), "r"(smem_u32(b2)), "r"(q2)
+      : "memory");
+  if (!ok0) mbar_wait(bar0, par0);
+  if (!ok1) mbar_wait(b1, q1);
+  if (!ok2) mbar_wait(b2, q2);
+}
 // cluster-scope acquire: for barriers that threads of the peer CTA arrive on
 DCCN_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;

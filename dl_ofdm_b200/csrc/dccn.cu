@@ -813,10 +813,11 @@ template <int BN>
 __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int n_mma, int per_commit, int mode, int dep, long long* clks) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + BN * 128);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (mode >= 2 ? 131072 : 16384 + BN * 128));
   uint64_t* bar2 = bar + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 2);
-  for (int i = threadIdx.x; i < (16384 + BN * 128) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.f;
+  for (int i = threadIdx.x; i < (mode >= 2 ? 131072 : 16384 + BN * 128) / 4; i += blockDim.x)
+    reinterpret_cast<float*>(smem)[i] = 0.f;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
     if ((threadIdx.x & 31) == 0) {
@@ -841,6 +842,25 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int n_mma, int per_comm
       const int batch = per_commit > 0 ? per_commit : n_mma;
       for (int i = 0; i < n_mma; i += batch) {
         const uint32_t d = tb + (dep ? 0u : (uint32_t)(((i / batch) & 1) * BN));   // dep=0: alternate two accumulators per batch
+        if (mode >= 2) {
+          // the parity GEMM's real operand pattern: batch i uses smem stage i % 4 (B_hi at +0, B_lo at +16 KB) and
+          // TMEM staging columns 256 + 64 * (i % 4); k-step k advances 32 B / 8 columns.  mode 2: order lo*hi, hi*lo,
+          // hi*hi (as shipped); mode 3: lo*hi, hi*hi, hi*lo (consecutive MMAs share an operand)
+          const int st = (i / batch) & 3;
+          const uint32_t bh = smem_u32(smem) + st * 32768, bl = bh + 16384, ta = tb + 256 + st * 64;
+          for (int k = 0; k < batch / 3; ++k) {
+            const uint64_t dbh = umma_desc_sw128(bh + (k & 3) * 32), dbl = umma_desc_sw128(bl + (k & 3) * 32);
+            const uint32_t ka = ta + (k & 3) * 8;
+            umma_tf32_ts(d, ka + 32, dbh, idesc, k ? 1u : 0u);
+            if (mode == 2) {
+              umma_tf32_ts(d, ka, dbl, idesc, 1u);
+              umma_tf32_ts(d, ka, dbh, idesc, 1u);
+            } else {
+              umma_tf32_ts(d, ka, dbh, idesc, 1u);
+              umma_tf32_ts(d, ka, dbl, idesc, 1u);
+            }
+          }
+        } else
         for (int j = 0; j < batch; ++j) {
           if (mode == 0) umma_tf32(d, da, db, idesc, 1u);
           else umma_tf32_ts(d, tb + 256, db, idesc, 1u);
@@ -1300,8 +1320,10 @@ int dccn_debug_tma_rate(const float* mat_dev, int rows, int cols, int ld, int st
 
 int dccn_debug_mma_rate(int bn, int n_mma, int per_commit, int mode, int dep, int grid, long long* clks_dev) {
   DCCN_CHECK(clks_dev && (bn == 128 || bn == 256), "bn must be 128 or 256");
-  const int smem = 16384 + bn * 128 + 1024 + 64;
+  const int smem = (mode >= 2 ? 131072 : 16384 + bn * 128) + 1024 + 64;
+  DCCN_CHECK(mode < 2 || (bn == 128 && per_commit > 0 && per_commit % 3 == 0), "mode 2/3: bn 128, per_commit = 3 * k-steps");
   if (bn == 128) {
+    DCCN_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     mma_rate_kernel<128><<<grid, 64, smem>>>(n_mma, per_commit, mode, dep, clks_dev);
   } else {
     DCCN_CUDA_OK(cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -302,16 +302,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         const TileK tk = decode(tile);
         for (int kb0 = tk.kb0; kb0 < tk.kb1; kb0 += kb_per_chunk) {
           const int kb1 = kb0 + kb_per_chunk < tk.kb1 ? kb0 + kb_per_chunk : tk.kb1;
-          if (PAIR) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
-          else wait_(&tempty[acc], acc_phase ^ 1);
-          if (!DCCN_ABL(128)) tc_fence_after();
+          if (lane == 0) DCCN_TRACE_EV(2);
+          if (PAIR) {
+            mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+          }
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = kb0; kb < kb1; ++kb) {
-            if (PAIR) mbar_wait_cluster(&ready[stage], phase);
-            else wait_(SPLIT ? &ready[stage] : &full[stage], phase);
-            if (DEC) wait_(&full[stage], phase);   // weight planes of this stage have landed too
+            if (PAIR) {
+              mbar_wait_cluster(&ready[stage], phase);
+            } else if (DCCN_ABL(1024)) {   // experiment: the old serial waits
+              if (kb == kb0) mbar_wait(&tempty[acc], acc_phase ^ 1);
+              mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
+              if (DEC) mbar_wait(&full[stage], phase);
+            } else {
+              // accumulator drained (first k-block of a chunk) + operands of this stage ready (+ DEC: weight planes
+              // landed): probed together -- the three round trips in series left the tensor pipe's short queue empty
+              mbar_wait_multi(SPLIT ? &ready[stage] : &full[stage], phase, DEC ? &full[stage] : nullptr, phase,
+                              kb == kb0 ? &tempty[acc] : nullptr, acc_phase ^ 1);
+            }
             if (lane == 0) DCCN_TRACE_EV(5);
-            if (!DCCN_ABL(128)) tc_fence_after();
+            tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint32_t a_lo = a_hi + C::A_BYTES;
             const uint32_t b_hi = a_hi + C::B_OFF;
@@ -349,7 +360,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             DCCN_TRACE_EV(9);
             if (PAIR) umma_commit_pair(&empty[stage], 0x3);   // slot released in both CTAs of the pair
             else umma_commit(&empty[stage]);                  // smem slot reusable once these MMAs retire
-            if (kb + 1 == kb1) {                              // K chunk complete -> epilogue(s) drain it
+            // K chunk complete -> epilogue(s) drain it.  With one k-block per chunk (kc = 1) the commit above already
+            // says so: the epilogue warps wait on empty[stage] themselves and the second commit (~90 clk of tensor-
+            // pipe time, measured) is dropped.
+            if (kb + 1 == kb1 && (PAIR || kb_per_chunk != 1)) {
               if (PAIR) umma_commit_pair(&tfull[acc], 0x3);
               else umma_commit(&tfull[acc]);
             }
@@ -399,7 +413,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const TileK tk = decode(tile);
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
         wait_(&fullA[sa], pa);
-        if (warp == 2 && lane == 0) DCCN_TRACE_EV(2);
         const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
         float hi[32], lo[32];
         if (DCCN_ABL(1)) {
@@ -433,7 +446,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         __syncwarp();
         if (lane == 0) mbar_arrive(&emptyA[sa]);                  // raw tile consumed
         wait_(&empty[stage], phase ^ 1);                      // TMEM staging slot is free again
-        if (warp == 2 && lane == 0) DCCN_TRACE_EV(3);
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
                             (uint32_t)(C::A_TMEM_COL0 + stage * C::A_TMEM_COLS);
@@ -528,6 +540,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     typename Epi::State st;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int estage = 0;                            // kc = 1: the smem-stage ring position of the chunk being drained
+    uint32_t ephase = 0;
+    const bool stage_signal = !PAIR && kb_per_chunk == 1;
     float r[C::NCH][32];
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
@@ -536,7 +551,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int row = row_base + lane;
       const int num_chunks = (tk.kb1 - tk.kb0 + kb_per_chunk - 1) / kb_per_chunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
-        wait_(&tfull[acc], acc_phase);
+        if (stage_signal) {
+          wait_(&empty[estage], ephase);
+          if (++estage == C::STAGES) {
+            estage = 0;
+            ephase ^= 1;
+          }
+        } else {
+          wait_(&tfull[acc], acc_phase);
+        }
         if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(6);
         tc_fence_after();
         const uint32_t t0 =

@@ -33,7 +33,7 @@ m.forward(xg, want_soft=False)
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(10, 4096)
 t0 = t[t > 0].min()
-names = ['epi tile0', 'epi tile12', 'spl gotA', 'spl gotTM', 'spl ready', 'mma ops', 'epi got', 'epi rel', 'mma commit', 'mma issued']
+names = ['epi tile0', 'epi tile12', 'mma top', 'mma tempty', 'spl ready', 'mma ops', 'epi got', 'epi rel', 'mma commit', 'mma issued']
 n = int(os.environ.get('N', 40))
 for r in range(10):
     v = t[r][t[r] > 0] - t0

@@ -301,8 +301,8 @@ def main():
     bits = bit_source_gpu(B * NDATA * NBITS, seed=1000 + rank, device=dev).view(B, NDATA, NBITS)
     tx = m.transmit(bits, ofdm, const_map(NBITS))
     chan = rayleigh_chan_lte(fl, ofdm.Fs, engine=m, seed=77 + rank)
-    x = chan.run(tx, torch.full((B,), SNR_DB, dtype=torch.float32, device=dev))
-    del tx
+    snr_t = torch.full((B,), SNR_DB, dtype=torch.float32, device=dev)
+    x = chan.run(tx, snr_t)
     torch.cuda.synchronize()
 
     def step():
@@ -342,7 +342,11 @@ def main():
     launches = launch_count() - l0
     sampler.stop_flag = True
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms_per_rank = [ms / args.steps]
     if world > 1:
+        allms = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(allms, tms)
+        ms_per_rank = [float(t[0]) / args.steps for t in allms]   # power capping differs from GPU to GPU
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms[0])
     value = world * B * args.steps / (ms * 1e-3)
@@ -374,6 +378,36 @@ def main():
                 'mma_passes': 3 if args.precision == 'parity' else 1,
                 'whole_step_algorithmic_tflops': MFLOP_PER_FRAME * 1e6 * value / world / 1e12,
                 'kernel_ms': {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}}
+
+    # ---- the HBM-bound kernels of the path against the measured copy bandwidth ------------
+    # algorithmic bytes per frame: the fp32 IQ record is 4 480 B; soft 10 240 B, hard / labels 1 280 B, out_iq 2 560 B
+    m.profile(True)
+    for _ in range(3):
+        chan.run(tx, snr_t)                      # feeder: Rayleigh FIR + AWGN (timed apart from the receiver pass)
+    cprof = m.profile_collect()
+    m.profile(False)
+    tevt = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    tevt[0].record()
+    for _ in range(3):
+        m.transmit(bits, ofdm, const_map(NBITS))
+    tevt[1].record()
+    torch.cuda.synchronize()
+    hbm_bytes = {'moments': 4480, 'prep_norm': 2 * 4480, 'rx_demod_head': 2560 + 1280 + 10240 + 1280,
+                 'chan_fir': 2 * 4480, 'chan_awgn': 2 * 4480}
+    hbm_kernels = {}
+    for k, bpf in hbm_bytes.items():
+        src = prof if k in prof else cprof
+        if k not in src:
+            continue
+        ms_k = src[k][0] / (args.steps if src is prof else 3)
+        gbs = bpf * B / (ms_k * 1e-3) / 1e9
+        hbm_kernels[k] = {'ms': round(ms_k, 4), 'bytes_per_frame': bpf, 'achieved_gbs': round(gbs, 1),
+                          'frac_of_hbm_peak': round(gbs / pk['hbm'], 3)}
+    ms_tx = tevt[0].elapsed_time(tevt[1]) / 3
+    hbm_kernels['tx_frame'] = {'ms': round(ms_tx, 4), 'bytes_per_frame': 1280 + 4480,
+                               'achieved_gbs': round((1280 + 4480) * B / (ms_tx * 1e-3) / 1e9, 1),
+                               'frac_of_hbm_peak': round((1280 + 4480) * B / (ms_tx * 1e-3) / 1e9 / pk['hbm'], 3)}
+    del tx
 
     # ---- opt-in folded schedule (DCCN_FWD_FOLDED), reported next to the headline, never as it -------
     folded = None
@@ -446,8 +480,9 @@ def main():
             'dtype': {'parity': 'tf32x3 (fp32-equivalent: 3-pass hi/lo split, fp32 accumulate)',
                       'fast': 'tf32', 'exact': 'f32'}[args.precision],
             'data': 'synthetic', 'config': workload_config(args, B),
-            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': sampler.summary(),
+            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': sampler.summary(), 'ms_per_step_per_rank': [round(t, 4) for t in ms_per_rank],
             'ber': ber, 'bits_counted': int(conf.sum()),
+            'hbm_kernels': {'peak_gbs': pk['hbm'], 'kernels': hbm_kernels},
             'train_config4': train, 'folded_schedule': folded,
             'target': {'frames_per_s_8gpu': 1e8, 'note': 'north_star target; random-init weights so BER ~ 0.5'},
         }

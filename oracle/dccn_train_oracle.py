@@ -279,3 +279,116 @@ def train_steps(xs, bits, w, nbits, init_learning=1e-3, global_step0=0, **kw):
         opt.step(w, g, learning_rate(init_learning, global_step0 + i))
         losses.append(ce)
     return w, losses
+
+
+# =============================================================================================
+# Training of the basic receiver itself (dev/py/ofdmreceiver_np.py:154-198, loop :211-274)
+# =============================================================================================
+# graph: tx_ofdm -> batch-moment norm -> ofdm_dense_rx -> softmax;  every variable is trainable:
+#   fft_like/conv3d/{kernel,bias}, demodulation/dense/{kernel,bias}, demodulation/conv2d/{kernel,bias},
+#   demodulation/dense_1/{kernel,bias}                                   (dev/py/model.py:1246-1288)
+# total_loss = ce_mean + berlin * REG_COEFF * sum(REGULARIZATION_LOSSES) + BER_COEFF * ber      (:173)
+#   REG_COEFF = 0.0001 (:162); regularisers l2(0.01) sit on demodulation/dense and demodulation/dense_1
+#   (kernel and bias; model.py:1269-1272, 1283-1286); conv3d / conv2d have none.
+#   berlin / ber come from tf.confusion_matrix(argmax(...)) (:165-169): integer ops, no gradient path -- for the
+#   gradient berlin is a per-step constant (the BER of THIS minibatch) and the BER_COEFF term contributes nothing.
+# optimiser: AdamOptimizer(exponential_decay(0.001, global_step, 500, 0.98, staircase)).minimize(total_loss)  (:186-189)
+# Dead taps of the (1,T) 'same' fft_like kernel only ever multiply zero padding: their gradient is exactly 0 and Adam
+# (m = v = 0) leaves them untouched, so only the centre tap [0,(T-1)//2,0] moves.
+REG_COEFF_RX = 0.0001
+RX_DENSE = ['demodulation/dense', 'demodulation/dense_1']
+RX_NAMES = ['fft_like/conv3d', 'demodulation/dense', 'demodulation/conv2d', 'demodulation/dense_1']
+
+
+def rx_trainable_names():
+    return [n + s for n in RX_NAMES for s in ('/kernel', '/bias')]
+
+
+def rx_loss_and_grads(x, bits, w, nbits, nfft=64, cp_len=16, use_cp=True, nfilter=64, dtype=np.float64,
+                      normalize=True, reg=True):
+    """x [B,S,T,2], bits [B,D,nbits] -> (ce_mean, reg_loss, berlin, grads, aux) for the basic receiver.
+
+    grads: d total_loss / d var for the eight receiver variables in the reference layouts.
+    """
+    A = lambda n: np.asarray(w[n], dtype=dtype)
+    x = np.asarray(x, dtype=dtype)
+    B, S, T, _ = x.shape
+    K, F = nfft, nfilter
+    z = orc.batch_moment_norm(x, dtype)[0] if normalize else x
+    Tin = T if use_cp else K
+    rin = z.reshape(B * S, 2 * T) if use_cp else z[:, :, cp_len:, :].reshape(B * S, 2 * K)
+    kfull = A('fft_like/conv3d/kernel')
+    tap = (Tin - 1) // 2
+    kf = kfull[0, tap, 0]                                              # live tap [Tin, 2F]
+    bfl = A('fft_like/conv3d/bias')
+    BpR, bpR = orc.pack_complex_kernel(kf[:, :F], kf[:, F:], bfl[:F], bfl[F:], dtype=dtype)
+    r1 = (rin @ BpR + bpR).reshape(B, S * F * 2)
+    Wd, bd = A('demodulation/dense/kernel'), A('demodulation/dense/bias')
+    oiq = (r1 @ Wd + bd).reshape(B, -1, 2)
+    D = oiq.shape[1]
+    Wc = A('demodulation/conv2d/kernel').reshape(2, -1)
+    bc = A('demodulation/conv2d/bias')
+    W1h, b1h = A('demodulation/dense_1/kernel'), A('demodulation/dense_1/bias')
+    MO = Wc.shape[1]
+    hpre = oiq @ Wc + bc
+    hh = np.maximum(orc.LEAKY_ALPHA * hpre, hpre)
+    hcat = np.concatenate([hh, oiq], -1)
+    lpre = hcat @ W1h + b1h
+    lg = np.maximum(orc.LEAKY_ALPHA * lpre, lpre).reshape(B, D, nbits, 2)
+    m = lg.max(-1, keepdims=True)
+    e = np.exp(lg - m)
+    soft = e / e.sum(-1, keepdims=True)
+    y = np.asarray(bits).astype(np.int64)
+    oh = np.stack([1 - y, y], -1).astype(dtype)
+    lse = np.log(np.exp(soft).sum(-1, keepdims=True))
+    N = B * D * nbits
+    ce_mean = float(np.sum(lse[..., 0] - np.sum(soft * oh, -1)) / N)
+    hard = (soft[..., 1] > soft[..., 0]).astype(np.int64)             # tf.argmax: first index on ties
+    berlin = float(np.sum(hard != y)) / N                             # util.ber_tensor: (cm01 + cm10) / sum
+    # ---- backward ----------------------------------------------------------------------------
+    dsoft = (np.exp(soft - lse) - oh) / N
+    dlg = soft * (dsoft - np.sum(dsoft * soft, -1, keepdims=True))
+    dlpre = dlg.reshape(B, D, 2 * nbits) * np.where(lpre > 0, 1.0, orc.LEAKY_ALPHA)
+    dhcat = dlpre @ W1h.T
+    dhpre = dhcat[..., :MO] * np.where(hpre > 0, 1.0, orc.LEAKY_ALPHA)
+    doiq = dhcat[..., MO:] + dhpre @ Wc.T
+    g = {}
+    g['demodulation/dense_1/kernel'] = hcat.reshape(-1, MO + 2).T @ dlpre.reshape(-1, 2 * nbits)
+    g['demodulation/dense_1/bias'] = dlpre.reshape(-1, 2 * nbits).sum(0)
+    g['demodulation/conv2d/kernel'] = oiq.reshape(-1, 2).T @ dhpre.reshape(-1, MO)
+    g['demodulation/conv2d/bias'] = dhpre.reshape(-1, MO).sum(0)
+    doiq2 = doiq.reshape(B, 2 * D)
+    g['demodulation/dense/kernel'] = r1.T @ doiq2
+    g['demodulation/dense/bias'] = doiq2.sum(0)
+    dr1 = (doiq2 @ Wd.T).reshape(B * S, 2 * F)
+    dBp, dbp = rin.T @ dr1, dr1.sum(0)
+    gWa = dBp[0::2, 0::2] - dBp[1::2, 1::2]
+    gWb = dBp[0::2, 1::2] - dBp[1::2, 0::2]
+    gk = np.zeros(kfull.shape, dtype=dtype)
+    gk[0, tap, 0] = np.concatenate([gWa, gWb], axis=1)
+    gba = dbp[0::2] - dbp[1::2]
+    g['fft_like/conv3d/kernel'] = gk
+    g['fft_like/conv3d/bias'] = np.concatenate([gba, -gba])
+    reg_loss = 0.0
+    for n in RX_DENSE:
+        for s in ('/kernel', '/bias'):
+            wv = A(n + s)
+            reg_loss += L2_L * float(np.sum(wv * wv))
+            if reg:
+                g[n + s] = g[n + s] + (2.0 * berlin * REG_COEFF_RX * L2_L) * wv
+    g = {k: np.asarray(v, dtype=dtype).reshape(np.shape(w[k])) for k, v in g.items()}
+    aux = dict(soft=soft, doiq=doiq, dr1=dr1, hard=hard)
+    return ce_mean, reg_loss, berlin, g, aux
+
+
+def rx_train_steps(xs, bits, w, nbits, init_learning=1e-3, global_step0=0, **kw):
+    """len(xs) training steps of the basic receiver; returns (weights, [ce_mean...], [berlin...])."""
+    w = {k: np.array(v, copy=True) for k, v in w.items()}
+    opt = Adam(rx_trainable_names(), w)
+    losses, bers = [], []
+    for i, (x, b) in enumerate(zip(xs, bits)):
+        ce, _, berl, g, _ = rx_loss_and_grads(x, b, w, nbits, **kw)
+        opt.step(w, g, learning_rate(init_learning, global_step0 + i))
+        losses.append(ce)
+        bers.append(berl)
+    return w, losses, bers

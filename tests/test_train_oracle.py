@@ -74,3 +74,50 @@ def test_training_reduces_loss():
     assert losses[-1] < losses[0]
     assert any(np.abs(w2[k] - w[k]).max() > 0 for k in tro.trainable_names())
     assert np.array_equal(w2['demodulation/dense/kernel'], w['demodulation/dense/kernel'])   # receiver frozen
+
+
+# ---- training of the basic receiver (dev/py/ofdmreceiver_np.py:154-198) ---------------------------------------
+def _rx_autograd(w, x, bits, nbits, use_cp=True):
+    m = TFMirror(w, nbits, use_cp=use_cp, equalizer=False)
+    m.w = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in w.items()}
+    z = m.norm(torch.tensor(x, dtype=torch.float64))
+    soft = m.dense_rx(z).reshape(-1, 2)
+    y = torch.tensor(bits.reshape(-1).astype(np.int64))
+    ce = torch.nn.functional.cross_entropy(soft, y)
+    berlin = float((soft.argmax(1) != y).double().mean())             # constant for the gradient (no path through argmax)
+    reg = sum(tro.L2_L * (m.w[n + s] ** 2).sum() for n in tro.RX_DENSE for s in ('/kernel', '/bias'))
+    total = ce + berlin * tro.REG_COEFF_RX * reg + berlin
+    total.backward()
+    return float(ce.detach()), float(reg.detach()), berlin, {k: v.grad.numpy() for k, v in m.w.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize('nbits,use_cp', [(1, True), (4, True), (2, False)])
+def test_rx_backward_matches_autograd(nbits, use_cp):
+    rng = np.random.default_rng(40 + nbits)
+    w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=False, bias_scale=0.05)
+    x = (rng.standard_normal((24, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (24, 320, nbits)).astype(np.uint8)
+    ce, reg, berl, g, _ = tro.rx_loss_and_grads(x, bits, w, nbits, use_cp=use_cp)
+    ce_t, reg_t, berl_t, g_t = _rx_autograd(w, x, bits, nbits, use_cp)
+    assert abs(ce - ce_t) < 1e-12 and abs(berl - berl_t) < 1e-15
+    assert abs(reg - reg_t) < 1e-9 * max(1.0, reg_t)
+    assert set(g) == set(tro.rx_trainable_names()) and set(g_t) >= set(g)
+    for k in g:
+        ref = g_t[k]
+        err = np.abs(g[k] - ref).max()
+        assert err <= 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-15, (k, err, np.abs(ref).max())
+    # dead taps of the (1,T) 'same' kernel never move
+    T = 80 if use_cp else 64
+    dead = np.ones(T, dtype=bool)
+    dead[(T - 1) // 2] = False
+    assert np.all(g_t['fft_like/conv3d/kernel'][0, dead] == 0)
+
+
+def test_rx_training_reduces_loss():
+    rng = np.random.default_rng(8)
+    w = orc.glorot_weights(rng, 2, equalizer=False, bias_scale=0.05)
+    x = (rng.standard_normal((32, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (32, 320, 2)).astype(np.uint8)
+    w2, losses, bers = tro.rx_train_steps([x] * 6, [bits] * 6, w, 2)
+    assert losses[-1] < losses[0]
+    assert all(np.abs(w2[k] - w[k]).max() > 0 for k in tro.rx_trainable_names())

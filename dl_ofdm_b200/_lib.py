@@ -26,7 +26,10 @@ class dccn_cfg(C.Structure):
 
 class dccn_train_cfg(C.Structure):
     _fields_ = [('reg_coeff', C.c_float), ('l2', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float),
-                ('eps', C.c_float), ('max_batch', C.c_int64)]
+                ('eps', C.c_float), ('max_batch', C.c_int64), ('mode', C.c_int32)]
+
+
+TRAIN_EQ, TRAIN_RX = 0, 1      # dccn_train_cfg.mode (include/dccn.h)
 
 
 class DccnError(RuntimeError):

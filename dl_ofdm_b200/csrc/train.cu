@@ -18,6 +18,12 @@
 //     [[a,b],[-b,-a]] tiling, Toeplitz expansion, row permutation): the gradient of the variable is the
 //     adjoint signed scatter-sum, done with one CSR kernel for all layer kinds;
 //   * pointwise backward kernels: demodulation head + loss, phase-only equaliser, tanh.
+//
+// mode DCCN_TRAIN_RX: training of the basic receiver itself (dev/py/ofdmreceiver_np.py:154-198): every variable of
+// ofdm_dense_rx is trainable, total_loss = ce_mean + berlin * 1e-4 * sum(l2) (+ ber, no gradient), berlin = the BER of the
+// minibatch (a constant for the gradient: it comes from tf.confusion_matrix(argmax)).  Same machinery: the two GEMM
+// layers (fft_like/conv3d, demodulation/dense) go through run_wgrad / the CSR maps, the 200 weights of the
+// per-subcarrier head get their gradient from head_wgrad_kernel (warp-shuffle reductions, fixed order).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -51,7 +57,15 @@ struct TrainState {
   int64_t maxB = 0;
   int64_t step = 0;
   std::vector<TrainParam> params;
+  int mode = 0;            // DCCN_TRAIN_EQ / DCCN_TRAIN_RX
+  int n_layers = 10;
   TrainLayer tl[10];
+  // DCCN_TRAIN_RX: the head's variables (conv2d kernel / bias, dense_1 kernel / bias) in `params`, partial sums of
+  // head_wgrad_kernel, pinned staging for the D2H refresh of dccn_handle::hw
+  int hp[4] = {-1, -1, -1, -1};
+  float* head_partial = nullptr;
+  int head_warps = 0;
+  float* head_host = nullptr;
   GemmLayer bw_r1, bw_r2;
   Act d_oiq, d_r1o, d_oeq, d_cat, d_eq, d_corr, d_f, d_f2, d_ch, dA, dB, dC, d_p32, d_t1;
   float* partial = nullptr;
@@ -67,6 +81,11 @@ static const char* kLayerVar[10] = {"Equalizer/dense",    "Equalizer/conv3d",   
                                     "Equalizer/conv3d_3", "Equalizer/dense_5"};
 static const int kBiasKind[10] = {0, 1, 0, 0, 0, 0, 2, 1, 1, 0};
 static const int kPerSymbol[10] = {1, 1, 0, 0, 0, 0, 0, 1, 1, 1};   // layer contracts over B*S rows (else B)
+static const char* kRxLayerVar[2] = {"fft_like/conv3d", "demodulation/dense"};
+static const int kRxBiasKind[2] = {1, 0};
+static const int kRxPerSymbol[2] = {1, 0};
+static const char* kRxHeadVar[4] = {"demodulation/conv2d/kernel", "demodulation/conv2d/bias", "demodulation/dense_1/kernel",
+                                    "demodulation/dense_1/bias"};
 
 // =========================================================================================
 // kernels
@@ -378,6 +397,118 @@ head_bwd_kernel(const float* __restrict__ out_iq, const uint8_t* __restrict__ bi
   }
 }
 
+// Gradients of the head's own weights (DCCN_TRAIN_RX).  Layout of one partial / of the result, NQ = 2*MO + MO +
+// (MO+2)*2NB + 2NB floats:  [dWc (2 x MO) | dbc (MO) | dW1 ((MO+2) x 2NB) | db1 (2NB)].
+// One thread per (frame, data subcarrier) position recomputes the head and its backward; every quantity is summed over
+// the warp with a shuffle butterfly and kept by lane q % 32 (slot q / 32), so a warp carries its NQ running sums in 7
+// registers per lane; partial[warp][q] is reduced in a fixed order by head_wgrad_reduce_kernel (deterministic).
+template <int NB>
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(const float* __restrict__ out_iq, const uint8_t* __restrict__ bits, const __grid_constant__ HeadWeights hw,
+                  long long total, float inv_n, float* __restrict__ partial) {
+  constexpr int MO = 1 << NB;
+  constexpr int NQ = 2 * MO + MO + (MO + 2) * 2 * NB + 2 * NB;
+  constexpr int NS = (NQ + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  float acc[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) acc[i] = 0.f;
+  auto add = [&](int q, float v) {   // q is a compile-time constant after unrolling
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == (q & 31)) acc[q >> 5] += v;
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long iters = (total + stride - 1) / stride;       // every lane runs every iteration (shuffles)
+  for (long long it = 0; it < iters; ++it) {
+    const long long i = i0 + it * stride;
+    const bool live = i < total;
+    const float2 iq = live ? __ldg(reinterpret_cast<const float2*>(out_iq) + i) : make_float2(0.f, 0.f);
+    const float I = iq.x, Q = iq.y;
+    float hpre[MO], hh[MO], dh[MO], dl[2 * NB];
+#pragma unroll
+    for (int m = 0; m < MO; ++m) {
+      hpre[m] = I * hw.Wc[0][m] + Q * hw.Wc[1][m] + hw.bc[m];
+      hh[m] = fmaxf(0.2f * hpre[m], hpre[m]);
+      dh[m] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      float l0 = hw.b1[2 * k], l1 = hw.b1[2 * k + 1];
+#pragma unroll
+      for (int m = 0; m < MO; ++m) {
+        l0 += hh[m] * hw.W1[m][2 * k];
+        l1 += hh[m] * hw.W1[m][2 * k + 1];
+      }
+      l0 += I * hw.W1[MO][2 * k] + Q * hw.W1[MO + 1][2 * k];
+      l1 += I * hw.W1[MO][2 * k + 1] + Q * hw.W1[MO + 1][2 * k + 1];
+      const float s0 = l0 > 0.f ? 1.f : 0.2f, s1 = l1 > 0.f ? 1.f : 0.2f;
+      const float a0 = fmaxf(0.2f * l0, l0), a1 = fmaxf(0.2f * l1, l1);
+      const float t = expf(-fabsf(a1 - a0));
+      const float pb = 1.0f / (1.0f + t), ps = t / (1.0f + t);
+      const bool one_big = a1 > a0;
+      const float p0 = one_big ? ps : pb, p1 = one_big ? pb : ps;
+      const float q1 = 1.0f / (1.0f + expf(p0 - p1)), q0 = 1.0f - q1;
+      const unsigned y = live ? (bits[i * NB + k] & 1u) : 0u;
+      const float dp0 = (q0 - (y ? 0.f : 1.f)) * inv_n, dp1 = (q1 - (y ? 1.f : 0.f)) * inv_n;
+      const float da0 = live ? p0 * p1 * (dp0 - dp1) : 0.f;
+      dl[2 * k] = da0 * s0;
+      dl[2 * k + 1] = -da0 * s1;
+#pragma unroll
+      for (int m = 0; m < MO; ++m) dh[m] += hw.W1[m][2 * k] * dl[2 * k] + hw.W1[m][2 * k + 1] * dl[2 * k + 1];
+    }
+    // dWc, dbc
+#pragma unroll
+    for (int m = 0; m < MO; ++m) {
+      const float d = dh[m] * (hpre[m] > 0.f ? 1.f : 0.2f);
+      add(m, I * d);
+      add(MO + m, Q * d);
+      add(2 * MO + m, d);
+    }
+    // dW1 (rows: hh[0..MO), I, Q), db1
+#pragma unroll
+    for (int j = 0; j < 2 * NB; ++j) {
+#pragma unroll
+      for (int m = 0; m < MO; ++m) add(3 * MO + m * 2 * NB + j, hh[m] * dl[j]);
+      add(3 * MO + MO * 2 * NB + j, I * dl[j]);
+      add(3 * MO + (MO + 1) * 2 * NB + j, Q * dl[j]);
+      add(3 * MO + (MO + 2) * 2 * NB + j, dl[j]);
+    }
+  }
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    const int q = sl * 32 + lane;
+    if (q < NQ) partial[warp_id * NQ + q] = acc[sl];
+  }
+}
+
+// g[q] = sum over warps of partial[w][q], fixed order; the four head variables are consecutive slices of the NQ vector
+__global__ void __launch_bounds__(256)
+head_wgrad_reduce_kernel(const float* __restrict__ partial, int warps, int NQ, float* __restrict__ g_wc, int n_wc,
+                         float* __restrict__ g_bc, int n_bc, float* __restrict__ g_w1, int n_w1, float* __restrict__ g_b1) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= NQ) return;
+  float s = 0.f;
+  for (int w = 0; w < warps; ++w) s += partial[(size_t)w * NQ + q];
+  if (q < n_wc) g_wc[q] = s;
+  else if (q < n_wc + n_bc) g_bc[q - n_wc] = s;
+  else if (q < n_wc + n_bc + n_w1) g_w1[q - n_wc - n_bc] = s;
+  else g_b1[q - n_wc - n_bc - n_w1] = s;
+}
+
+// g += (coef * berlin) * w with berlin = (c01 + c10) / sum of this minibatch's confusion matrix (ofdmreceiver_np.py:173)
+__global__ void __launch_bounds__(256)
+add_l2_ber_kernel(float* __restrict__ g, const float* __restrict__ w, long long n, float coef,
+                  const unsigned long long* __restrict__ conf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double tot = (double)(conf[0] + conf[1] + conf[2] + conf[3]);
+  const float berlin = tot > 0.0 ? (float)((double)(conf[1] + conf[2]) / tot) : 0.f;
+  g[i] = fmaf(coef * berlin, w[i], g[i]);
+}
+
 // phase-only equaliser eq = f * conj(c)/|c|, corr = |eq|^2 (dev/py/model.py:430-437), per complex point
 __global__ void __launch_bounds__(256)
 phaseeq_bwd_kernel(const float2* __restrict__ deq, const float* __restrict__ dcorr, const float2* __restrict__ f,
@@ -504,7 +635,7 @@ static int run_dgrad(dccn_handle* h, const GemmLayer& bw, const Act& dY, int col
 static int repack_all(dccn_handle* h, cudaStream_t s) {
   TrainState* tr = h->tr;
   const bool split = h->cfg.precision == DCCN_PREC_PARITY;
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < tr->n_layers; ++i) {
     TrainLayer& t = tr->tl[i];
     const int K = t.L->K, N = t.L->N;
     LaunchScope ls(h, SLOT_T_REPACK, s, 3);
@@ -542,6 +673,7 @@ static int upload_params(dccn_handle* h, cudaStream_t s) {
 }
 
 void train_free(dccn_handle* h) {
+  if (h->tr && h->tr->head_host) cudaFreeHost(h->tr->head_host);
   delete h->tr;   // device memory is owned by the handle's allocation list
   h->tr = nullptr;
 }
@@ -645,12 +777,88 @@ static int backward(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t
   return 0;
 }
 
+template <int NB>
+static void launch_head_grads(dccn_handle* h, TrainState* tr, const uint8_t* bits, long long total, float inv_n,
+                              unsigned blocks, cudaStream_t s) {
+  constexpr int MO = 1 << NB;
+  constexpr int NQ = 2 * MO + MO + (MO + 2) * 2 * NB + 2 * NB;
+  head_bwd_kernel<NB><<<blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0);
+  head_wgrad_kernel<NB><<<(unsigned)(tr->head_warps / 8), 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n,
+                                                                      tr->head_partial);
+  head_wgrad_reduce_kernel<<<blocks_for(NQ), 256, 0, s>>>(tr->head_partial, tr->head_warps, NQ, tr->params[tr->hp[0]].g,
+                                                         2 * MO, tr->params[tr->hp[1]].g, MO, tr->params[tr->hp[2]].g,
+                                                         (MO + 2) * 2 * NB, tr->params[tr->hp[3]].g);
+}
+
+// DCCN_TRAIN_RX: d total_loss / d (every ofdm_dense_rx variable)      dev/py/ofdmreceiver_np.py:154-189
+static int backward_rx(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t s) {
+  TrainState* tr = h->tr;
+  const int S = h->S, T = h->T, Tin = h->Tin, D = h->D, NB = h->NB, F = h->F;
+  const int64_t MS = B * S;
+  const int cp_off = (T - Tin) * 2;
+  int rc;
+  {
+    LaunchScope ls(h, SLOT_T_HEAD, s, 3);
+    const long long total = (long long)B * D;
+    const float inv_n = (float)(1.0 / ((double)B * D * NB));
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+    switch (NB) {
+      case 1: launch_head_grads<1>(h, tr, bits, total, inv_n, (unsigned)blocks, s); break;
+      case 2: launch_head_grads<2>(h, tr, bits, total, inv_n, (unsigned)blocks, s); break;
+      case 3: launch_head_grads<3>(h, tr, bits, total, inv_n, (unsigned)blocks, s); break;
+      default: launch_head_grads<4>(h, tr, bits, total, inv_n, (unsigned)blocks, s); break;
+    }
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  TrainLayer* tl = tr->tl;
+  // demodulation/dense [S*F*2 -> 2D], contraction over the B frames                                  model.py:1269
+  if ((rc = run_wgrad(h, tl[1], h->r1o.p0, S * F * 2, tr->d_oiq.p0, 2 * D, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[1].bw, tr->d_oiq, 0, B, tr->d_r1o, 0, s))) return rc;
+  // fft_like/conv3d: the live tap as a per-symbol [2Tin -> 2F] layer, contraction over the B*S symbols   model.py:1249
+  if ((rc = run_wgrad(h, tl[0], h->a0.p0 + cp_off, 2 * T, tr->d_r1o.p0, 2 * F, MS, s))) return rc;
+  // regulariser: berlin * REG_COEFF * l2 * sum(w^2) on the two tf.layers.dense (kernel + bias)           :162-173
+  {
+    LaunchScope ls(h, SLOT_T_ADAM, s, 4);
+    for (TrainParam& p : tr->params)
+      if (p.l2g != 0.f) add_l2_ber_kernel<<<blocks_for(p.n), 256, 0, s>>>(p.g, p.w, p.n, p.l2g, h->d_conf);
+  }
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// the head kernels take their 200 weights by value (dccn_handle::hw, host memory): fetch the updated variables.
+// Synchronises the stream (a receiver-training step is not asynchronous).
+static int refresh_head(dccn_handle* h, cudaStream_t s) {
+  TrainState* tr = h->tr;
+  const int NB = h->NB, MO = 1 << NB;
+  size_t off[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    off[i + 1] = off[i] + (size_t)tr->params[tr->hp[i]].n;
+    DCCN_CUDA_OK(cudaMemcpyAsync(tr->head_host + off[i], tr->params[tr->hp[i]].w, (size_t)tr->params[tr->hp[i]].n * 4,
+                                 cudaMemcpyDeviceToHost, s));
+  }
+  DCCN_CUDA_OK(cudaStreamSynchronize(s));
+  const float *kc = tr->head_host + off[0], *bc = tr->head_host + off[1], *k1 = tr->head_host + off[2],
+              *b1 = tr->head_host + off[3];
+  for (int i = 0; i < 2; ++i)
+    for (int m = 0; m < MO; ++m) h->hw.Wc[i][m] = kc[i * MO + m];
+  for (int m = 0; m < MO; ++m) h->hw.bc[m] = bc[m];
+  for (int m = 0; m < MO + 2; ++m)
+    for (int j = 0; j < 2 * NB; ++j) h->hw.W1[m][j] = k1[m * 2 * NB + j];
+  for (int j = 0; j < 2 * NB; ++j) h->hw.b1[j] = b1[j];
+  return 0;
+}
+
 }  // namespace dccn
 
 using namespace dccn;
 
 static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stream) {
-  DCCN_CHECK(h->cfg.equalizer, "training updates the Equalizer/* variables: the handle has no equalizer");
+  const bool rx_mode = cfg->mode == DCCN_TRAIN_RX;
+  DCCN_CHECK(cfg->mode == DCCN_TRAIN_EQ || cfg->mode == DCCN_TRAIN_RX, "unknown training mode %d", (int)cfg->mode);
+  DCCN_CHECK(rx_mode || h->cfg.equalizer, "DCCN_TRAIN_EQ updates the Equalizer/* variables: the handle has no equalizer");
+  DCCN_CHECK(!rx_mode || !h->cfg.equalizer, "DCCN_TRAIN_RX trains the basic receiver: create the handle without equalizer");
   DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
   DCCN_CHECK(h->cfg.precision == DCCN_PREC_EXACT || h->cfg.precision == DCCN_PREC_PARITY,
              "training needs fp32-class arithmetic (precision exact or parity)");
@@ -665,39 +873,48 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   h->tr = tr;
   tr->cfg = *cfg;
   tr->maxB = MB;
-  if (!h->ws_train) h->ws_train = h->ws_dirty = true;   // the backward pass needs u3 (tanh output) and chest
+  tr->mode = cfg->mode;
+  const int NL = tr->n_layers = rx_mode ? 2 : 10;
+  const char* const* layer_var = rx_mode ? kRxLayerVar : kLayerVar;
+  const int* bias_kind = rx_mode ? kRxBiasKind : kBiasKind;
+  const int* per_symbol = rx_mode ? kRxPerSymbol : kPerSymbol;
+  if (!rx_mode && !h->ws_train) h->ws_train = h->ws_dirty = true;   // the backward pass needs u3 (tanh output) and chest
   if ((rc = ensure_workspace(h, MB))) return rc;
   // ---- gather maps of the ten layers: run the host packers on index-valued variables ------------------
   GemmLayer* Ls[10] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
-  std::vector<std::vector<float>> backup(10);
-  for (int i = 0; i < 10; ++i) {
-    HostTensor& t = h->raw[std::string(kLayerVar[i]) + "/kernel"];
+  if (rx_mode) {
+    Ls[0] = &h->r1;
+    Ls[1] = &h->r2;
+  }
+  std::vector<std::vector<float>> backup(NL);
+  for (int i = 0; i < NL; ++i) {
+    HostTensor& t = h->raw[std::string(layer_var[i]) + "/kernel"];
     DCCN_CHECK(t.data.size() < (1u << 24), "variable too large for the index trick");
     backup[i] = t.data;
     for (size_t p = 0; p < t.data.size(); ++p) t.data[p] = (float)(p + 1);
   }
   rc = pack_layers_host(h);
-  std::vector<std::vector<int32_t>> maps(10);
+  std::vector<std::vector<int32_t>> maps(NL);
   if (!rc)
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < NL; ++i) {
       maps[i].resize(Ls[i]->W.size());
       for (size_t e = 0; e < maps[i].size(); ++e) maps[i][e] = (int32_t)Ls[i]->W[e];
     }
-  for (int i = 0; i < 10; ++i) h->raw[std::string(kLayerVar[i]) + "/kernel"].data = backup[i];
+  for (int i = 0; i < NL; ++i) h->raw[std::string(layer_var[i]) + "/kernel"].data = backup[i];
   if (rc) return rc;
   if ((rc = pack_layers_host(h))) return rc;
   // ---- variables, optimiser slots, maps, operands ----------------------------------------------------------
   const float l2g = 2.0f * cfg->reg_coeff * cfg->l2;
-  tr->params.reserve(20);
+  tr->params.reserve(24);
   size_t max_partial = 0;
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < NL; ++i) {
     TrainLayer& t = tr->tl[i];
     t.L = Ls[i];
-    t.bias_kind = kBiasKind[i];
-    const bool dense = kBiasKind[i] == 0;
+    t.bias_kind = bias_kind[i];
+    const bool dense = bias_kind[i] == 0;
     for (int kb = 0; kb < 2; ++kb) {
       TrainParam p;
-      p.name = std::string(kLayerVar[i]) + (kb == 0 ? "/kernel" : "/bias");
+      p.name = std::string(layer_var[i]) + (kb == 0 ? "/kernel" : "/bias");
       const HostTensor* ht = find(h, p.name);
       DCCN_CHECK(ht, "weight '%s' was not set", p.name.c_str());
       p.n = (int64_t)ht->data.size();
@@ -745,7 +962,7 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
     DCCN_CUDA_OK(cudaStreamSynchronize(s));
     if ((rc = make_bw_layer(h, *t.L, &t.bw, s))) return rc;
     // wgrad scratch: splits x (K+1) x N for the batch this layer contracts over
-    const int64_t M = kPerSymbol[i] ? MB * S : MB;
+    const int64_t M = per_symbol[i] ? MB * S : MB;
     const int rps = rows_per_split(M);
     size_t need = (size_t)((M + rps - 1) / rps) * (kn + Nl);
     if (need > max_partial) max_partial = need;
@@ -765,14 +982,51 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
     rc |= dev_alloc(h, (void**)&tr->yT1, tr->yT_floats * 4);
     if (rc) return rc;
   }
-  if ((rc = make_bw_layer(h, h->r1, &tr->bw_r1, s))) return rc;
-  if ((rc = make_bw_layer(h, h->r2, &tr->bw_r2, s))) return rc;
+  if (!rx_mode) {
+    if ((rc = make_bw_layer(h, h->r1, &tr->bw_r1, s))) return rc;
+    if ((rc = make_bw_layer(h, h->r2, &tr->bw_r2, s))) return rc;
+  }
   tr->partial_floats = max_partial;
   rc |= dev_alloc(h, (void**)&tr->partial, max_partial * 4);
+  if (rx_mode) {
+    // the head's four variables: plain parameters (no packed operand), l2 on dense_1 only
+    const int MO = 1 << h->NB;
+    const int NQ = 2 * MO + MO + (MO + 2) * 2 * h->NB + 2 * h->NB;
+    for (int i = 0; i < 4; ++i) {
+      TrainParam p;
+      p.name = kRxHeadVar[i];
+      const HostTensor* ht = find(h, p.name);
+      DCCN_CHECK(ht, "weight '%s' was not set", p.name.c_str());
+      p.n = (int64_t)ht->data.size();
+      p.l2g = i >= 2 ? l2g : 0.f;
+      rc |= dev_alloc(h, (void**)&p.w, (size_t)p.n * 4);
+      rc |= dev_alloc(h, (void**)&p.m, (size_t)p.n * 4);
+      rc |= dev_alloc(h, (void**)&p.v, (size_t)p.n * 4);
+      rc |= dev_alloc(h, (void**)&p.g, (size_t)p.n * 4);
+      if (rc) return rc;
+      DCCN_CUDA_OK(cudaMemsetAsync(p.m, 0, (size_t)p.n * 4, s));
+      DCCN_CUDA_OK(cudaMemsetAsync(p.v, 0, (size_t)p.n * 4, s));
+      DCCN_CUDA_OK(cudaMemsetAsync(p.g, 0, (size_t)p.n * 4, s));
+      tr->hp[i] = (int)tr->params.size();
+      tr->params.push_back(p);
+    }
+    DCCN_CHECK(tr->params[tr->hp[0]].n == 2 * MO && tr->params[tr->hp[1]].n == MO &&
+                   tr->params[tr->hp[2]].n == (MO + 2) * 2 * h->NB && tr->params[tr->hp[3]].n == 2 * h->NB,
+               "head variables do not have the dev-head shapes");
+    tr->head_warps = h->num_sms * 8 * 8;                      // 8 blocks of 8 warps per SM
+    rc |= dev_alloc(h, (void**)&tr->head_partial, (size_t)tr->head_warps * NQ * 4);
+    if (cudaMallocHost((void**)&tr->head_host, (size_t)NQ * 4) != cudaSuccess) rc = set_error(-1, "cudaMallocHost failed");
+    if (rc) return rc;
+  }
   // ---- gradient activations -------------------------------------------------------------------------------
   const int SK2 = S * K * 2;
   rc |= alloc_act(h, &tr->d_oiq, MB, 2 * D, false);
   rc |= alloc_act(h, &tr->d_r1o, MB, S * F * 2, false);
+  if (rx_mode) {
+    if (rc) return rc;
+    if ((rc = upload_params(h, s))) return rc;
+    return repack_all(h, s);
+  }
   rc |= alloc_act(h, &tr->d_oeq, MB, S * T * 2, false);
   rc |= alloc_act(h, &tr->d_cat, MB * S, 4 * K, false);
   rc |= alloc_act(h, &tr->d_eq, MB, SK2, false);
@@ -805,21 +1059,23 @@ int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t
   DCCN_CHECK(h && x_dev && bits_dev, "null argument");
   DCCN_CHECK(h->tr, "dccn_train_init was not called");
   DCCN_CHECK(B > 0 && B <= h->tr->maxB, "batch %lld outside 1..max_batch (%lld)", (long long)B, (long long)h->tr->maxB);
-  DCCN_CHECK(!(flags & (DCCN_FWD_EQ_ONLY | DCCN_FWD_SKIP_EQ)), "a training step runs equalizer + receiver");
+  DCCN_CHECK(!(flags & (DCCN_FWD_EQ_ONLY | DCCN_FWD_SKIP_EQ)), "a training step runs the whole graph");
   cudaStream_t s = (cudaStream_t)stream;
   TrainState* tr = h->tr;
+  const bool rx_mode = tr->mode == DCCN_TRAIN_RX;
   int rc = 0;
   // ---- forward, keeping every activation ------------------------------------------------------------------
   if (!(flags & DCCN_FWD_NO_NORM) && (rc = run_moments(h, x_dev, B, h->d_mean, h->d_rstd, s))) return rc;
-  if (conf_dev) DCCN_CUDA_OK(cudaMemsetAsync(h->d_conf, 0, 4 * sizeof(unsigned long long), s));
-  h->train_fwd = true;
-  rc = run_chunk(h, x_dev, B, bits_dev, nullptr, nullptr, nullptr, nullptr, conf_dev ? h->d_conf : nullptr, ce_sum_dev,
-                 flags, s);
+  // (the receiver's loss needs this minibatch's confusion matrix: berlin scales the regulariser)
+  if (conf_dev || rx_mode) DCCN_CUDA_OK(cudaMemsetAsync(h->d_conf, 0, 4 * sizeof(unsigned long long), s));
+  h->train_fwd = !rx_mode;
+  rc = run_chunk(h, x_dev, B, bits_dev, nullptr, nullptr, nullptr, nullptr, (conf_dev || rx_mode) ? h->d_conf : nullptr,
+                 ce_sum_dev, flags, s);
   h->train_fwd = false;
   if (rc) return rc;
   if (conf_dev) conf_accumulate(h->d_conf, conf_dev, s);
   // ---- backward ------------------------------------------------------------------------------------------------
-  if ((rc = backward(h, B, bits_dev, s))) return rc;
+  if ((rc = rx_mode ? backward_rx(h, B, bits_dev, s) : backward(h, B, bits_dev, s))) return rc;
   if (!apply_update) return 0;
   // ---- Adam (dev/py/ofdmreceiver_np_mp.py:345-347) ------------------------------------------------------------
   tr->step += 1;
@@ -832,7 +1088,8 @@ int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t
       adam_kernel<<<blocks_for(p.n), 256, 0, s>>>(p.w, p.m, p.v, p.g, p.n, lr_t, tr->cfg.beta1, tr->cfg.beta2, tr->cfg.eps);
     DCCN_CUDA_OK(cudaGetLastError());
   }
-  return repack_all(h, s);
+  if ((rc = repack_all(h, s))) return rc;
+  return rx_mode ? refresh_head(h, s) : 0;
 }
 
 int64_t dccn_train_get_grad(dccn_handle* h, const char* tf_name, float* host, int64_t capacity) {

@@ -184,10 +184,20 @@ class DCCN:
         _lib.check(self.lib.dccn_get_weight(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), n))
         return out
 
-    def train_init(self, max_batch, reg_coeff=0.001, l2=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
-        """Optimiser state for ``optimizer.minimize(total_loss, var_list=Equalizer vars)``
-        (dev/py/ofdmreceiver_np_mp.py:335-347)."""
-        cfg = dccn_train_cfg(reg_coeff=reg_coeff, l2=l2, beta1=beta1, beta2=beta2, eps=eps, max_batch=int(max_batch))
+    def train_init(self, max_batch, reg_coeff=None, l2=0.01, beta1=0.9, beta2=0.999, eps=1e-8, mode=None):
+        """Optimiser state for a training graph of the reference.
+
+        mode 'eq' (default when the model has an equalizer): ``optimizer.minimize(total_loss, var_list=Equalizer vars)``
+        in front of the frozen receiver, REG_COEFF 0.001 (dev/py/ofdmreceiver_np_mp.py:335-347).
+        mode 'rx' (default otherwise): training of the basic receiver itself, every ofdm_dense_rx variable trainable,
+        ``total_loss = ce_mean + berlin * 1e-4 * sum(reg) + ber`` (dev/py/ofdmreceiver_np.py:154-189)."""
+        if mode is None:
+            mode = 'eq' if self.equalizer else 'rx'
+        assert mode in ('eq', 'rx'), mode
+        if reg_coeff is None:
+            reg_coeff = 0.001 if mode == 'eq' else 0.0001
+        cfg = dccn_train_cfg(reg_coeff=reg_coeff, l2=l2, beta1=beta1, beta2=beta2, eps=eps, max_batch=int(max_batch),
+                             mode=_lib.TRAIN_EQ if mode == 'eq' else _lib.TRAIN_RX)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dccn_train_init(self._h, C.byref(cfg), _stream()))
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCCN_ABI_VERSION 1
+#define DCCN_ABI_VERSION 2
 
 /* arithmetic of the GEMM layers */
 enum {
@@ -190,7 +190,17 @@ typedef struct dccn_train_cfg {
   float beta1, beta2; /* tf.train.AdamOptimizer defaults 0.9, 0.999                           */
   float eps;          /* 1e-8                                                                 */
   int64_t max_batch;  /* largest B of dccn_train_step (<= chunk_frames)                       */
+  int32_t mode;       /* DCCN_TRAIN_EQ (above) or DCCN_TRAIN_RX (below)                       */
 } dccn_train_cfg;
+/* DCCN_TRAIN_RX: training of the basic receiver itself, `session.run([train_op, ...])` of
+ * dev/py/ofdmreceiver_np.py:234 with the graph of :154-189 -- every ofdm_dense_rx variable is trainable
+ * (fft_like/conv3d, demodulation/dense, demodulation/conv2d, demodulation/dense_1; kernel + bias),
+ * total_loss = ce_mean + berlin * REG_COEFF * sum(l2 * sum(w^2) over demodulation/dense and demodulation/dense_1)
+ * [+ BER_COEFF * ber, which has no gradient], berlin = BER of the minibatch, REG_COEFF = 1e-4 (pass it as reg_coeff).
+ * The handle must have been created without equalizer.  A DCCN_TRAIN_RX step synchronises the stream once (the head
+ * kernels take their weights by value). */
+#define DCCN_TRAIN_EQ 0
+#define DCCN_TRAIN_RX 1
 /* Allocates optimiser slots / gradient buffers and derives the backward operands; weights must be committed. */
 int dccn_train_init(dccn_handle* h, const dccn_train_cfg* cfg, void* stream);
 /* One minibatch: forward (batch-moment norm included unless DCCN_FWD_NO_NORM), backward of total_loss w.r.t. every

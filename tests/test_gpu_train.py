@@ -151,7 +151,7 @@ def test_train_errors(libdccn):
     m = DCCN(nbits=2, equalizer=False, precision='exact')
     m.load_weights(w)
     with pytest.raises(DccnError):
-        m.train_init(16)                       # no equalizer -> nothing to train
+        m.train_init(16, mode='eq')            # no equalizer -> no Equalizer/* variables to train
     m.close()
     w = orc.glorot_weights(rng, 2, equalizer=True, chest_bias=(0.6, -0.4))
     m = DCCN(nbits=2, equalizer=True, precision='exact')
@@ -160,6 +160,8 @@ def test_train_errors(libdccn):
     bits = torch.zeros((8, 320, 2), device='cuda', dtype=torch.uint8)
     with pytest.raises(DccnError):
         m.train_step(x, bits, 1e-3)            # train_init not called
+    with pytest.raises(DccnError):
+        m.train_init(4, mode='rx')             # receiver training is defined for the handle without equalizer
     m.train_init(4)
     with pytest.raises(DccnError):
         m.train_step(x, bits, 1e-3)            # batch larger than max_batch
@@ -197,3 +199,90 @@ def test_train_equalizer_driver(libdccn, tmp_path):
         assert torch.equal(a, b)
     s2.close()
     session.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# training of the basic receiver itself (DCCN_TRAIN_RX; dev/py/ofdmreceiver_np.py:154-189)
+# ---------------------------------------------------------------------------------------------
+def _rx_case(seed, B, nbits, use_cp=True):
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(seed)
+    w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=False, bias_scale=0.05)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nbits)).astype(np.uint8)
+    return w, x, bits
+
+
+def _rx_engine(w, nbits, precision, max_batch, use_cp=True):
+    from dl_ofdm_b200.engine import DCCN
+    m = DCCN(nbits=nbits, equalizer=False, precision=precision, use_cp=use_cp)
+    m.load_weights(w)
+    m.train_init(max_batch)          # no equalizer -> mode 'rx', REG_COEFF 1e-4
+    return m
+
+
+@pytest.mark.parametrize('precision,nbits,use_cp,B', [
+    ('exact', 2, True, 96), ('parity', 1, True, 64), ('parity', 4, True, 200), ('parity', 2, False, 72), ('exact', 3, False, 33)])
+def test_rx_gradients_match_oracle(libdccn, precision, nbits, use_cp, B):
+    from oracle import dccn_train_oracle as tro
+    w, x, bits = _rx_case(60 + nbits, B, nbits, use_cp)
+    ce, _, berl, g64, _ = tro.rx_loss_and_grads(x, bits, w, nbits, use_cp=use_cp)
+    m = _rx_engine(w, nbits, precision, B, use_cp)
+    out = m.train_step(_cuda(x), _cuda(bits), 1e-3, apply_update=False)
+    torch.cuda.synchronize()
+    assert abs(float(out['ce_sum'][0]) / out['n_bits'] - ce) < 5e-6
+    conf = out['conf'].cpu().numpy()
+    assert abs(float(conf[0, 1] + conf[1, 0]) / conf.sum() - berl) < 1e-12        # the berlin that scales the regulariser
+    for name in tro.rx_trainable_names():
+        g = m.get_grad(name).astype(np.float64).reshape(g64[name].shape)
+        scale = np.abs(g64[name]).max()
+        err = np.abs(g - g64[name]).max()
+        assert err <= GRAD_RTOL * scale + 1e-9, (name, err, scale)
+    assert np.array_equal(m.get_weight('demodulation/dense/kernel'), w['demodulation/dense/kernel'].ravel())
+    m.close()
+
+
+def test_rx_training_steps_match_oracle(libdccn):
+    """Three training steps of the basic receiver on three minibatches: the loss trajectory follows the fp64 oracle,
+    every update is TF's Adam applied to the GPU's own gradients (which test_rx_gradients_match_oracle pins; Adam's first
+    steps are ~ lr * sign(g), so weights are not compared where a gradient sits at the fp32 noise floor), and the inference
+    path afterwards runs on the updated variables (GEMM operands and head weights)."""
+    from oracle import dccn_oracle as orc
+    from oracle import dccn_train_oracle as tro
+    w, x, bits = _rx_case(71, 3 * 80, 2)
+    xs = [x[i * 80:(i + 1) * 80] for i in range(3)]
+    bs = [bits[i * 80:(i + 1) * 80] for i in range(3)]
+    w_ref, losses_ref, _ = tro.rx_train_steps(xs, bs, w, 2)
+    names = tro.rx_trainable_names()
+    m = _rx_engine(w, 2, 'parity', 80)
+    opt = tro.Adam(names, w, dtype=np.float64)
+    wr = {k: np.array(v, dtype=np.float64) for k, v in w.items()}
+    losses = []
+    for i in range(3):
+        lr = tro.learning_rate(1e-3, i)
+        out = m.train_step(_cuda(xs[i]), _cuda(bs[i]), lr)
+        losses.append(float(out['ce_sum'][0]) / out['n_bits'])
+        grads = {n: m.get_grad(n).astype(np.float64).reshape(w[n].shape) for n in names}
+        opt.step(wr, grads, lr)
+        for n in names:
+            got = m.get_weight(n).reshape(w[n].shape)
+            assert np.abs(got - wr[n]).max() <= 2e-6, (i, n, np.abs(got - wr[n]).max())
+            wr[n] = got.astype(np.float64)
+    assert np.allclose(losses, losses_ref, rtol=0, atol=5e-6), (losses, losses_ref)
+    assert m.global_step == 3
+    w_gpu = dict(w)
+    for n in names:
+        w_gpu[n] = m.get_weight(n).reshape(w[n].shape)
+        ref = np.asarray(w_ref[n], dtype=np.float64)
+        # the bulk of every variable follows the oracle trajectory closely
+        assert np.median(np.abs(w_gpu[n] - ref)) <= 3e-5, n
+    # dead taps of the (1,T) 'same' kernel are untouched
+    k0, k1 = w['fft_like/conv3d/kernel'], w_gpu['fft_like/conv3d/kernel']
+    dead = np.ones(80, dtype=bool)
+    dead[39] = False
+    assert np.array_equal(k0[0, dead], k1[0, dead]) and not np.array_equal(k0[0, 39], k1[0, 39])
+    # forward on the trained variables == oracle on the same (GPU-trained) variables
+    o = m.forward(_cuda(xs[0]), _cuda(bs[0]))
+    soft_ref = orc.basic_receiver(xs[0], w_gpu, 2, 16)
+    assert np.abs(o['soft'].cpu().numpy() - soft_ref).max() < 2e-5
+    m.close()

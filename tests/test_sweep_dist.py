@@ -64,9 +64,18 @@ def test_single_process_sweep_and_csv(tmp_path):
 def test_launcher_job_list_matches_reference_order():
     from dl_ofdm_b200.run_local_ofdm import job_list
     from dl_ofdm_b200.flags import parse_flags
-    jobs = job_list(True)
-    assert len(jobs) == 2 * 4 * 2 + 2
-    f = parse_flags(jobs[0][1].split())
-    assert (f.nbits, f.cp, f.longcp, f.channel, f.nfilter, f.SNR) == (4, False, False, 'AWGN', 64, 20.0)
+    save_dir, result_dir, jobs = job_list(True)
+    assert save_dir == './ofdm_lte_ext_64_longcp_mobile/' and result_dir == './test_ext_64_long_cross_mobile'
+    assert len(jobs) == 2 * (4 * 2 + 2)
+    script, flags, csv = jobs[0]                      # reversed([4,3,2,1]) starts with BPSK (run_local_ofdm.py:66)
+    f = parse_flags(flags.split())
+    assert script == 'ofdmreceiver_np' and csv == 'Test_DCCN_OFDM_Dense3_1mod_snr5_cpFalse_AWGN.csv'
+    assert (f.nbits, f.cp, f.longcp, f.channel, f.nfilter, f.SNR, f.max_epoch_num, f.early_stop, f.test) == \
+        (1, False, False, 'AWGN', 64, 5.0, 1200, 200, False)
+    script, flags, csv = jobs[8]
+    f = parse_flags(flags.split())
+    assert script == 'ofdmreceiver_np_mp' and csv == 'Test_DCCN_OFDM_Dense3_1mod_snr5_cpTrue_Equalizer0_mixRayleigh_test_chan_Custom.csv'
+    assert (f.channel, f.opt, f.nbits, f.cp, f.mobile, f.max_epoch_num, f.token) == \
+        ('mixRayleigh', 0, 1, True, True, 4000, 'OFDM_Dense3_1mod_snr5_cpTrue')
     f = parse_flags(jobs[-1][1].split())
-    assert (f.channel, f.opt, f.nbits, f.cp) == ('mixRayleigh', 0, 1, True)
+    assert (f.longcp, f.cp) == (True, False)

@@ -21,7 +21,7 @@ PRECISIONS = {'exact': PREC_EXACT, 'parity': PREC_PARITY, 'fast': PREC_FAST}
 class dccn_cfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'nfft', 'cp_len', 'nsymbol', 'nfilter', 'nbits', 'use_cp', 'n_data', 'pilot_size',
-        'head', 'equalizer', 'precision', 'chunk_frames')]
+        'head', 'equalizer', 'precision', 'chunk_frames', 'eq_opt')]
 
 
 class dccn_train_cfg(C.Structure):

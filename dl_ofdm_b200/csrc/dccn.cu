@@ -270,6 +270,42 @@ int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   const HostTensor* var = find(h, name);                          \
   DCCN_CHECK(var != nullptr, "weight '%s' was not set", name)
 
+// (S,K) 'same' complex conv with one filter -> dense Toeplitz [S*K*2, S*K*2]      (dev/py/model.py:426)
+static int pack_toeplitz_layer(dccn_handle* h, const char* kn, const char* bn, GemmLayer* L) {
+  const int S = h->S, K = h->K, SK2 = S * K * 2;
+  NEED(k, kn);
+  NEED(b, bn);
+  DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == S && k->shape[1] == K && k->shape[4] == 2,
+             "%s: expected [%d,%d,1,1,2]", kn, S, K);
+  L->K = SK2; L->N = SK2;
+  L->W.assign((size_t)SK2 * SK2, 0.f);
+  const int pl = (S - 1) / 2, pw = (K - 1) / 2;
+  for (int d = 0; d < S; ++d)
+    for (int hh = 0; hh < K; ++hh) {
+      const int co = (d * K + hh) * 2;                 // output column (re)
+      for (int i = 0; i < S; ++i) {
+        const int di = d + i - pl;
+        if (di < 0 || di >= S) continue;
+        for (int j = 0; j < K; ++j) {
+          const int hj = hh + j - pw;
+          if (hj < 0 || hj >= K) continue;
+          const float wa = k->data[(size_t)(i * K + j) * 2], wb = k->data[(size_t)(i * K + j) * 2 + 1];
+          const int ri = (di * K + hj) * 2;            // input row (re)
+          L->W[(size_t)ri * SK2 + co] = wa;
+          L->W[(size_t)ri * SK2 + co + 1] = wb;
+          L->W[(size_t)(ri + 1) * SK2 + co] = -wb;
+          L->W[(size_t)(ri + 1) * SK2 + co + 1] = -wa;
+        }
+      }
+    }
+  L->bias.resize(SK2);
+  for (int i = 0; i < SK2; i += 2) {
+    L->bias[i] = b->data[0] - b->data[1];
+    L->bias[i + 1] = b->data[1] - b->data[0];
+  }
+  return 0;
+}
+
 int pack_layers_host(dccn_handle* h) {
   const dccn_cfg& c = h->cfg;
   const int S = h->S, K = h->K, F = h->F, Tin = h->Tin, NB = h->NB, D = h->D;
@@ -320,9 +356,70 @@ int pack_layers_host(dccn_handle* h) {
   h->r2.fused = h->fused_head != 0;
   h->g7.fused = true;
   if (!c.equalizer) return 0;
+  const int SK2 = S * K * 2;
+  if (h->eq_opt != 0) {
+    // ---- ablation equalizers (dev/py/model.py:482-1084): same primitives, other wiring --------------------------
+    // TF-1 auto-numbers the layers of a variable scope in creation order: dense, dense_1, ...; conv3d, conv3d_1, ...
+    const EqSpec& sp = h->eqs;
+    int nd = 0, ncv = 0;
+    auto next_name = [](const char* base, int& ctr) {
+      std::string n = std::string("Equalizer/") + base + (ctr == 0 ? "" : "_" + std::to_string(ctr));
+      ++ctr;
+      return n;
+    };
+    auto dense = [&](GemmLayer* L, int rows, int cols) -> int {
+      const std::string n = next_name("dense", nd);
+      const HostTensor* k = find(h, n + "/kernel");
+      const HostTensor* b = find(h, n + "/bias");
+      DCCN_CHECK(k && b, "weight '%s/{kernel,bias}' was not set (--opt=%d)", n.c_str(), h->eq_opt);
+      DCCN_CHECK(k->shape.size() == 2 && k->shape[0] == rows && k->shape[1] == cols && (int)b->data.size() == cols,
+                 "%s/kernel: expected [%d,%d] (--opt=%d)", n.c_str(), rows, cols, h->eq_opt);
+      pack_dense(*k, *b, L);
+      return 0;
+    };
+    if ((rc = dense(&h->g1, Tin * 2, 2 * K))) return rc;                                   // front1
+    if (sp.front2_cconv) {                                                                 // front2
+      const std::string n = next_name("conv3d", ncv);
+      const HostTensor* k = find(h, n + "/kernel");
+      const HostTensor* b = find(h, n + "/bias");
+      DCCN_CHECK(k && b, "weight '%s/{kernel,bias}' was not set (--opt=%d)", n.c_str(), h->eq_opt);
+      DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == 1 && k->shape[1] == K && k->shape[3] == 1 && k->shape[4] == 2 * K,
+                 "%s/kernel: expected [1,%d,1,1,%d]", n.c_str(), K, 2 * K);
+      pack_complex(k->data.data(), k->data.data() + K, 2 * K, K, K, b->data.data(), &h->g2);
+    } else if ((rc = dense(&h->g2, 2 * K, 2 * K))) return rc;
+    if ((rc = dense(&h->g3, SK2, 2 * c.pilot_size))) return rc;                            // pilot bottleneck
+    GemmLayer* chain[4] = {&h->g4, &h->g5, &h->g6, &h->gx0};
+    for (int i = 0; i < sp.n_chain; ++i)
+      if ((rc = dense(chain[i], i == 0 ? 2 * c.pilot_size : SK2, SK2))) return rc;
+    if (sp.toeplitz) {
+      const std::string n = next_name("conv3d", ncv);
+      if ((rc = pack_toeplitz_layer(h, (n + "/kernel").c_str(), (n + "/bias").c_str(), &h->g7))) return rc;
+    } else {
+      chain[sp.n_chain - 1]->fused = true;                                                 // carries the phase equaliser
+    }
+    if (sp.tail == 1) {
+      if ((rc = dense(&h->g9, 2 * K, 2 * K))) return rc;
+    } else {
+      // tf.ifft over the K subcarriers of a symbol as a constant [2K, 2K] layer (standard complex product, 1/K scale)
+      GemmLayer* L = &h->g9;
+      L->K = 2 * K; L->N = 2 * K;
+      L->W.assign((size_t)4 * K * K, 0.f);
+      L->bias.assign(2 * K, 0.f);
+      const double PI2 = 6.283185307179586476925286766559;
+      for (int kk = 0; kk < K; ++kk)
+        for (int n = 0; n < K; ++n) {
+          const double a = PI2 * (double)((kk * n) % K) / K;
+          const float cs = (float)(cos(a) / K), sn = (float)(sin(a) / K);
+          L->W[(size_t)(2 * kk) * 2 * K + 2 * n] = cs;
+          L->W[(size_t)(2 * kk + 1) * 2 * K + 2 * n] = -sn;
+          L->W[(size_t)(2 * kk) * 2 * K + 2 * n + 1] = sn;
+          L->W[(size_t)(2 * kk + 1) * 2 * K + 2 * n + 1] = cs;
+        }
+    }
+    return dense(&h->g10, 2 * K, 2 * h->T);
+  }
 
   // ---- equalizer_ofdm -----------------------------------------------------------
-  const int SK2 = S * K * 2;
   {
     NEED(k, "Equalizer/dense/kernel");
     NEED(b, "Equalizer/dense/bias");
@@ -372,40 +469,7 @@ int pack_layers_host(dccn_handle* h) {
     DCCN_CHECK(k->shape[0] == SK2 && k->shape[1] == SK2, "Equalizer/dense_4/kernel shape");
     pack_dense(*k, *b, &h->g6);
   }
-  {
-    // (S,K) 'same' complex conv with one filter -> dense Toeplitz [S*K*2, S*K*2]
-    NEED(k, "Equalizer/conv3d_1/kernel");
-    NEED(b, "Equalizer/conv3d_1/bias");
-    DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == S && k->shape[1] == K && k->shape[4] == 2,
-               "Equalizer/conv3d_1/kernel: expected [%d,%d,1,1,2]", S, K);
-    GemmLayer* L = &h->g7;
-    L->K = SK2; L->N = SK2;
-    L->W.assign((size_t)SK2 * SK2, 0.f);
-    const int pl = (S - 1) / 2, pw = (K - 1) / 2;
-    for (int d = 0; d < S; ++d)
-      for (int hh = 0; hh < K; ++hh) {
-        const int co = (d * K + hh) * 2;                 // output column (re)
-        for (int i = 0; i < S; ++i) {
-          const int di = d + i - pl;
-          if (di < 0 || di >= S) continue;
-          for (int j = 0; j < K; ++j) {
-            const int hj = hh + j - pw;
-            if (hj < 0 || hj >= K) continue;
-            const float wa = k->data[(size_t)(i * K + j) * 2], wb = k->data[(size_t)(i * K + j) * 2 + 1];
-            const int ri = (di * K + hj) * 2;            // input row (re)
-            L->W[(size_t)ri * SK2 + co] = wa;
-            L->W[(size_t)ri * SK2 + co + 1] = wb;
-            L->W[(size_t)(ri + 1) * SK2 + co] = -wb;
-            L->W[(size_t)(ri + 1) * SK2 + co + 1] = -wa;
-          }
-        }
-      }
-    L->bias.resize(SK2);
-    for (int i = 0; i < SK2; i += 2) {
-      L->bias[i] = b->data[0] - b->data[1];
-      L->bias[i + 1] = b->data[1] - b->data[0];
-    }
-  }
+  if ((rc = pack_toeplitz_layer(h, "Equalizer/conv3d_1/kernel", "Equalizer/conv3d_1/bias", &h->g7))) return rc;
   if ((rc = pack_1xK("Equalizer/conv3d_2/kernel", "Equalizer/conv3d_2/bias", &h->g8, true))) return rc;
   if ((rc = pack_1xK("Equalizer/conv3d_3/kernel", "Equalizer/conv3d_3/bias", &h->g9, false))) return rc;
   {
@@ -434,6 +498,16 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
   if ((rc = upload_layer(h, &h->r1, s))) return rc;
   if ((rc = upload_layer(h, &h->r2, s))) return rc;
   if (!h->cfg.equalizer) return 0;
+  if (h->eq_opt != 0) {
+    const EqSpec& sp = h->eqs;
+    std::vector<GemmLayer*> ls = {&h->g1, &h->g2, &h->g3, &h->g9, &h->g10};
+    GemmLayer* chain[4] = {&h->g4, &h->g5, &h->g6, &h->gx0};
+    for (int i = 0; i < sp.n_chain; ++i) ls.push_back(chain[i]);
+    if (sp.toeplitz) ls.push_back(&h->g7);
+    for (GemmLayer* L : ls)
+      if ((rc = upload_layer(h, L, s))) return rc;
+    return 0;
+  }
   GemmLayer* ls[] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
   for (GemmLayer* L : ls)
     if ((rc = upload_layer(h, L, s))) return rc;
@@ -663,7 +737,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     DCCN_CUDA_OK(cudaGetLastError());
   }
   const Act* rx_in = &h->a0;
-  const bool folded = use_eq && (flags & DCCN_FWD_FOLDED) && !h->train_fwd && !h->tr && !eq_out &&
+  const bool folded = use_eq && h->eq_opt == 0 && (flags & DCCN_FWD_FOLDED) && !h->train_fwd && !h->tr && !eq_out &&
                       !(flags & DCCN_FWD_EQ_ONLY);
   if (folded) {
     // ---- same function, 5 GEMMs: consecutive linear layers were pre-multiplied (build_folded) ----------
@@ -696,7 +770,56 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     if ((rc = run_gemm(h, SLOT_F9, h->f9, eqcv, 0, MS, store_epi(h->f9, r1v, 0, MS), s))) return rc;
     return run_head_dispatch(h, Bc, bits, soft, hard, conf, ce, s);
   }
-  if (use_eq) {
+  if (use_eq && h->eq_opt != 0) {
+    // ---- ablation equalizers: front (2 per-symbol layers) -> pilot -> dense chain [-> Toeplitz] + phase equaliser -> tail
+    const EqSpec& sp = h->eqs;
+    const int64_t MS = Bc * S;
+    Act a0v = h->a0;  a0v.ld = 2 * T;
+    Act t1v = h->t1;  t1v.ld = 2 * K;
+    Act fv = h->f;    fv.ld = 2 * K;
+    Act eqv = h->eq;  eqv.ld = 2 * K;
+    Act midv = h->cat; midv.ld = 2 * K;                 // tail intermediate [MS, 2K] (the cat buffer is [MS, 4K])
+    Act oeqv = h->oeq; oeqv.ld = 2 * T;
+    if ((rc = run_gemm(h, SLOT_G1, h->g1, a0v, cp_off, MS, store_epi(h->g1, t1v, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G2, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
+    GemmLayer* chain[4] = {&h->g4, &h->g5, &h->g6, &h->gx0};
+    const int chain_slot[4] = {SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G6};
+    const Act* src = &h->p32;
+    auto phase_eq = [&](const GemmLayer& L, const Act& in, int act, bool band) -> int {
+      EpiPhaseEq e;
+      e.bias = L.dBias;
+      e.f0 = h->f.p0;
+      e.f1 = h->f.p1;
+      e.ld_f = h->f.ld;
+      e.eq = out_of(h->eq);
+      e.corr = ActOut{nullptr, nullptr, 0, 0};          // no correlation branch in these graphs
+      e.chest_out = chest_out;
+      e.act = act;
+      e.M = (int)Bc;
+      e.N = L.N;
+      KSched ks;
+      if (band && h->band_skip && L.BN == 2 * K && (2 * K) % 32 == 0) ks.band = ((S - 1) / 2) * (2 * K / 32);
+      return run_gemm(h, SLOT_G7_PHASEEQ, L, in, 0, Bc, e, s, ks);
+    };
+    for (int i = 0; i < sp.n_chain; ++i) {
+      const bool last = (i == sp.n_chain - 1) && !sp.toeplitz;
+      if (last) {
+        if ((rc = phase_eq(*chain[i], *src, sp.chain_act[i], false))) return rc;
+      } else {
+        const Act* dst = (i & 1) ? &h->u2 : &h->u1;
+        if ((rc = run_gemm(h, chain_slot[i], *chain[i], *src, 0, Bc, store_epi(*chain[i], *dst, 0, Bc, sp.chain_act[i]), s)))
+          return rc;
+        src = dst;
+      }
+    }
+    if (sp.toeplitz && (rc = phase_eq(h->g7, *src, 0, true))) return rc;
+    // tail: dense(2K) or the constant inverse DFT per symbol, then dense(2T) per symbol
+    if ((rc = run_gemm(h, SLOT_G9, h->g9, eqv, 0, MS, store_epi(h->g9, midv, 0, MS), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G10, h->g10, midv, 0, MS, store_epi(h->g10, oeqv, 0, MS, 0, eq_out, 2 * T), s))) return rc;
+    rx_in = &h->oeq;
+    if (flags & DCCN_FWD_EQ_ONLY) return 0;
+  } else if (use_eq) {
     const int64_t MS = Bc * S;
     // views: [Bc, S*X] buffers are addressed as [Bc*S, X] by the per-symbol layers
     Act a0v = h->a0;  a0v.ld = 2 * T;
@@ -925,6 +1048,22 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   h->D = cfg->n_data;
   h->NB = cfg->nbits;
   h->P = h->S * h->T * 2;
+  if (cfg->equalizer && cfg->eq_opt != 0) {
+    // wiring of the ablation graphs (dev/py/ofdmreceiver_np_mp.py:292-311 -> dev/py/model.py:482-1084)
+    EqSpec sp;
+    switch (cfg->eq_opt) {
+      case 1: sp.front2_cconv = 0; sp.n_chain = 3; sp.chain_act[0] = 0; sp.chain_act[1] = 0; sp.chain_act[2] = 1; sp.toeplitz = 1; sp.tail = 1; break;
+      case 2: sp.front2_cconv = 1; sp.n_chain = 1; sp.chain_act[0] = 0; sp.toeplitz = 0; sp.tail = 2; break;
+      case 4: sp.front2_cconv = 1; sp.n_chain = 2; sp.chain_act[0] = 0; sp.chain_act[1] = 1; sp.toeplitz = 0; sp.tail = 2; break;
+      case 5: sp.front2_cconv = 1; sp.n_chain = 4; sp.chain_act[0] = 0; sp.chain_act[1] = 1; sp.chain_act[2] = 1; sp.chain_act[3] = 1; sp.toeplitz = 0; sp.tail = 2; break;
+      case 3: sp.front2_cconv = 0; sp.n_chain = 4; sp.chain_act[0] = 1; sp.chain_act[1] = 1; sp.chain_act[2] = 1; sp.chain_act[3] = 1; sp.toeplitz = 0; sp.tail = 1; break;
+      default:
+        delete h;
+        return set_error(-2, "eq_opt=%d: implemented equalizer graphs are --opt 0,1,2,3,4,5", (int)cfg->eq_opt);
+    }
+    h->eqs = sp;
+    h->eq_opt = cfg->eq_opt;
+  }
   h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 65536;   // per-launch overheads (~10 us x 15 kernels) amortise over the pass
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);

@@ -182,6 +182,7 @@ struct EpiPhaseEqT {
   // real corr value of complex point j at  s * sym_stride + j % (sym_cols / 2)  (+ the ActOut column offsets), i.e.
   // both interleave per symbol in one [M*S, 3K] operand.  !SYM: plain [M, N] / [M, N/2] matrices.
   int sym_cols = 0, sym_stride = 0;
+  int act = 0;          // 1: chest = tanh(acc + bias) (ablation graphs whose chest is a tanh dense, model.py:775-779)
   CUtensorMap tm_eq;    // tensor-core path: view of eq.p0 + eq.col_off, box 32 x 32 (set by run_gemm)
   CUtensorMap tm_chest; // same for chest_out
   struct State {};
@@ -211,8 +212,12 @@ struct EpiPhaseEqT {
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       const float4 bq = b4[i >> 2], fq = f4[i >> 2];
-      const float cr = v[i] + ((i & 2) ? bq.z : bq.x);
-      const float ci = v[i + 1] + ((i & 2) ? bq.w : bq.y);
+      float cr = v[i] + ((i & 2) ? bq.z : bq.x);
+      float ci = v[i + 1] + ((i & 2) ? bq.w : bq.y);
+      if (act == 1) {
+        cr = tanhf(cr);
+        ci = tanhf(ci);
+      }
       const float2 f = (i & 2) ? make_float2(fq.z, fq.w) : make_float2(fq.x, fq.y);
       const float inv = rsqrtf(cr * cr + ci * ci);
       const float nr = cr * inv, ni = (-ci) * inv;
@@ -225,7 +230,7 @@ struct EpiPhaseEqT {
     }
     store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch);
     if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch);
-    if (ok) store_act<16>(corr, row, corr_col(col0 / 2), c);
+    if (ok && corr.p0) store_act<16>(corr, row, corr_col(col0 / 2), c);
   }
 
   template <int NC>
@@ -238,6 +243,10 @@ struct EpiPhaseEqT {
     for (int i = 0; i < NC; i += 2) {
       float cr = v[i] + __ldg(bias + col0 + i);
       float ci = v[i + 1] + __ldg(bias + col0 + i + 1);
+      if (act == 1) {
+        cr = tanhf(cr);
+        ci = tanhf(ci);
+      }
       float2 f = *reinterpret_cast<const float2*>(fp0 + i);
       if (fp1) {
         float2 fl = *reinterpret_cast<const float2*>(fp1 + i);
@@ -258,7 +267,7 @@ struct EpiPhaseEqT {
       v[i + 1] = ci;
     }
     store_act<NC>(eq, row, eq_col(col0), e);
-    store_act<NC / 2>(corr, row, corr_col(col0 / 2), c);
+    if (corr.p0) store_act<NC / 2>(corr, row, corr_col(col0 / 2), c);
     if (chest_out) {
       float* d = chest_out + (size_t)row * N + col0;
 #pragma unroll

@@ -37,6 +37,15 @@ struct GemmLayer {
   bool mc = false;              // run as cta_group::2 CTA pairs (each CTA holds half of the weight tile)
 };
 
+// wiring of an equalizer graph (--opt), see pack_layers_host / run_chunk
+struct EqSpec {
+  int front2_cconv = 1;       // 1: (1,K) 'valid' complex conv, 0: dense 2K -> 2K
+  int n_chain = 3;            // frame-level dense layers after the pilot bottleneck
+  int chain_act[4] = {0, 0, 1, 0};   // 0 linear, 1 tanh
+  int toeplitz = 1;           // (S,K) 'same' complex conv behind the chain
+  int tail = 0;               // 0: cconv(eq) | cconv(corr) -> dense, 1: dense(2K) -> dense(2T), 2: tf.ifft -> dense(2T)
+};
+
 struct HostTensor {
   std::vector<int64_t> shape;
   std::vector<float> data;
@@ -77,6 +86,9 @@ struct dccn_handle {
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
   dccn::GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
+  dccn::GemmLayer gx0;              // 4th chain layer of the ablation graphs (--opt 3, 5)
+  int eq_opt = 0;                   // cfg.eq_opt; != 0: the roles of g1..g10 follow `eqs` (pack_layers_host)
+  dccn::EqSpec eqs;
   dccn::HeadWeights hw;
   // DCCN_FWD_FOLDED: consecutive linear layers pre-multiplied (built on first use, from the committed weights)
   dccn::GemmLayer f1, f4, f9;       // dense.conv3d | dense_2.dense_3.dense_4(tanh) | (conv3d_3,conv3d_2).dense_5.fft_like

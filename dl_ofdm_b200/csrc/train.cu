@@ -859,6 +859,7 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   DCCN_CHECK(cfg->mode == DCCN_TRAIN_EQ || cfg->mode == DCCN_TRAIN_RX, "unknown training mode %d", (int)cfg->mode);
   DCCN_CHECK(rx_mode || h->cfg.equalizer, "DCCN_TRAIN_EQ updates the Equalizer/* variables: the handle has no equalizer");
   DCCN_CHECK(!rx_mode || !h->cfg.equalizer, "DCCN_TRAIN_RX trains the basic receiver: create the handle without equalizer");
+  DCCN_CHECK(h->eq_opt == 0, "training is implemented for equalizer_ofdm (--opt=0); --opt=%d is inference only", h->eq_opt);
   DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
   DCCN_CHECK(h->cfg.precision == DCCN_PREC_EXACT || h->cfg.precision == DCCN_PREC_PARITY,
              "training needs fp32-class arithmetic (precision exact or parity)");

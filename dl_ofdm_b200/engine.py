@@ -35,7 +35,7 @@ class DCCN:
 
     def __init__(self, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data=320, pilot_size=16,
                  use_cp=True, head='dev', equalizer=False, precision='parity', chunk_frames=0,
-                 device=None):
+                 device=None, eq_opt=0):
         if not torch.cuda.is_available():
             raise DccnError('dl_ofdm_b200 needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
@@ -44,7 +44,8 @@ class DCCN:
                             use_cp=int(bool(use_cp)), n_data=n_data, pilot_size=pilot_size,
                             head=_lib.HEAD_V1 if head == 'v1' else _lib.HEAD_DEV,
                             equalizer=int(bool(equalizer)), precision=_lib.PRECISIONS[precision],
-                            chunk_frames=chunk_frames)
+                            chunk_frames=chunk_frames, eq_opt=int(eq_opt) if equalizer else 0)
+        self.eq_opt = int(eq_opt) if equalizer else 0
         self.nbits, self.S, self.K, self.T, self.D = nbits, nsymbol, nfft, nfft + cp_len, n_data
         self.equalizer = bool(equalizer)
         self.precision = precision
@@ -68,7 +69,8 @@ class DCCN:
 
     @classmethod
     def from_ofdm(cls, FLAGS, ofdmobj, equalizer=False, precision='parity', head='dev', **kw):
-        """Build from the reference's FLAGS + ofdm_tx object (same fields the TF builders read)."""
+        """Build from the reference's FLAGS + ofdm_tx object (same fields the TF builders read).  ``eq_opt`` (keyword)
+        selects the equalizer graph: 0 equalizer_ofdm (default), 1 nocconv, 2 noresdl, 3 dnnE, 4 noresdl2, 5 noresdl4."""
         return cls(nbits=FLAGS.nbits, nfft=ofdmobj.K, cp_len=ofdmobj.CP, nsymbol=ofdmobj.nSymbol,
                    nfilter=FLAGS.nfilter, n_data=ofdmobj.frame_size, pilot_size=ofdmobj.pilot_size,
                    use_cp=FLAGS.cp, head=head, equalizer=equalizer, precision=precision, **kw)

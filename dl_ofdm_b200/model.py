@@ -13,14 +13,15 @@ import torch
 
 from . import _lib, tfbundle
 from .engine import DCCN
+from .init import detect_eq_opt
 
 _CACHE = {}
 
 
-def _engine(FLAGS, ofdmobj, weights, equalizer, head, precision):
-    key = (id(weights), equalizer, head, precision, FLAGS.nbits, FLAGS.cp, torch.cuda.current_device())
+def _engine(FLAGS, ofdmobj, weights, equalizer, head, precision, eq_opt=0):
+    key = (id(weights), equalizer, head, precision, FLAGS.nbits, FLAGS.cp, torch.cuda.current_device(), eq_opt)
     if key not in _CACHE:
-        m = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=equalizer, precision=precision, head=head)
+        m = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=equalizer, precision=precision, head=head, eq_opt=eq_opt)
         m.load_weights(weights)
         _CACHE[key] = m
     return _CACHE[key]
@@ -38,10 +39,39 @@ def ofdm_dense_rx(inputs, FLAGS, ofdmobj, outshape=None, weights=None, head='dev
 def equalizer_ofdm(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
     """Normalised IQ [B,S,T,2] -> (equalized [B,S,T,2], snr_db placeholder, chest complex [B,S,K])
     (dev/py/model.py:349-478).  The snr_db monitor of the reference is not computed (None)."""
-    m = _engine(FLAGS, ofdmobj, weights, True, 'dev', precision)
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 0)
+
+
+def _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, opt):
+    m = _engine(FLAGS, ofdmobj, weights, True, 'dev', precision, opt)
     o = m.forward(inputs.contiguous(), want_soft=False, want_hard=False, want_eq=True, want_chest=True,
                   flags=_lib.FWD_NO_NORM | _lib.FWD_EQ_ONLY)
     return o['eq'], None, torch.view_as_complex(o['chest'])
+
+
+def equalizer_nocconv(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """--opt=1 (dev/py/model.py:482-609): dense instead of the learned-DFT conv, dense -> dense tail."""
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 1)
+
+
+def equalizer_noresdl(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """--opt=2 (dev/py/model.py:612-714): one dense after the pilots, tf.ifft tail."""
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 2)
+
+
+def equalizer_dnnE(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """--opt=3 (dev/py/model.py:953-1084): all-dense equalizer."""
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 3)
+
+
+def equalizer_noresdl2(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """--opt=4 (dev/py/model.py:718-826)."""
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 4)
+
+
+def equalizer_noresdl4(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """--opt=5 (dev/py/model.py:829-950)."""
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 5)
 
 
 class Session:
@@ -55,8 +85,9 @@ class Session:
         has_eq = any(k.startswith('Equalizer/') for k in weights)
         if head is None:
             head = 'v1' if 'demodulation/conv2d_1/kernel' in weights else 'dev'
+        # the Equalizer/* variable names identify the graph (--opt) a checkpoint was trained with
         self.engine = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=has_eq, precision=precision, head=head,
-                                     chunk_frames=chunk_frames)
+                                     chunk_frames=chunk_frames, eq_opt=detect_eq_opt(weights) if has_eq else 0)
         self.engine.load_weights(weights)
 
     def run(self, fetches, feed):

@@ -252,6 +252,118 @@ def equalizer_ofdm(z, w, nfft, cp_len, use_cp=True, dtype=np.float64,
 
 
 # ---------------------------------------------------------------------------
+# ablation equalizers, --opt != 0  (dev/py/ofdmreceiver_np_mp.py:292-311)
+# ---------------------------------------------------------------------------
+# All of them are rewirings of equalizer_ofdm's template:
+#   layer_norm -> [CP slice] -> dense(2K) per symbol -> FRONT2 -> inputs_complex
+#   -> flatten -> dense(pilot) -> CHAIN of frame-level dense layers (linear / tanh) -> [(S,K) 'same' complex conv]
+#   -> chest -> phase-only equalise -> TAIL -> [B,S,T,2]
+# opt  function (dev/py/model.py)        FRONT2        CHAIN (0 lin, 1 tanh)   conv   TAIL
+#  0   equalizer_ofdm      :349-478      cconv (1,K)   0 0 1                   yes    cconv(eq) | cconv(corr) -> concat -> dense
+#  1   equalizer_nocconv   :482-609      dense(2K)     0 0 1                   yes    dense(2K) -> dense(2T)
+#  2   equalizer_noresdl   :612-714      cconv (1,K)   0                       no     tf.ifft -> dense(2T)
+#  4   equalizer_noresdl2  :718-826      cconv (1,K)   0 1                     no     tf.ifft -> dense(2T)
+#  5   equalizer_noresdl4  :829-950      cconv (1,K)   0 1 1 1                 no     tf.ifft -> dense(2T)
+#  3   equalizer_dnnE      :953-1084     dense(2K)     1 1 1 1                 no     dense(2K) -> dense(2T)
+# (opt 6 equalizer_doppler and opt 7 equalizer_separateIQ / layers_conv2d_vector are not restated.)
+# Variable names follow TF-1's per-scope auto-numbering in creation order (dense, dense_1, ...; conv3d, conv3d_1, ...).
+EQ_SPECS = {
+    0: dict(front2='cconv', chain=(0, 0, 1), toeplitz=True, tail='corr'),
+    1: dict(front2='dense', chain=(0, 0, 1), toeplitz=True, tail='dense2'),
+    2: dict(front2='cconv', chain=(0,), toeplitz=False, tail='ifft'),
+    4: dict(front2='cconv', chain=(0, 1), toeplitz=False, tail='ifft'),
+    5: dict(front2='cconv', chain=(0, 1, 1, 1), toeplitz=False, tail='ifft'),
+    3: dict(front2='dense', chain=(1, 1, 1, 1), toeplitz=False, tail='dense2'),
+}
+
+
+def eq_layer_names(opt):
+    """Creation-ordered layer list of ``--opt``: [(role, tf layer name)] with roles front1, front2, pilot, chain<i>,
+    toeplitz, tail_corr, tail_eq, tail1, tail2."""
+    sp = EQ_SPECS[opt]
+    nd = nc = 0
+    out = []
+
+    def dense(role):
+        nonlocal nd
+        out.append((role, 'dense' if nd == 0 else 'dense_%d' % nd))
+        nd += 1
+
+    def conv(role):
+        nonlocal nc
+        out.append((role, 'conv3d' if nc == 0 else 'conv3d_%d' % nc))
+        nc += 1
+
+    dense('front1')
+    conv('front2') if sp['front2'] == 'cconv' else dense('front2')
+    dense('pilot')
+    for i in range(len(sp['chain'])):
+        dense('chain%d' % i)
+    if sp['toeplitz']:
+        conv('toeplitz')
+    if sp['tail'] == 'corr':
+        conv('tail_corr')
+        conv('tail_eq')
+        dense('tail2')
+    elif sp['tail'] == 'dense2':
+        dense('tail1')
+        dense('tail2')
+    else:
+        dense('tail2')
+    return out
+
+
+def equalizer_variant(z, w, opt, nfft, cp_len, use_cp=True, dtype=np.float64, prefix='Equalizer/'):
+    """Ablation equalizers (and opt 0) op by op in complex arithmetic: normalised IQ [B,S,T,2] -> (equalised
+    [B,S,T,2], chest complex [B,S,K]).  Line numbers: see the table above."""
+    sp = EQ_SPECS[opt]
+    names = dict(eq_layer_names(opt))
+
+    def g(role, what):
+        return np.asarray(w[prefix + names[role] + '/' + what], dtype=dtype)
+
+    def dense(x, role, act=0):
+        y = x @ g(role, 'kernel') + g(role, 'bias')
+        return np.tanh(y) if act else y
+
+    z = np.asarray(z, dtype=dtype)
+    B, S, T, _ = z.shape
+    K = nfft
+    c = layer_norm(z, dtype)
+    c = c[:, :, cp_len:cp_len + K, :].reshape(B, S, K * 2) if not use_cp else c.reshape(B, S, T * 2)
+    c = dense(c, 'front1')                                              # [B,S,2K]
+    if sp['front2'] == 'cconv':
+        f = conv2d_complex(c.reshape(B, S, K, 1, 2), g('front2', 'kernel'), g('front2', 'bias'), 'valid', dtype)
+        f = np.transpose(f, (0, 1, 3, 2, 4))[:, :, :, 0, :]             # [B,S,K,2]
+    else:
+        f = dense(c, 'front2').reshape(B, S, K, 2)
+    inputs_c = f[..., 0] + 1j * f[..., 1]                               # [B,S,K]
+    c = dense(f.reshape(B, S * K * 2), 'pilot')
+    for i, act in enumerate(sp['chain']):
+        c = dense(c, 'chain%d' % i, act)
+    c5 = c.reshape(B, S, K, 1, 2)
+    if sp['toeplitz']:
+        c5 = conv2d_complex(c5, g('toeplitz', 'kernel'), g('toeplitz', 'bias'), 'same', dtype)
+    chest_c = (c5[..., 0] + 1j * c5[..., 1])[:, :, :, 0]                # [B,S,K]
+    ab = np.abs(chest_c)
+    eq = inputs_c * (np.real(chest_c) / ab - 1j * (np.imag(chest_c) / ab))     # phase-only equalise, no eps
+    if sp['tail'] == 'corr':
+        corr = eq * np.conj(eq)
+        def cc(v, role):
+            v5 = np.stack([v.real, v.imag], -1).reshape(B, S, K, 1, 2)
+            o = conv2d_complex(v5, g(role, 'kernel'), g(role, 'bias'), 'valid', dtype)
+            return np.transpose(o, (0, 1, 3, 2, 4))[:, :, :, 0, :]
+        t = np.concatenate([cc(eq, 'tail_eq'), cc(corr, 'tail_corr')], -1).reshape(B, S, K * 4)
+    elif sp['tail'] == 'dense2':
+        t = dense(np.stack([eq.real, eq.imag], -1).reshape(B, S, K * 2), 'tail1')
+    else:
+        e = np.fft.ifft(eq, axis=-1)                                    # tf.ifft over the K subcarriers of a symbol
+        t = np.stack([e.real, e.imag], -1).reshape(B, S, K * 2).astype(dtype)
+    out = dense(t, 'tail2').reshape(B, S, T, 2)
+    return out, chest_c
+
+
+# ---------------------------------------------------------------------------
 # a5  BER head / loss  (dev/py/ofdmreceiver_np.py:154-169, dev/py/util.py:44-48)
 # ---------------------------------------------------------------------------
 def ber_head(soft, bits):
@@ -374,10 +486,13 @@ def basic_receiver(x, w, nbits, cp_len, use_cp=True, head='dev', nfilter=64,
 
 
 def equalized_receiver(x, w, nbits, nfft, cp_len, use_cp=True, nfilter=64,
-                       dtype=np.float64):
+                       dtype=np.float64, opt=0):
     """tx_ofdm -> a2 -> a4 -> (+0) -> a3   (dev/py/ofdmreceiver_np_mp.py:292-320)."""
     z, _, _ = batch_moment_norm(x, dtype)
-    eq, chest = equalizer_ofdm(z, w, nfft, cp_len, use_cp, dtype)
+    if opt == 0:
+        eq, chest = equalizer_ofdm(z, w, nfft, cp_len, use_cp, dtype)
+    else:
+        eq, chest = equalizer_variant(z, w, opt, nfft, cp_len, use_cp, dtype)
     soft = ofdm_dense_rx(eq, w, nbits, cp_len, use_cp, 'dev', nfilter, dtype)
     return soft, eq, chest
 
@@ -387,7 +502,7 @@ def equalized_receiver(x, w, nbits, nfft, cp_len, use_cp=True, nfilter=64,
 # ---------------------------------------------------------------------------
 def glorot_weights(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data=320,
                    pilot_size=16, use_cp=True, head='dev', equalizer=True,
-                   bias_scale=0.0, chest_bias=None):
+                   bias_scale=0.0, chest_bias=None, eq_opt=0):
     """Seeded weights with the reference's variable names, layouts and init.
 
     ``bias_scale`` > 0 draws small non-zero biases so parity tests exercise the
@@ -429,7 +544,35 @@ def glorot_weights(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data
         w['demodulation/conv2d_1/kernel'] = glorot((1, 1, M, M), M, M)
         w['demodulation/conv2d_1/bias'] = bias(M)
     dense('demodulation/dense_1', M + 2, 2 * nbits)
-    if equalizer:
+    if equalizer and eq_opt != 0:
+        e = 'Equalizer/'
+        sp = EQ_SPECS[eq_opt]
+        SK2 = S * K * 2
+        shapes = {'front1': ('d', T * 2, K * 2), 'front2': ('c', 1, K, 2 * K) if sp['front2'] == 'cconv' else ('d', K * 2, K * 2),
+                  'pilot': ('d', SK2, pilot_size * 2), 'toeplitz': ('c', S, K, 2), 'tail_corr': ('c', 1, K, 2 * K),
+                  'tail_eq': ('c', 1, K, 2 * K), 'tail1': ('d', K * 2, K * 2),
+                  'tail2': ('d', K * 4 if sp['tail'] == 'corr' else K * 2, (nfft + cp_len) * 2)}
+        for i in range(len(sp['chain'])):
+            shapes['chain%d' % i] = ('d', pilot_size * 2 if i == 0 else SK2, SK2)
+        layers = eq_layer_names(eq_opt)
+        for role, name in layers:
+            sh = shapes[role]
+            if sh[0] == 'd':
+                dense(e + name, sh[1], sh[2])
+            else:
+                conv3d(e + name, sh[1], sh[2], 1, sh[3])
+        if chest_bias is not None:
+            # keep the channel estimate away from 0 (no epsilon in the phase-only equaliser)
+            names = dict(layers)
+            if sp['toeplitz']:
+                w[e + names['toeplitz'] + '/bias'] = np.asarray(chest_bias, dtype=np.float32)
+            else:
+                last = e + names['chain%d' % (len(sp['chain']) - 1)]
+                w[last + '/kernel'] = (0.3 * w[last + '/kernel']).astype(np.float32)
+                b = np.empty(SK2, dtype=np.float32)
+                b[0::2], b[1::2] = chest_bias[0], chest_bias[1]
+                w[last + '/bias'] = b
+    elif equalizer:
         e = 'Equalizer/'
         dense(e + 'dense', T * 2, K * 2)
         conv3d(e + 'conv3d', 1, K, 1, 2 * K)

@@ -567,3 +567,68 @@ def test_folded_schedule_matches_oracle(libdccn, precision, cp, nb):
     eq = m.forward(_cuda(x), want_eq=True, flags=_lib.FWD_FOLDED)
     assert torch.equal(eq['soft'], plain['soft'])
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# ablation equalizers, --opt = 1, 2, 3, 4, 5 (dev/py/model.py:482-1084): the library's packed-GEMM
+# wiring (constant inverse-DFT layer for tf.ifft, phase equaliser fused behind a tanh dense, ...) against the
+# oracle's op-by-op complex arithmetic (np.fft.ifft).  Parity unpinned against TF itself, like every dev-graph test.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('opt,precision,cp', [(1, 'parity', True), (2, 'parity', True), (3, 'parity', True),
+                                              (4, 'parity', False), (5, 'parity', True), (1, 'exact', False),
+                                              (2, 'exact', True), (3, 'exact', False), (5, 'exact', False)])
+def test_ablation_equalizers_seeded(libdccn, opt, precision, cp):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(500 + opt)
+    nb, B = 2, 200
+    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), eq_opt=opt)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    soft_ref, eq_ref, chest_ref = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64, opt=opt)
+    m = DCCN(nbits=nb, use_cp=cp, equalizer=True, precision=precision, eq_opt=opt)
+    m.load_weights(w)
+    out = m.forward(_cuda(x), _cuda(bits), want_eq=True, want_chest=True)
+    chest = out['chest'].cpu().numpy()
+    chest = chest[..., 0] + 1j * chest[..., 1]
+    assert np.abs(chest - chest_ref).max() < 2e-5 * max(1.0, np.abs(chest_ref).max())
+    good = np.abs(chest_ref).reshape(B, -1).min(axis=1) > 2e-2          # no epsilon in |chest| (see test_equalizer_seeded)
+    assert good.sum() > B // 4
+    eq = out['eq'].cpu().numpy()
+    scale = max(1.0, np.abs(eq_ref[good]).max())
+    assert np.abs(eq[good] - eq_ref[good]).max() < 1e-3 * scale
+    assert np.quantile(np.abs(eq[good] - eq_ref[good]), 0.99) < 5e-5 * scale
+    soft = out['soft'].cpu().numpy()
+    assert np.quantile(np.abs(soft[good] - soft_ref[good]), 0.999) < 2e-4
+    hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+    decided = (np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-3) & good[:, None, None]
+    assert np.array_equal(out['hard'].cpu().numpy()[decided], hard_ref[decided])
+    m.close()
+
+
+def test_ablation_host_surface(libdccn):
+    """model.equalizer_dnnE & co keep the reference's call shape; Session picks the graph from the variable names."""
+    from dl_ofdm_b200 import init, model
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from oracle import dccn_oracle as orc
+    FLAGS = Flags(nbits=2, channel='EPA')
+    ofdmobj = ofdm_tx(FLAGS)
+    rng = np.random.default_rng(9)
+    x = (rng.standard_normal((64, 7, 80, 2)) * 0.2).astype(np.float32)
+    z = orc.batch_moment_norm(x, np.float64)[0]
+    for opt, fn in ((3, model.equalizer_dnnE), (4, model.equalizer_noresdl2)):
+        w = init.receiver_variables(rng, 2)
+        w.update(init.equalizer_variables(rng, opt=opt, chest_bias=(0.6, -0.4)))
+        eq, _, chest = fn(_cuda(z.astype(np.float32)), FLAGS, ofdmobj, weights=w)
+        eq_ref, chest_ref = orc.equalizer_variant(z, w, opt, 64, 16)
+        assert np.abs(chest.cpu().numpy() - chest_ref).max() < 2e-5 * max(1.0, np.abs(chest_ref).max())
+        good = np.abs(chest_ref).reshape(64, -1).min(axis=1) > 2e-2
+        assert good.sum() > 16
+        assert np.quantile(np.abs(eq.cpu().numpy()[good] - eq_ref[good]), 0.99) < 5e-5 * max(1.0, np.abs(eq_ref[good]).max())
+        s = model.Session(FLAGS, ofdmobj, w)
+        assert s.engine.eq_opt == opt
+        s.close()
+    with pytest.raises(Exception):
+        from dl_ofdm_b200.engine import DCCN
+        DCCN(nbits=2, equalizer=True, eq_opt=7)          # equalizer_separateIQ is not implemented

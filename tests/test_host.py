@@ -110,3 +110,18 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+
+
+def test_equalizer_graph_tables_agree():
+    """The host's --opt wiring table (variable names, shapes, detection) == the oracle's independent copy."""
+    from dl_ofdm_b200 import init
+    from oracle import dccn_oracle as orc
+    for opt in (0, 1, 2, 3, 4, 5):
+        w = init.equalizer_variables(np.random.default_rng(0), opt=opt)
+        wo = {k: v for k, v in orc.glorot_weights(np.random.default_rng(0), 2, equalizer=True, eq_opt=opt).items()
+              if k.startswith('Equalizer/')}
+        assert {k: v.shape for k, v in w.items()} == {k: v.shape for k, v in wo.items()}, opt
+        assert init.detect_eq_opt(w) == opt
+    # dense_8 only exists in equalizer_dnnE (dense, dense_1, ..., dense_8; no conv3d)
+    assert [n for _, n in init.eq_layer_roles(3)][-1] == 'dense_8'
+    assert [n for _, n in init.eq_layer_roles(2)] == ['dense', 'conv3d', 'dense_1', 'dense_2', 'dense_3']

@@ -101,3 +101,22 @@ def test_ber_head_counts():
     assert hard.reshape(-1).tolist() == [0, 0, 1]                       # tie -> index 0
     assert conf.tolist() == [[1, 0], [1, 1]]
     assert abs(ber - 1 / 3) < 1e-12
+
+
+def test_equalizer_variant_template_reduces_to_equalizer_ofdm():
+    """The generic --opt template of the oracle with opt = 0 is exactly equalizer_ofdm (which the TF mirror pins)."""
+    import numpy as np
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(4)
+    w = orc.glorot_weights(rng, 2, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    z = orc.batch_moment_norm((rng.standard_normal((5, 7, 80, 2)) * 0.3).astype(np.float32))[0]
+    for cp in (True, False):
+        wc = orc.glorot_weights(np.random.default_rng(5), 2, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), use_cp=cp)
+        a, ca = orc.equalizer_ofdm(z, wc, 64, 16, use_cp=cp)
+        b, cb = orc.equalizer_variant(z, wc, 0, 64, 16, use_cp=cp)
+        assert np.array_equal(a, b) and np.array_equal(ca, cb)
+    for opt in (1, 2, 3, 4, 5):
+        wv = orc.glorot_weights(np.random.default_rng(opt), 2, equalizer=True, chest_bias=(0.6, -0.4), eq_opt=opt)
+        out, chest = orc.equalizer_variant(z, wv, opt, 64, 16)
+        assert out.shape == (5, 7, 80, 2) and chest.shape == (5, 7, 64) and np.isfinite(out).all()
+        assert np.abs(chest).min() > 0.05

@@ -275,11 +275,39 @@ static int pack_toeplitz_layer(dccn_handle* h, const char* kn, const char* bn, G
   const int S = h->S, K = h->K, SK2 = S * K * 2;
   NEED(k, kn);
   NEED(b, bn);
-  DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == S && k->shape[1] == K && k->shape[4] == 2,
-             "%s: expected [%d,%d,1,1,2]", kn, S, K);
+  const bool vec = h->eqs.vector != 0;   // layers_conv2d_vector: kernel [S,K,2,1,2], re / im = channels 0 / 1 at IQ position 0
+  DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == S && k->shape[1] == K && k->shape[4] == 2 &&
+                 k->shape[2] == (vec ? 2 : 1),
+             "%s: expected [%d,%d,%d,1,2]", kn, S, K, vec ? 2 : 1);
   L->K = SK2; L->N = SK2;
   L->W.assign((size_t)SK2 * SK2, 0.f);
   const int pl = (S - 1) / 2, pw = (K - 1) / 2;
+  if (vec) {
+    for (int d = 0; d < S; ++d)
+      for (int hh = 0; hh < K; ++hh) {
+        const int co = (d * K + hh) * 2;
+        for (int i = 0; i < S; ++i) {
+          const int di = d + i - pl;
+          if (di < 0 || di >= S) continue;
+          for (int j = 0; j < K; ++j) {
+            const int hj = hh + j - pw;
+            if (hj < 0 || hj >= K) continue;
+            const float* kp = &k->data[(size_t)(i * K + j) * 4];      // [iq][ch]
+            const int ri = (di * K + hj) * 2;
+            L->W[(size_t)ri * SK2 + co] = kp[0];
+            L->W[(size_t)ri * SK2 + co + 1] = kp[1];
+            L->W[(size_t)(ri + 1) * SK2 + co] = kp[2];
+            L->W[(size_t)(ri + 1) * SK2 + co + 1] = kp[3];
+          }
+        }
+      }
+    L->bias.resize(SK2);
+    for (int i = 0; i < SK2; i += 2) {
+      L->bias[i] = b->data[0];
+      L->bias[i + 1] = b->data[1];
+    }
+    return 0;
+  }
   for (int d = 0; d < S; ++d)
     for (int hh = 0; hh < K; ++hh) {
       const int co = (d * K + hh) * 2;                 // output column (re)
@@ -357,7 +385,7 @@ int pack_layers_host(dccn_handle* h) {
   h->g7.fused = true;
   if (!c.equalizer) return 0;
   const int SK2 = S * K * 2;
-  if (h->eq_opt != 0) {
+  if (h->eqs.generic) {
     // ---- ablation equalizers (dev/py/model.py:482-1084): same primitives, other wiring --------------------------
     // TF-1 auto-numbers the layers of a variable scope in creation order: dense, dense_1, ...; conv3d, conv3d_1, ...
     const EqSpec& sp = h->eqs;
@@ -426,14 +454,35 @@ int pack_layers_host(dccn_handle* h) {
     DCCN_CHECK(k->shape.size() == 2 && k->shape[0] == Tin * 2 && k->shape[1] == 2 * K, "Equalizer/dense/kernel shape");
     pack_dense(*k, *b, &h->g1);
   }
+  const bool vec = h->eqs.vector != 0;
   auto pack_1xK = [&](const char* kn, const char* bn, GemmLayer* L, bool real_only) -> int {
     NEED(k, kn);
     NEED(b, bn);
+    GemmLayer full;
+    if (vec) {
+      // layers_conv2d_vector, (1,K) 'valid' (complex.py:199-255): kernel [1,K,2,1,2F]; a plain real map of the 2K inputs
+      // (k, iq) onto F real parts (channels [0,F)) and F imaginary parts (channels [F,2F)); no recombination
+      DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == 1 && k->shape[1] == K && k->shape[2] == 2 && k->shape[3] == 1 &&
+                     k->shape[4] == 2 * K,
+                 "%s: expected [1,%d,2,1,%d] (layers_conv2d_vector)", kn, K, 2 * K);
+      full.K = 2 * K; full.N = 2 * K;
+      full.W.resize((size_t)4 * K * K);
+      full.bias.resize(2 * K);
+      for (int kk = 0; kk < K; ++kk)
+        for (int iq = 0; iq < 2; ++iq)
+          for (int f = 0; f < K; ++f)
+            for (int part = 0; part < 2; ++part)
+              full.W[(size_t)(2 * kk + iq) * 2 * K + 2 * f + part] = k->data[((size_t)kk * 2 + iq) * 2 * K + part * K + f];
+      for (int f = 0; f < K; ++f) {
+        full.bias[2 * f] = b->data[f];
+        full.bias[2 * f + 1] = b->data[K + f];
+      }
+    } else {
     DCCN_CHECK(k->shape.size() == 5 && k->shape[0] == 1 && k->shape[1] == K && k->shape[3] == 1 &&
                    k->shape[4] == 2 * K,
                "%s: expected [1,%d,1,1,%d]", kn, K, 2 * K);
-    GemmLayer full;
     pack_complex(k->data.data(), k->data.data() + K, 2 * K, K, K, b->data.data(), &full);
+    }
     if (!real_only) {
       L->K = full.K; L->N = full.N; L->W = full.W; L->bias = full.bias;
     } else {   // input imag part is identically 0: keep the xr rows only
@@ -498,7 +547,7 @@ static int build_layers(dccn_handle* h, cudaStream_t s) {
   if ((rc = upload_layer(h, &h->r1, s))) return rc;
   if ((rc = upload_layer(h, &h->r2, s))) return rc;
   if (!h->cfg.equalizer) return 0;
-  if (h->eq_opt != 0) {
+  if (h->eqs.generic) {
     const EqSpec& sp = h->eqs;
     std::vector<GemmLayer*> ls = {&h->g1, &h->g2, &h->g3, &h->g9, &h->g10};
     GemmLayer* chain[4] = {&h->g4, &h->g5, &h->g6, &h->gx0};
@@ -770,7 +819,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     if ((rc = run_gemm(h, SLOT_F9, h->f9, eqcv, 0, MS, store_epi(h->f9, r1v, 0, MS), s))) return rc;
     return run_head_dispatch(h, Bc, bits, soft, hard, conf, ce, s);
   }
-  if (use_eq && h->eq_opt != 0) {
+  if (use_eq && h->eqs.generic) {
     // ---- ablation equalizers: front (2 per-symbol layers) -> pilot -> dense chain [-> Toeplitz] + phase equaliser -> tail
     const EqSpec& sp = h->eqs;
     const int64_t MS = Bc * S;
@@ -835,8 +884,9 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     if ((rc = run_gemm(h, SLOT_G2, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
     // pilot bottleneck and channel-estimate MLP                    model.py:393-424
     if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
-    if ((rc = run_gemm(h, SLOT_G4, h->g4, h->p32, 0, Bc, store_epi(h->g4, h->u1, 0, Bc), s))) return rc;
-    if ((rc = run_gemm(h, SLOT_G5, h->g5, h->u1, 0, Bc, store_epi(h->g5, h->u2, 0, Bc), s))) return rc;
+    // (chain activations: linear, linear, tanh for equalizer_ofdm; tanh x3 for equalizer_separateIQ, model.py:1140-1162)
+    if ((rc = run_gemm(h, SLOT_G4, h->g4, h->p32, 0, Bc, store_epi(h->g4, h->u1, 0, Bc, h->eqs.chain_act[0]), s))) return rc;
+    if ((rc = run_gemm(h, SLOT_G5, h->g5, h->u1, 0, Bc, store_epi(h->g5, h->u2, 0, Bc, h->eqs.chain_act[1]), s))) return rc;
     // (a training forward keeps dense_2's output in u1 and writes the tanh output to u3)
     const Act& c4 = h->train_fwd ? h->u3 : h->u1;
     if (h->train_fwd && !chest_out) chest_out = h->chest_buf;
@@ -1057,10 +1107,12 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
       case 4: sp.front2_cconv = 1; sp.n_chain = 2; sp.chain_act[0] = 0; sp.chain_act[1] = 1; sp.toeplitz = 0; sp.tail = 2; break;
       case 5: sp.front2_cconv = 1; sp.n_chain = 4; sp.chain_act[0] = 0; sp.chain_act[1] = 1; sp.chain_act[2] = 1; sp.chain_act[3] = 1; sp.toeplitz = 0; sp.tail = 2; break;
       case 3: sp.front2_cconv = 0; sp.n_chain = 4; sp.chain_act[0] = 1; sp.chain_act[1] = 1; sp.chain_act[2] = 1; sp.chain_act[3] = 1; sp.toeplitz = 0; sp.tail = 1; break;
+      case 7: sp.front2_cconv = 1; sp.n_chain = 3; sp.chain_act[0] = 1; sp.chain_act[1] = 1; sp.chain_act[2] = 1; sp.toeplitz = 1; sp.tail = 0; sp.vector = 1; break;
       default:
         delete h;
-        return set_error(-2, "eq_opt=%d: implemented equalizer graphs are --opt 0,1,2,3,4,5", (int)cfg->eq_opt);
+        return set_error(-2, "eq_opt=%d: implemented equalizer graphs are --opt 0,1,2,3,4,5,7", (int)cfg->eq_opt);
     }
+    sp.generic = cfg->eq_opt != 7;
     h->eqs = sp;
     h->eq_opt = cfg->eq_opt;
   }

@@ -44,6 +44,8 @@ struct EqSpec {
   int chain_act[4] = {0, 0, 1, 0};   // 0 linear, 1 tanh
   int toeplitz = 1;           // (S,K) 'same' complex conv behind the chain
   int tail = 0;               // 0: cconv(eq) | cconv(corr) -> dense, 1: dense(2K) -> dense(2T), 2: tf.ifft -> dense(2T)
+  int vector = 0;             // 1: the complex convs are layers_conv2d_vector (complex.py:199-255), --opt 7
+  int generic = 0;            // 1: run through the generic wiring of run_chunk (opts 1-5); 0: equalizer_ofdm's own path
 };
 
 struct HostTensor {

@@ -44,8 +44,9 @@ class DCCN:
                             use_cp=int(bool(use_cp)), n_data=n_data, pilot_size=pilot_size,
                             head=_lib.HEAD_V1 if head == 'v1' else _lib.HEAD_DEV,
                             equalizer=int(bool(equalizer)), precision=_lib.PRECISIONS[precision],
-                            chunk_frames=chunk_frames, eq_opt=int(eq_opt) if equalizer else 0)
-        self.eq_opt = int(eq_opt) if equalizer else 0
+                            chunk_frames=chunk_frames,
+                            eq_opt=(0 if int(eq_opt) in (9, 10) else int(eq_opt)) if equalizer else 0)   # --opt 9 / 10 build equalizer_ofdm
+        self.eq_opt = int(self.cfg.eq_opt)
         self.nbits, self.S, self.K, self.T, self.D = nbits, nsymbol, nfft, nfft + cp_len, n_data
         self.equalizer = bool(equalizer)
         self.precision = precision

@@ -41,7 +41,10 @@ def receiver_variables(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_
 #   4 equalizer_noresdl2 (:718), 5 equalizer_noresdl4 (:829).
 # front2: second per-symbol layer ('cconv' = (1,K) valid complex conv, 'dense'); chain: frame-level dense layers after
 # the pilot bottleneck (0 linear, 1 tanh); toeplitz: (S,K) 'same' complex conv; tail: 'corr' | 'dense2' | 'ifft'.
+#   opt 7 equalizer_separateIQ (:1088): equalizer_ofdm's wiring with layers_conv2d_vector (complex.py:199-255) and tanh chain.
+#   (opt 6 names equalizer_doppler, which dev/py/model.py does not define; opt 9 / 10 build equalizer_ofdm.)
 EQ_SPECS = {
+    7: dict(front2='cconv', chain=(1, 1, 1), toeplitz=True, tail='corr', vector=True),
     0: dict(front2='cconv', chain=(0, 0, 1), toeplitz=True, tail='corr'),
     1: dict(front2='dense', chain=(0, 0, 1), toeplitz=True, tail='dense2'),
     2: dict(front2='cconv', chain=(0,), toeplitz=False, tail='ifft'),
@@ -80,8 +83,10 @@ def eq_layer_roles(opt):
 def detect_eq_opt(weights):
     """Which --opt graph a variable dict belongs to (the layer counts of the six graphs are all different)."""
     names = {k.split('/')[1] for k in weights if k.startswith('Equalizer/') and k.endswith('/kernel')}
-    for opt in EQ_SPECS:
+    for opt in (0, 1, 2, 3, 4, 5):
         if names == {n for _, n in eq_layer_roles(opt)}:
+            if opt == 0 and np.shape(weights['Equalizer/conv3d/kernel'])[2] == 2:
+                return 7          # same layer list, conv3d kernels of depth 2 across IQ (layers_conv2d_vector)
             return opt
     raise ValueError('Equalizer/* variables match none of the implemented graphs (--opt 0,1,2,3,4,5): %s' % sorted(names))
 
@@ -95,6 +100,8 @@ def equalizer_variables(rng, nfft=64, cp_len=16, nsymbol=7, pilot_size=16, use_c
     Tin = K + cp_len if use_cp else K
     e = 'Equalizer/'
     SK2 = S * K * 2
+    if opt in (9, 10):
+        opt = 0
     if opt != 0:
         return _variant_variables(rng, opt, K, S, Tin, K + cp_len, pilot_size, chest_bias)
 
@@ -137,6 +144,10 @@ def _variant_variables(rng, opt, K, S, Tin, T, pilot_size, chest_bias):
         if len(sh) == 2:
             w[e + name + '/kernel'] = _glorot(rng, sh, sh[0], sh[1])
             w[e + name + '/bias'] = np.zeros(sh[1], np.float32)
+        elif sp.get('vector'):
+            rf = sh[0] * sh[1] * 2
+            w[e + name + '/kernel'] = _glorot(rng, (sh[0], sh[1], 2, 1, sh[2]), rf, rf * sh[2])
+            w[e + name + '/bias'] = np.zeros(sh[2], np.float32)
         else:
             rf = sh[0] * sh[1]
             w[e + name + '/kernel'] = _glorot(rng, (sh[0], sh[1], 1, 1, sh[2]), rf, rf * sh[2])

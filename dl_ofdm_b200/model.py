@@ -69,6 +69,11 @@ def equalizer_noresdl2(inputs, FLAGS, ofdmobj, weights=None, precision='parity')
     return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 4)
 
 
+def equalizer_separateIQ(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
+    """--opt=7 (dev/py/model.py:1088-1218): equalizer_ofdm's wiring with layers_conv2d_vector and a tanh chain."""
+    return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 7)
+
+
 def equalizer_noresdl4(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
     """--opt=5 (dev/py/model.py:829-950)."""
     return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 5)

@@ -66,7 +66,8 @@ typedef struct dccn_cfg {
   int32_t chunk_frames;/* most frames per internal pass (0 = 65536); buffers grow on demand */
   int32_t eq_opt;      /* FLAGS.opt       which equalizer graph when equalizer != 0 (ofdmreceiver_np_mp.py:292-311):
                           0 equalizer_ofdm, 1 equalizer_nocconv, 2 equalizer_noresdl, 3 equalizer_dnnE,
-                          4 equalizer_noresdl2, 5 equalizer_noresdl4 (dev/py/model.py:349-1084); inference only for != 0 */
+                          4 equalizer_noresdl2, 5 equalizer_noresdl4, 7 equalizer_separateIQ (dev/py/model.py:349-1218);
+                          inference only for != 0 */
 } dccn_cfg;
 
 typedef struct dccn_handle dccn_handle;

@@ -265,9 +265,43 @@ def equalizer_ofdm(z, w, nfft, cp_len, use_cp=True, dtype=np.float64,
 #  4   equalizer_noresdl2  :718-826      cconv (1,K)   0 1                     no     tf.ifft -> dense(2T)
 #  5   equalizer_noresdl4  :829-950      cconv (1,K)   0 1 1 1                 no     tf.ifft -> dense(2T)
 #  3   equalizer_dnnE      :953-1084     dense(2K)     1 1 1 1                 no     dense(2K) -> dense(2T)
-# (opt 6 equalizer_doppler and opt 7 equalizer_separateIQ / layers_conv2d_vector are not restated.)
+#  7   equalizer_separateIQ:1088-1218    vconv (1,K)   1 1 1                   yes(v) vconv(eq) | vconv(corr) -> concat -> dense   [layers_conv2d_vector]
+# (opt 6 names equalizer_doppler, which does not exist in dev/py/model.py -- the reference itself raises NameError; opt 9 / 10 are equalizer_ofdm.)
 # Variable names follow TF-1's per-scope auto-numbering in creation order (dense, dense_1, ...; conv3d, conv3d_1, ...).
+def conv2d_vector(x, kernel, bias, padding='valid', dtype=np.float64):
+    """layers_conv2d_vector (dev/py/complex.py:199-255): one real conv3d over (length, width, IQ) with kernel depth 2
+    across IQ and 2*filters channels, NO complex recombination.
+    x [B,L,W,1,2] (one input channel), kernel [kl,kw,2,1,2F], bias [2F] -> [B,L',W',F,2].
+    'valid': the IQ axis collapses to one position, channels [0,F) are the real parts, [F,2F) the imaginary parts
+    (reshape [..,1,2F] -> [..,2,F], :245-249).  'same' (used with F = 1): TF pads the size-2 IQ axis (0 before, 1 after);
+    the reshape merges (IQ position, channel) and keeps merged indices 0 and 1 = IQ position 0, channels 0 and 1."""
+    x = np.asarray(x, dtype=dtype)
+    k = np.asarray(kernel, dtype=dtype)
+    b = np.asarray(bias, dtype=dtype)
+    B, L, W, C, _ = x.shape
+    assert C == 1 and k.shape[2] == 2 and k.shape[3] == 1
+    kl, kw = k.shape[0], k.shape[1]
+    F = k.shape[4] // 2
+    xs = x[:, :, :, 0, :]                                            # [B,L,W,2]
+    if padding == 'valid':
+        Lo, Wo = L - kl + 1, W - kw + 1
+        xp = xs
+    else:
+        assert F == 1, "'same' vector conv is only used with one filter"
+        Lo, Wo = L, W
+        pl, pw = (kl - 1) // 2, (kw - 1) // 2
+        xp = np.zeros((B, L + kl - 1, W + kw - 1, 2), dtype=dtype)
+        xp[:, pl:pl + L, pw:pw + W, :] = xs
+    out = np.zeros((B, Lo, Wo, 2 * F), dtype=dtype)
+    for i in range(kl):
+        for j in range(kw):
+            out += xp[:, i:i + Lo, j:j + Wo, :] @ k[i, j, :, 0, :]   # [.,2] @ [2,2F]
+    out = out + b
+    return np.stack([out[..., :F], out[..., F:]], axis=-1)           # [B,Lo,Wo,F,2]
+
+
 EQ_SPECS = {
+    7: dict(front2='vconv', chain=(1, 1, 1), toeplitz=True, tail='corr', vector=True),   # equalizer_separateIQ :1088-1218
     0: dict(front2='cconv', chain=(0, 0, 1), toeplitz=True, tail='corr'),
     1: dict(front2='dense', chain=(0, 0, 1), toeplitz=True, tail='dense2'),
     2: dict(front2='cconv', chain=(0,), toeplitz=False, tail='ifft'),
@@ -295,7 +329,7 @@ def eq_layer_names(opt):
         nc += 1
 
     dense('front1')
-    conv('front2') if sp['front2'] == 'cconv' else dense('front2')
+    conv('front2') if sp['front2'] in ('cconv', 'vconv') else dense('front2')
     dense('pilot')
     for i in range(len(sp['chain'])):
         dense('chain%d' % i)
@@ -332,8 +366,10 @@ def equalizer_variant(z, w, opt, nfft, cp_len, use_cp=True, dtype=np.float64, pr
     c = layer_norm(z, dtype)
     c = c[:, :, cp_len:cp_len + K, :].reshape(B, S, K * 2) if not use_cp else c.reshape(B, S, T * 2)
     c = dense(c, 'front1')                                              # [B,S,2K]
-    if sp['front2'] == 'cconv':
-        f = conv2d_complex(c.reshape(B, S, K, 1, 2), g('front2', 'kernel'), g('front2', 'bias'), 'valid', dtype)
+    vec = sp.get('vector', False)
+    cconv = conv2d_vector if vec else conv2d_complex
+    if sp['front2'] in ('cconv', 'vconv'):
+        f = cconv(c.reshape(B, S, K, 1, 2), g('front2', 'kernel'), g('front2', 'bias'), 'valid', dtype)
         f = np.transpose(f, (0, 1, 3, 2, 4))[:, :, :, 0, :]             # [B,S,K,2]
     else:
         f = dense(c, 'front2').reshape(B, S, K, 2)
@@ -343,7 +379,7 @@ def equalizer_variant(z, w, opt, nfft, cp_len, use_cp=True, dtype=np.float64, pr
         c = dense(c, 'chain%d' % i, act)
     c5 = c.reshape(B, S, K, 1, 2)
     if sp['toeplitz']:
-        c5 = conv2d_complex(c5, g('toeplitz', 'kernel'), g('toeplitz', 'bias'), 'same', dtype)
+        c5 = cconv(c5, g('toeplitz', 'kernel'), g('toeplitz', 'bias'), 'same', dtype)
     chest_c = (c5[..., 0] + 1j * c5[..., 1])[:, :, :, 0]                # [B,S,K]
     ab = np.abs(chest_c)
     eq = inputs_c * (np.real(chest_c) / ab - 1j * (np.imag(chest_c) / ab))     # phase-only equalise, no eps
@@ -351,7 +387,7 @@ def equalizer_variant(z, w, opt, nfft, cp_len, use_cp=True, dtype=np.float64, pr
         corr = eq * np.conj(eq)
         def cc(v, role):
             v5 = np.stack([v.real, v.imag], -1).reshape(B, S, K, 1, 2)
-            o = conv2d_complex(v5, g(role, 'kernel'), g(role, 'bias'), 'valid', dtype)
+            o = cconv(v5, g(role, 'kernel'), g(role, 'bias'), 'valid', dtype)
             return np.transpose(o, (0, 1, 3, 2, 4))[:, :, :, 0, :]
         t = np.concatenate([cc(eq, 'tail_eq'), cc(corr, 'tail_corr')], -1).reshape(B, S, K * 4)
     elif sp['tail'] == 'dense2':
@@ -548,7 +584,7 @@ def glorot_weights(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data
         e = 'Equalizer/'
         sp = EQ_SPECS[eq_opt]
         SK2 = S * K * 2
-        shapes = {'front1': ('d', T * 2, K * 2), 'front2': ('c', 1, K, 2 * K) if sp['front2'] == 'cconv' else ('d', K * 2, K * 2),
+        shapes = {'front1': ('d', T * 2, K * 2), 'front2': ('c', 1, K, 2 * K) if sp['front2'] in ('cconv', 'vconv') else ('d', K * 2, K * 2),
                   'pilot': ('d', SK2, pilot_size * 2), 'toeplitz': ('c', S, K, 2), 'tail_corr': ('c', 1, K, 2 * K),
                   'tail_eq': ('c', 1, K, 2 * K), 'tail1': ('d', K * 2, K * 2),
                   'tail2': ('d', K * 4 if sp['tail'] == 'corr' else K * 2, (nfft + cp_len) * 2)}
@@ -559,6 +595,10 @@ def glorot_weights(rng, nbits, nfft=64, cp_len=16, nsymbol=7, nfilter=64, n_data
             sh = shapes[role]
             if sh[0] == 'd':
                 dense(e + name, sh[1], sh[2])
+            elif sp.get('vector', False):      # layers_conv2d_vector: conv3d kernel [kl, kw, 2, 1, 2F]
+                rf = sh[1] * sh[2] * 2
+                w[e + name + '/kernel'] = glorot((sh[1], sh[2], 2, 1, sh[3]), rf, rf * sh[3])
+                w[e + name + '/bias'] = bias(sh[3])
             else:
                 conv3d(e + name, sh[1], sh[2], 1, sh[3])
         if chest_bias is not None:

@@ -570,13 +570,14 @@ def test_folded_schedule_matches_oracle(libdccn, precision, cp, nb):
 
 
 # ---------------------------------------------------------------------------------------------
-# ablation equalizers, --opt = 1, 2, 3, 4, 5 (dev/py/model.py:482-1084): the library's packed-GEMM
+# ablation equalizers, --opt = 1, 2, 3, 4, 5, 7 (dev/py/model.py:482-1218): the library's packed-GEMM
 # wiring (constant inverse-DFT layer for tf.ifft, phase equaliser fused behind a tanh dense, ...) against the
 # oracle's op-by-op complex arithmetic (np.fft.ifft).  Parity unpinned against TF itself, like every dev-graph test.
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('opt,precision,cp', [(1, 'parity', True), (2, 'parity', True), (3, 'parity', True),
                                               (4, 'parity', False), (5, 'parity', True), (1, 'exact', False),
-                                              (2, 'exact', True), (3, 'exact', False), (5, 'exact', False)])
+                                              (2, 'exact', True), (3, 'exact', False), (5, 'exact', False),
+                                              (7, 'parity', True), (7, 'parity', False), (7, 'exact', True)])
 def test_ablation_equalizers_seeded(libdccn, opt, precision, cp):
     from dl_ofdm_b200.engine import DCCN
     from oracle import dccn_oracle as orc
@@ -617,7 +618,7 @@ def test_ablation_host_surface(libdccn):
     rng = np.random.default_rng(9)
     x = (rng.standard_normal((64, 7, 80, 2)) * 0.2).astype(np.float32)
     z = orc.batch_moment_norm(x, np.float64)[0]
-    for opt, fn in ((3, model.equalizer_dnnE), (4, model.equalizer_noresdl2)):
+    for opt, fn in ((3, model.equalizer_dnnE), (4, model.equalizer_noresdl2), (7, model.equalizer_separateIQ)):
         w = init.receiver_variables(rng, 2)
         w.update(init.equalizer_variables(rng, opt=opt, chest_bias=(0.6, -0.4)))
         eq, _, chest = fn(_cuda(z.astype(np.float32)), FLAGS, ofdmobj, weights=w)
@@ -631,4 +632,4 @@ def test_ablation_host_surface(libdccn):
         s.close()
     with pytest.raises(Exception):
         from dl_ofdm_b200.engine import DCCN
-        DCCN(nbits=2, equalizer=True, eq_opt=7)          # equalizer_separateIQ is not implemented
+        DCCN(nbits=2, equalizer=True, eq_opt=6)          # equalizer_doppler does not exist in the reference either

@@ -116,7 +116,7 @@ def test_equalizer_graph_tables_agree():
     """The host's --opt wiring table (variable names, shapes, detection) == the oracle's independent copy."""
     from dl_ofdm_b200 import init
     from oracle import dccn_oracle as orc
-    for opt in (0, 1, 2, 3, 4, 5):
+    for opt in (0, 1, 2, 3, 4, 5, 7):
         w = init.equalizer_variables(np.random.default_rng(0), opt=opt)
         wo = {k: v for k, v in orc.glorot_weights(np.random.default_rng(0), 2, equalizer=True, eq_opt=opt).items()
               if k.startswith('Equalizer/')}

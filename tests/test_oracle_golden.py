@@ -120,3 +120,34 @@ def test_equalizer_variant_template_reduces_to_equalizer_ofdm():
         out, chest = orc.equalizer_variant(z, wv, opt, 64, 16)
         assert out.shape == (5, 7, 80, 2) and chest.shape == (5, 7, 64) and np.isfinite(out).all()
         assert np.abs(chest).min() > 0.05
+
+
+def test_conv2d_vector_matches_literal_conv3d():
+    """layers_conv2d_vector (dev/py/complex.py:199-255) restated in the oracle vs a literal conv3d over (length, width,
+    IQ) with TF's SAME padding (pad_before = (k-1)//2; the size-2 IQ axis gets 0 before / 1 after) and the reference's
+    reshape / slice of the (IQ position, channel) axes."""
+    import numpy as np
+    import torch
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((3, 7, 64, 1, 2))
+    # 'same', one filter: kernel [7,64,2,1,2]
+    k = rng.standard_normal((7, 64, 2, 1, 2)) * 0.1
+    b = rng.standard_normal(2)
+    ref = orc.conv2d_vector(x, k, b, 'same')
+    xt = torch.nn.functional.pad(torch.tensor(x[:, :, :, 0, :]).unsqueeze(1), (0, 1, 31, 32, 3, 3))
+    y = torch.nn.functional.conv3d(xt, torch.tensor(np.transpose(k[:, :, :, 0, :], (3, 0, 1, 2))).unsqueeze(1),
+                                   torch.tensor(b)).numpy()                     # [B, ch, L, W, IQ position]
+    merged = np.transpose(y, (0, 2, 3, 4, 1)).reshape(3, 7, 64, 4)             # (IQ position, channel) merged, :243
+    assert np.abs(ref[:, :, :, 0, 0] - merged[..., 0]).max() < 1e-12           # conv_re = merged index 0, :245
+    assert np.abs(ref[:, :, :, 0, 1] - merged[..., 1]).max() < 1e-12           # conv_im = merged index 1, :246
+    # 'valid', (1,K) with K filters: kernel [1,64,2,1,128]
+    k2 = rng.standard_normal((1, 64, 2, 1, 128)) * 0.1
+    b2 = rng.standard_normal(128)
+    ref2 = orc.conv2d_vector(x, k2, b2, 'valid')                               # [B,7,1,64,2]
+    y2 = torch.nn.functional.conv3d(torch.tensor(x[:, :, :, 0, :]).unsqueeze(1),
+                                    torch.tensor(np.transpose(k2[:, :, :, 0, :], (3, 0, 1, 2))).unsqueeze(1),
+                                    torch.tensor(b2)).numpy()                   # [B,128,7,1,1]
+    m2 = np.transpose(y2[:, :, :, 0, 0], (0, 2, 1)).reshape(3, 7, 2, 64)       # [.., 1*2, filters], :243
+    assert np.abs(ref2[:, :, 0, :, 0] - m2[:, :, 0, :]).max() < 1e-12
+    assert np.abs(ref2[:, :, 0, :, 1] - m2[:, :, 1, :]).max() < 1e-12

@@ -392,3 +392,189 @@ def rx_train_steps(xs, bits, w, nbits, init_learning=1e-3, global_step0=0, **kw)
         losses.append(ce)
         bers.append(berl)
     return w, losses, bers
+
+
+# =============================================================================================
+# Transfer learning of the ablation equalizers (--opt 1, 2, 3, 4, 5) in front of the frozen receiver
+# =============================================================================================
+# Same loss / optimiser as config 4 (dev/py/ofdmreceiver_np_mp.py:335-347); only the graph inside scope 'Equalizer'
+# changes (dev/py/model.py:482-1084, wiring table in dccn_oracle.EQ_SPECS).  Every tf.layers.dense of those functions
+# carries l2(0.01) on kernel and bias; the conv3d layers have no regulariser; tf.ifft has no variables.
+def variant_trainable_names(opt, prefix='Equalizer/'):
+    return [prefix + n + s for _, n in orc.eq_layer_names(opt) for s in ('/kernel', '/bias')]
+
+
+def _ifft_matrix(K, dtype):
+    """tf.ifft over K points as a real [2K, 2K] map on interleaved (re, im): standard complex product, 1/K."""
+    k = np.arange(K)
+    ang = 2.0 * np.pi * np.outer(k, k) / K
+    c, s_ = np.cos(ang) / K, np.sin(ang) / K
+    M = np.zeros((2 * K, 2 * K), dtype=dtype)
+    M[0::2, 0::2] = c
+    M[1::2, 0::2] = -s_
+    M[0::2, 1::2] = s_
+    M[1::2, 1::2] = c
+    return M
+
+
+def variant_loss_and_grads(x, bits, w, nbits, opt, nfft=64, cp_len=16, use_cp=True, nfilter=64, dtype=np.float64,
+                           normalize=True, reg=True):
+    """(ce_mean, reg_loss, grads, aux) for the --opt graph: d total_loss / d (every Equalizer/* variable)."""
+    sp = orc.EQ_SPECS[opt]
+    assert not sp.get('vector', False), 'the layers_conv2d_vector graph (--opt 7) is inference only'
+    names = dict(orc.eq_layer_names(opt))
+    pre = 'Equalizer/'
+    A = lambda n: np.asarray(w[n], dtype=dtype)
+    KV = lambda role: A(pre + names[role] + '/kernel')
+    BV = lambda role: A(pre + names[role] + '/bias')
+    x = np.asarray(x, dtype=dtype)
+    B, S, T, _ = x.shape
+    K, F = nfft, nfilter
+    SK2 = S * K * 2
+    z = orc.batch_moment_norm(x, dtype)[0] if normalize else x
+    a0 = orc.layer_norm(z, dtype)
+    a0 = a0.reshape(B * S, T * 2) if use_cp else a0[:, :, cp_len:cp_len + K, :].reshape(B * S, K * 2)
+    # ---- forward, GEMM form ---------------------------------------------------------------------------------------
+    W1, b1 = KV('front1'), BV('front1')
+    t1 = a0 @ W1 + b1
+    if sp['front2'] == 'cconv':
+        Bp2, bp2 = _pack_1xk(KV('front2'), BV('front2'))
+    else:
+        Bp2, bp2 = KV('front2'), BV('front2')
+    f = t1 @ Bp2 + bp2                                              # [BS, 2K] inputs_complex
+    fl = f.reshape(B, SK2)
+    Wp, bpil = KV('pilot'), BV('pilot')
+    p = fl @ Wp + bpil
+    cin, couts = [p], []
+    for i, act in enumerate(sp['chain']):
+        y = cin[-1] @ KV('chain%d' % i) + BV('chain%d' % i)
+        y = np.tanh(y) if act else y
+        couts.append(y)
+        cin.append(y)
+    if sp['toeplitz']:
+        Bp7, bp7 = _pack_toeplitz(KV('toeplitz'), BV('toeplitz'), S, K)
+        ch = couts[-1] @ Bp7 + bp7
+    else:
+        ch = couts[-1]
+    cr, ci = ch[:, 0::2], ch[:, 1::2]
+    fr, fi = fl[:, 0::2], fl[:, 1::2]
+    ab = np.sqrt(cr * cr + ci * ci)
+    nr, ni = cr / ab, -ci / ab
+    er, ei = fr * nr - fi * ni, fr * ni + fi * nr
+    eqv = np.stack([er, ei], -1).reshape(B * S, 2 * K)
+    if sp['tail'] == 'dense2':
+        Wt1, bt1 = KV('tail1'), BV('tail1')
+        mid = eqv @ Wt1 + bt1
+    else:
+        Wt1 = _ifft_matrix(K, dtype)
+        mid = eqv @ Wt1
+    Wt2, bt2 = KV('tail2'), BV('tail2')
+    oeq = (mid @ Wt2 + bt2).reshape(B, S, T, 2)
+    # ---- frozen receiver + loss: reuse the receiver part of the config-4 oracle through its helper ---------------------
+    ce_mean, doeq, soft = _rx_loss_and_input_grad(oeq, bits, w, nbits, nfft, cp_len, use_cp, nfilter, dtype)
+    # ---- backward --------------------------------------------------------------------------------------------------
+    g = {}
+
+    def put(role, gk, gb):
+        g[pre + names[role] + '/kernel'] = gk
+        g[pre + names[role] + '/bias'] = gb
+
+    put('tail2', mid.T @ doeq, doeq.sum(0))
+    dmid = doeq @ Wt2.T
+    if sp['tail'] == 'dense2':
+        put('tail1', eqv.T @ dmid, dmid.sum(0))
+    deqv = (dmid @ Wt1.T).reshape(B, S * K, 2)
+    der, dei = deqv[:, :, 0], deqv[:, :, 1]
+    dfr = der * nr + dei * ni
+    dfi = -der * ni + dei * nr
+    dnr = der * fr + dei * fi
+    dni = -der * fi + dei * fr
+    com = (dnr * ci + dni * cr) / (ab ** 3)
+    dch = np.stack([ci * com, -cr * com], -1).reshape(B, SK2)
+    if sp['toeplitz']:
+        gk, gb = _unpack_toeplitz(couts[-1].T @ dch, dch.sum(0), S, K)
+        put('toeplitz', gk, gb)
+        dy = dch @ Bp7.T
+    else:
+        dy = dch
+    for i in range(len(sp['chain']) - 1, -1, -1):
+        if sp['chain'][i]:
+            dy = dy * (1 - couts[i] * couts[i])
+        put('chain%d' % i, cin[i].T @ dy, dy.sum(0))
+        dy = dy @ KV('chain%d' % i).T
+    put('pilot', fl.T @ dy, dy.sum(0))
+    dfl = dy @ Wp.T + np.stack([dfr, dfi], -1).reshape(B, SK2)
+    df = dfl.reshape(B * S, 2 * K)
+    if sp['front2'] == 'cconv':
+        gk, gb = _unpack_1xk(t1.T @ df, df.sum(0), w[pre + names['front2'] + '/kernel'].shape)
+        put('front2', gk, gb)
+    else:
+        put('front2', t1.T @ df, df.sum(0))
+    dt1 = df @ Bp2.T
+    put('front1', a0.T @ dt1, dt1.sum(0))
+    # ---- regulariser on every tf.layers.dense (kernel + bias) --------------------------------------------------------
+    reg_loss = 0.0
+    for role, n in orc.eq_layer_names(opt):
+        if not n.startswith('dense'):
+            continue
+        for s in ('/kernel', '/bias'):
+            wv = A(pre + n + s)
+            reg_loss += L2_L * float(np.sum(wv * wv))
+            if reg:
+                g[pre + n + s] = g[pre + n + s] + (2.0 * REG_COEFF * L2_L) * wv
+    g = {k: np.asarray(v, dtype=dtype).reshape(np.shape(w[k])) for k, v in g.items()}
+    return ce_mean, reg_loss, g, dict(soft=soft, oeq=oeq, doeq=doeq.reshape(B, S, T, 2), dch=dch)
+
+
+def _rx_loss_and_input_grad(oeq, bits, w, nbits, nfft, cp_len, use_cp, nfilter, dtype):
+    """Frozen ofdm_dense_rx + ce_mean on equalised frames oeq [B,S,T,2]: (ce_mean, d ce_mean / d oeq [BS, 2T], soft)."""
+    A = lambda n: np.asarray(w[n], dtype=dtype)
+    B, S, T, _ = oeq.shape
+    K, F = nfft, nfilter
+    Tin = T if use_cp else K
+    rin = oeq.reshape(B * S, 2 * T) if use_cp else oeq[:, :, cp_len:, :].reshape(B * S, 2 * K)
+    kf = A('fft_like/conv3d/kernel')[0, (Tin - 1) // 2, 0]
+    bfl = A('fft_like/conv3d/bias')
+    BpR, bpR = orc.pack_complex_kernel(kf[:, :F], kf[:, F:], bfl[:F], bfl[F:], dtype=dtype)
+    r1 = (rin @ BpR + bpR).reshape(B, S * F * 2)
+    Wd, bd = A('demodulation/dense/kernel'), A('demodulation/dense/bias')
+    oiq = (r1 @ Wd + bd).reshape(B, -1, 2)
+    D = oiq.shape[1]
+    Wc = A('demodulation/conv2d/kernel').reshape(2, -1)
+    bc = A('demodulation/conv2d/bias')
+    W1h, b1h = A('demodulation/dense_1/kernel'), A('demodulation/dense_1/bias')
+    hpre = oiq @ Wc + bc
+    hh = np.maximum(orc.LEAKY_ALPHA * hpre, hpre)
+    lpre = np.concatenate([hh, oiq], -1) @ W1h + b1h
+    lg = np.maximum(orc.LEAKY_ALPHA * lpre, lpre).reshape(B, D, nbits, 2)
+    e = np.exp(lg - lg.max(-1, keepdims=True))
+    soft = e / e.sum(-1, keepdims=True)
+    y = np.asarray(bits).astype(np.int64)
+    oh = np.stack([1 - y, y], -1).astype(dtype)
+    lse = np.log(np.exp(soft).sum(-1, keepdims=True))
+    N = B * D * nbits
+    ce_mean = float(np.sum(lse[..., 0] - np.sum(soft * oh, -1)) / N)
+    dsoft = (np.exp(soft - lse) - oh) / N
+    dlg = soft * (dsoft - np.sum(dsoft * soft, -1, keepdims=True))
+    dlpre = dlg.reshape(B, D, 2 * nbits) * np.where(lpre > 0, 1.0, orc.LEAKY_ALPHA)
+    dhcat = dlpre @ W1h.T
+    MO = Wc.shape[1]
+    dhpre = dhcat[..., :MO] * np.where(hpre > 0, 1.0, orc.LEAKY_ALPHA)
+    doiq = dhcat[..., MO:] + dhpre @ Wc.T
+    drin = (doiq.reshape(B, 2 * D) @ Wd.T).reshape(B * S, 2 * F) @ BpR.T
+    if use_cp:
+        return ce_mean, drin, soft
+    doeq = np.zeros((B * S, T, 2), dtype=dtype)
+    doeq[:, cp_len:, :] = drin.reshape(B * S, K, 2)
+    return ce_mean, doeq.reshape(B * S, 2 * T), soft
+
+
+def variant_train_steps(xs, bits, w, nbits, opt, init_learning=1e-3, global_step0=0, **kw):
+    w = {k: np.array(v, copy=True) for k, v in w.items()}
+    optm = Adam(variant_trainable_names(opt), w)
+    losses = []
+    for i, (x, b) in enumerate(zip(xs, bits)):
+        ce, _, g, _ = variant_loss_and_grads(x, b, w, nbits, opt, **kw)
+        optm.step(w, g, learning_rate(init_learning, global_step0 + i))
+        losses.append(ce)
+    return w, losses

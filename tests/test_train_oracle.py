@@ -121,3 +121,67 @@ def test_rx_training_reduces_loss():
     w2, losses, bers = tro.rx_train_steps([x] * 6, [bits] * 6, w, 2)
     assert losses[-1] < losses[0]
     assert all(np.abs(w2[k] - w[k]).max() > 0 for k in tro.rx_trainable_names())
+
+
+# ---- transfer learning of the ablation equalizers (--opt 1..5) ---------------------------------------------------------
+def _variant_forward_torch(m, z, opt):
+    """equalizer_<variant> op by op in torch (complex arithmetic, torch.fft.ifft, padded conv3d for the complex convs):
+    independent of the oracle's packed-GEMM backward."""
+    from oracle.tf_mirror import conv2d_complex_tf
+    sp = orc.EQ_SPECS[opt]
+    names = dict(orc.eq_layer_names(opt))
+    W = lambda role, s: m.w['Equalizer/' + names[role] + '/' + s]
+    B, S, T, _ = z.shape
+    K = 64
+    mu = z.reshape(B, -1).mean(1).reshape(B, 1, 1, 1)
+    var = ((z - mu) ** 2).reshape(B, -1).mean(1).reshape(B, 1, 1, 1)
+    c = (z - mu) / torch.sqrt(var + orc.LN_EPS)
+    c = c.reshape(B, S, T * 2) if m.use_cp else c[:, :, m.CP:m.CP + K, :].reshape(B, S, K * 2)
+    c = c @ W('front1', 'kernel') + W('front1', 'bias')
+    if sp['front2'] == 'cconv':
+        f = conv2d_complex_tf(c.reshape(B, S, K, 1, 2), W('front2', 'kernel'), W('front2', 'bias'), 'valid')
+        f = f.permute(0, 1, 3, 2, 4)[:, :, :, 0, :]
+    else:
+        f = (c @ W('front2', 'kernel') + W('front2', 'bias')).reshape(B, S, K, 2)
+    inputs_c = torch.complex(f[..., 0], f[..., 1])
+    c = f.reshape(B, S * K * 2) @ W('pilot', 'kernel') + W('pilot', 'bias')
+    for i, act in enumerate(sp['chain']):
+        c = c @ W('chain%d' % i, 'kernel') + W('chain%d' % i, 'bias')
+        c = torch.tanh(c) if act else c
+    c5 = c.reshape(B, S, K, 1, 2)
+    if sp['toeplitz']:
+        c5 = conv2d_complex_tf(c5, W('toeplitz', 'kernel'), W('toeplitz', 'bias'), 'same')
+    chest = torch.complex(c5[..., 0], c5[..., 1])[:, :, :, 0]
+    ab = torch.abs(chest)
+    eq = inputs_c * torch.complex(chest.real / ab, -chest.imag / ab)
+    if sp['tail'] == 'dense2':
+        t = torch.stack([eq.real, eq.imag], -1).reshape(B, S, K * 2) @ W('tail1', 'kernel') + W('tail1', 'bias')
+    else:
+        e = torch.fft.ifft(eq, dim=-1)
+        t = torch.stack([e.real, e.imag], -1).reshape(B, S, K * 2)
+    return (t @ W('tail2', 'kernel') + W('tail2', 'bias')).reshape(B, S, T, 2)
+
+
+@pytest.mark.parametrize('opt,nbits,use_cp', [(1, 2, True), (2, 2, True), (3, 1, False), (4, 4, True), (5, 2, False)])
+def test_variant_backward_matches_autograd(opt, nbits, use_cp):
+    rng = np.random.default_rng(90 + opt)
+    w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), eq_opt=opt)
+    x = (rng.standard_normal((20, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (20, 320, nbits)).astype(np.uint8)
+    ce, reg, g, aux = tro.variant_loss_and_grads(x, bits, w, nbits, opt, use_cp=use_cp)
+    m = TFMirror(w, nbits, use_cp=use_cp, equalizer=False)
+    m.w = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=k.startswith('Equalizer/')) for k, v in w.items()}
+    z = m.norm(torch.tensor(x, dtype=torch.float64))
+    oeq = _variant_forward_torch(m, z, opt)
+    soft = m.dense_rx(oeq).reshape(-1, 2)
+    ce_t = torch.nn.functional.cross_entropy(soft, torch.tensor(bits.reshape(-1).astype(np.int64)))
+    reg_t = sum(tro.L2_L * (m.w['Equalizer/' + n + s] ** 2).sum() for _, n in orc.eq_layer_names(opt) if n.startswith('dense')
+                for s in ('/kernel', '/bias'))
+    (ce_t + tro.REG_COEFF * reg_t).backward()
+    assert abs(ce - float(ce_t.detach())) < 1e-12
+    assert np.abs(aux['oeq'] - oeq.detach().numpy()).max() < 1e-10
+    assert set(g) == set(tro.variant_trainable_names(opt))
+    for k in g:
+        ref = m.w[k].grad.numpy()
+        err = np.abs(g[k] - ref).max()
+        assert err <= 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-15, (k, err, np.abs(ref).max())

@@ -835,6 +835,9 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     GemmLayer* chain[4] = {&h->g4, &h->g5, &h->g6, &h->gx0};
     const int chain_slot[4] = {SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G6};
     const Act* src = &h->p32;
+    // a training forward keeps every chain output (u1, u2, u3) and the channel estimate (chest_buf) for the backward pass
+    const Act* keep[3] = {&h->u1, &h->u2, &h->u3};
+    if (h->train_fwd && !chest_out) chest_out = h->chest_buf;
     auto phase_eq = [&](const GemmLayer& L, const Act& in, int act, bool band) -> int {
       EpiPhaseEq e;
       e.bias = L.dBias;
@@ -856,7 +859,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       if (last) {
         if ((rc = phase_eq(*chain[i], *src, sp.chain_act[i], false))) return rc;
       } else {
-        const Act* dst = (i & 1) ? &h->u2 : &h->u1;
+        const Act* dst = h->train_fwd ? keep[i] : ((i & 1) ? &h->u2 : &h->u1);
         if ((rc = run_gemm(h, chain_slot[i], *chain[i], *src, 0, Bc, store_epi(*chain[i], *dst, 0, Bc, sp.chain_act[i]), s)))
           return rc;
         src = dst;

@@ -62,6 +62,9 @@ struct TrainState {
   TrainLayer tl[10];
   // DCCN_TRAIN_RX: the head's variables (conv2d kernel / bias, dense_1 kernel / bias) in `params`, partial sums of
   // head_wgrad_kernel, pinned staging for the D2H refresh of dccn_handle::hw
+  // generic equalizer graphs (--opt 1..5): positions of the roles in tl[] (-1 = the graph has no such layer)
+  int ix_front1 = -1, ix_front2 = -1, ix_pilot = -1, ix_chain[4] = {-1, -1, -1, -1}, ix_toep = -1, ix_tail1 = -1, ix_tail2 = -1;
+  GemmLayer bw_ifft;       // dgrad companion of the constant inverse-DFT layer (tail 'ifft')
   int hp[4] = {-1, -1, -1, -1};
   float* head_partial = nullptr;
   int head_warps = 0;
@@ -517,7 +520,7 @@ phaseeq_bwd_kernel(const float2* __restrict__ deq, const float* __restrict__ dco
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float2 e = eq[i], c = ch[i], ff = f[i], de = deq[i];
-  const float dc = dcorr[i];
+  const float dc = dcorr ? dcorr[i] : 0.f;     // graphs without the correlation branch pass nullptr
   const float der = fmaf(2.f * e.x, dc, de.x), dei = fmaf(2.f * e.y, dc, de.y);
   const float inv = rsqrtf(c.x * c.x + c.y * c.y);
   const float nr = c.x * inv, ni = -c.y * inv;
@@ -777,6 +780,100 @@ static int backward(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t
   return 0;
 }
 
+// --opt 1..5: backward of ce_mean + reg through the generic equalizer wiring (run_chunk's generic path kept the chain
+// outputs in u1, u2, u3 and the channel estimate -- after its tanh, if the last chain layer has one -- in chest_buf).
+static int backward_generic(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t s) {
+  TrainState* tr = h->tr;
+  const EqSpec& sp = h->eqs;
+  const int S = h->S, K = h->K, T = h->T, Tin = h->Tin, D = h->D, NB = h->NB, F = h->F;
+  const int64_t MS = B * S;
+  const int cp_off = (T - Tin) * 2;
+  const int SK2 = S * K * 2;
+  int rc;
+  {
+    LaunchScope ls(h, SLOT_T_HEAD, s);
+    const long long total = (long long)B * D;
+    const float inv_n = (float)(1.0 / ((double)B * D * NB));
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+    switch (NB) {
+      case 1: head_bwd_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+      case 2: head_bwd_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+      case 3: head_bwd_kernel<3><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+      default: head_bwd_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(h->out_iq.p0, bits, h->hw, total, inv_n, tr->d_oiq.p0); break;
+    }
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  // frozen receiver: data gradients only
+  if ((rc = run_dgrad(h, tr->bw_r2, tr->d_oiq, 0, B, tr->d_r1o, 0, s))) return rc;
+  Act d_r1v = tr->d_r1o;  d_r1v.ld = 2 * F;
+  Act d_oeqv = tr->d_oeq; d_oeqv.ld = 2 * T;
+  if (cp_off) DCCN_CUDA_OK(cudaMemsetAsync(tr->d_oeq.p0, 0, (size_t)B * h->P * 4, s));
+  if ((rc = run_dgrad(h, tr->bw_r1, d_r1v, 0, MS, d_oeqv, cp_off, s))) return rc;
+  TrainLayer* tl = tr->tl;
+  Act d_midv = tr->d_cat; d_midv.ld = 2 * K;       // [MS, 2K] inside the [MS, 4K] buffer
+  Act d_eqv = tr->d_eq;   d_eqv.ld = 2 * K;
+  Act d_fv = tr->d_f;     d_fv.ld = 2 * K;
+  Act d_t1v = tr->d_t1;   d_t1v.ld = 2 * K;
+  // tail: dense(2T) <- [dense(2K) | constant inverse DFT] <- eq
+  if ((rc = run_wgrad(h, tl[tr->ix_tail2], h->cat.p0, 2 * K, d_oeqv.p0, 2 * T, MS, s))) return rc;
+  if ((rc = run_dgrad(h, tl[tr->ix_tail2].bw, d_oeqv, 0, MS, d_midv, 0, s))) return rc;
+  if (sp.tail == 1) {
+    if ((rc = run_wgrad(h, tl[tr->ix_tail1], h->eq.p0, 2 * K, d_midv.p0, 2 * K, MS, s))) return rc;
+    if ((rc = run_dgrad(h, tl[tr->ix_tail1].bw, d_midv, 0, MS, d_eqv, 0, s))) return rc;
+  } else if ((rc = run_dgrad(h, tr->bw_ifft, d_midv, 0, MS, d_eqv, 0, s))) return rc;
+  // phase-only equaliser (no correlation branch in these graphs)
+  {
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    const long long total = (long long)B * S * K;
+    phaseeq_bwd_kernel<<<blocks_for(total), 256, 0, s>>>((const float2*)tr->d_eq.p0, nullptr, (const float2*)h->f.p0,
+                                                         (const float2*)h->chest_buf, (const float2*)h->eq.p0, total,
+                                                         (float2*)tr->d_f.p0, (float2*)tr->d_ch.p0);
+  }
+  const Act* chain_out[3] = {&h->u1, &h->u2, &h->u3};
+  Act* ring[3] = {&tr->dA, &tr->dB, &tr->dC};
+  int rp = 0;
+  const Act* cur = &tr->d_ch;
+  if (sp.toeplitz) {
+    if ((rc = run_wgrad(h, tl[tr->ix_toep], chain_out[sp.n_chain - 1]->p0, SK2, cur->p0, SK2, B, s))) return rc;
+    if ((rc = run_dgrad(h, tl[tr->ix_toep].bw, *cur, 0, B, *ring[rp], 0, s))) return rc;
+    cur = ring[rp];
+    rp = (rp + 1) % 3;
+  }
+  for (int i = sp.n_chain - 1; i >= 0; --i) {
+    const bool fused = (i == sp.n_chain - 1) && !sp.toeplitz;          // this layer's output is the channel estimate
+    if (sp.chain_act[i]) {
+      LaunchScope ls(h, SLOT_T_POINT, s);
+      tanh_bwd_kernel<<<blocks_for((long long)B * SK2), 256, 0, s>>>(cur->p0, fused ? h->chest_buf : chain_out[i]->p0,
+                                                                     (long long)B * SK2);
+    }
+    const float* X = i == 0 ? h->p32.p0 : chain_out[i - 1]->p0;
+    const int ldx = i == 0 ? h->p32.ld : SK2;
+    if ((rc = run_wgrad(h, tl[tr->ix_chain[i]], X, ldx, cur->p0, SK2, B, s))) return rc;
+    const Act* nxt = i == 0 ? &tr->d_p32 : ring[rp];
+    if ((rc = run_dgrad(h, tl[tr->ix_chain[i]].bw, *cur, 0, B, *nxt, 0, s))) return rc;
+    cur = nxt;
+    if (i != 0) rp = (rp + 1) % 3;
+  }
+  // pilot bottleneck, then the two per-symbol front layers
+  if ((rc = run_wgrad(h, tl[tr->ix_pilot], h->f.p0, SK2, tr->d_p32.p0, tr->d_p32.ld, B, s))) return rc;
+  if ((rc = run_dgrad(h, tl[tr->ix_pilot].bw, tr->d_p32, 0, B, tr->d_f2, 0, s))) return rc;
+  {
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    add_kernel<<<blocks_for((long long)B * SK2), 256, 0, s>>>(tr->d_f.p0, tr->d_f2.p0, (long long)B * SK2);
+  }
+  if ((rc = run_wgrad(h, tl[tr->ix_front2], h->t1.p0, 2 * K, tr->d_f.p0, 2 * K, MS, s))) return rc;
+  if ((rc = run_dgrad(h, tl[tr->ix_front2].bw, d_fv, 0, MS, d_t1v, 0, s))) return rc;
+  if ((rc = run_wgrad(h, tl[tr->ix_front1], h->a0.p0 + cp_off, 2 * T, tr->d_t1.p0, 2 * K, MS, s))) return rc;
+  {
+    LaunchScope ls(h, SLOT_T_ADAM, s, 12);
+    for (TrainParam& p : tr->params)
+      if (p.l2g != 0.f) add_l2_kernel<<<blocks_for(p.n), 256, 0, s>>>(p.g, p.w, p.n, p.l2g);
+  }
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <int NB>
 static void launch_head_grads(dccn_handle* h, TrainState* tr, const uint8_t* bits, long long total, float inv_n,
                               unsigned blocks, cudaStream_t s) {
@@ -859,7 +956,8 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   DCCN_CHECK(cfg->mode == DCCN_TRAIN_EQ || cfg->mode == DCCN_TRAIN_RX, "unknown training mode %d", (int)cfg->mode);
   DCCN_CHECK(rx_mode || h->cfg.equalizer, "DCCN_TRAIN_EQ updates the Equalizer/* variables: the handle has no equalizer");
   DCCN_CHECK(!rx_mode || !h->cfg.equalizer, "DCCN_TRAIN_RX trains the basic receiver: create the handle without equalizer");
-  DCCN_CHECK(h->eq_opt == 0, "training is implemented for equalizer_ofdm (--opt=0); --opt=%d is inference only", h->eq_opt);
+  DCCN_CHECK(h->eq_opt == 0 || h->eqs.generic,
+             "training is implemented for --opt 0..5; --opt=%d (layers_conv2d_vector) is inference only", h->eq_opt);
   DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
   DCCN_CHECK(h->cfg.precision == DCCN_PREC_EXACT || h->cfg.precision == DCCN_PREC_PARITY,
              "training needs fp32-class arithmetic (precision exact or parity)");
@@ -875,21 +973,54 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   tr->cfg = *cfg;
   tr->maxB = MB;
   tr->mode = cfg->mode;
-  const int NL = tr->n_layers = rx_mode ? 2 : 10;
-  const char* const* layer_var = rx_mode ? kRxLayerVar : kLayerVar;
-  const int* bias_kind = rx_mode ? kRxBiasKind : kBiasKind;
-  const int* per_symbol = rx_mode ? kRxPerSymbol : kPerSymbol;
+  const bool generic = !rx_mode && h->eqs.generic;
+  std::vector<GemmLayer*> Ls;
+  std::vector<std::string> layer_var;
+  std::vector<int> bias_kind, per_symbol;
+  if (rx_mode) {
+    Ls = {&h->r1, &h->r2};
+    for (int i = 0; i < 2; ++i) {
+      layer_var.push_back(kRxLayerVar[i]);
+      bias_kind.push_back(kRxBiasKind[i]);
+      per_symbol.push_back(kRxPerSymbol[i]);
+    }
+  } else if (!generic) {
+    Ls = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
+    for (int i = 0; i < 10; ++i) {
+      layer_var.push_back(kLayerVar[i]);
+      bias_kind.push_back(kBiasKind[i]);
+      per_symbol.push_back(kPerSymbol[i]);
+    }
+  } else {
+    // the trainable layers of the --opt graph in creation order, named by TF-1's per-scope auto-numbering
+    const EqSpec& sp = h->eqs;
+    int nd = 0, ncv = 0;
+    auto add = [&](GemmLayer* L, bool conv, int kind, int persym) {
+      int& ctr = conv ? ncv : nd;
+      layer_var.push_back(std::string("Equalizer/") + (conv ? "conv3d" : "dense") + (ctr == 0 ? "" : "_" + std::to_string(ctr)));
+      ++ctr;
+      Ls.push_back(L);
+      bias_kind.push_back(kind);
+      per_symbol.push_back(persym);
+      return (int)Ls.size() - 1;
+    };
+    tr->ix_front1 = add(&h->g1, false, 0, 1);
+    tr->ix_front2 = sp.front2_cconv ? add(&h->g2, true, 1, 1) : add(&h->g2, false, 0, 1);
+    tr->ix_pilot = add(&h->g3, false, 0, 0);
+    GemmLayer* chain[4] = {&h->g4, &h->g5, &h->g6, &h->gx0};
+    for (int i = 0; i < sp.n_chain; ++i) tr->ix_chain[i] = add(chain[i], false, 0, 0);
+    if (sp.toeplitz) tr->ix_toep = add(&h->g7, true, 2, 0);
+    if (sp.tail == 1) tr->ix_tail1 = add(&h->g9, false, 0, 1);
+    tr->ix_tail2 = add(&h->g10, false, 0, 1);
+  }
+  const int NL = tr->n_layers = (int)Ls.size();
+  DCCN_CHECK(NL <= 10, "too many trainable layers");
   if (!rx_mode && !h->ws_train) h->ws_train = h->ws_dirty = true;   // the backward pass needs u3 (tanh output) and chest
   if ((rc = ensure_workspace(h, MB))) return rc;
-  // ---- gather maps of the ten layers: run the host packers on index-valued variables ------------------
-  GemmLayer* Ls[10] = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
-  if (rx_mode) {
-    Ls[0] = &h->r1;
-    Ls[1] = &h->r2;
-  }
+  // ---- gather maps of the layers: run the host packers on index-valued variables ------------------------
   std::vector<std::vector<float>> backup(NL);
   for (int i = 0; i < NL; ++i) {
-    HostTensor& t = h->raw[std::string(layer_var[i]) + "/kernel"];
+    HostTensor& t = h->raw[layer_var[i] + "/kernel"];
     DCCN_CHECK(t.data.size() < (1u << 24), "variable too large for the index trick");
     backup[i] = t.data;
     for (size_t p = 0; p < t.data.size(); ++p) t.data[p] = (float)(p + 1);
@@ -901,7 +1032,7 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
       maps[i].resize(Ls[i]->W.size());
       for (size_t e = 0; e < maps[i].size(); ++e) maps[i][e] = (int32_t)Ls[i]->W[e];
     }
-  for (int i = 0; i < NL; ++i) h->raw[std::string(layer_var[i]) + "/kernel"].data = backup[i];
+  for (int i = 0; i < NL; ++i) h->raw[layer_var[i] + "/kernel"].data = backup[i];
   if (rc) return rc;
   if ((rc = pack_layers_host(h))) return rc;
   // ---- variables, optimiser slots, maps, operands ----------------------------------------------------------
@@ -915,7 +1046,7 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
     const bool dense = bias_kind[i] == 0;
     for (int kb = 0; kb < 2; ++kb) {
       TrainParam p;
-      p.name = std::string(layer_var[i]) + (kb == 0 ? "/kernel" : "/bias");
+      p.name = layer_var[i] + (kb == 0 ? "/kernel" : "/bias");
       const HostTensor* ht = find(h, p.name);
       DCCN_CHECK(ht, "weight '%s' was not set", p.name.c_str());
       p.n = (int64_t)ht->data.size();
@@ -986,6 +1117,7 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   if (!rx_mode) {
     if ((rc = make_bw_layer(h, h->r1, &tr->bw_r1, s))) return rc;
     if ((rc = make_bw_layer(h, h->r2, &tr->bw_r2, s))) return rc;
+    if (generic && h->eqs.tail == 2 && (rc = make_bw_layer(h, h->g9, &tr->bw_ifft, s))) return rc;
   }
   tr->partial_floats = max_partial;
   rc |= dev_alloc(h, (void**)&tr->partial, max_partial * 4);
@@ -1076,7 +1208,9 @@ int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t
   if (rc) return rc;
   if (conf_dev) conf_accumulate(h->d_conf, conf_dev, s);
   // ---- backward ------------------------------------------------------------------------------------------------
-  if ((rc = rx_mode ? backward_rx(h, B, bits_dev, s) : backward(h, B, bits_dev, s))) return rc;
+  if ((rc = rx_mode ? backward_rx(h, B, bits_dev, s)
+                    : (h->eqs.generic ? backward_generic(h, B, bits_dev, s) : backward(h, B, bits_dev, s))))
+    return rc;
   if (!apply_update) return 0;
   // ---- Adam (dev/py/ofdmreceiver_np_mp.py:345-347) ------------------------------------------------------------
   tr->step += 1;

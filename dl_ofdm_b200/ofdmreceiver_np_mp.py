@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 from . import sweep, tfbundle
 from .flags import parse_flags
-from .init import equalizer_variables
+from .init import eq_layer_roles, equalizer_variables
 from .model import Session, load_model_np, save_model
 from .ofdm import const_map, ofdm_tx
 from .radio import rayleigh_chan_lte
@@ -74,13 +74,15 @@ def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=N
                     save=True, seed=None, log=print):
     """Transfer learning of equalizer_ofdm in front of the frozen receiver ``rx_weights`` (TF names -> arrays).
     Returns (session, history) where history is a list of per-epoch dicts (train_loss, test_loss, test_ber)."""
-    if FLAGS.opt != 0:
-        raise NotImplementedError('--opt=%d: only equalizer_ofdm (--opt=0) is implemented' % FLAGS.opt)
+    opt = 0 if FLAGS.opt in (9, 10) else FLAGS.opt                   # 9 / 10 build equalizer_ofdm (_mp.py:309-312)
+    if opt not in (0, 1, 2, 3, 4, 5):
+        raise NotImplementedError('--opt=%d: transfer learning is implemented for the graphs --opt 0..5' % FLAGS.opt)
     seed = FLAGS.seed if seed is None else seed
     rng = np.random.default_rng(seed)
     weights = dict(rx_weights)
     weights.update(eq_weights if eq_weights is not None else
-                   equalizer_variables(rng, ofdmobj.K, ofdmobj.CP, ofdmobj.nSymbol, ofdmobj.pilot_size, FLAGS.cp))
+                   equalizer_variables(rng, ofdmobj.K, ofdmobj.CP, ofdmobj.nSymbol, ofdmobj.pilot_size, FLAGS.cp, opt=opt))
+    trainable = ['Equalizer/' + n + sfx for _, n in eq_layer_roles(opt) for sfx in ('/kernel', '/bias')]
     batch = FLAGS.batch_size // ofdmobj.nSymbol                       # _mp.py:358
     frame_cnt = FLAGS.msg_length // FLAGS.nsymbol if frame_cnt is None else frame_cnt
     session = Session(FLAGS, ofdmobj, weights, precision=FLAGS.precision,
@@ -111,7 +113,7 @@ def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=N
             epoch_min_loss, test_loss_min = epoch, train_loss
             if save:
                 w = dict(weights)
-                for n in TRAINABLE:
+                for n in trainable:
                     w[n] = eng.get_weight(n).reshape(np.shape(weights[n]))
                 save_model(name, w, global_step=eng.global_step)
         if epoch - FLAGS.early_stop > epoch_min_loss:                 # _mp.py:460-461

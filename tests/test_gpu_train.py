@@ -317,3 +317,99 @@ def test_train_receiver_driver(libdccn, tmp_path):
         assert torch.equal(session.engine.forward(x)['soft'], s2.engine.forward(x)['soft'])
         s2.close()
     session.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# transfer learning of the ablation equalizers (--opt 1..5) in front of the frozen receiver
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('opt,precision,nbits,use_cp,B', [
+    (1, 'parity', 2, True, 96), (2, 'parity', 2, True, 96), (3, 'parity', 1, False, 64), (4, 'parity', 4, True, 120),
+    (5, 'parity', 2, False, 72), (3, 'exact', 2, True, 40), (5, 'exact', 2, True, 40)])
+def test_variant_gradients_match_oracle(libdccn, opt, precision, nbits, use_cp, B):
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle import dccn_train_oracle as tro
+    rng = np.random.default_rng(300 + opt)
+    w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), eq_opt=opt)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nbits)).astype(np.uint8)
+    ce, _, g64, _ = tro.variant_loss_and_grads(x, bits, w, nbits, opt, use_cp=use_cp)
+    m = DCCN(nbits=nbits, equalizer=True, precision=precision, use_cp=use_cp, eq_opt=opt)
+    m.load_weights(w)
+    m.train_init(B)
+    out = m.train_step(_cuda(x), _cuda(bits), 1e-3, apply_update=False)
+    torch.cuda.synchronize()
+    assert abs(float(out['ce_sum'][0]) / out['n_bits'] - ce) < 5e-6
+    for name in tro.variant_trainable_names(opt):
+        g = m.get_grad(name).astype(np.float64).reshape(g64[name].shape)
+        scale = np.abs(g64[name]).max()
+        err = np.abs(g - g64[name]).max()
+        assert err <= GRAD_RTOL * scale + 1e-9, (name, err, scale)
+    m.close()
+
+
+def test_variant_training_steps(libdccn):
+    """--opt 5 (tf.ifft tail, tanh-fused channel estimate): three steps, Adam exact on the GPU's own gradients, loss
+    trajectory follows the fp64 oracle, the receiver stays frozen, inference sees the update."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle import dccn_train_oracle as tro
+    opt, nbits = 5, 2
+    rng = np.random.default_rng(77)
+    w = orc.glorot_weights(rng, nbits, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), eq_opt=opt)
+    x = (rng.standard_normal((3 * 64, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (3 * 64, 320, nbits)).astype(np.uint8)
+    xs = [x[i * 64:(i + 1) * 64] for i in range(3)]
+    bs = [bits[i * 64:(i + 1) * 64] for i in range(3)]
+    _, losses_ref = tro.variant_train_steps(xs, bs, w, nbits, opt)
+    names = tro.variant_trainable_names(opt)
+    m = DCCN(nbits=nbits, equalizer=True, precision='parity', eq_opt=opt)
+    m.load_weights(w)
+    m.train_init(64)
+    optm = tro.Adam(names, w, dtype=np.float64)
+    wr = {k: np.array(v, dtype=np.float64) for k, v in w.items()}
+    losses = []
+    for i in range(3):
+        lr = tro.learning_rate(1e-3, i)
+        out = m.train_step(_cuda(xs[i]), _cuda(bs[i]), lr)
+        losses.append(float(out['ce_sum'][0]) / out['n_bits'])
+        grads = {n: m.get_grad(n).astype(np.float64).reshape(w[n].shape) for n in names}
+        optm.step(wr, grads, lr)
+        for n in names:
+            got = m.get_weight(n).reshape(w[n].shape)
+            assert np.abs(got - wr[n]).max() <= 2e-6, (i, n)
+            wr[n] = got.astype(np.float64)
+    assert np.allclose(losses, losses_ref, rtol=0, atol=1e-5), (losses, losses_ref)
+    assert np.array_equal(m.get_weight('demodulation/dense/kernel'), w['demodulation/dense/kernel'].ravel())
+    w_gpu = dict(w)
+    for n in names:
+        w_gpu[n] = m.get_weight(n).reshape(w[n].shape)
+    o = m.forward(_cuda(xs[0]), _cuda(bs[0]))
+    soft_ref, _, chest_ref = orc.equalized_receiver(xs[0], w_gpu, nbits, 64, 16, opt=opt)
+    good = np.abs(chest_ref).reshape(64, -1).min(axis=1) > 2e-2
+    assert good.sum() > 16
+    assert np.quantile(np.abs(o['soft'].cpu().numpy()[good] - soft_ref[good]), 0.999) < 2e-4
+    m.close()
+
+
+def test_train_equalizer_driver_ablation(libdccn, tmp_path):
+    """train_equalizer with --opt=3 (equalizer_dnnE): checkpoint under the reference's name, reload picks the graph."""
+    from dl_ofdm_b200 import tfbundle
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.init import receiver_variables
+    from dl_ofdm_b200.model import load_model_np
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from dl_ofdm_b200.ofdmreceiver_np_mp import train_equalizer
+    FLAGS = Flags(nbits=2, channel='EPA', batch_size=7 * 256, msg_length=7 * 1024, opt=3, token='T',
+                  save_dir=str(tmp_path) + '/', precision='parity', early_stop=400)
+    ofdmobj = ofdm_tx(FLAGS)
+    rx = receiver_variables(np.random.default_rng(3), 2)
+    session, hist = train_equalizer(FLAGS, ofdmobj, rx, max_epoch_num=2, log=lambda *a: None)
+    assert len(hist) == 2 and session.engine.global_step == 8 and session.engine.eq_opt == 3
+    assert all(np.isfinite(h['train_loss']) for h in hist)
+    ck = tfbundle.read_checkpoint(str(tmp_path) + '/T_Equalizer3_EPA')
+    assert 'Equalizer/dense_8/kernel' in ck and 'Equalizer/conv3d/kernel' not in ck
+    s2 = load_model_np(str(tmp_path) + '/T_Equalizer3_EPA', FLAGS=FLAGS, ofdmobj=ofdmobj, precision='parity')
+    assert s2.engine.eq_opt == 3
+    s2.close()
+    session.close()

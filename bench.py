@@ -53,18 +53,21 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+    ONE sampler process for the whole job (rank 0 watches the GPUs of every rank): N concurrent nvidia-smi pollers
+    contend for the driver and showed up as launch gaps that grew with the number of ranks."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.indices = [int(i) for i in (indices if isinstance(indices, (list, tuple)) else [indices])]
+        self.rows, self.stop_flag = [], False
 
     def run(self):
         try:
-            p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+            p = subprocess.Popen(['nvidia-smi', '-i', ','.join(str(i) for i in self.indices), '--query-gpu=' + self.Q,
                                   '--format=csv,noheader,nounits', '-lms', '100'],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
@@ -77,18 +80,20 @@ class ClockSampler(threading.Thread):
         p.terminate()
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons = {}, 0.0, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                sm.setdefault(int(r[0]), []).append(float(r[1])); mx = max(mx, float(r[2]))
             except Exception:
                 continue
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(names, r[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        med = {g: float(np.median(v)) for g, v in sm.items()}
+        return {'sm_mhz': min(med.values()) if med else None, 'sm_max_mhz': mx or None,
+                'sm_mhz_per_gpu': [med[g] for g in sorted(med)] if len(med) > 1 else None,
+                'reasons': sorted(reasons), 'samples': sum(len(v) for v in sm.values())}
 
 
 def bind_to_gpu_numa(index):
@@ -359,8 +364,8 @@ def main():
         out = step()
     barrier()
     # ---- timed region (device events, max over ranks) -------------------------------------
-    sampler = ClockSampler(local)
-    if not os.environ.get('BENCH_NO_SAMPLER'):
+    sampler = ClockSampler(list(range(world)) if world > 1 else local)    # rank 0 samples every GPU of the job
+    if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
         sampler.start()
     # keep the GPU busy while nvidia-smi starts sampling: an idle gap here lets the clocks ramp down and the first
     # timed steps then pay the ramp-up (measured: +5 ms on the first step after a 150 ms sleep)

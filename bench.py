@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             p = subprocess.Popen(['nvidia-smi', '-i', ','.join(str(i) for i in self.indices), '--query-gpu=' + self.Q,
-                                  '--format=csv,noheader,nounits', '-lms', '100'],
+                                  '--format=csv,noheader,nounits', '-lms', '200'],      # the recipe's period
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return

@@ -43,7 +43,8 @@ struct TrainLayer {
   GemmLayer* L = nullptr;   // forward layer (lives in the handle)
   GemmLayer bw;             // dgrad companion: C[M, K] = dY[M, N] * W^T
   int kp = -1, bp = -1;     // indices of kernel / bias in TrainState::params
-  int bias_kind = 0;        // 0 dense, 1 complex (ba-bb, bb-ba), 2 one complex filter broadcast (Toeplitz layer)
+  int bias_kind = 0;        // 0 dense, 1 complex (ba-bb, bb-ba), 2 one complex filter broadcast (Toeplitz layer),
+                            // 3 / 4: the layers_conv2d_vector forms of 1 / 2 (re | im channel blocks; (b0, b1) broadcast)
   float* Wp = nullptr;      // [K, N] packed fp32 operand (exact mode: the forward operand itself)
   int32_t* map = nullptr;   // [K*N]  +-(param index + 1), 0 = structural zero
   int32_t* csr_off = nullptr;
@@ -252,7 +253,9 @@ pack_bias_kernel(const float* __restrict__ b, int kind, int N, float* __restrict
   else if (kind == 1) {
     const int F = N >> 1, f = j >> 1;
     out[j] = (j & 1) ? b[F + f] - b[f] : b[f] - b[F + f];
-  } else out[j] = (j & 1) ? b[1] - b[0] : b[0] - b[1];
+  } else if (kind == 2) out[j] = (j & 1) ? b[1] - b[0] : b[0] - b[1];
+  else if (kind == 3) out[j] = (j & 1) ? b[(N >> 1) + (j >> 1)] : b[j >> 1];   // layers_conv2d_vector: re / im channel blocks
+  else out[j] = b[j & 1];                                                     // vector (S,K) layer: (b0, b1) broadcast
 }
 
 // one block; dbp = packed bias gradient [N]
@@ -260,6 +263,33 @@ __global__ void __launch_bounds__(256)
 grad_bias_kernel(const float* __restrict__ dbp, int kind, int N, float* __restrict__ g) {
   if (kind == 0) {
     for (int j = threadIdx.x; j < N; j += blockDim.x) g[j] = dbp[j];
+  } else if (kind == 3) {
+    const int F = N >> 1;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      g[f] = dbp[2 * f];
+      g[F + f] = dbp[2 * f + 1];
+    }
+  } else if (kind == 4) {
+    __shared__ float red0[256], red1[256];
+    float s0 = 0.f, s1 = 0.f;
+    for (int f = threadIdx.x; f < (N >> 1); f += blockDim.x) {
+      s0 += dbp[2 * f];
+      s1 += dbp[2 * f + 1];
+    }
+    red0[threadIdx.x] = s0;
+    red1[threadIdx.x] = s1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) {
+        red0[threadIdx.x] += red0[threadIdx.x + o];
+        red1[threadIdx.x] += red1[threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      g[0] = red0[0];
+      g[1] = red1[0];
+    }
   } else if (kind == 1) {
     const int F = N >> 1;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -756,8 +786,16 @@ static int backward(dccn_handle* h, int64_t B, const uint8_t* bits, cudaStream_t
   }
   if ((rc = run_wgrad(h, tl[5], h->u2.p0, SK2, tr->dA.p0, SK2, B, s))) return rc;
   if ((rc = run_dgrad(h, tl[5].bw, tr->dA, 0, B, tr->dB, 0, s))) return rc;
+  if (h->eqs.chain_act[1]) {   // equalizer_separateIQ: dense_3 has a tanh (model.py:1146-1150); its output is u2
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    tanh_bwd_kernel<<<blocks_for((long long)B * SK2), 256, 0, s>>>(tr->dB.p0, h->u2.p0, (long long)B * SK2);
+  }
   if ((rc = run_wgrad(h, tl[4], h->u1.p0, SK2, tr->dB.p0, SK2, B, s))) return rc;
   if ((rc = run_dgrad(h, tl[4].bw, tr->dB, 0, B, tr->dC, 0, s))) return rc;
+  if (h->eqs.chain_act[0]) {   // ... and dense_2 (model.py:1140-1144); its output is u1
+    LaunchScope ls(h, SLOT_T_POINT, s);
+    tanh_bwd_kernel<<<blocks_for((long long)B * SK2), 256, 0, s>>>(tr->dC.p0, h->u1.p0, (long long)B * SK2);
+  }
   if ((rc = run_wgrad(h, tl[3], h->p32.p0, h->p32.ld, tr->dC.p0, SK2, B, s))) return rc;
   if ((rc = run_dgrad(h, tl[3].bw, tr->dC, 0, B, tr->d_p32, 0, s))) return rc;
   if ((rc = run_wgrad(h, tl[2], h->f.p0, SK2, tr->d_p32.p0, tr->d_p32.ld, B, s))) return rc;
@@ -956,8 +994,6 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
   DCCN_CHECK(cfg->mode == DCCN_TRAIN_EQ || cfg->mode == DCCN_TRAIN_RX, "unknown training mode %d", (int)cfg->mode);
   DCCN_CHECK(rx_mode || h->cfg.equalizer, "DCCN_TRAIN_EQ updates the Equalizer/* variables: the handle has no equalizer");
   DCCN_CHECK(!rx_mode || !h->cfg.equalizer, "DCCN_TRAIN_RX trains the basic receiver: create the handle without equalizer");
-  DCCN_CHECK(h->eq_opt == 0 || h->eqs.generic,
-             "training is implemented for --opt 0..5; --opt=%d (layers_conv2d_vector) is inference only", h->eq_opt);
   DCCN_CHECK(h->committed, "weights not committed (dccn_commit_weights)");
   DCCN_CHECK(h->cfg.precision == DCCN_PREC_EXACT || h->cfg.precision == DCCN_PREC_PARITY,
              "training needs fp32-class arithmetic (precision exact or parity)");
@@ -988,7 +1024,8 @@ static int train_init_impl(dccn_handle* h, const dccn_train_cfg* cfg, void* stre
     Ls = {&h->g1, &h->g2, &h->g3, &h->g4, &h->g5, &h->g6, &h->g7, &h->g8, &h->g9, &h->g10};
     for (int i = 0; i < 10; ++i) {
       layer_var.push_back(kLayerVar[i]);
-      bias_kind.push_back(kBiasKind[i]);
+      // --opt 7: the four conv3d layers are layers_conv2d_vector (bias kinds 3 / 4 instead of 1 / 2)
+      bias_kind.push_back(h->eqs.vector && kBiasKind[i] ? kBiasKind[i] + 2 : kBiasKind[i]);
       per_symbol.push_back(kPerSymbol[i]);
     }
   } else {

@@ -75,8 +75,8 @@ def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=N
     """Transfer learning of equalizer_ofdm in front of the frozen receiver ``rx_weights`` (TF names -> arrays).
     Returns (session, history) where history is a list of per-epoch dicts (train_loss, test_loss, test_ber)."""
     opt = 0 if FLAGS.opt in (9, 10) else FLAGS.opt                   # 9 / 10 build equalizer_ofdm (_mp.py:309-312)
-    if opt not in (0, 1, 2, 3, 4, 5):
-        raise NotImplementedError('--opt=%d: transfer learning is implemented for the graphs --opt 0..5' % FLAGS.opt)
+    if opt not in (0, 1, 2, 3, 4, 5, 7):
+        raise NotImplementedError('--opt=%d: dev/py/model.py defines the graphs --opt 0..5, 7 (9, 10 = 0)' % FLAGS.opt)
     seed = FLAGS.seed if seed is None else seed
     rng = np.random.default_rng(seed)
     weights = dict(rx_weights)

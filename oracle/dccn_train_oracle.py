@@ -100,16 +100,77 @@ def _unpack_toeplitz(dBp, dbp, S, K):
     return gk, np.array([g0, -g0], dtype=dBp.dtype)
 
 
+# layers_conv2d_vector (--opt 7, dev/py/complex.py:199-255): plain real maps, no complex recombination
+def _pack_vec_1xk(kernel, bias):
+    """(1,K) 'valid', kernel [1,K,2,1,2F]: rows (k, iq), columns (f, part) with part 0 = channels [0,F), 1 = [F,2F)."""
+    k = kernel[0, :, :, 0, :]                                 # [K, 2, 2F]
+    K, _, F2 = k.shape
+    F = F2 // 2
+    Bp = k.reshape(K, 2, 2, F).transpose(0, 1, 3, 2).reshape(2 * K, 2 * F)
+    bp = bias.reshape(2, F).T.reshape(2 * F)
+    return np.ascontiguousarray(Bp), np.ascontiguousarray(bp)
+
+
+def _unpack_vec_1xk(dBp, dbp, shape):
+    K, F = shape[1], shape[4] // 2
+    gk = dBp.reshape(K, 2, F, 2).transpose(0, 1, 3, 2).reshape(shape)
+    return gk, dbp.reshape(F, 2).T.reshape(2 * F)
+
+
+def _pack_vec_toeplitz(kernel, bias, S, K):
+    """(S,K) 'same', one filter, kernel [S,K,2,1,2]: re / im = channels 0 / 1 at IQ position 0."""
+    n = S * K * 2
+    Bp = np.zeros((n, n), dtype=kernel.dtype)
+    pl, pw = (S - 1) // 2, (K - 1) // 2
+    for i in range(S):
+        for j in range(K):
+            d = np.arange(max(0, pl - i), min(S, S + pl - i))
+            h = np.arange(max(0, pw - j), min(K, K + pw - j))
+            co = ((d[:, None] * K + h[None, :]) * 2).ravel()
+            ri = (((d[:, None] + i - pl) * K + (h[None, :] + j - pw)) * 2).ravel()
+            for iq in range(2):
+                for ch in range(2):
+                    Bp[ri + iq, co + ch] = kernel[i, j, iq, 0, ch]
+    bp = np.zeros(n, dtype=kernel.dtype)
+    bp[0::2], bp[1::2] = bias[0], bias[1]
+    return Bp, bp
+
+
+def _unpack_vec_toeplitz(dBp, dbp, S, K):
+    gk = np.zeros((S, K, 2, 1, 2), dtype=dBp.dtype)
+    pl, pw = (S - 1) // 2, (K - 1) // 2
+    for i in range(S):
+        for j in range(K):
+            d = np.arange(max(0, pl - i), min(S, S + pl - i))
+            h = np.arange(max(0, pw - j), min(K, K + pw - j))
+            co = ((d[:, None] * K + h[None, :]) * 2).ravel()
+            ri = (((d[:, None] + i - pl) * K + (h[None, :] + j - pw)) * 2).ravel()
+            for iq in range(2):
+                for ch in range(2):
+                    gk[i, j, iq, 0, ch] = np.sum(dBp[ri + iq, co + ch])
+    return gk, np.array([dbp[0::2].sum(), dbp[1::2].sum()], dtype=dBp.dtype)
+
+
 # ---------------------------------------------------------------------------------------------
 # forward + backward of  ce_mean + REG_COEFF * sum(l2)  w.r.t. the Equalizer variables
 # ---------------------------------------------------------------------------------------------
 def loss_and_grads(x, bits, w, nbits, nfft=64, cp_len=16, use_cp=True, nfilter=64, dtype=np.float64,
-                   normalize=True, reg=True):
+                   normalize=True, reg=True, opt=0):
     """x [B,S,T,2] ('tx_ofdm' feed), bits [B,D,nbits] -> (ce_mean, reg_loss, grads, aux).
+
+    opt 0: equalizer_ofdm.  opt 7: equalizer_separateIQ (dev/py/model.py:1088-1218) -- the same wiring with
+    layers_conv2d_vector in place of the complex convs and tanh on all three chain layers (:1140-1162).
 
     grads: TF variable name -> d total_loss / d var for every 'Equalizer/*' variable, in the
     reference layout.  aux holds intermediate tensors for layer-level checks.
     """
+    assert opt in (0, 7)
+    vec = opt == 7
+    acts = (1, 1, 1) if vec else (0, 0, 1)
+    _pack_1xk = _pack_vec_1xk if vec else globals()['_pack_1xk']
+    _unpack_1xk = _unpack_vec_1xk if vec else globals()['_unpack_1xk']
+    _pack_toeplitz = _pack_vec_toeplitz if vec else globals()['_pack_toeplitz']
+    _unpack_toeplitz = _unpack_vec_toeplitz if vec else globals()['_unpack_toeplitz']
     A = lambda n: np.asarray(w[n], dtype=dtype)
     x = np.asarray(x, dtype=dtype)
     B, S, T, _ = x.shape
@@ -134,7 +195,9 @@ def loss_and_grads(x, bits, w, nbits, nfft=64, cp_len=16, use_cp=True, nfilter=6
     fl = f.reshape(B, S * K * 2)                        # model.py:391
     p = fl @ W3 + b3                                    # model.py:393
     c2 = p @ W4 + b4                                    # model.py:401
+    c2 = np.tanh(c2) if acts[0] else c2
     c3 = c2 @ W5 + b5                                   # model.py:407
+    c3 = np.tanh(c3) if acts[1] else c3
     c4 = np.tanh(c3 @ W6 + b6)                          # model.py:419
     ch = c4 @ Bp7 + bp7                                 # [B, 2SK] chest        model.py:426
     cr, ci = ch[:, 0::2], ch[:, 1::2]
@@ -219,9 +282,13 @@ def loss_and_grads(x, bits, w, nbits, nfft=64, cp_len=16, use_cp=True, nfilter=6
     g[pre + 'dense_4/kernel'] = c3.T @ dpre4
     g[pre + 'dense_4/bias'] = dpre4.sum(0)
     dc3 = dpre4 @ W6.T
+    if acts[1]:
+        dc3 = dc3 * (1 - c3 * c3)
     g[pre + 'dense_3/kernel'] = c2.T @ dc3
     g[pre + 'dense_3/bias'] = dc3.sum(0)
     dc2 = dc3 @ W5.T
+    if acts[0]:
+        dc2 = dc2 * (1 - c2 * c2)
     g[pre + 'dense_2/kernel'] = p.T @ dc2
     g[pre + 'dense_2/bias'] = dc2.sum(0)
     dp = dc2 @ W4.T

@@ -413,3 +413,40 @@ def test_train_equalizer_driver_ablation(libdccn, tmp_path):
     assert s2.engine.eq_opt == 3
     s2.close()
     session.close()
+
+
+@pytest.mark.parametrize('precision,B', [('parity', 96), ('exact', 40)])
+def test_separateIQ_gradients_match_oracle(libdccn, precision, B):
+    """--opt 7 (equalizer_separateIQ): layers_conv2d_vector layers are other packers for the same operands, so the
+    config-4 backward applies with two extra tanh's; gradients of all 20 variables vs the fp64 oracle."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle import dccn_train_oracle as tro
+    nbits = 2
+    rng = np.random.default_rng(407)
+    w = orc.glorot_weights(rng, nbits, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), eq_opt=7)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nbits)).astype(np.uint8)
+    ce, _, g64, _ = tro.loss_and_grads(x, bits, w, nbits, opt=7)
+    m = DCCN(nbits=nbits, equalizer=True, precision=precision, eq_opt=7)
+    m.load_weights(w)
+    m.train_init(B)
+    out = m.train_step(_cuda(x), _cuda(bits), 1e-3, apply_update=False)
+    torch.cuda.synchronize()
+    assert abs(float(out['ce_sum'][0]) / out['n_bits'] - ce) < 5e-6
+    for name in tro.trainable_names():
+        g = m.get_grad(name).astype(np.float64).reshape(g64[name].shape)
+        scale = np.abs(g64[name]).max()
+        err = np.abs(g - g64[name]).max()
+        assert err <= GRAD_RTOL * scale + 1e-9, (name, err, scale)
+    # one update, then the inference path runs on the re-packed operands (bias kinds 3 / 4)
+    m.train_step(_cuda(x), _cuda(bits), 1e-3)
+    w_gpu = dict(w)
+    for n in tro.trainable_names():
+        w_gpu[n] = m.get_weight(n).reshape(w[n].shape)
+    o = m.forward(_cuda(x), _cuda(bits))
+    soft_ref, _, chest_ref = orc.equalized_receiver(x, w_gpu, nbits, 64, 16, opt=7)
+    good = np.abs(chest_ref).reshape(B, -1).min(axis=1) > 2e-2
+    assert good.sum() > B // 4
+    assert np.quantile(np.abs(o['soft'].cpu().numpy()[good] - soft_ref[good]), 0.999) < 2e-4
+    m.close()

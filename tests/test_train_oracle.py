@@ -185,3 +185,70 @@ def test_variant_backward_matches_autograd(opt, nbits, use_cp):
         ref = m.w[k].grad.numpy()
         err = np.abs(g[k] - ref).max()
         assert err <= 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-15, (k, err, np.abs(ref).max())
+
+
+# ---- --opt 7: equalizer_separateIQ (layers_conv2d_vector) -----------------------------------------------------------
+def _vconv_torch(x5, kernel, bias, padding):
+    """layers_conv2d_vector as the literal conv3d over (length, width, IQ) with TF's SAME padding (complex.py:199-255)."""
+    import torch.nn.functional as Fn
+    xt = x5[:, :, :, 0, :].unsqueeze(1)                                  # [B,1,L,W,2]
+    kl, kw = kernel.shape[0], kernel.shape[1]
+    wt = kernel[:, :, :, 0, :].permute(3, 0, 1, 2).unsqueeze(1)           # [2F,1,kl,kw,2]
+    if padding == 'same':
+        xt = Fn.pad(xt, (0, 1, (kw - 1) // 2, kw - 1 - (kw - 1) // 2, (kl - 1) // 2, kl - 1 - (kl - 1) // 2))
+    y = Fn.conv3d(xt, wt, bias)[..., 0]                                   # IQ position 0: [B,2F,L',W']
+    F_ = kernel.shape[4] // 2
+    return torch.stack([y[:, :F_], y[:, F_:]], -1).permute(0, 2, 3, 1, 4)  # [B,L',W',F,2]
+
+
+def _separateIQ_forward_torch(m, z):
+    W = lambda n: m.w['Equalizer/' + n]
+    B, S, T, _ = z.shape
+    K = 64
+    mu = z.reshape(B, -1).mean(1).reshape(B, 1, 1, 1)
+    var = ((z - mu) ** 2).reshape(B, -1).mean(1).reshape(B, 1, 1, 1)
+    c = ((z - mu) / torch.sqrt(var + orc.LN_EPS)).reshape(B, S, T * 2)
+    c = c @ W('dense/kernel') + W('dense/bias')
+    f = _vconv_torch(c.reshape(B, S, K, 1, 2), W('conv3d/kernel'), W('conv3d/bias'), 'valid')     # [B,S,1,K,2]
+    f = f.permute(0, 1, 3, 2, 4)[:, :, :, 0, :]
+    inputs_c = torch.complex(f[..., 0], f[..., 1])
+    c = f.reshape(B, S * K * 2) @ W('dense_1/kernel') + W('dense_1/bias')
+    for n in ('dense_2', 'dense_3', 'dense_4'):
+        c = torch.tanh(c @ W(n + '/kernel') + W(n + '/bias'))
+    c5 = _vconv_torch(c.reshape(B, S, K, 1, 2), W('conv3d_1/kernel'), W('conv3d_1/bias'), 'same')
+    chest = torch.complex(c5[..., 0], c5[..., 1])[:, :, :, 0]
+    ab = torch.abs(chest)
+    eq = inputs_c * torch.complex(chest.real / ab, -chest.imag / ab)
+    corr = eq * torch.conj(eq)
+
+    def vc(v, n):
+        o = _vconv_torch(torch.stack([v.real, v.imag], -1).reshape(B, S, K, 1, 2), W(n + '/kernel'), W(n + '/bias'), 'valid')
+        return o.permute(0, 1, 3, 2, 4)[:, :, :, 0, :]
+    cat = torch.cat([vc(eq, 'conv3d_3'), vc(corr, 'conv3d_2')], -1).reshape(B, S, K * 4)
+    return (cat @ W('dense_5/kernel') + W('dense_5/bias')).reshape(B, S, T, 2)
+
+
+def test_separateIQ_backward_matches_autograd():
+    nbits = 2
+    rng = np.random.default_rng(97)
+    w = orc.glorot_weights(rng, nbits, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4), eq_opt=7)
+    x = (rng.standard_normal((16, 7, 80, 2)) * 0.3).astype(np.float32)
+    bits = rng.integers(0, 2, (16, 320, nbits)).astype(np.uint8)
+    ce, reg, g, aux = tro.loss_and_grads(x, bits, w, nbits, opt=7)
+    # forward of the GEMM-form oracle == the op-by-op restatement (conv2d_vector pinned against a literal conv3d)
+    _, eq_ref, _ = orc.equalized_receiver(x, w, nbits, 64, 16, opt=7)
+    assert np.abs(aux['oeq'] - eq_ref).max() < 1e-10
+    m = TFMirror(w, nbits, equalizer=False)
+    m.w = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=k.startswith('Equalizer/')) for k, v in w.items()}
+    oeq = _separateIQ_forward_torch(m, m.norm(torch.tensor(x, dtype=torch.float64)))
+    assert np.abs(aux['oeq'] - oeq.detach().numpy()).max() < 1e-10
+    soft = m.dense_rx(oeq).reshape(-1, 2)
+    ce_t = torch.nn.functional.cross_entropy(soft, torch.tensor(bits.reshape(-1).astype(np.int64)))
+    reg_t = sum(tro.L2_L * (m.w['Equalizer/' + n + s] ** 2).sum() for n in tro.DENSE_NAMES for s in ('/kernel', '/bias'))
+    (ce_t + tro.REG_COEFF * reg_t).backward()
+    assert abs(ce - float(ce_t.detach())) < 1e-12
+    assert set(g) == set(tro.trainable_names())
+    for k in g:
+        ref = m.w[k].grad.numpy()
+        err = np.abs(g[k] - ref).max()
+        assert err <= 1e-9 * max(np.abs(ref).max(), 1e-12) + 1e-15, (k, err, np.abs(ref).max())

@@ -54,8 +54,9 @@ def peaks():
 
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
-    ONE sampler process for the whole job (rank 0 watches the GPUs of every rank): N concurrent nvidia-smi pollers
-    contend for the driver and showed up as launch gaps that grew with the number of ranks."""
+    ONE sampler process for the whole job (rank 0 watches the GPUs of every rank) at the recipe's 200 ms period: every
+    poll stalls the GPU's queue for a moment -- N concurrent pollers at 100 ms cost 0.3-1 ms per 5 ms step, and an
+    in-process NVML poll every 20 ms was worse (+0.56 ms per step, measured)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -63,7 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, indices):
         super().__init__(daemon=True)
         self.indices = [int(i) for i in (indices if isinstance(indices, (list, tuple)) else [indices])]
-        self.rows, self.stop_flag = [], False
+        self.rows, self.stop_flag, self.source = [], False, None
 
     def run(self):
         try:
@@ -72,6 +73,7 @@ class ClockSampler(threading.Thread):
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return
+        self.source = 'nvidia-smi -lms 200'
         while not self.stop_flag:
             line = p.stdout.readline()
             if not line:
@@ -93,7 +95,7 @@ class ClockSampler(threading.Thread):
         med = {g: float(np.median(v)) for g, v in sm.items()}
         return {'sm_mhz': min(med.values()) if med else None, 'sm_max_mhz': mx or None,
                 'sm_mhz_per_gpu': [med[g] for g in sorted(med)] if len(med) > 1 else None,
-                'reasons': sorted(reasons), 'samples': sum(len(v) for v in sm.values())}
+                'reasons': sorted(reasons), 'samples': sum(len(v) for v in sm.values()), 'source': self.source}
 
 
 def bind_to_gpu_numa(index):
@@ -370,9 +372,12 @@ def main():
     # keep the GPU busy while nvidia-smi starts sampling: an idle gap here lets the clocks ramp down and the first
     # timed steps then pay the ramp-up (measured: +5 ms on the first step after a 150 ms sleep)
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.25:
+    while True:
         step()
         torch.cuda.synchronize()
+        el = time.perf_counter() - t_spin
+        if el > 2.0 or (el > 0.25 and (rank != 0 or len(sampler.rows) >= 2 or not sampler.is_alive())):
+            break
     l0 = launch_count()
     conf_total = torch.zeros((2, 2), dtype=torch.int64, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -456,6 +461,37 @@ def main():
                                'frac_of_hbm_peak': round((1280 + 4480) * B / (ms_tx * 1e-3) / 1e9 / pk['hbm'], 3)}
     del tx
 
+    # ---- the K-chunk knob (DCCN_KC): the headline drains the TMEM accumulator every k-block (kc = 1, the most accurate
+    # setting, more accurate than fp32 FFMA); kc = 2 is still fp32-class (profiles/accuracy_r1.txt: same error as the
+    # library's fp32 'exact' mode) and faster.  Reported next to the headline, never as it.
+    kc2 = None
+    if not args.no_folded and args.precision == 'parity':
+        os.environ['DCCN_KC'] = '2'
+        try:
+            m2 = DCCN.from_ofdm(fl, ofdm, equalizer=True, precision=args.precision, chunk_frames=args.chunk)
+        finally:
+            del os.environ['DCCN_KC']
+        m2.load_weights(w)
+        for _ in range(args.warmup):
+            o2 = m2.forward(x, bits, want_soft=True, want_hard=True)
+        barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            o2 = m2.forward(x, bits, want_soft=True, want_hard=True)
+        k1.record()
+        barrier()
+        kms = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+        kc2 = {'value': world * B * args.steps / (float(kms[0]) * 1e-3), 'unit': 'frames/s',
+               'ms_per_step': float(kms[0]) / args.steps,
+               'what': 'same layer-by-layer pass with the TMEM accumulator drained every 2 k-blocks (DCCN_KC=2); opt-in',
+               'hard_bits_equal_to_kc1': float((o2['hard'] == out['hard']).float().mean()),
+               'max_abs_soft_diff_vs_kc1': float((o2['soft'] - out['soft']).abs().max())}
+        m2.close()
+        del o2
+
     # ---- opt-in folded schedule (DCCN_FWD_FOLDED), reported next to the headline, never as it -------
     folded = None
     if not args.no_folded:
@@ -534,7 +570,7 @@ def main():
             'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': sampler.summary(), 'ms_per_step_per_rank': [round(t, 4) for t in ms_per_rank],
             'ber': ber, 'bits_counted': int(conf.sum()),
             'hbm_kernels': {'peak_gbs': pk['hbm'], 'kernels': hbm_kernels},
-            'train_config4': train, 'train_receiver': train_rx, 'folded_schedule': folded,
+            'train_config4': train, 'train_receiver': train_rx, 'kc2_schedule': kc2, 'folded_schedule': folded,
             'target': {'frames_per_s_8gpu': 1e8, 'note': 'north_star target; random-init weights so BER ~ 0.5'},
         }
         if world == 1 and not args.no_cpu_baseline:

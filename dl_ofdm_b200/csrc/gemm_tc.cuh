@@ -360,10 +360,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             DCCN_TRACE_EV(9);
             if (PAIR) umma_commit_pair(&empty[stage], 0x3);   // slot released in both CTAs of the pair
             else umma_commit(&empty[stage]);                  // smem slot reusable once these MMAs retire
-            // K chunk complete -> epilogue(s) drain it.  With one k-block per chunk (kc = 1) the commit above already
-            // says so: the epilogue warps wait on empty[stage] themselves and the second commit (~90 clk of tensor-
-            // pipe time, measured) is dropped.
-            if (kb + 1 == kb1 && (PAIR || kb_per_chunk != 1)) {
+            // K chunk complete -> epilogue(s) drain it.  The commit above already says so when the chunk is short
+            // (2 * kc <= STAGES, so the stage barrier of the chunk's last k-block cannot complete another phase before
+            // the epilogue has seen this one): the epilogue warps wait on empty[stage of the last k-block] themselves
+            // and the second commit (~90 clk of tensor-pipe time, measured) is dropped.
+            if (kb + 1 == kb1 && (PAIR || 2 * kb_per_chunk > C::STAGES)) {
               if (PAIR) umma_commit_pair(&tfull[acc], 0x3);
               else umma_commit(&tfull[acc]);
             }
@@ -542,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     uint32_t acc_phase = 0;
     int estage = 0;                            // kc = 1: the smem-stage ring position of the chunk being drained
     uint32_t ephase = 0;
-    const bool stage_signal = !PAIR && kb_per_chunk == 1;
+    const bool stage_signal = !PAIR && 2 * kb_per_chunk <= C::STAGES;
     float r[C::NCH][32];
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
@@ -552,9 +553,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int num_chunks = (tk.kb1 - tk.kb0 + kb_per_chunk - 1) / kb_per_chunk;
       for (int ch = 0; ch < num_chunks; ++ch) {
         if (stage_signal) {
-          wait_(&empty[estage], ephase);
-          if (++estage == C::STAGES) {
-            estage = 0;
+          // (estage, ephase) = ring position of the chunk's FIRST k-block; wait for its last one, then step over the chunk
+          const int len = (ch + 1 == num_chunks) ? (tk.kb1 - tk.kb0) - ch * kb_per_chunk : kb_per_chunk;
+          int ls = estage + len - 1;
+          uint32_t lp = ephase;
+          if (ls >= C::STAGES) {
+            ls -= C::STAGES;
+            lp ^= 1;
+          }
+          wait_(&empty[ls], lp);
+          estage += len;
+          if (estage >= C::STAGES) {
+            estage -= C::STAGES;
             ephase ^= 1;
           }
         } else {

@@ -633,3 +633,35 @@ def test_ablation_host_surface(libdccn):
     with pytest.raises(Exception):
         from dl_ofdm_b200.engine import DCCN
         DCCN(nbits=2, equalizer=True, eq_opt=6)          # equalizer_doppler does not exist in the reference either
+
+
+@pytest.mark.parametrize('kc', ['2', '4'])
+def test_kc_knob(libdccn, kc, monkeypatch):
+    """DCCN_KC (k-blocks accumulated inside TMEM between fp32 register adds; default 1): same function, fp32-class
+    error for kc = 2, slightly above for kc = 4 (profiles/accuracy_r1.txt) -- well inside this suite's bounds."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(61)
+    nb, B = 4, 300
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    soft_ref, eq_ref, chest_ref = orc.equalized_receiver(x, w, nb, 64, 16, dtype=np.float64)
+    monkeypatch.setenv('DCCN_KC', kc)
+    m = DCCN(nbits=nb, equalizer=True, precision='parity')
+    monkeypatch.delenv('DCCN_KC')
+    m.load_weights(w)
+    out = m.forward(_cuda(x), _cuda(bits), want_eq=True)
+    good = np.abs(chest_ref).reshape(B, -1).min(axis=1) > 2e-2
+    assert good.sum() > B // 4
+    soft = out['soft'].cpu().numpy()
+    assert np.quantile(np.abs(soft[good] - soft_ref[good]), 0.999) < 2e-4
+    hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+    decided = (np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-3) & good[:, None, None]
+    assert np.array_equal(out['hard'].cpu().numpy()[decided], hard_ref[decided])
+    m1 = DCCN(nbits=nb, equalizer=True, precision='parity')
+    m1.load_weights(w)
+    o1 = m1.forward(_cuda(x), _cuda(bits))
+    assert float((o1['soft'] - out['soft']).abs()[torch.as_tensor(good).cuda()].max()) < 2e-4
+    m.close()
+    m1.close()

@@ -1340,6 +1340,27 @@ int dccn_cconv2d(const float* x_dev, int64_t B, int L, int W, int C, const float
   return 0;
 }
 
+int dccn_vconv2d(const float* x_dev, int64_t B, int L, int W, int C, const float* kernel_dev, const float* bias_dev,
+                 int filters, int kl, int kw, int padding, float* y_dev, void* stream) {
+  DCCN_CHECK(x_dev && kernel_dev && bias_dev && y_dev, "null argument");
+  DCCN_CHECK(B > 0 && L > 0 && W > 0 && C > 0 && filters > 0 && kl > 0 && kw > 0, "bad shape");
+  DCCN_CHECK(padding == 0 || padding == 1, "padding must be 0 ('valid') or 1 ('same')");
+  int Lo, Wo, pl = 0, pw = 0;
+  if (padding == 1) {
+    Lo = L; Wo = W; pl = (kl - 1) / 2; pw = (kw - 1) / 2;
+  } else {
+    Lo = L - kl + 1; Wo = W - kw + 1;
+    DCCN_CHECK(Lo > 0 && Wo > 0, "'valid' kernel larger than the input");
+  }
+  const long long total = (long long)B * Lo * Wo * filters;
+  g_launches += 1;
+  vconv2d_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const float2*)x_dev, (long long)B, L, W, C, kernel_dev, bias_dev, filters, kl, kw, pl, pw, Lo, Wo,
+      (float2*)y_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_samp, const double* alpha_dev,
                        const double* coeff_dev, int n_taps, int n_fir, const double* z_dev, const float* snr_db_dev,
                        const double* normals_dev, uint64_t seed, float* rx_dev, float* fir_only_dev, void* stream) {

@@ -487,4 +487,46 @@ __global__ void __launch_bounds__(128) cconv2d_kernel(const float2* __restrict__
   y[i] = make_float2(c0 - c3, c1 - c2);   // complex.py:187-188
 }
 
+// =====================================================================================
+// op-level: direct evaluation of layers_conv2d_vector (complex.py:199-255): one real conv3d over (length, width, IQ)
+// with kernel depth 2 across IQ, 2F channels, no complex recombination.  kernel [kl,kw,2,C,2F], bias [2F].
+// After the reference's reshape / slice both paddings reduce to: IQ position 0, channels [0,F) = real parts,
+// [F,2F) = imaginary parts ('same' pads the size-2 IQ axis 0 before / 1 after, so position 0 sees both components).
+// One thread per output element (b, l, w, f).
+// =====================================================================================
+__global__ void __launch_bounds__(128) vconv2d_kernel(const float2* __restrict__ x, long long B, int L, int W, int C,
+                                                      const float* __restrict__ kernel, const float* __restrict__ bias,
+                                                      int F, int kl, int kw, int pl, int pw, int Lo, int Wo,
+                                                      float2* __restrict__ y) {
+  const long long total = B * Lo * Wo * F;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = (int)(i % F);
+  long long r = i / F;
+  const int w = (int)(r % Wo);
+  r /= Wo;
+  const int l = (int)(r % Lo);
+  const long long b = r / Lo;
+  float re = bias[f], im = bias[F + f];
+  for (int ii = 0; ii < kl; ++ii) {
+    const int li = l + ii - pl;
+    if (li < 0 || li >= L) continue;
+    for (int jj = 0; jj < kw; ++jj) {
+      const int wj = w + jj - pw;
+      if (wj < 0 || wj >= W) continue;
+      const float2* xp = x + (((size_t)b * L + li) * W + wj) * C;
+      const float* k0 = kernel + ((size_t)(ii * kw + jj) * 2) * C * (2 * F);   // IQ tap 0
+      const float* k1 = k0 + (size_t)C * 2 * F;                                // IQ tap 1
+      for (int c = 0; c < C; ++c) {
+        const float2 xv = __ldg(xp + c);
+        re = fmaf(xv.x, __ldg(k0 + (size_t)c * 2 * F + f), re);
+        re = fmaf(xv.y, __ldg(k1 + (size_t)c * 2 * F + f), re);
+        im = fmaf(xv.x, __ldg(k0 + (size_t)c * 2 * F + F + f), im);
+        im = fmaf(xv.y, __ldg(k1 + (size_t)c * 2 * F + F + f), im);
+      }
+    }
+  }
+  y[i] = make_float2(re, im);
+}
+
 }  // namespace dccn

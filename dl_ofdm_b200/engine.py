@@ -309,8 +309,9 @@ def bit_source_gpu(n, seed, device='cuda'):
     return out
 
 
-def cconv2d(x, kernel, bias, filters, kernal, padding='valid'):
-    """Op-level layers_conv2d_complex on CUDA tensors (dev/py/complex.py:140)."""
+def cconv2d(x, kernel, bias, filters, kernal, padding='valid', vector=False):
+    """Op-level layers_conv2d_complex (dev/py/complex.py:140) or, with ``vector``, layers_conv2d_vector (:199) on CUDA
+    tensors."""
     lib = _lib.load()
     assert x.is_cuda and x.dim() == 5 and x.shape[-1] == 2
     B, L, W, Cc, _ = x.shape
@@ -319,8 +320,9 @@ def cconv2d(x, kernel, bias, filters, kernal, padding='valid'):
     Lo, Wo = (L, W) if pad else (L - kl + 1, W - kw + 1)
     y = torch.empty((B, Lo, Wo, filters, 2), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.dccn_cconv2d(_ptr(x.contiguous()), B, L, W, Cc, _ptr(kernel.contiguous()),
-                                    _ptr(bias.contiguous()), filters, kl, kw, pad, _ptr(y), _stream()))
+        fn = lib.dccn_vconv2d if vector else lib.dccn_cconv2d
+        _lib.check(fn(_ptr(x.contiguous()), B, L, W, Cc, _ptr(kernel.contiguous()),
+                      _ptr(bias.contiguous()), filters, kl, kw, pad, _ptr(y), _stream()))
     return y
 
 

@@ -141,6 +141,13 @@ int dccn_cconv2d(const float* x_dev, int64_t B, int L, int W, int C,
                  const float* kernel_dev, const float* bias_dev, int filters, int kl, int kw,
                  int padding, float* y_dev, void* stream);
 
+/* -- layers_conv2d_vector(inputs, filters, kernal, strides=1, padding) (dev/py/complex.py:199-255), op-level: the
+ * layer of equalizer_separateIQ (--opt 7).  x_dev [B,L,W,C,2], kernel_dev [kl,kw,2,C,2*filters] (conv3d kernel of depth
+ * 2 across IQ), bias_dev [2*filters], y_dev [B,L',W',filters,2]; padding 0 = 'valid', 1 = 'same'. */
+int dccn_vconv2d(const float* x_dev, int64_t B, int L, int W, int C,
+                 const float* kernel_dev, const float* bias_dev, int filters, int kl, int kw,
+                 int padding, float* y_dev, void* stream);
+
 /* -- a6 + a7: rayleigh_chan_lte static branch (dev/py/radio.py:432-437,491-506)
  * followed by AWGN_channel_np (dev/py/radio.py:513-526).
  *   tx_dev      float32 [B, n_samp, 2]  complex IQ of the transmitted frames (n_samp = S*T)

@@ -665,3 +665,20 @@ def test_kc_knob(libdccn, kc, monkeypatch):
     assert float((o1['soft'] - out['soft']).abs()[torch.as_tensor(good).cuda()].max()) < 2e-4
     m.close()
     m1.close()
+
+
+@pytest.mark.parametrize('padding,shape,filters', [('valid', (1, 64), 64), ('same', (7, 64), 1), ('same', (3, 5), 1)])
+def test_conv2d_vector_op(libdccn, padding, shape, filters):
+    """Op-level layers_conv2d_vector (dev/py/complex.py:199-255) vs the oracle (pinned against a literal conv3d)."""
+    from dl_ofdm_b200.complex import layers_conv2d_vector
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((5, 7, 64, 1, 2)).astype(np.float32)
+    k = (rng.standard_normal((shape[0], shape[1], 2, 1, 2 * filters)) * 0.1).astype(np.float32)
+    b = rng.standard_normal(2 * filters).astype(np.float32)
+    ref = orc.conv2d_vector(x, k, b, padding)
+    y = layers_conv2d_vector(_cuda(x), filters, shape, padding=padding, kernel=_cuda(k), bias=_cuda(b)).cpu().numpy()
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+    yc = layers_conv2d_vector(torch.view_as_complex(_cuda(x)), filters, shape, padding=padding, kernel=_cuda(k), bias=_cuda(b))
+    assert yc.is_complex() and np.abs(torch.view_as_real(yc).cpu().numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())

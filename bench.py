@@ -207,7 +207,8 @@ def workload_config(args, frames_per_step):
                         'norm -> equalizer_ofdm -> ofdm_dense_rx -> BER' % SNR_DB,
             'frames_per_step_per_gpu': frames_per_step, 'nbits': NBITS, 'precision': args.precision,
             'chunk_frames': args.chunk, 'parallelism': 'grid cells sharded, 1 all-reduce of the confusion matrix',
-            'l2': 'inputs per step (%.0f MB) exceed the 126 MB L2' % (frames_per_step * 4480 / 1e6)}
+            'l2': ('inputs per step (%.0f MB) exceed the 126 MB L2' % (frames_per_step * 4480 / 1e6)
+                   if args.impl == 'b200' else 'n/a (CPU arm: a bounded %d-frame sample of the workload per step)' % frames_per_step)}
 
 
 def bench_train(args, dev, rank, B=4096, nbits=2):

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -334,6 +335,33 @@ DCCN_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
 //   [15] a_major=0 [16] b_major=0  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int n, int m = 128) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- fp16 hi/lo operands (DCCN_F16X3, staged: not yet run on a GPU) ---------------------------------------------
+// kind::f16 with fp16 inputs and fp32 accumulate: a_format = b_format = 0 (F16); K = 16 per instruction, i.e. the same
+// 32 bytes of K per k-step as kind::tf32 at twice the MACs.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// TS form with a 16-bit A operand: TMEM lane = row, each 32-bit column holds two consecutive K elements (even k in the
+// low half), so one K = 16 instruction reads 8 columns -- the column arithmetic of the tf32 form carries over unchanged.
+DCCN_DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// (v0, v1) -> packed fp16 pairs hi = fp16(v), lo = fp16(v - hi); v0 in the low half.  hi + lo carries 22 significand
+// bits like the tf32 pair as long as lo stays a normal fp16 (|v| >= 2^-3); below that the error is bounded by the
+// fp16 subnormal quantum, 2^-25 absolute.  |v| > 65504 overflows: the caller's scale must keep operands below that.
+DCCN_DEVINL void f16_split_pack(float v0, float v1, float& hi, float& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  hi = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+  lo = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
 }
 
 DCCN_DEVINL bool elect_one() {

@@ -8,6 +8,7 @@
 // Every complex layer is `layers_conv2d_complex` (dev/py/complex.py:140-196) and is packed
 // into ONE real GEMM on IQ-interleaved activations with the reference's own sign
 // convention ([[a, b], [-b, -a]] per complex weight, bias (ba-bb, bb-ba)).
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <type_traits>
@@ -64,6 +65,24 @@ int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCCN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%d", (int)r,
+             (long long)rows, (long long)cols, (long long)ld, box_rows);
+  return 0;
+}
+
+// fp16 matrix [rows, cols] with row pitch ld (elements); box = [box_rows x 64 cols] (128-byte rows), 128B swizzle
+static int make_tmap_f16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  DCCN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+  DCCN_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
+             "TMA operand must be 16-byte aligned (base %p, ld %lld)", base, (long long)ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCCN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16) failed (%d) rows=%lld cols=%lld ld=%lld box=%d", (int)r,
              (long long)rows, (long long)cols, (long long)ld, box_rows);
   return 0;
 }
@@ -263,6 +282,37 @@ int upload_layer(dccn_handle* h, GemmLayer* L, cudaStream_t s) {
   int rc = make_tmap(&L->tmB0, L->dWt0, N, K, K, box);
   if (rc) return rc;
   if (prec == DCCN_PREC_PARITY) rc = make_tmap(&L->tmB1, L->dWt1, N, K, K, box);
+  if (rc) return rc;
+  // DCCN_F16X3 (staged): fp16 hi / lo planes of W * 2^e for the kind::f16 form (128- and 32-wide A-in-TMEM tiles)
+  L->f16_ok = false;
+  if (h->f16x3 && prec == DCCN_PREC_PARITY && h->a_tmem && !L->mc && (L->BN == 128 || L->BN == 32) && K % 8 == 0) {
+    float wmax = 0.f;
+    for (float w : L->W) wmax = fmaxf(wmax, fabsf(w));
+    int e = 0;
+    if (wmax > 0.f && std::isfinite(wmax)) e = 13 - (int)floorf(log2f(wmax));
+    if (e > 60) e = 60;
+    if (e < -60) e = -60;
+    const float sc = ldexpf(1.f, e);
+    L->w_scale_inv = ldexpf(1.f, -e);
+    std::vector<__half> h0((size_t)K * N), h1((size_t)K * N);
+    for (int k = 0; k < K; ++k)
+      for (int n = 0; n < N; ++n) {
+        const float w = L->W[(size_t)k * N + n] * sc;
+        const __half hi = __float2half_rn(w);
+        h0[(size_t)n * K + k] = hi;
+        h1[(size_t)n * K + k] = __float2half_rn(w - __half2float(hi));
+      }
+    if (!L->dWh0) {
+      if ((rc = dev_alloc(h, &L->dWh0, (size_t)K * N * 2))) return rc;
+      if ((rc = dev_alloc(h, &L->dWh1, (size_t)K * N * 2))) return rc;
+    }
+    DCCN_CUDA_OK(cudaMemcpyAsync(L->dWh0, h0.data(), h0.size() * 2, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaMemcpyAsync(L->dWh1, h1.data(), h1.size() * 2, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaStreamSynchronize(s));
+    if ((rc = make_tmap_f16(&L->tmH0, L->dWh0, N, K, K, L->BN))) return rc;
+    if ((rc = make_tmap_f16(&L->tmH1, L->dWh1, N, K, K, L->BN))) return rc;
+    L->f16_ok = true;
+  }
   return rc;
 }
 
@@ -680,6 +730,24 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
   if (split) op.b1 = L.tmB1;
+  // DCCN_F16X3 (staged, inference only: the training step re-derives only the tf32 planes on the device)
+  if constexpr (std::is_same<Epi, EpiStore>::value || std::is_same<Epi, EpiPhaseEq>::value ||
+                std::is_same<Epi, EpiPhaseEqSym>::value) {
+    if (split && h->f16x3 && L.f16_ok && !h->tr && !h->train_fwd && ks.ksplit <= 1) {
+      op.b0 = L.tmH0;
+      op.b1 = L.tmH1;
+      if constexpr (std::is_same<Epi, EpiStore>::value) {
+        if (L.BN == 32)
+          return launch_gemm_tc<32, true, 1, true, false, Epi, true>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f,
+                                                                     L.w_scale_inv);
+      }
+      if (L.BN == 128)
+        return launch_gemm_tc<128, true, 2, true, false, Epi, true>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f,
+                                                                    L.w_scale_inv);
+      op.b0 = L.tmB0;
+      op.b1 = L.tmB1;
+    }
+  }
   // parity mode on 128-wide tiles: A staged in TMEM (TS-form MMA) + cta_group::2 CTA pairs (half a weight tile per SM)
 #define DCCN_TC_PAR(BNV, CGV)                                                                                \
   do {                                                                                                       \
@@ -1128,6 +1196,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_PAIR")) h->multicast = atoi(e);
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
+  if (const char* e = getenv("DCCN_F16X3")) h->f16x3 = atoi(e);
   if (const char* e = getenv("DCCN_BN192")) h->bn192 = atoi(e);
   if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {

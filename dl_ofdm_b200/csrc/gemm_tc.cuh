@@ -83,13 +83,24 @@ constexpr int imin(int a, int b) { return a < b ? a : b; }
 // it (long before the MMAs that use it retire), so A tiles are fetched far ahead and the splitters
 // already hold the next tile in registers when a TMEM staging slot frees up: the per-stage
 // dependency loop no longer contains "TMA latency of A + split", only "commit -> tcgen05.st".
-template <int BN, bool SPLIT, int CG, bool ATM = false, bool DEC = false>
+//
+// F16 (DEC only; `DCCN_F16X3=1`, STAGED -- written without a GPU at hand, not yet run or measured): the (hi, lo) pairs
+// are fp16 instead of tf32 (same 11-bit significands, tools/acc_split_emul.py) and the MMAs are kind::f16, which
+// contracts K = 16 per instruction at the instruction rate of kind::tf32's K = 8.  A k-block is then 64 K-elements: the
+// weight planes are [BN x 64 fp16] boxes (128-byte rows, same shared-memory descriptors and the same 32-byte advance
+// per k-step), the raw fp32 A tile arrives as TWO [128 x 32 fp32] boxes (two A-ring slots), and the splitters pack the
+// 64 values of a row into 32 + 32 TMEM columns (two fp16 per column) -- the same staging footprint as the tf32 form.
+// The instruction count per k-block is unchanged (12), the K it covers doubles.
+template <int BN, bool SPLIT, int CG, bool ATM = false, bool DEC = false, bool F16 = false>
 struct TcCfg {
   static_assert(!ATM || SPLIT, "A-in-TMEM is the parity (3xTF32) configuration");
   static_assert(!DEC || ATM, "the decoupled A ring feeds the TMEM staging");
+  static_assert(!F16 || DEC, "the fp16 hi/lo form is built on the decoupled A-in-TMEM pipeline");
   static constexpr int BM = 128;
   static constexpr int BK = 32;                       // 32 fp32 = one 128-byte swizzle row
-  static constexpr int UMMA_K = 8;                    // kind::tf32: 32 bytes of K per instruction
+  static constexpr int KB = F16 ? 64 : 32;            // K elements one k-block contracts
+  static constexpr int A_BOXES = F16 ? 2 : 1;         // [128 x 32 fp32] boxes of raw A per k-block
+  static constexpr int UMMA_K = 8;                    // 32 bytes of K per instruction: 8 tf32 / 8 TMEM columns of 2 fp16
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int PLANES = SPLIT ? 2 : 1;
@@ -134,7 +145,7 @@ struct TileK {
   int m_blk, n_blk, kslice, kb0, kb1;
 };
 
-template <int BN>
+template <int BN, int KBE = 32>
 DCCN_DEVINL TileK tile_decode(int tile, int m_tiles, int n_tiles, int num_kb, int ksplit, int band) {
   TileK t;
   if (ksplit <= 1) {
@@ -144,7 +155,7 @@ DCCN_DEVINL TileK tile_decode(int tile, int m_tiles, int n_tiles, int num_kb, in
     t.kb0 = 0;
     t.kb1 = num_kb;
     if (band >= 0) {
-      constexpr int KBN = BN / 32;
+      constexpr int KBN = BN / KBE;
       const int lo = t.n_blk * KBN - band, hi = (t.n_blk + 1) * KBN + band;
       t.kb0 = lo > 0 ? lo : 0;
       t.kb1 = hi < num_kb ? hi : num_kb;
@@ -167,13 +178,14 @@ struct TcOperands {
   CUtensorMap b0, b1;   // B hi / lo (b1 unused when !SPLIT)
 };
 
-template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
-__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR)>::THREADS, 1)
+template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi, bool F16 = false>
+__global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR), F16>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               int M, int N, int K, int kc, int ksplit, int band, const __grid_constant__ Epi epi) {
+               int M, int N, int K, int kc, int ksplit, int band, float a_scale, float out_scale,
+               const __grid_constant__ Epi epi) {
   constexpr bool DEC = ATM && !PAIR;
-  using C = TcCfg<BN, SPLIT, CG, ATM, DEC>;
+  using C = TcCfg<BN, SPLIT, CG, ATM, DEC, F16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem + C::STAGES * C::STAGE_BYTES;                       // DEC: SA raw fp32 A tiles
@@ -202,12 +214,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   constexpr int BROWS = PAIR ? BN / 2 : BN;            // weight rows this CTA holds
   constexpr int BH = BROWS * C::BK * 4;                // bytes of one weight plane in a stage
   constexpr int TX = (DEC ? 0 : C::A_BYTES) + C::PLANES * BH;   // bytes TMA lands in THIS CTA per (B) stage
-  const int num_kb = (K + C::BK - 1) / C::BK;
+  const int num_kb = (K + C::KB - 1) / C::KB;
   const int kb_per_chunk = (kc <= 0 || kc > num_kb) ? num_kb : kc;
   // (m_blk, n_blk, k-block range) of a tile index
   auto decode = [=](int tile) -> TileK {
     if constexpr (PAIR) return TileK{(tile / n_tiles) * 2 + crank, tile % n_tiles, 0, 0, num_kb};
-    else return tile_decode<BN>(tile, m_tiles, n_tiles, num_kb, ksplit, band);
+    else return tile_decode<BN, C::KB>(tile, m_tiles, n_tiles, num_kb, ksplit, F16 && band > 0 ? band / 2 : band);
   };
 
   if (warp == 0 && lane == 0) {
@@ -279,8 +291,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             if (!DEC) tma_load_2d(st, &tmA0, &full[stage], kb * C::BK, m_blk * C::BM);
             // PAIR: only my half of the weight tile (rows crank*BN/2 ...)
             const int brow = n_blk * BN + crank * BROWS;
-            tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::BK, brow);
-            if (SPLIT) tma_load_2d(st + C::B_OFF + BH, &tmB1, &full[stage], kb * C::BK, brow);
+            tma_load_2d(st + C::B_OFF, &tmB0, &full[stage], kb * C::KB, brow);
+            if (SPLIT) tma_load_2d(st + C::B_OFF + BH, &tmB1, &full[stage], kb * C::KB, brow);
           }
           __syncwarp();
           if (++stage == C::STAGES) {
@@ -293,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (crank == 0) {   // whole warp, warp-uniform control flow; one elected lane issues
-      constexpr uint32_t idesc = umma_idesc_tf32(BN, PAIR ? 256 : 128);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(BN, 128) : umma_idesc_tf32(BN, PAIR ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -343,10 +355,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 umma_tf32_ts_pair(d, ka, db_hi, idesc, 1u);                 // A_hi * B_hi
               } else if constexpr (ATM) {
                 const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
-                const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);      // 8 tf32 columns per k-step
-                umma_tf32_ts(d, ka + 32, db_hi, idesc, accum);              // A_lo * B_hi
-                umma_tf32_ts(d, ka, db_lo, idesc, 1u);                      // A_hi * B_lo
-                umma_tf32_ts(d, ka, db_hi, idesc, 1u);                      // A_hi * B_hi
+                const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);      // 8 columns per k-step (8 tf32 / 16 fp16)
+                if constexpr (F16) {
+                  umma_f16_ts(d, ka + 32, db_hi, idesc, accum);             // A_lo * B_hi
+                  umma_f16_ts(d, ka, db_lo, idesc, 1u);                     // A_hi * B_lo
+                  umma_f16_ts(d, ka, db_hi, idesc, 1u);                     // A_hi * B_hi
+                } else {
+                  umma_tf32_ts(d, ka + 32, db_hi, idesc, accum);            // A_lo * B_hi
+                  umma_tf32_ts(d, ka, db_lo, idesc, 1u);                    // A_hi * B_lo
+                  umma_tf32_ts(d, ka, db_hi, idesc, 1u);                    // A_hi * B_hi
+                }
               } else if (SPLIT) {
                 const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
                 const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
@@ -389,17 +407,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const TileK tk = decode(tile);
       const int m_blk = tk.m_blk;
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
-        wait_(&emptyA[sa], pa ^ 1);
-        if (DCCN_ABL(16)) {
-          if (elect_one()) mbar_arrive(&fullA[sa]);
-        } else if (elect_one()) {
-          mbar_expect_tx(&fullA[sa], C::A_BYTES);
-          tma_load_2d(a_ring + sa * C::A_BYTES, &tmA0, &fullA[sa], kb * C::BK, m_blk * C::BM);
-        }
-        __syncwarp();
-        if (++sa == C::SA) {
-          sa = 0;
-          pa ^= 1;
+#pragma unroll
+        for (int bx = 0; bx < C::A_BOXES; ++bx) {
+          wait_(&emptyA[sa], pa ^ 1);
+          if (DCCN_ABL(16)) {
+            if (elect_one()) mbar_arrive(&fullA[sa]);
+          } else if (elect_one()) {
+            mbar_expect_tx(&fullA[sa], C::A_BYTES);
+            tma_load_2d(a_ring + sa * C::A_BYTES, &tmA0, &fullA[sa], kb * C::KB + bx * C::BK, m_blk * C::BM);
+          }
+          __syncwarp();
+          if (++sa == C::SA) {
+            sa = 0;
+            pa ^= 1;
+          }
         }
       }
     }
@@ -413,9 +434,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
+        float hi[32], lo[32];
+        if constexpr (F16) {
+          // two raw boxes per k-block; box bx fills packed columns [16 bx, 16 bx + 16) of hi / lo
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx) {
+            wait_(&fullA[sa], pa);
+            const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
+              f16_split_pack(v.x * a_scale, v.y * a_scale, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
+              f16_split_pack(v.z * a_scale, v.w * a_scale, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) asm volatile("" : "+f"(hi[16 * bx + c]));   // loads done before the release (below)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyA[sa]);                // raw box consumed
+            if (++sa == C::SA) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        } else {
         wait_(&fullA[sa], pa);
         const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
-        float hi[32], lo[32];
         if (DCCN_ABL(1)) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) hi[c] = lo[c] = 0.f;
@@ -446,6 +489,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         for (int c = 0; c < 32; ++c) asm volatile("" : "+f"(hi[c]));
         __syncwarp();
         if (lane == 0) mbar_arrive(&emptyA[sa]);                  // raw tile consumed
+        if (++sa == C::SA) {
+          sa = 0;
+          pa ^= 1;
+        }
+        }
         wait_(&empty[stage], phase ^ 1);                      // TMEM staging slot is free again
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
@@ -462,10 +510,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
-        }
-        if (++sa == C::SA) {
-          sa = 0;
-          pa ^= 1;
         }
       }
     }
@@ -604,6 +648,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int j = 0; j < C::NCH; ++j) {
         if (warp == C::EPI_WARP0 && lane == 0 && j > 0) DCCN_TRACE_EV(1);
         const int col = n_blk * BN + cg * C::COLS_PER_GROUP + j * 32;
+        if constexpr (F16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[j][i] *= out_scale;
+        }
         if constexpr (Epi::kWarpStore)
           epi.run_warp(st, row_base, lane, col, r[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
         else
@@ -623,12 +671,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   }
 }
 
-template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi>
+template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi, bool F16 = false>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
-                          int num_sms, KSched ks = KSched()) {
-  using C = TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR)>;
+                          int num_sms, KSched ks = KSched(), float a_scale = 1.f, float out_scale = 1.f) {
+  using C = TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR), F16>;
   if (M <= 0) return 0;
-  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi, F16>;
   static bool attr_set = false;
   if (!attr_set) {
     DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -648,7 +696,7 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    const int num_kb = (K + C::BK - 1) / C::BK;
+    const int num_kb = (K + C::KB - 1) / C::KB;
     if (ks.ksplit > 1) {   // every slice must own at least one k-block
       const int per = (num_kb + ks.ksplit - 1) / ks.ksplit;
       ks.ksplit = (num_kb + per - 1) / per;
@@ -662,7 +710,8 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
   if (PAIR) ks = KSched();
-  DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, ks.ksplit, ks.band, epi));
+  DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, ks.ksplit, ks.band, a_scale,
+                                  out_scale, epi));
   return 0;
 }
 

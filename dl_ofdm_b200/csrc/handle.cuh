@@ -32,6 +32,13 @@ struct GemmLayer {
   float* dWt1 = nullptr;        // [N, K] tf32-lo (PARITY only)
   float* dBias = nullptr;
   CUtensorMap tmB0, tmB1;
+  // DCCN_F16X3 (staged): [N, K] fp16 hi / lo planes of W * w_scale (w_scale = a power of two that puts max|W| in
+  // [2^13, 2^14), so that the lo plane stays a normal fp16), their [BN x 64] tensor maps, and 1 / w_scale
+  void* dWh0 = nullptr;
+  void* dWh1 = nullptr;
+  CUtensorMap tmH0, tmH1;
+  float w_scale_inv = 1.f;
+  bool f16_ok = false;
   bool built = false;
   bool fused = false;           // consumed by a fused (phase-eq / demod-head) epilogue
   bool mc = false;              // run as cta_group::2 CTA pairs (each CTA holds half of the weight tile)
@@ -85,6 +92,7 @@ struct dccn_handle {
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   int bn192 = 0;       // 1: 192-wide tiles for 128 < N <= 192 (2-stage smem-split form); 0: two 128-wide A-in-TMEM tiles
   int band_skip = 1;   // skip the structurally-zero k-blocks of the Toeplitz ((S,K) 'same' conv) operand
+  int f16x3 = 0;       // DCCN_F16X3=1: inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (staged)
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
   dccn::GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer

@@ -151,3 +151,20 @@ def test_conv2d_vector_matches_literal_conv3d():
     m2 = np.transpose(y2[:, :, :, 0, 0], (0, 2, 1)).reshape(3, 7, 2, 64)       # [.., 1*2, filters], :243
     assert np.abs(ref2[:, :, 0, :, 0] - m2[:, :, 0, :]).max() < 1e-12
     assert np.abs(ref2[:, :, 0, :, 1] - m2[:, :, 1, :]).max() < 1e-12
+
+
+def test_fp16_split_operand_error_matches_tf32_split():
+    """The staged fp16 hi/lo GEMM form (DCCN_F16X3): with the weights pre-scaled by a power of two its
+    operand representation error on the shipped 16-QAM checkpoint equals the tf32 pair's (CPU emulation, exact products)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location('acc_split_emul', os.path.join(ROOT, 'tools', 'acc_split_emul.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.run(n_frames=200, verbose=False)
+    tf32, f16 = r['tf32x3'], r['fp16x3, weights x 2^k']
+    assert tf32[2] == 0 and f16[2] == 0                      # no hard-bit flips against the fp64 oracle
+    assert f16[0] < 1.5 * tf32[0] and f16[1] < 2.0 * tf32[1]
+    assert f16[1] < 1e-5                                      # the north-star tolerance on soft outputs
+    assert r['fp16x3 unscaled'][0] > 2.0 * f16[0]            # the weight scale is what keeps the lo plane normal

@@ -87,10 +87,10 @@ def head_from_out_iq(out_iq, w, nb):
     return e / e.sum(-1, keepdims=True)
 
 
-def main():
+def run(n_frames=700, verbose=True):
     nb = 4
     w = v1_weights(np.load(os.path.join(GOLDEN, 'v1_4mod_cpTrue.npz')))
-    x, _ = v1_frames(nb, 10, 700)
+    x, _ = v1_frames(nb, 10, n_frames)
     ref = orc.basic_receiver(x, w, nb, 16, head='v1', dtype=np.float64)
     hard_ref = ref[..., 1] > ref[..., 0]
 
@@ -104,17 +104,23 @@ def main():
         ('fp16x3 unscaled', split_fp16, lambda W: split_fp16),
         ('fp16x3, weights x 2^k', split_fp16, lambda W: (lambda v, s=wscale(W): split_fp16(v, s))),
     ]
-    print('# tools/acc_split_emul.py (CPU emulation): shipped v1 checkpoint OFDM_Dense3_4mod_snr12_cpTrue, 700 frames @ 10 dB')
-    print('# (1 030 400 bit decisions), |soft - soft_fp64oracle|; exact products, float64 accumulation (operand error only)')
+    out = {}
+    if verbose:
+        print('# tools/acc_split_emul.py (CPU emulation): shipped v1 checkpoint OFDM_Dense3_4mod_snr12_cpTrue, %d frames @ 10 dB' % n_frames)
+        print('# (%d bit decisions), |soft - soft_fp64oracle|; exact products, float64 accumulation (operand error only)' % hard_ref.size)
     for name, sa, sb in schemes:
         soft = head_from_out_iq(receiver(x, w, nb, sa, sb), w, nb)
         e = np.abs(soft - ref)
         flips = int(((soft[..., 1] > soft[..., 0]) != hard_ref).sum())
-        print('%-26s: p99.9 %.3g max %.3g flips %d' % (name, np.quantile(e, .999), e.max(), flips))
-    a = orc.batch_moment_norm(x, dtype=np.float32)[0]
-    print('# operand ranges: max|z| = %.3g, max|W fft_like| = %.3g, max|W dense| = %.3g (fp16 max 65504, min normal 6.1e-5)'
-          % (np.abs(a).max(), np.abs(w['fft_like/conv3d/kernel']).max(), np.abs(w['demodulation/dense/kernel']).max()))
+        out[name] = (float(np.quantile(e, .999)), float(e.max()), flips)
+        if verbose:
+            print('%-26s: p99.9 %.3g max %.3g flips %d' % ((name,) + out[name]))
+    if verbose:
+        a = orc.batch_moment_norm(x, dtype=np.float32)[0]
+        print('# operand ranges: max|z| = %.3g, max|W fft_like| = %.3g, max|W dense| = %.3g (fp16 max 65504, min normal 6.1e-5)'
+              % (np.abs(a).max(), np.abs(w['fft_like/conv3d/kernel']).max(), np.abs(w['demodulation/dense/kernel']).max()))
+    return out
 
 
 if __name__ == '__main__':
-    main()
+    run()

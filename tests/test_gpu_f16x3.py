@@ -1,0 +1,111 @@
+"""Parity tests of the STAGED fp16 hi/lo GEMM form (DCCN_F16X3=1).
+
+The form was written in a session without GPU time and has not run yet, so these tests are skipped unless
+DCCN_TEST_F16X3=1 is set; once `tools/f16x3_probe.py` is green on a B200 the gate goes away and the cases fold into
+test_gpu_parity.py's parametrisation.  Same oracle, same bounds as the default parity mode.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import v1_weights
+
+torch = pytest.importorskip('torch')
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('DCCN_TEST_F16X3') != '1',
+                                 reason='staged kernel form, not yet run on a GPU: set DCCN_TEST_F16X3=1')]
+
+
+def _helpers():
+    import test_gpu_parity as tp
+    return tp._cuda, tp._check_soft
+
+
+@pytest.mark.parametrize('fixture,nb,cp', [('v1_4mod_cpTrue.npz', 4, True), ('v1_1mod_cpFalse.npz', 1, False)])
+def test_f16x3_v1_checkpoint_receiver(libdccn, golden, monkeypatch, fixture, nb, cp):
+    monkeypatch.setenv('DCCN_F16X3', '1')
+    _cuda, _check_soft = _helpers()
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle.v1_recipe import v1_frames
+    w = v1_weights(golden(fixture))
+    snr = 10 if nb == 4 else 0
+    x, bits = v1_frames(nb, snr, 700)
+    soft_ref = orc.basic_receiver(x, w, nb, 16, use_cp=cp, head='v1', dtype=np.float64)
+    soft_ref32 = orc.basic_receiver(x, w, nb, 16, use_cp=cp, head='v1', dtype=np.float32)
+    _, conf_ref, _, ce_ref = orc.ber_head(soft_ref, bits)
+    m = DCCN(nbits=nb, nsymbol=8, n_data=368, use_cp=cp, head='v1', precision='parity', chunk_frames=256)
+    m.load_weights(w)
+    out = m.forward(_cuda(x), _cuda(bits))
+    torch.cuda.synchronize()
+    soft, hard = out['soft'].cpu().numpy(), out['hard'].cpu().numpy()
+    flips = _check_soft(soft, soft_ref, hard, soft_ref32)
+    conf = out['conf'].cpu().numpy()
+    assert conf.sum() == bits.size and np.abs(conf - conf_ref).sum() <= 2 * flips
+    assert abs(float(out['ce_sum'].cpu()[0]) / bits.size - ce_ref) < 1e-5
+    m.close()
+
+
+@pytest.mark.parametrize('cp', [True, False])
+@pytest.mark.parametrize('folded', [0, 1])
+def test_f16x3_equalizer_matches_default_parity_mode(libdccn, monkeypatch, cp, folded):
+    """eq + rx on seeded weights (all twelve GEMMs: N = 32, K = 32, K = 136 tails, the banded Toeplitz operand):
+    the fp16 form against the fp64 oracle with the default mode's bounds, and against the default mode itself."""
+    _cuda, _ = _helpers()
+    from dl_ofdm_b200 import _lib
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(78)
+    nb, B = 4, 300                                    # ragged: 300 frames = 2100 symbol rows, not multiples of 128
+    w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    soft_ref, eq_ref, chest_ref = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64)
+    flags = _lib.FWD_FOLDED if folded else 0
+    outs = {}
+    for f16 in ('0', '1'):
+        monkeypatch.setenv('DCCN_F16X3', f16)
+        m = DCCN(nbits=nb, use_cp=cp, equalizer=True, precision='parity', chunk_frames=128)
+        m.load_weights(w)
+        o = m.forward(_cuda(x), _cuda(bits), flags=flags)
+        torch.cuda.synchronize()
+        outs[f16] = (o['soft'].cpu().numpy(), o['hard'].cpu().numpy(), o['conf'].cpu().numpy())
+        m.close()
+    good = np.abs(chest_ref).reshape(B, -1).min(axis=1) > 2e-2      # phase equaliser divides by |chest| (no epsilon)
+    assert good.sum() > B // 4
+    for f16 in ('0', '1'):
+        soft, hard, conf = outs[f16]
+        assert np.isfinite(soft).all() and conf.sum() == bits.size
+        err = np.abs(soft[good] - soft_ref[good])
+        assert np.quantile(err, 0.999) < 2e-4, (f16, np.quantile(err, 0.999))
+        hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+        decided = (np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= 1e-3) & good[:, None, None]
+        assert np.array_equal(hard[decided], hard_ref[decided]), f16
+    d = np.abs(outs['1'][0][good] - outs['0'][0][good])
+    assert np.quantile(d, 0.999) < 2e-4
+
+
+def test_f16x3_chunk_invariance_full_size(libdccn, monkeypatch):
+    """65 536 frames in one pass == the same frames in 4 096-frame passes (the batch moments are taken over the whole
+    batch first, so the internal chunking must not change a single hard bit) -- the regression test that found the
+    A-slot release race of the tf32 form (test_gpu_parity.py::test_full_size_properties)."""
+    monkeypatch.setenv('DCCN_F16X3', '1')
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(5)
+    nb, B = 4, 65536
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    x = torch.randn((B, 7, 80, 2), device='cuda') * 0.2
+    bits = torch.randint(0, 2, (B, 320, nb), device='cuda', dtype=torch.uint8)
+    res = []
+    for chunk in (0, 4096):
+        m = DCCN(nbits=nb, equalizer=True, precision='parity', chunk_frames=chunk)
+        m.load_weights(w)
+        o = m.forward(x, bits, want_soft=False)
+        torch.cuda.synchronize()
+        res.append((o['hard'].clone(), o['conf'].cpu().numpy()))
+        m.close()
+    assert res[0][1].sum() == B * 320 * nb
+    assert torch.equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])

@@ -547,6 +547,28 @@ def main():
            'h2d_gbps': round(args.steps * (xh.numel() * 4 + bh.numel()) / float(te[0]) / 1e9, 1),
            'numa_local_cpus': numa, 'pipelined': 'H2D of step i+1 overlaps the pass over step i (2 slots)'}
 
+    # ---- staged (never run on a GPU yet, opt-in with BENCH_STAGED=1): the same end-to-end loop with the labels packed
+    # 8 per byte (dccn_forward_host_begin_packed): 4 640 instead of 5 760 B per frame over PCIe
+    e2e_packed = None
+    if os.environ.get('BENCH_STAGED'):
+        ph = torch.as_tensor(np.packbits(bh.numpy().reshape(-1), bitorder='little')).pin_memory()
+        m.forward_host_begin_packed(0, xh, ph)
+        conf_p, _ = m.forward_host_end(0)
+        barrier()
+        t0 = time.perf_counter()
+        m.forward_host_begin_packed(0, xh, ph)
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                m.forward_host_begin_packed((i + 1) & 1, xh, ph)
+            conf_p, _ = m.forward_host_end(i & 1)
+        barrier()
+        tp_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp_, op=dist.ReduceOp.MAX)
+        e2e_packed = {'value': world * B * args.steps / float(tp_[0]), 'unit': 'frames/s',
+                      'h2d_bytes_per_step': int(xh.numel() * 4 + ph.numel()),
+                      'conf_equal_to_unpacked': bool(np.array_equal(conf_p, conf_h))}
+
     conf = conf_total.cpu().numpy()
     ber = float(conf[0, 1] + conf[1, 0]) / float(conf.sum())
     train = train_rx = None
@@ -571,6 +593,7 @@ def main():
             'ber': ber, 'bits_counted': int(conf.sum()),
             'hbm_kernels': {'peak_gbs': pk['hbm'], 'kernels': hbm_kernels},
             'train_config4': train, 'train_receiver': train_rx, 'kc2_schedule': kc2, 'folded_schedule': folded,
+            'e2e_packed_labels': e2e_packed,
             'target': {'frames_per_s_8gpu': 1e8, 'note': 'north_star target; random-init weights so BER ~ 0.5'},
         }
         if world == 1 and not args.no_cpu_baseline:

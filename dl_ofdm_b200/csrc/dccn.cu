@@ -1371,6 +1371,52 @@ int dccn_forward_host_begin(dccn_handle* h, int slot, const float* x_host, int64
   return 0;
 }
 
+// Same as dccn_forward_host_begin with the labels packed 8 per byte (staged: written without a GPU at hand).
+int dccn_forward_host_begin_packed(dccn_handle* h, int slot, const float* x_host, int64_t B,
+                                   const uint8_t* bits_packed_host, void* stream) {
+  DCCN_CHECK(h && x_host && bits_packed_host && B > 0 && (slot == 0 || slot == 1), "bad argument");
+  dccn_handle::HostSlot& S = h->slot[slot];
+  DCCN_CHECK(!S.busy, "slot %d still in flight: call dccn_forward_host_end first", slot);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nb = (size_t)h->D * h->NB;
+  DCCN_CHECK(((size_t)B * nb) % 8 == 0, "packed labels need B * n_data * nbits to be a multiple of 8");
+  const size_t n_bytes = (size_t)B * nb / 8;
+  if (S.frames < B) {
+    int rc = dev_alloc(h, (void**)&S.d_x, (size_t)B * h->P * 4);
+    rc |= dev_alloc(h, (void**)&S.d_bits, (size_t)B * nb);
+    rc |= dev_alloc(h, (void**)&S.d_hard, (size_t)B * nb);
+    if (rc) return rc;
+    S.frames = B;
+  }
+  if (S.pack_frames < B) {
+    int rc = dev_alloc(h, (void**)&S.d_pack, n_bytes);
+    if (rc) return rc;
+    S.pack_frames = B;
+  }
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.d_x, x_host, (size_t)B * h->P * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.d_pack, bits_packed_host, n_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  DCCN_CUDA_OK(cudaEventRecord(S.copied, h->copy_stream));
+  DCCN_CUDA_OK(cudaStreamWaitEvent(s, S.copied, 0));
+  {
+    g_launches += 1;
+    long long blocks = ((long long)n_bytes + 255) / 256;
+    const long long cap = (long long)h->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    unpack_bits_kernel<<<(unsigned)blocks, 256, 0, s>>>(S.d_pack, (long long)n_bytes, S.d_bits);
+    DCCN_CUDA_OK(cudaGetLastError());
+  }
+  DCCN_CUDA_OK(cudaMemsetAsync(S.d_conf, 0, 4 * sizeof(int64_t), s));
+  DCCN_CUDA_OK(cudaMemsetAsync(S.d_ce, 0, sizeof(double), s));
+  int rc = dccn_forward(h, S.d_x, B, S.d_bits, nullptr, nullptr, nullptr, nullptr, S.d_conf, S.d_ce, 0, s);
+  if (rc) return rc;
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_conf, S.d_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_ce, S.d_ce, sizeof(double), cudaMemcpyDeviceToHost, s));
+  DCCN_CUDA_OK(cudaEventRecord(S.done, s));
+  S.busy = true;
+  S.B = B;
+  return 0;
+}
+
 int dccn_forward_host_end(dccn_handle* h, int slot, int64_t* conf_host, double* ce_sum_host) {
   DCCN_CHECK(h && (slot == 0 || slot == 1), "bad argument");
   dccn_handle::HostSlot& S = h->slot[slot];

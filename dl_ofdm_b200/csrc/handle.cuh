@@ -125,6 +125,8 @@ struct dccn_handle {
     float* d_x = nullptr;
     uint8_t* d_bits = nullptr;
     uint8_t* d_hard = nullptr;
+    uint8_t* d_pack = nullptr;     // labels packed 8 per byte (dccn_forward_host_begin_packed)
+    int64_t pack_frames = 0;
     int64_t frames = 0;            // capacity
     int64_t B = 0;                 // batch in flight
     int64_t* d_conf = nullptr;     // device results

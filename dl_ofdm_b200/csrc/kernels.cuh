@@ -433,6 +433,20 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ out
   epi.flush(st);
 }
 
+// labels packed 8 per byte (bit j of byte i = label 8 i + j, i.e. numpy.packbits(bitorder='little')) -> one uint8 per
+// label, the layout the head reads (dccn_forward_host_begin_packed: 160 instead of 1 280 label bytes per 16-QAM frame
+// over PCIe)
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint8_t* __restrict__ packed, long long n_bytes,
+                                                          uint8_t* __restrict__ bits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t b = packed[i];
+    uint2 o;
+    o.x = (b & 1u) | (((b >> 1) & 1u) << 8) | (((b >> 2) & 1u) << 16) | (((b >> 3) & 1u) << 24);
+    o.y = ((b >> 4) & 1u) | (((b >> 5) & 1u) << 8) | (((b >> 6) & 1u) << 16) | (((b >> 7) & 1u) << 24);
+    *reinterpret_cast<uint2*>(bits + 8 * i) = o;
+  }
+}
+
 // a5: confusion matrix of hard decisions vs bits (rows = truth)
 __global__ void __launch_bounds__(256) ber_accum_kernel(const uint8_t* __restrict__ hard,
                                                         const uint8_t* __restrict__ bits, long long n,

@@ -133,6 +133,14 @@ int dccn_forward_host_begin(dccn_handle* h, int slot, const float* x_host, int64
                             const uint8_t* bits_host, uint8_t* hard_host, void* stream);
 int dccn_forward_host_end(dccn_handle* h, int slot, int64_t* conf_host, double* ce_sum_host);
 
+/* `begin` with the labels packed 8 per byte: bits_packed_host holds B * n_data * nbits / 8 bytes, bit j of byte i
+ * = label 8 i + j of the flattened [B, n_data, nbits] array (numpy.packbits(bitorder='little')); the device unpacks
+ * them.  The reference feeds `bits_in` as int32 [B, D, nbits] (dev/py/ofdmreceiver_np.py:123) -- 5 120 B per 16-QAM
+ * frame; this form moves 160 B, so the host-buffer call is bound by the fp32 IQ alone (4 480 B per frame).
+ * STAGED: written without a GPU at hand, not yet run (tests/test_gpu_staged.py, DCCN_TEST_STAGED=1). */
+int dccn_forward_host_begin_packed(dccn_handle* h, int slot, const float* x_host, int64_t B,
+                                   const uint8_t* bits_packed_host, void* stream);
+
 /* -- a1: layers_conv2d_complex(inputs, filters, kernal, strides=1, padding)
  * (dev/py/complex.py:140-196), op-level.  x_dev [B,L,W,C,2], kernel_dev
  * [kl,kw,1,C,2*filters], bias_dev [2*filters], y_dev [B,L',W',filters,2];

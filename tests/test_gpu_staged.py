@@ -1,8 +1,9 @@
-"""Parity tests of the STAGED fp16 hi/lo GEMM form (DCCN_F16X3=1).
+"""Parity tests of STAGED code: the fp16 hi/lo GEMM form (DCCN_F16X3=1) and the packed-label host entry
+point (dccn_forward_host_begin_packed).
 
-The form was written in a session without GPU time and has not run yet, so these tests are skipped unless
-DCCN_TEST_F16X3=1 is set; once `tools/f16x3_probe.py` is green on a B200 the gate goes away and the cases fold into
-test_gpu_parity.py's parametrisation.  Same oracle, same bounds as the default parity mode.
+Both were written in a session without GPU time and have not run yet, so these tests are skipped unless
+DCCN_TEST_STAGED=1 is set; once `tools/f16x3_probe.py` and these cases are green on a B200 the gate goes away and the
+cases fold into test_gpu_parity.py.  Same oracle, same bounds as the default parity mode.
 """
 import os
 
@@ -13,8 +14,8 @@ from conftest import v1_weights
 
 torch = pytest.importorskip('torch')
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('DCCN_TEST_F16X3') != '1',
-                                 reason='staged kernel form, not yet run on a GPU: set DCCN_TEST_F16X3=1')]
+              pytest.mark.skipif(os.environ.get('DCCN_TEST_STAGED') != '1',
+                                 reason='staged code, not yet run on a GPU: set DCCN_TEST_STAGED=1')]
 
 
 def _helpers():
@@ -109,3 +110,26 @@ def test_f16x3_chunk_invariance_full_size(libdccn, monkeypatch):
     assert res[0][1].sum() == B * 320 * nb
     assert torch.equal(res[0][0], res[1][0])
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_packed_labels_host_entry(libdccn):
+    """dccn_forward_host_begin_packed (labels 8 per byte) == dccn_forward_host_begin (one uint8 per label): same
+    confusion matrix and loss, through both slots; ragged batch."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(9)
+    nb, B = 4, 333
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    x = torch.as_tensor((rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)).pin_memory()
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    packed = torch.as_tensor(np.packbits(bits.reshape(-1), bitorder='little')).pin_memory()
+    bh = torch.as_tensor(bits).pin_memory()
+    m = DCCN(nbits=nb, equalizer=True, precision='parity')
+    m.load_weights(w)
+    conf_ref, ce_ref, _ = m.forward_host(x, bh)
+    assert conf_ref.sum() == bits.size
+    for slot in (0, 1, 0):
+        m.forward_host_begin_packed(slot, x, packed)
+        conf, ce = m.forward_host_end(slot)
+        assert np.array_equal(conf, conf_ref) and ce == ce_ref
+    m.close()

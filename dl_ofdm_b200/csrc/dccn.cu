@@ -1197,6 +1197,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
   if (const char* e = getenv("DCCN_F16X3")) h->f16x3 = atoi(e);
+  if (const char* e = getenv("DCCN_TX_V2")) h->tx_v2 = atoi(e);
   if (const char* e = getenv("DCCN_BN192")) h->bn192 = atoi(e);
   if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;
   if (h->P % 4 != 0 || (2 * h->T) % 4 != 0) {
@@ -1561,6 +1562,22 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
   DCCN_CHECK(n_data == h->D, "n_data (%d) != cfg.n_data (%d)", n_data, h->D);
   cudaStream_t s = (cudaStream_t)stream;
   const int S = h->S, K = h->K;
+  // DCCN_TX_V2 (staged): the role map is cached on the index arrays' device pointers (the host keeps them alive per
+  // ofdm_tx object), so a call is one asynchronous launch -- no D2H, cudaMalloc or stream synchronisation
+  const bool v2 = h->tx_v2 && K == 64 && h->cfg.cp_len > 0 && h->cfg.cp_len < 64;
+  if (v2 && h->d_txmap && h->txmap_key[0] == data_sc_dev && h->txmap_key[1] == pilot_sc_dev &&
+      h->txmap_n[0] == n_data && h->txmap_n[1] == n_pilot) {
+    const long long syms2 = (long long)B * S;
+    long long blocks = (syms2 + 7) / 8;
+    const long long cap = (long long)h->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    g_launches += 1;
+    tx64_kernel<<<(unsigned)blocks, 256, 0, s>>>(bits_dev, (long long)B, S, h->cfg.cp_len, h->NB, h->D, h->d_txmap,
+                                                 (const float2*)constellation_dev, make_float2(pilot_re, pilot_im),
+                                                 (float2*)tx_dev);
+    DCCN_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   // subcarrier role map built on the fly (tiny): -1 guard, -2 pilot, >=0 data index
   std::vector<int32_t> hd(n_data), hp(n_pilot > 0 ? n_pilot : 1);
   DCCN_CUDA_OK(cudaMemcpyAsync(hd.data(), data_sc_dev, (size_t)n_data * 4, cudaMemcpyDeviceToHost, s));
@@ -1575,6 +1592,20 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
   for (int i = 0; i < n_pilot; ++i) {
     DCCN_CHECK(hp[i] >= 0 && hp[i] < S * K, "pilot subcarrier index out of range");
     map[hp[i]] = -2;
+  }
+  if (v2) {   // first call with these index arrays: keep the map, then take the cached path above
+    if (!h->d_txmap) {
+      int rc = dev_alloc(h, (void**)&h->d_txmap, map.size() * 4);
+      if (rc) return rc;
+    }
+    DCCN_CUDA_OK(cudaMemcpyAsync(h->d_txmap, map.data(), map.size() * 4, cudaMemcpyHostToDevice, s));
+    DCCN_CUDA_OK(cudaStreamSynchronize(s));
+    h->txmap_key[0] = data_sc_dev;
+    h->txmap_key[1] = pilot_sc_dev;
+    h->txmap_n[0] = n_data;
+    h->txmap_n[1] = n_pilot;
+    return dccn_tx_frames(h, bits_dev, B, data_sc_dev, n_data, pilot_sc_dev, n_pilot, constellation_dev, pilot_re,
+                          pilot_im, tx_dev, stream);
   }
   int32_t* d_map = nullptr;
   DCCN_CUDA_OK(cudaMalloc((void**)&d_map, map.size() * 4));

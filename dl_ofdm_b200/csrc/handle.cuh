@@ -92,6 +92,10 @@ struct dccn_handle {
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   int bn192 = 0;       // 1: 192-wide tiles for 128 < N <= 192 (2-stage smem-split form); 0: two 128-wide A-in-TMEM tiles
   int band_skip = 1;   // skip the structurally-zero k-blocks of the Toeplitz ((S,K) 'same' conv) operand
+  int tx_v2 = 0;       // DCCN_TX_V2=1: 8 x 8 IDFT transmitter kernel + cached subcarrier map (staged)
+  int32_t* d_txmap = nullptr;           // tx_v2: subcarrier role map of the last (data_sc, pilot_sc) pointers seen
+  const void* txmap_key[2] = {nullptr, nullptr};
+  int txmap_n[2] = {0, 0};
   int f16x3 = 0;       // DCCN_F16X3=1: inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (staged)
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense

@@ -401,6 +401,93 @@ __global__ void __launch_bounds__(256) tx_kernel(const uint8_t* __restrict__ bit
   }
 }
 
+// STAGED (DCCN_TX_V2=1; written without a GPU at hand, never run): the same transmitter for K = 64 with the IDFT as
+// 8 x 8 (n = 8 n1 + n2, k = k1 + 8 k2):  Y[k1][n2] = sum_k2 X[k1 + 8 k2] W8^(n2 k2),  Z = Y * W64^(n2 k1),
+// x[8 n1 + n2] = sum_k1 Z[k1][n2] W8^(n1 k1) / 64  -- 1 024 + 64 complex fp64 MACs per symbol instead of 4 096, the
+// eight W8 powers a lane needs held in registers (lane & 7 selects n2 in the first pass and n1 in the second, so one
+// set serves both), warps loop over symbols (twiddles computed once per thread), output staged in shared memory and
+// written with the cyclic prefix as 80 consecutive float2.
+__global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ bits, long long B, int S, int CP, int nbits,
+                                                   int D, const int* __restrict__ sc_map,
+                                                   const float2* __restrict__ constellation, float2 pilot,
+                                                   float2* __restrict__ tx) {
+  constexpr int K = 64;
+  __shared__ double2 sm_g[8][K];      // per warp: frequency grid, later the time-domain symbol
+  __shared__ double2 sm_z[8][K];      // per warp: Z[k1 * 8 + n2]
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = lane & 7, b = lane >> 3;              // b in 0..3; the lane's second output uses b + 4
+  double2 w8[8];                                      // W8^(a j), j = 0..7
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double sn, cs;
+    sincospi(0.25 * (double)((a * j) & 7), &sn, &cs);
+    w8[j] = make_double2(cs, sn);
+  }
+  double2 w64[2];                                     // W64^(n2 k1) for (n2 = a, k1 = b) and (n2 = a, k1 = b + 4)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    double sn, cs;
+    sincospi((double)((a * (b + 4 * h)) & 63) / 32.0, &sn, &cs);
+    w64[h] = make_double2(cs, sn);
+  }
+  double2* g = sm_g[wib];
+  double2* z = sm_z[wib];
+  const int T = K + CP;
+  const long long total = B * S;
+  for (long long sym = (long long)blockIdx.x * 8 + wib; sym < total; sym += (long long)gridDim.x * 8) {
+    const long long frame = sym / S;
+    const int s = (int)(sym - frame * S);
+#pragma unroll
+    for (int k = lane; k < K; k += 32) {
+      const int m = sc_map[s * K + k];
+      float2 v = make_float2(0.f, 0.f);
+      if (m == -2) v = pilot;
+      else if (m >= 0) {
+        int idx = 0;
+        const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
+        for (int q = 0; q < nbits; ++q) idx = (idx << 1) | bp[q];
+        v = constellation[idx];
+      }
+      g[k] = make_double2(v.x, v.y);
+    }
+    __syncwarp();
+    // pass 1 (+ twiddle): outputs (k1 = b + 4 h, n2 = a)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k1 = b + 4 * h;
+      double yr = 0.0, yi = 0.0;
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const double2 x = g[k1 + 8 * k2];
+        yr += x.x * w8[k2].x - x.y * w8[k2].y;
+        yi += x.x * w8[k2].y + x.y * w8[k2].x;
+      }
+      z[k1 * 8 + a] = make_double2(yr * w64[h].x - yi * w64[h].y, yr * w64[h].y + yi * w64[h].x);
+    }
+    __syncwarp();
+    // pass 2: outputs n = 8 n1 + n2 with n1 = a, n2 = b + 4 h (g is free: every lane finished pass 1)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n2 = b + 4 * h;
+      double xr = 0.0, xi = 0.0;
+#pragma unroll
+      for (int k1 = 0; k1 < 8; ++k1) {
+        const double2 v = z[k1 * 8 + n2];
+        xr += v.x * w8[k1].x - v.y * w8[k1].y;
+        xi += v.x * w8[k1].y + v.y * w8[k1].x;
+      }
+      g[8 * a + n2] = make_double2(xr * (1.0 / K), xi * (1.0 / K));
+    }
+    __syncwarp();
+    float2* o = tx + (size_t)sym * T;
+    for (int t = lane; t < T; t += 32) {
+      const double2 v = g[(t + K - CP) & (K - 1)];     // cyclic prefix = the last CP samples, then the symbol
+      o[t] = make_float2((float)v.x, (float)v.y);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint64_t seed) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x);   // 16 bytes per thread
   if (i * 16 >= n) return;

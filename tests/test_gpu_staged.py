@@ -133,3 +133,29 @@ def test_packed_labels_host_entry(libdccn):
         conf, ce = m.forward_host_end(slot)
         assert np.array_equal(conf, conf_ref) and ce == ce_ref
     m.close()
+
+
+@pytest.mark.parametrize('tag,nb,pilot,nsym', [('lte_4b', 4, 'lte', 7), ('lte_1b', 1, 'lte', 7),
+                                              ('scattered_4b', 4, 'scattered', 8)])
+def test_tx_v2_golden(libdccn, golden, monkeypatch, tag, nb, pilot, nsym):
+    """DCCN_TX_V2 (8 x 8 IDFT, cached subcarrier map) against the reference transmitter's own output, first call (map
+    built) and second call (cached path), and against the default kernel."""
+    _cuda, _ = _helpers()
+    from dl_ofdm_b200.engine import DCCN
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import ofdm_tx, const_map
+    g = golden('ofdm_tx_%s.npz' % tag)
+    fl = Flags(nbits=nb, pilot=pilot, nsymbol=nsym)
+    o = ofdm_tx(fl)
+    bits = _cuda(g['bits'])
+    res = {}
+    for v2 in ('0', '1'):
+        monkeypatch.setenv('DCCN_TX_V2', v2)
+        m = DCCN(nbits=nb, nsymbol=nsym, n_data=o.frame_size, precision='exact')
+        a = m.transmit(bits, o, const_map(nb)).cpu().numpy()
+        b = m.transmit(bits, o, const_map(nb)).cpu().numpy()
+        assert np.array_equal(a, b)
+        assert np.abs(a - g['real']).max() < 5e-7
+        res[v2] = a
+        m.close()
+    assert np.abs(res['0'] - res['1']).max() < 1.2e-7          # both round an fp64 result: at most one fp32 ulp apart

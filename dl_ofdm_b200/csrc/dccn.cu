@@ -179,6 +179,13 @@ int ensure_workspace(dccn_handle* h, int64_t frames) {
     }
   }
   if (rc) return rc;
+  {   // one max-|activation| word per inter-layer buffer (zeroed at the start of every pass, run_chunk)
+    int i = 0;
+    for (Act* a : {&h->a0, &h->t1, &h->f, &h->p32, &h->u1, &h->u2, &h->eq, &h->corr, &h->cat, &h->oeq, &h->r1o,
+                   &h->out_iq, &h->eqc, &h->u3})
+      a->amax = h->d_amax + (i++);
+    static_assert(14 <= kAmaxSlots, "amax slots");
+  }
   h->ws_frames = C;
   return 0;
 }
@@ -739,11 +746,11 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
       if constexpr (std::is_same<Epi, EpiStore>::value) {
         if (L.BN == 32)
           return launch_gemm_tc<32, true, 1, true, false, Epi, true>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f,
-                                                                     L.w_scale_inv);
+                                                                     L.w_scale_inv, A.amax);
       }
       if (L.BN == 128)
         return launch_gemm_tc<128, true, 2, true, false, Epi, true>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f,
-                                                                    L.w_scale_inv);
+                                                                    L.w_scale_inv, A.amax);
       op.b0 = L.tmB0;
       op.b1 = L.tmB1;
     }
@@ -843,6 +850,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
   const int S = h->S, K = h->K, T = h->T, Tin = h->Tin, P = h->P;
   const int cp_off = (T - Tin) * 2;            // receiver / equalizer skip the CP when !use_cp
   int rc;
+  DCCN_CUDA_OK(cudaMemsetAsync(h->d_amax, 0, kAmaxSlots * sizeof(unsigned), s));
   // ---- a2 (+ layer norm) ---------------------------------------------------------
   {
     const int warps_per_block = 8;
@@ -850,7 +858,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     DCCN_CHECK(P <= 10 * 128, "frame of %d floats exceeds the prep kernel's register tile", P);
     LaunchScope ls(h, SLOT_PREP, s);
     prep_kernel<10><<<grid, 256, 0, s>>>(x, (long long)Bc, P, h->d_mean, h->d_rstd,
-                                         (flags & DCCN_FWD_NO_NORM) ? 0 : 1, use_eq ? 1 : 0, out_of(h->a0));
+                                         (flags & DCCN_FWD_NO_NORM) ? 0 : 1, use_eq ? 1 : 0, out_of(h->a0), h->a0.amax);
     DCCN_CUDA_OK(cudaGetLastError());
   }
   const Act* rx_in = &h->a0;
@@ -875,6 +883,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       e.ld_f = h->f.ld;
       e.eq = ActOut{h->eqc.p0, nullptr, S * 3 * K, 0};      // row = frame; per symbol [eq | corr]
       e.corr = ActOut{h->eqc.p0, nullptr, S * 3 * K, 2 * K};
+      e.amax_eq = e.amax_corr = h->eqc.amax;
       e.sym_cols = 2 * K;
       e.sym_stride = 3 * K;
       e.chest_out = chest_out;
@@ -913,6 +922,7 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       e.f1 = h->f.p1;
       e.ld_f = h->f.ld;
       e.eq = out_of(h->eq);
+      e.amax_eq = h->eq.amax;
       e.corr = ActOut{nullptr, nullptr, 0, 0};          // no correlation branch in these graphs
       e.chest_out = chest_out;
       e.act = act;
@@ -971,6 +981,8 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       e.ld_f = h->f.ld;
       e.eq = out_of(h->eq);
       e.corr = out_of(h->corr);
+      e.amax_eq = h->eq.amax;
+      e.amax_corr = h->corr.amax;
       e.chest_out = chest_out;
       e.M = (int)Bc;
       e.N = h->g7.N;
@@ -1196,7 +1208,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_PAIR")) h->multicast = atoi(e);
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
-  if (const char* e = getenv("DCCN_F16X3")) h->f16x3 = atoi(e);
+  if (const char* e = getenv("DCCN_F16X3")) h->f16x3 = atoi(e);   // 0: tf32 hi/lo pairs (the round-1 form)
   if (const char* e = getenv("DCCN_TX_V2")) h->tx_v2 = atoi(e);
   if (const char* e = getenv("DCCN_BN192")) h->bn192 = atoi(e);
   if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;
@@ -1217,6 +1229,8 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   rc |= dev_alloc(h, (void**)&h->d_power, sizeof(double));
   rc |= dev_alloc(h, (void**)&h->d_conf, 4 * sizeof(unsigned long long));
   rc |= dev_alloc(h, (void**)&h->d_ce, sizeof(double));
+  rc |= dev_alloc(h, (void**)&h->d_amax, kAmaxSlots * sizeof(unsigned));
+  rc |= dev_alloc(h, (void**)&h->d_txmap, (size_t)h->S * h->K * sizeof(int32_t));
   for (int i = 0; i < 2 && !rc; ++i) {
     rc |= dev_alloc(h, (void**)&h->slot[i].d_conf, 4 * sizeof(int64_t));
     rc |= dev_alloc(h, (void**)&h->slot[i].d_ce, sizeof(double));
@@ -1562,62 +1576,27 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
   DCCN_CHECK(n_data == h->D, "n_data (%d) != cfg.n_data (%d)", n_data, h->D);
   cudaStream_t s = (cudaStream_t)stream;
   const int S = h->S, K = h->K;
-  // DCCN_TX_V2 (staged): the role map is cached on the index arrays' device pointers (the host keeps them alive per
-  // ofdm_tx object), so a call is one asynchronous launch -- no D2H, cudaMalloc or stream synchronisation
-  const bool v2 = h->tx_v2 && K == 64 && h->cfg.cp_len > 0 && h->cfg.cp_len < 64;
-  if (v2 && h->d_txmap && h->txmap_key[0] == data_sc_dev && h->txmap_key[1] == pilot_sc_dev &&
-      h->txmap_n[0] == n_data && h->txmap_n[1] == n_pilot) {
-    const long long syms2 = (long long)B * S;
-    long long blocks = (syms2 + 7) / 8;
+  DCCN_CHECK(n_pilot >= 0 && (n_pilot == 0 || pilot_sc_dev), "pilot_sc_dev missing");
+  // subcarrier role map (-1 guard, -2 pilot, >= 0 data index), rebuilt on the device from the caller's index arrays by
+  // one tiny kernel: the call stays fully asynchronous (no D2H, no allocation, no stream synchronisation) and nothing
+  // is cached across calls, so the index arrays may change between calls
+  g_launches += 2;
+  txmap_kernel<<<1, 512, 0, s>>>(data_sc_dev, n_data, pilot_sc_dev, n_pilot, S * K, h->d_txmap);
+  const long long syms = (long long)B * S;
+  if (h->tx_v2 && K == 64 && h->cfg.cp_len > 0 && h->cfg.cp_len < 64) {
+    long long blocks = (syms + 7) / 8;
     const long long cap = (long long)h->num_sms * 8;
     if (blocks > cap) blocks = cap;
-    g_launches += 1;
     tx64_kernel<<<(unsigned)blocks, 256, 0, s>>>(bits_dev, (long long)B, S, h->cfg.cp_len, h->NB, h->D, h->d_txmap,
                                                  (const float2*)constellation_dev, make_float2(pilot_re, pilot_im),
                                                  (float2*)tx_dev);
-    DCCN_CUDA_OK(cudaGetLastError());
-    return 0;
+  } else {
+    const size_t smem = (size_t)9 * K * sizeof(double2);
+    tx_kernel<<<(unsigned)((syms + 7) / 8), 256, smem, s>>>(bits_dev, (long long)B, S, K, h->cfg.cp_len, h->NB, h->D,
+                                                            h->d_txmap, (const float2*)constellation_dev,
+                                                            make_float2(pilot_re, pilot_im), (float2*)tx_dev);
   }
-  // subcarrier role map built on the fly (tiny): -1 guard, -2 pilot, >=0 data index
-  std::vector<int32_t> hd(n_data), hp(n_pilot > 0 ? n_pilot : 1);
-  DCCN_CUDA_OK(cudaMemcpyAsync(hd.data(), data_sc_dev, (size_t)n_data * 4, cudaMemcpyDeviceToHost, s));
-  if (n_pilot > 0)
-    DCCN_CUDA_OK(cudaMemcpyAsync(hp.data(), pilot_sc_dev, (size_t)n_pilot * 4, cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaStreamSynchronize(s));
-  std::vector<int32_t> map((size_t)S * K, -1);
-  for (int i = 0; i < n_data; ++i) {
-    DCCN_CHECK(hd[i] >= 0 && hd[i] < S * K, "data subcarrier index out of range");
-    map[hd[i]] = i;
-  }
-  for (int i = 0; i < n_pilot; ++i) {
-    DCCN_CHECK(hp[i] >= 0 && hp[i] < S * K, "pilot subcarrier index out of range");
-    map[hp[i]] = -2;
-  }
-  if (v2) {   // first call with these index arrays: keep the map, then take the cached path above
-    if (!h->d_txmap) {
-      int rc = dev_alloc(h, (void**)&h->d_txmap, map.size() * 4);
-      if (rc) return rc;
-    }
-    DCCN_CUDA_OK(cudaMemcpyAsync(h->d_txmap, map.data(), map.size() * 4, cudaMemcpyHostToDevice, s));
-    DCCN_CUDA_OK(cudaStreamSynchronize(s));
-    h->txmap_key[0] = data_sc_dev;
-    h->txmap_key[1] = pilot_sc_dev;
-    h->txmap_n[0] = n_data;
-    h->txmap_n[1] = n_pilot;
-    return dccn_tx_frames(h, bits_dev, B, data_sc_dev, n_data, pilot_sc_dev, n_pilot, constellation_dev, pilot_re,
-                          pilot_im, tx_dev, stream);
-  }
-  int32_t* d_map = nullptr;
-  DCCN_CUDA_OK(cudaMalloc((void**)&d_map, map.size() * 4));
-  DCCN_CUDA_OK(cudaMemcpyAsync(d_map, map.data(), map.size() * 4, cudaMemcpyHostToDevice, s));
-  const long long syms = (long long)B * S;
-  const size_t smem = (size_t)9 * K * sizeof(double2);
-  tx_kernel<<<(unsigned)((syms + 7) / 8), 256, smem, s>>>(bits_dev, (long long)B, S, K, h->cfg.cp_len, h->NB, h->D,
-                                                          d_map, (const float2*)constellation_dev,
-                                                          make_float2(pilot_re, pilot_im), (float2*)tx_dev);
   DCCN_CUDA_OK(cudaGetLastError());
-  DCCN_CUDA_OK(cudaStreamSynchronize(s));
-  cudaFree(d_map);
   return 0;
 }
 

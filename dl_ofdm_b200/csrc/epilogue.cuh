@@ -102,6 +102,19 @@ DCCN_DEVINL void store_block_tma(const CUtensorMap* tm0, int col0_0, const CUten
   }
 }
 
+// max |y| of a produced activation, kept per buffer as the bit pattern of a non-negative float (unsigned order = float
+// order).  The fp16 hi/lo GEMM that consumes the buffer derives its power-of-two operand scale from it (gemm_tc.cuh,
+// `amax_in`), so that no trained weight set can push an operand past fp16's 65 504.  One redux + one RED per 32x32 block.
+template <int NV>
+DCCN_DEVINL void amax_update_warp(unsigned* amax, const float (&y)[NV], bool row_ok) {
+  unsigned m = 0u;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) m = max(m, __float_as_uint(y[i]) & 0x7FFFFFFFu);
+  if (!row_ok) m = 0u;
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(amax, m);
+}
+
 // -------------------------------------------------------------------------------------
 // y = act(acc + bias)  ->  activation planes      (tf.layers.dense / packed complex layers)
 // -------------------------------------------------------------------------------------
@@ -112,6 +125,7 @@ struct EpiStore {
   int aux_ld;
   int act;             // 0 = linear, 1 = tanh
   int M, N;
+  unsigned* amax = nullptr;   // optional: running max |y| of the destination buffer (see amax_update_warp)
   CUtensorMap tm_out;  // tensor-core path: [M, N] view of out.p0 + out.col_off, box 32 x 32 (set by run_gemm)
   CUtensorMap tm_aux;  // same for aux
   struct State {};
@@ -156,6 +170,10 @@ struct EpiStore {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
     }
+    if (amax) {
+      // columns >= N of a ragged tile hold bias-padding zeros + accumulated zeros (TMA zero-fills the weight rows)
+      amax_update_warp<32>(amax, v, row0 + lane < M);
+    }
     store_block_tma(&tm_out, col0, aux ? &tm_aux : nullptr, col0, row0, lane, v, patch);
   }
   DCCN_DEVINL void flush(State&) const { tma_store_wait_read(); }   // shared memory outlives the last bulk store
@@ -183,6 +201,8 @@ struct EpiPhaseEqT {
   // both interleave per symbol in one [M*S, 3K] operand.  !SYM: plain [M, N] / [M, N/2] matrices.
   int sym_cols = 0, sym_stride = 0;
   int act = 0;          // 1: chest = tanh(acc + bias) (ablation graphs whose chest is a tanh dense, model.py:775-779)
+  unsigned* amax_eq = nullptr;     // optional running max |eq| / max corr of the destination buffers (amax_update_warp)
+  unsigned* amax_corr = nullptr;
   CUtensorMap tm_eq;    // tensor-core path: view of eq.p0 + eq.col_off, box 32 x 32 (set by run_gemm)
   CUtensorMap tm_chest; // same for chest_out
   struct State {};
@@ -228,6 +248,8 @@ struct EpiPhaseEqT {
       v[i] = cr;
       v[i + 1] = ci;
     }
+    if (amax_eq) amax_update_warp<32>(amax_eq, e, ok);
+    if (amax_corr && corr.p0) amax_update_warp<16>(amax_corr, c, ok);
     store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch);
     if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch);
     if (ok && corr.p0) store_act<16>(corr, row, corr_col(col0 / 2), c);

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR), F16>
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                int M, int N, int K, int kc, int ksplit, int band, float a_scale, float out_scale,
-               const __grid_constant__ Epi epi) {
+               const unsigned* __restrict__ amax_in, const __grid_constant__ Epi epi) {
   constexpr bool DEC = ATM && !PAIR;
   using C = TcCfg<BN, SPLIT, CG, ATM, DEC, F16>;
   extern __shared__ uint8_t smem_raw[];
@@ -202,6 +202,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DCCN_TRACE_DECL;
   DCCN_ABL_DECL;
+  if constexpr (F16) {
+    // Operand scale of the activations: a power of two that puts max |A| (recorded by the producing kernel, see
+    // amax_update_warp) into [2^13, 2^14) -- far from fp16's 65 504, and as far from its subnormals as the range allows.
+    // Exact (power of two), undone together with the weight scale by `out_scale` in the tile epilogue.
+    if (amax_in) {
+      const unsigned bits = __ldg(amax_in);
+      const int e = (int)(bits >> 23) - 127;                       // amax in [2^e, 2^(e+1))
+      if (bits != 0u && e > -100 && e < 100) {                     // 0, denormal-ish, inf / NaN: leave the operands alone
+        a_scale = __uint_as_float((uint32_t)(13 - e + 127) << 23);
+        out_scale *= __uint_as_float((uint32_t)(e - 13 + 127) << 23);
+      }
+    }
+  }
   const int n_tiles = (N + BN - 1) / BN;
   static_assert(!PAIR || ATM, "the CTA-pair form is built on the A-in-TMEM configuration");
   // PAIR: "tile" below is a pair tile (two consecutive M-tiles x one N-tile); CTA rank r of the
@@ -673,7 +686,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
 template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi, bool F16 = false>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
-                          int num_sms, KSched ks = KSched(), float a_scale = 1.f, float out_scale = 1.f) {
+                          int num_sms, KSched ks = KSched(), float a_scale = 1.f, float out_scale = 1.f,
+                          const unsigned* amax_in = nullptr) {
   using C = TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR), F16>;
   if (M <= 0) return 0;
   auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi, F16>;
@@ -711,7 +725,7 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
   cfg.stream = s;
   if (PAIR) ks = KSched();
   DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, ks.ksplit, ks.band, a_scale,
-                                  out_scale, epi));
+                                  out_scale, amax_in, epi));
   return 0;
 }
 

@@ -20,6 +20,8 @@ struct Act {          // activation matrix, 1 or 2 planes
   float* p0 = nullptr;
   float* p1 = nullptr;
   int ld = 0;
+  unsigned* amax = nullptr;   // device word: max |v| written by the producer(s) of this buffer in the current pass
+                              // (bit pattern of a float >= 0); feeds the operand scale of the fp16 hi/lo GEMM form
 };
 
 struct GemmLayer {
@@ -92,11 +94,10 @@ struct dccn_handle {
   int fused_head = 0;  // 1: demod head inside the GEMM epilogue; 0: separate full-occupancy kernel
   int bn192 = 0;       // 1: 192-wide tiles for 128 < N <= 192 (2-stage smem-split form); 0: two 128-wide A-in-TMEM tiles
   int band_skip = 1;   // skip the structurally-zero k-blocks of the Toeplitz ((S,K) 'same' conv) operand
-  int tx_v2 = 0;       // DCCN_TX_V2=1: 8 x 8 IDFT transmitter kernel + cached subcarrier map (staged)
-  int32_t* d_txmap = nullptr;           // tx_v2: subcarrier role map of the last (data_sc, pilot_sc) pointers seen
-  const void* txmap_key[2] = {nullptr, nullptr};
-  int txmap_n[2] = {0, 0};
-  int f16x3 = 0;       // DCCN_F16X3=1: inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (staged)
+  int tx_v2 = 1;       // 8 x 8 IDFT transmitter kernel for nfft = 64 (DCCN_TX_V2=0: the generic K-point DFT kernel)
+  int32_t* d_txmap = nullptr;           // [S*K] subcarrier role map, rebuilt on the device by every dccn_tx_frames call
+  int f16x3 = 1;       // inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (DCCN_F16X3=0: tf32 pairs)
+  unsigned* d_amax = nullptr;           // [kAmaxSlots] per-buffer max |activation| of the current pass (Act::amax)
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense
   dccn::GemmLayer g1, g2, g3, g4, g5, g6, g7, g8, g9, g10;   // equalizer
@@ -190,9 +191,12 @@ int train_fetch_weight(dccn_handle* h, const char* tf_name, HostTensor* t);
 
 inline ActOut out_of(const Act& a, int col_off = 0) { return ActOut{a.p0, a.p1, a.ld, col_off}; }
 
+constexpr int kAmaxSlots = 32;
+
 inline EpiStore store_epi(const GemmLayer& L, const Act& dst, int col_off, int64_t M, int act = 0, float* aux = nullptr,
                           int aux_ld = 0) {
   EpiStore e;
+  e.amax = dst.amax;
   e.bias = L.dBias;
   e.out = out_of(dst, col_off);
   e.aux = aux;

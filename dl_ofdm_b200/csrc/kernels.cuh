@@ -54,7 +54,7 @@ __global__ void moments_final_kernel(const double* __restrict__ sums, long long 
 template <int MAXV>   // MAXV float4 per lane: P <= MAXV*128
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ x, long long B, int P,
                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                   int do_norm, int do_ln, ActOut out) {
+                                                   int do_norm, int do_ln, ActOut out, unsigned* __restrict__ amax) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
@@ -106,13 +106,20 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ x, 
       z[i].w = __fadd_rn(__fmul_rn(z[i].w, inv), sh);
     }
   }
+  unsigned mx = 0u;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
       float y[4] = {z[i].x, z[i].y, z[i].z, z[i].w};
       store_act<4>(out, warp, idx * 4, y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx = max(mx, __float_as_uint(y[j]) & 0x7FFFFFFFu);
     }
+  }
+  if (amax) {   // max |y| of the pass: operand scale of the fp16 hi/lo GEMM that reads this buffer (amax_update_warp)
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0 && mx) atomicMax(amax, mx);
   }
 }
 
@@ -401,7 +408,23 @@ __global__ void __launch_bounds__(256) tx_kernel(const uint8_t* __restrict__ bit
   }
 }
 
-// STAGED (DCCN_TX_V2=1; written without a GPU at hand, never run): the same transmitter for K = 64 with the IDFT as
+// subcarrier role map of a frame: -1 guard / unused, -2 pilot, >= 0 index of the data symbol carried (one block)
+__global__ void txmap_kernel(const int* __restrict__ data_sc, int n_data, const int* __restrict__ pilot_sc, int n_pilot,
+                             int n, int* __restrict__ map) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) map[i] = -1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_data; i += blockDim.x) {
+    const int k = data_sc[i];
+    if (k >= 0 && k < n) map[k] = i;        // out-of-range indices are ignored (the host validates ofdmobj.dataSc)
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_pilot; i += blockDim.x) {
+    const int k = pilot_sc[i];
+    if (k >= 0 && k < n) map[k] = -2;
+  }
+}
+
+// The same transmitter for K = 64 (the default since round 2; DCCN_TX_V2=0 selects tx_kernel) with the IDFT as
 // 8 x 8 (n = 8 n1 + n2, k = k1 + 8 k2):  Y[k1][n2] = sum_k2 X[k1 + 8 k2] W8^(n2 k2),  Z = Y * W64^(n2 k1),
 // x[8 n1 + n2] = sum_k1 Z[k1][n2] W8^(n1 k1) / 64  -- 1 024 + 64 complex fp64 MACs per symbol instead of 4 096, the
 // eight W8 powers a lane needs held in registers (lane & 7 selects n2 in the first pass and n1 in the second, so one

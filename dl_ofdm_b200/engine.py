@@ -290,6 +290,10 @@ class DCCN:
         dev = bits.device
         key = ('tx', id(ofdmobj))
         if key not in self._scratch:
+            for sc in (ofdmobj.dataSc, ofdmobj.pilotSc):        # the device-side map builder ignores bad indices
+                sc = np.asarray(sc)
+                if sc.size and (sc.min() < 0 or sc.max() >= self.S * self.K):
+                    raise DccnError('subcarrier index out of range [0, %d)' % (self.S * self.K))
             self._scratch[key] = (torch.as_tensor(np.asarray(ofdmobj.dataSc, dtype=np.int32), device=dev),
                                   torch.as_tensor(np.asarray(ofdmobj.pilotSc, dtype=np.int32), device=dev),
                                   torch.as_tensor(np.stack([constellation.real, constellation.imag], -1)

@@ -92,10 +92,12 @@ def detect_eq_opt(weights):
 
 
 def equalizer_variables(rng, nfft=64, cp_len=16, nsymbol=7, pilot_size=16, use_cp=True,
-                        chest_bias=(1.0, 0.0), opt=0):
-    """Variables of scope 'Equalizer'.  ``chest_bias`` seeds conv3d_1's bias so that an UNTRAINED
-    channel estimate starts near 1+0j instead of 0 (the phase-only equaliser divides by |chest|
-    without an epsilon, dev/py/model.py:430-433); pass (0, 0) for TF's literal zero init."""
+                        chest_bias=(0.0, 0.0), opt=0):
+    """Variables of scope 'Equalizer' with TF's initialisers (glorot-uniform kernels, zero biases).
+    ``chest_bias`` is an explicit opt-in that is NOT in the reference: (1, 0) seeds conv3d_1's bias (the last chain
+    bias in the graphs without that layer) so that an UNTRAINED channel estimate starts near 1+0j instead of 0 -- the
+    phase-only equaliser divides by |chest| without an epsilon (dev/py/model.py:430-433).  The default (0, 0) is the
+    reference's trajectory."""
     K, S = nfft, nsymbol
     Tin = K + cp_len if use_cp else K
     e = 'Equalizer/'

@@ -71,7 +71,7 @@ class _DataGen:
 
 
 def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=None, frame_cnt=None, test_frames=1024,
-                    save=True, seed=None, log=print):
+                    save=True, seed=None, log=print, chest_bias=(0.0, 0.0)):
     """Transfer learning of equalizer_ofdm in front of the frozen receiver ``rx_weights`` (TF names -> arrays).
     Returns (session, history) where history is a list of per-epoch dicts (train_loss, test_loss, test_ber)."""
     opt = 0 if FLAGS.opt in (9, 10) else FLAGS.opt                   # 9 / 10 build equalizer_ofdm (_mp.py:309-312)
@@ -81,7 +81,8 @@ def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=N
     rng = np.random.default_rng(seed)
     weights = dict(rx_weights)
     weights.update(eq_weights if eq_weights is not None else
-                   equalizer_variables(rng, ofdmobj.K, ofdmobj.CP, ofdmobj.nSymbol, ofdmobj.pilot_size, FLAGS.cp, opt=opt))
+                   equalizer_variables(rng, ofdmobj.K, ofdmobj.CP, ofdmobj.nSymbol, ofdmobj.pilot_size, FLAGS.cp, opt=opt,
+                                       chest_bias=chest_bias))
     trainable = ['Equalizer/' + n + sfx for _, n in eq_layer_roles(opt) for sfx in ('/kernel', '/bias')]
     batch = FLAGS.batch_size // ofdmobj.nSymbol                       # _mp.py:358
     frame_cnt = FLAGS.msg_length // FLAGS.nsymbol if frame_cnt is None else frame_cnt

@@ -49,8 +49,10 @@ _FD = {'etu': 300.0, 'epa': 5.0, 'eva': 70.0, 'custom': 80.0}      # Doppler spr
 
 
 def doppler_hz(chan, mobile):
-    """Maximum Doppler shift of a profile: 0 when static; the single-tap channel uses 5 Hz (radio.py:363-366)."""
-    if not mobile:
+    """Maximum Doppler shift of a profile: 0 when static; the single-tap channel uses 5 Hz (radio.py:363-366).
+    'awgn' has no path to fade: the reference passes those frames through untouched whatever Fd is
+    (radio.py:443-446, 470-474), so its Doppler is 0."""
+    if not mobile or chan.lower() == 'awgn':
         return 0.0
     return _FD.get(chan.lower(), 5.0)
 

@@ -1,9 +1,7 @@
-"""Parity tests of STAGED code: the fp16 hi/lo GEMM form (DCCN_F16X3=1) and the packed-label host entry
-point (dccn_forward_host_begin_packed).
-
-Both were written in a session without GPU time and have not run yet, so these tests are skipped unless
-DCCN_TEST_STAGED=1 is set; once `tools/f16x3_probe.py` and these cases are green on a B200 the gate goes away and the
-cases fold into test_gpu_parity.py.  Same oracle, same bounds as the default parity mode.
+"""GPU tests of the alternative forms of the same kernels: the fp16 hi/lo GEMM form (default since round 2) against
+the tf32 hi/lo form of round 1 (DCCN_F16X3=0, still used by the training step) and against the oracle; the dynamic
+operand scale that keeps the fp16 form inside fp16's range; the packed-label host entry point; the 8x8-IDFT transmitter
+against the generic DFT kernel.  Same oracle, same bounds as tests/test_gpu_parity.py.
 """
 import os
 
@@ -13,9 +11,7 @@ import pytest
 from conftest import v1_weights
 
 torch = pytest.importorskip('torch')
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('DCCN_TEST_STAGED') != '1',
-                                 reason='staged code, not yet run on a GPU: set DCCN_TEST_STAGED=1')]
+pytestmark = pytest.mark.gpu
 
 
 def _helpers():
@@ -24,8 +20,9 @@ def _helpers():
 
 
 @pytest.mark.parametrize('fixture,nb,cp', [('v1_4mod_cpTrue.npz', 4, True), ('v1_1mod_cpFalse.npz', 1, False)])
-def test_f16x3_v1_checkpoint_receiver(libdccn, golden, monkeypatch, fixture, nb, cp):
-    monkeypatch.setenv('DCCN_F16X3', '1')
+@pytest.mark.parametrize('f16', ['0', '1'])
+def test_gemm_forms_v1_checkpoint_receiver(libdccn, golden, monkeypatch, fixture, nb, cp, f16):
+    monkeypatch.setenv('DCCN_F16X3', f16)
     _cuda, _check_soft = _helpers()
     from dl_ofdm_b200.engine import DCCN
     from oracle import dccn_oracle as orc
@@ -50,7 +47,7 @@ def test_f16x3_v1_checkpoint_receiver(libdccn, golden, monkeypatch, fixture, nb,
 
 @pytest.mark.parametrize('cp', [True, False])
 @pytest.mark.parametrize('folded', [0, 1])
-def test_f16x3_equalizer_matches_default_parity_mode(libdccn, monkeypatch, cp, folded):
+def test_gemm_forms_equalizer_agree(libdccn, monkeypatch, cp, folded):
     """eq + rx on seeded weights (all twelve GEMMs: N = 32, K = 32, K = 136 tails, the banded Toeplitz operand):
     the fp16 form against the fp64 oracle with the default mode's bounds, and against the default mode itself."""
     _cuda, _ = _helpers()
@@ -87,11 +84,35 @@ def test_f16x3_equalizer_matches_default_parity_mode(libdccn, monkeypatch, cp, f
     assert np.quantile(d, 0.999) < 2e-4
 
 
-def test_f16x3_chunk_invariance_full_size(libdccn, monkeypatch):
+def test_f16_form_survives_fp16_range(libdccn, monkeypatch):
+    """Activations far outside fp16's range (|x| up to ~1e6, and ~1e-6) with the first layer's weights scaled the other
+    way: mathematically the same network, so the outputs must equal the nominal ones -- the per-pass operand scale
+    (max |activation| recorded by the producing kernel) keeps the fp16 hi/lo operands finite and normal."""
+    from dl_ofdm_b200 import _lib
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(11)
+    nb, B = 2, 200
+    w = orc.glorot_weights(rng, nb, equalizer=False, bias_scale=0.05)
+    z = (rng.standard_normal((B, 7, 80, 2)) * 0.7).astype(np.float32)
+    soft_ref = orc.ofdm_dense_rx(z.astype(np.float64), w, nb, 16)
+    for scale in (1.0, 2.0 ** 20, 2.0 ** -20):
+        ws = dict(w)
+        ws['fft_like/conv3d/kernel'] = (w['fft_like/conv3d/kernel'] / scale).astype(np.float32)   # power of two: exact
+        m = DCCN(nbits=nb, equalizer=False, precision='parity')
+        m.load_weights(ws)
+        o = m.forward(torch.as_tensor(z * np.float32(scale)).cuda(), flags=_lib.FWD_NO_NORM)
+        soft = o['soft'].cpu().numpy()
+        assert np.isfinite(soft).all(), scale
+        err = np.abs(soft - soft_ref)
+        assert np.quantile(err, 0.999) <= 1e-5 and err.max() <= 5e-5, (scale, np.quantile(err, 0.999), err.max())
+        m.close()
+
+
+def test_f16_form_chunk_invariance_full_size(libdccn, monkeypatch):
     """65 536 frames in one pass == the same frames in 4 096-frame passes (the batch moments are taken over the whole
     batch first, so the internal chunking must not change a single hard bit) -- the regression test that found the
     A-slot release race of the tf32 form (test_gpu_parity.py::test_full_size_properties)."""
-    monkeypatch.setenv('DCCN_F16X3', '1')
     from dl_ofdm_b200.engine import DCCN
     from oracle import dccn_oracle as orc
     rng = np.random.default_rng(5)
@@ -138,8 +159,8 @@ def test_packed_labels_host_entry(libdccn):
 @pytest.mark.parametrize('tag,nb,pilot,nsym', [('lte_4b', 4, 'lte', 7), ('lte_1b', 1, 'lte', 7),
                                               ('scattered_4b', 4, 'scattered', 8)])
 def test_tx_v2_golden(libdccn, golden, monkeypatch, tag, nb, pilot, nsym):
-    """DCCN_TX_V2 (8 x 8 IDFT, cached subcarrier map) against the reference transmitter's own output, first call (map
-    built) and second call (cached path), and against the default kernel."""
+    """The 8 x 8 IDFT transmitter kernel (default for nfft = 64) and the generic K-point DFT kernel (DCCN_TX_V2=0) against
+    the reference transmitter's own output, twice (the subcarrier map is rebuilt per call), and against each other."""
     _cuda, _ = _helpers()
     from dl_ofdm_b200.engine import DCCN
     from dl_ofdm_b200.flags import Flags

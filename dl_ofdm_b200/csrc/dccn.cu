@@ -743,13 +743,16 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
     if (split && h->f16x3 && L.f16_ok && !h->tr && !h->train_fwd && ks.ksplit <= 1) {
       op.b0 = L.tmH0;
       op.b1 = L.tmH1;
+      // short-K layers (the per-symbol maps, K <= 256 = 4 k-blocks): the dependent MMA chain the K-chunked accumulation
+      // exists for is short anyway, and with the whole K in one accumulator the epilogue warps leave the k-block loop
+      const int kc = (L.K <= h->kc_whole_k) ? 0 : h->kc;
       if constexpr (std::is_same<Epi, EpiStore>::value) {
         if (L.BN == 32)
-          return launch_gemm_tc<32, true, 1, true, false, Epi, true>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f,
+          return launch_gemm_tc<32, true, 1, true, false, Epi, true>(op, (int)M, L.N, L.K, kc, epi, s, h->num_sms, ks, 1.f,
                                                                      L.w_scale_inv, A.amax);
       }
       if (L.BN == 128)
-        return launch_gemm_tc<128, true, 2, true, false, Epi, true>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f,
+        return launch_gemm_tc<128, true, 2, true, false, Epi, true>(op, (int)M, L.N, L.K, kc, epi, s, h->num_sms, ks, 1.f,
                                                                     L.w_scale_inv, A.amax);
       op.b0 = L.tmB0;
       op.b1 = L.tmB1;
@@ -1201,6 +1204,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   }
   h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 65536;   // per-launch overheads (~10 us x 15 kernels) amortise over the pass
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
+  if (const char* e = getenv("DCCN_KC_WHOLE_K")) h->kc_whole_k = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
   if (const char* e = getenv("DCCN_A_TMEM")) h->a_tmem = atoi(e);
@@ -1507,9 +1511,8 @@ int dccn_chan_fir_awgn(dccn_handle* h, const float* tx_dev, int64_t B, int n_sam
                                                            h->d_power);
   }
   LaunchScope ls2(h, SLOT_AWGN, s);
-  const long long total = (long long)B * n_samp;
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+  long long blocks = (B + 7) / 8;                    // one warp per frame, grid-stride
+  if (blocks > (long long)h->num_sms * 8) blocks = (long long)h->num_sms * 8;
   awgn_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2*)faded, (long long)B, n_samp, h->d_power, snr_db_dev,
                                                normals_dev, seed ^ 0x9E3779B97F4A7C15ull, (float2*)rx_dev);
   DCCN_CUDA_OK(cudaGetLastError());
@@ -1549,9 +1552,8 @@ int dccn_chan_awgn(dccn_handle* h, const float* faded_dev, int64_t B, int n_samp
   DCCN_CHECK(h && faded_dev && rx_dev && snr_db_dev && B > 0 && n_samp > 0, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(h, SLOT_AWGN, s);
-  const long long total = (long long)B * n_samp;
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+  long long blocks = (B + 7) / 8;                    // one warp per frame, grid-stride
+  if (blocks > (long long)h->num_sms * 8) blocks = (long long)h->num_sms * 8;
   awgn_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2*)faded_dev, (long long)B, n_samp, h->d_power, snr_db_dev,
                                                normals_dev, seed ^ 0x9E3779B97F4A7C15ull, (float2*)rx_dev);
   DCCN_CUDA_OK(cudaGetLastError());
@@ -1596,6 +1598,35 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int
                                                             h->d_txmap, (const float2*)constellation_dev,
                                                             make_float2(pilot_re, pilot_im), (float2*)tx_dev);
   }
+  DCCN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+/* bits -> OFDM frames -> static Rayleigh FIR in one kernel (nfft = 64): the transmitted frame stays in shared memory */
+int dccn_tx_fade(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int32_t* data_sc_dev, int n_data,
+                 const int32_t* pilot_sc_dev, int n_pilot, const float* constellation_dev, float pilot_re, float pilot_im,
+                 const double* alpha_dev, const double* coeff_dev, int n_taps, int n_fir, const double* z_dev,
+                 uint64_t seed, int reset_power, float* tx_dev, float* faded_dev, void* stream) {
+  DCCN_CHECK(h && bits_dev && data_sc_dev && constellation_dev && faded_dev && B > 0, "bad argument");
+  DCCN_CHECK(n_data == h->D, "n_data (%d) != cfg.n_data (%d)", n_data, h->D);
+  DCCN_CHECK(n_pilot >= 0 && (n_pilot == 0 || pilot_sc_dev), "pilot_sc_dev missing");
+  DCCN_CHECK(h->K == 64 && h->cfg.cp_len > 0 && h->cfg.cp_len <= 16 && h->S <= 8,
+             "dccn_tx_fade is the nfft = 64 feeder (cp <= 16, <= 8 symbols); use dccn_tx_frames + dccn_chan_fading");
+  DCCN_CHECK(n_taps >= 0 && n_taps <= 32 && n_fir >= 1 && n_fir <= kMaxFir, "at most 32 paths / FIR taps");
+  DCCN_CHECK(n_taps == 0 || coeff_dev != nullptr, "coeff_dev missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (reset_power) DCCN_CUDA_OK(cudaMemsetAsync(h->d_power, 0, sizeof(double), s));
+  g_launches += 1;
+  txmap_kernel<<<1, 512, 0, s>>>(data_sc_dev, n_data, pilot_sc_dev, n_pilot, h->S * h->K, h->d_txmap);
+  LaunchScope ls(h, SLOT_CHAN_FIR, s);
+  long long blocks = (B + kGenWarps - 1) / kGenWarps;
+  const long long cap = (long long)h->num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  tx_fade_kernel<<<(unsigned)blocks, 32 * kGenWarps, 0, s>>>(bits_dev, (long long)B, h->S, h->cfg.cp_len, h->NB, h->D,
+                                                           h->d_txmap, (const float2*)constellation_dev,
+                                                           make_float2(pilot_re, pilot_im), alpha_dev, coeff_dev, n_taps,
+                                                           n_fir, z_dev, seed, (float2*)tx_dev, (float2*)faded_dev,
+                                                           h->d_power);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1672,6 +1703,36 @@ int dccn_debug_mma_rate(int bn, int n_mma, int per_commit, int mode, int dep, in
   DCCN_CUDA_OK(cudaGetLastError());
   DCCN_CUDA_OK(cudaDeviceSynchronize());
   return 0;
+}
+
+uint32_t dccn_crc32c(const void* data_host, size_t n, uint32_t crc) {
+  // slicing-by-8 over tables built on first use (reflected polynomial 0x82F63B78)
+  static uint32_t tbl[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tbl[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tbl[t][i] = (tbl[t - 1][i] >> 8) ^ tbl[0][tbl[t - 1][i] & 0xFFu];
+    ready = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data_host);
+  crc = ~crc;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= crc;
+    crc = tbl[7][lo & 0xFFu] ^ tbl[6][(lo >> 8) & 0xFFu] ^ tbl[5][(lo >> 16) & 0xFFu] ^ tbl[4][lo >> 24] ^
+          tbl[3][hi & 0xFFu] ^ tbl[2][(hi >> 8) & 0xFFu] ^ tbl[1][(hi >> 16) & 0xFFu] ^ tbl[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) crc = tbl[0][(crc ^ *p++) & 0xFFu] ^ (crc >> 8);
+  return ~crc;
 }
 
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream) {

@@ -132,6 +132,13 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ x, 
 // =====================================================================================
 constexpr int kMaxFir = 32;
 
+// acc += g * x (complex128) with a FIXED contraction, shared by every FIR kernel so that the fused feeder
+// (tx_fade_kernel) and the stand-alone chan_fir_kernel round identically
+DCCN_DEVINL void fir_cmac(double& ar, double& ai, const double2 g, const double xr, const double xi) {
+  ar = fma(-g.y, xi, fma(g.x, xr, ar));
+  ai = fma(g.y, xr, fma(g.x, xi, ai));
+}
+
 __global__ void __launch_bounds__(256) chan_fir_kernel(const float2* __restrict__ tx, long long B, int n_samp,
                                                        const double* __restrict__ alpha,
                                                        const double* __restrict__ coeff, int n_taps, int n_fir,
@@ -170,8 +177,8 @@ __global__ void __launch_bounds__(256) chan_fir_kernel(const float2* __restrict_
       const double ai = __shfl_sync(0xffffffffu, a.y, t);
       if (lane < n_fir) {
         const double al = alpha ? alpha[t * n_fir + lane] : 1.0;
-        g.x += ar * al;
-        g.y += ai * al;
+        g.x = fma(ar, al, g.x);
+        g.y = fma(ai, al, g.y);
       }
     }
     if (lane < n_fir) gsm[wib][lane] = g;
@@ -196,9 +203,7 @@ __global__ void __launch_bounds__(256) chan_fir_kernel(const float2* __restrict_
       const int sl = (lane + dlt) & 31;
       const double xr = __shfl_sync(0xffffffffu, supply.x, sl);
       const double xi = __shfl_sync(0xffffffffu, supply.y, sl);
-      const double2 g = gsm[wib][j];
-      accr += g.x * xr - g.y * xi;
-      acci += g.x * xi + g.y * xr;
+      fir_cmac(accr, acci, gsm[wib][j], xr, xi);
     }
     if (base + lane < n_samp) {
       const float2 o = make_float2((float)accr, (float)acci);
@@ -288,8 +293,8 @@ __global__ void __launch_bounds__(256) chan_doppler_kernel(const float2* __restr
       const double ar = const1 * sr * c, ai = const1 * si * c;       // zck * ch_coeff
       if (lane < n_fir) {
         const double al = alpha ? alpha[t * n_fir + lane] : 1.0;
-        g.x += ar * al;
-        g.y += ai * al;
+        g.x = fma(ar, al, g.x);
+        g.y = fma(ai, al, g.y);
       }
     }
     __syncwarp();
@@ -325,33 +330,61 @@ __global__ void __launch_bounds__(256) chan_doppler_kernel(const float2* __restr
 // =====================================================================================
 // a7: AWGN_channel_np -- x / sqrt(mean power of the whole batch) + N(0,1)*sqrt(.5)*10^(-SNR/20)
 // float64 arithmetic like the reference, output rounded to fp32 (the TF feed dtype).
-// One thread per complex sample.
+// One warp per frame (grid-stride over frames): the per-frame noise deviation -- a float64 pow -- and the batch scale are
+// evaluated once per frame instead of once per sample, and the flat index needs no 64-bit divide; a thread handles two
+// adjacent complex samples (one 16-byte load / store) with ONE Philox-4x32 call (4 uniforms -> 2 Box-Muller pairs).
+// Round 1 did pow() + a 64-bit divide + a half-used Philox call per sample: 17 % of the HBM roofline.
 // =====================================================================================
 __global__ void __launch_bounds__(256) awgn_kernel(const float2* __restrict__ xin, long long B, int n_samp,
                                                    const double* __restrict__ power_sum,
                                                    const float* __restrict__ snr_db,
                                                    const double* __restrict__ normals, uint64_t seed,
                                                    float2* __restrict__ out) {
-  const long long total = B * n_samp;
-  const double inv = 1.0 / sqrt(*power_sum / (double)total);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / n_samp;
-    const double std_b = sqrt(0.5) * pow(10.0, -(double)__ldg(snr_db + b) / 20.0);
-    double n0, n1;
-    if (normals) {
-      n0 = normals[i * 2];
-      n1 = normals[i * 2 + 1];
-    } else {
-      uint32_t r[4];
-      Philox{seed}((uint64_t)i, 0xB0B0u, r);
-      float f0, f1;
-      box_muller(r[0], r[1], f0, f1);
-      n0 = f0;
-      n1 = f1;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const double inv = 1.0 / sqrt(*power_sum / (double)(B * n_samp));
+  const int npair = n_samp >> 1;                       // n_samp is even for every frame geometry (S * T, T even)
+  for (long long b = warp0; b < B; b += nwarps) {
+    double std_b = 0.0;
+    if (lane == 0) std_b = sqrt(0.5) * pow(10.0, -(double)__ldg(snr_db + b) / 20.0);
+    std_b = __shfl_sync(0xffffffffu, std_b, 0);
+    const float4* xi = reinterpret_cast<const float4*>(xin + b * n_samp);
+    float4* xo = reinterpret_cast<float4*>(out + b * n_samp);
+    for (int p = lane; p < npair; p += 32) {
+      const float4 v = __ldg(xi + p);
+      double n0, n1, n2, n3;
+      if (normals) {
+        const double2* np_ = reinterpret_cast<const double2*>(normals + (b * n_samp + 2 * p) * 2);
+        const double2 t0 = np_[0], t1 = np_[1];
+        n0 = t0.x; n1 = t0.y; n2 = t1.x; n3 = t1.y;
+      } else {
+        uint32_t r[4];
+        Philox{seed}((uint64_t)(b * npair + p), 0xB0B0u, r);
+        float f0, f1, f2, f3;
+        box_muller(r[0], r[1], f0, f1);
+        box_muller(r[2], r[3], f2, f3);
+        n0 = f0; n1 = f1; n2 = f2; n3 = f3;
+      }
+      xo[p] = make_float4((float)((double)v.x * inv + n0 * std_b), (float)((double)v.y * inv + n1 * std_b),
+                          (float)((double)v.z * inv + n2 * std_b), (float)((double)v.w * inv + n3 * std_b));
     }
-    const float2 v = xin[i];
-    out[i] = make_float2((float)((double)v.x * inv + n0 * std_b), (float)((double)v.y * inv + n1 * std_b));
+    if ((n_samp & 1) && lane == 0) {                   // odd tail (not reached by the LTE geometries)
+      const int i = n_samp - 1;
+      const float2 v = xin[b * n_samp + i];
+      double n0, n1;
+      if (normals) {
+        n0 = normals[(b * n_samp + i) * 2];
+        n1 = normals[(b * n_samp + i) * 2 + 1];
+      } else {
+        uint32_t r[4];
+        Philox{seed}((uint64_t)(B * npair + b), 0xB0B1u, r);
+        float f0, f1;
+        box_muller(r[0], r[1], f0, f1);
+        n0 = f0; n1 = f1;
+      }
+      out[b * n_samp + i] = make_float2((float)((double)v.x * inv + n0 * std_b), (float)((double)v.y * inv + n1 * std_b));
+    }
   }
 }
 
@@ -424,6 +457,74 @@ __global__ void txmap_kernel(const int* __restrict__ data_sc, int n_data, const 
   }
 }
 
+// ---- shared by tx64_kernel and tx_fade_kernel: one OFDM symbol of K = 64 subcarriers by one warp ------------------------
+struct Tx64Twiddles {
+  double2 w8[8];     // W8^(a j), j = 0..7      (a = lane & 7)
+  double2 w64[2];    // W64^(a (b + 4 h))       (b = lane >> 3)
+};
+DCCN_DEVINL void tx64_twiddles(int lane, Tx64Twiddles& tw) {
+  const int a = lane & 7, b = lane >> 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double sn, cs;
+    sincospi(0.25 * (double)((a * j) & 7), &sn, &cs);
+    tw.w8[j] = make_double2(cs, sn);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    double sn, cs;
+    sincospi((double)((a * (b + 4 * h)) & 63) / 32.0, &sn, &cs);
+    tw.w64[h] = make_double2(cs, sn);
+  }
+}
+// acc += x * w (complex128, fixed contraction)
+DCCN_DEVINL void cmac64(double& ar, double& ai, const double2 x, const double2 w) {
+  ar = fma(-x.y, w.y, fma(x.x, w.x, ar));
+  ai = fma(x.y, w.x, fma(x.x, w.y, ai));
+}
+// frequency grid of symbol s of `frame` -> g[0..63]; 8 x 8 IDFT through z; time-domain symbol (no CP, scaled 1/64) left
+// in g[n].  Ends with a __syncwarp, so the caller may read g at once.
+DCCN_DEVINL void tx64_symbol(const uint8_t* __restrict__ bits, long long frame, int s, int nbits, int D,
+                             const int* __restrict__ sc_map, const float2* __restrict__ constellation, float2 pilot,
+                             int lane, const Tx64Twiddles& tw, double2* g, double2* z) {
+  constexpr int K = 64;
+  const int a = lane & 7, b = lane >> 3;
+#pragma unroll
+  for (int k = lane; k < K; k += 32) {
+    const int m = sc_map[s * K + k];
+    float2 v = make_float2(0.f, 0.f);
+    if (m == -2) v = pilot;
+    else if (m >= 0) {
+      int idx = 0;
+      const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
+      for (int q = 0; q < nbits; ++q) idx = (idx << 1) | bp[q];
+      v = constellation[idx];
+    }
+    g[k] = make_double2(v.x, v.y);
+  }
+  __syncwarp();
+  // pass 1 (+ twiddle): outputs (k1 = b + 4 h, n2 = a)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int k1 = b + 4 * h;
+    double yr = 0.0, yi = 0.0;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) cmac64(yr, yi, g[k1 + 8 * k2], tw.w8[k2]);
+    z[k1 * 8 + a] = make_double2(fma(-yi, tw.w64[h].y, yr * tw.w64[h].x), fma(yi, tw.w64[h].x, yr * tw.w64[h].y));
+  }
+  __syncwarp();
+  // pass 2: outputs n = 8 n1 + n2 with n1 = a, n2 = b + 4 h (g is free: every lane finished pass 1)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int n2 = b + 4 * h;
+    double xr = 0.0, xi = 0.0;
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) cmac64(xr, xi, z[k1 * 8 + n2], tw.w8[k1]);
+    g[8 * a + n2] = make_double2(xr * (1.0 / K), xi * (1.0 / K));
+  }
+  __syncwarp();
+}
+
 // The same transmitter for K = 64 (the default since round 2; DCCN_TX_V2=0 selects tx_kernel) with the IDFT as
 // 8 x 8 (n = 8 n1 + n2, k = k1 + 8 k2):  Y[k1][n2] = sum_k2 X[k1 + 8 k2] W8^(n2 k2),  Z = Y * W64^(n2 k1),
 // x[8 n1 + n2] = sum_k1 Z[k1][n2] W8^(n1 k1) / 64  -- 1 024 + 64 complex fp64 MACs per symbol instead of 4 096, the
@@ -438,21 +539,8 @@ __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ b
   __shared__ double2 sm_g[8][K];      // per warp: frequency grid, later the time-domain symbol
   __shared__ double2 sm_z[8][K];      // per warp: Z[k1 * 8 + n2]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = lane & 7, b = lane >> 3;              // b in 0..3; the lane's second output uses b + 4
-  double2 w8[8];                                      // W8^(a j), j = 0..7
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    double sn, cs;
-    sincospi(0.25 * (double)((a * j) & 7), &sn, &cs);
-    w8[j] = make_double2(cs, sn);
-  }
-  double2 w64[2];                                     // W64^(n2 k1) for (n2 = a, k1 = b) and (n2 = a, k1 = b + 4)
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    double sn, cs;
-    sincospi((double)((a * (b + 4 * h)) & 63) / 32.0, &sn, &cs);
-    w64[h] = make_double2(cs, sn);
-  }
+  Tx64Twiddles tw;
+  tx64_twiddles(lane, tw);
   double2* g = sm_g[wib];
   double2* z = sm_z[wib];
   const int T = K + CP;
@@ -460,48 +548,7 @@ __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ b
   for (long long sym = (long long)blockIdx.x * 8 + wib; sym < total; sym += (long long)gridDim.x * 8) {
     const long long frame = sym / S;
     const int s = (int)(sym - frame * S);
-#pragma unroll
-    for (int k = lane; k < K; k += 32) {
-      const int m = sc_map[s * K + k];
-      float2 v = make_float2(0.f, 0.f);
-      if (m == -2) v = pilot;
-      else if (m >= 0) {
-        int idx = 0;
-        const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
-        for (int q = 0; q < nbits; ++q) idx = (idx << 1) | bp[q];
-        v = constellation[idx];
-      }
-      g[k] = make_double2(v.x, v.y);
-    }
-    __syncwarp();
-    // pass 1 (+ twiddle): outputs (k1 = b + 4 h, n2 = a)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k1 = b + 4 * h;
-      double yr = 0.0, yi = 0.0;
-#pragma unroll
-      for (int k2 = 0; k2 < 8; ++k2) {
-        const double2 x = g[k1 + 8 * k2];
-        yr += x.x * w8[k2].x - x.y * w8[k2].y;
-        yi += x.x * w8[k2].y + x.y * w8[k2].x;
-      }
-      z[k1 * 8 + a] = make_double2(yr * w64[h].x - yi * w64[h].y, yr * w64[h].y + yi * w64[h].x);
-    }
-    __syncwarp();
-    // pass 2: outputs n = 8 n1 + n2 with n1 = a, n2 = b + 4 h (g is free: every lane finished pass 1)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int n2 = b + 4 * h;
-      double xr = 0.0, xi = 0.0;
-#pragma unroll
-      for (int k1 = 0; k1 < 8; ++k1) {
-        const double2 v = z[k1 * 8 + n2];
-        xr += v.x * w8[k1].x - v.y * w8[k1].y;
-        xi += v.x * w8[k1].y + v.y * w8[k1].x;
-      }
-      g[8 * a + n2] = make_double2(xr * (1.0 / K), xi * (1.0 / K));
-    }
-    __syncwarp();
+    tx64_symbol(bits, frame, s, nbits, D, sc_map, constellation, pilot, lane, tw, g, z);
     float2* o = tx + (size_t)sym * T;
     for (int t = lane; t < T; t += 32) {
       const double2 v = g[(t + K - CP) & (K - 1)];     // cyclic prefix = the last CP samples, then the symbol
@@ -509,6 +556,106 @@ __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ b
     }
     __syncwarp();
   }
+}
+
+// =====================================================================================
+// Fused feeder: bits -> constellation -> 8 x 8 IDFT -> CP (tx64_kernel's arithmetic) -> static Rayleigh FIR
+// (chan_fir_kernel's arithmetic) for nfft = 64, one warp per frame.  The transmitted frame lives in shared memory as the
+// fp32 samples tx64_kernel would have written (the reference's complex64 `iq_tx_cmpx`, dev/py/ofdm.py:380), so the
+// result is bit-identical to chan_fir_kernel(tx64_kernel(bits)) while the 4 480-byte frame is neither written to nor
+// read back from HBM (a sweep cell generates its frames once and never looks at the unfaded signal):
+// replaces the call pair ofdm_tx_frame_np + rayleigh_chan_lte.run of dev/py/ofdmreceiver_np.py:227-228.
+//   tx_out: optional [B, S*T] copy of the transmitted frames (nullptr = not wanted)
+// =====================================================================================
+constexpr int kGenWarps = 4;
+constexpr int kGenMaxSamp = 8 * 80;     // S <= 8 symbols of K + CP <= 80 samples
+
+__global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
+    const uint8_t* __restrict__ bits, long long B, int S, int CP, int nbits, int D, const int* __restrict__ sc_map,
+    const float2* __restrict__ constellation, float2 pilot, const double* __restrict__ alpha,
+    const double* __restrict__ coeff, int n_taps, int n_fir, const double* __restrict__ z_in, uint64_t seed,
+    float2* __restrict__ tx_out, float2* __restrict__ rx, double* __restrict__ power_sum) {
+  constexpr int K = 64;
+  __shared__ double2 sm_g[kGenWarps][K];
+  __shared__ double2 sm_z[kGenWarps][K];
+  __shared__ double2 gsm[kGenWarps][kMaxFir];
+  __shared__ float2 sm_fr[kGenWarps][kGenMaxSamp];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Tx64Twiddles tw;
+  tx64_twiddles(lane, tw);
+  double2* g = sm_g[wib];
+  double2* z = sm_z[wib];
+  float2* fr = sm_fr[wib];
+  const int T = K + CP, n_samp = S * T;
+  const int M = n_taps == 0 ? 1 : n_fir;
+  const int off = (M - 1) - (M >> 1);
+  double pw = 0.0;
+  for (long long frame = (long long)blockIdx.x * kGenWarps + wib; frame < B; frame += (long long)gridDim.x * kGenWarps) {
+    // ---- path gains -> sample-spaced FIR (chan_fir_kernel) ----
+    if (n_taps == 0) {
+      if (lane == 0) gsm[wib][0] = make_double2(1.0, 0.0);
+    } else {
+      double2 pa = make_double2(0.0, 0.0);
+      if (lane < n_taps) {
+        double zr, zi;
+        if (z_in) {
+          zr = z_in[((size_t)frame * n_taps + lane) * 2];
+          zi = z_in[((size_t)frame * n_taps + lane) * 2 + 1];
+        } else {
+          uint32_t r[4];
+          Philox{seed}((uint64_t)frame * 64 + lane, 0xA11CEu, r);
+          float n0, n1;
+          box_muller(r[0], r[1], n0, n1);
+          zr = (double)n0 * 0.70710678118654752;
+          zi = (double)n1 * 0.70710678118654752;
+        }
+        const double c = coeff[lane];
+        pa = make_double2(zr * c, zi * c);
+      }
+      double2 gt = make_double2(0.0, 0.0);
+      for (int t = 0; t < n_taps; ++t) {
+        const double ar = __shfl_sync(0xffffffffu, pa.x, t);
+        const double ai = __shfl_sync(0xffffffffu, pa.y, t);
+        if (lane < n_fir) {
+          const double al = alpha ? alpha[t * n_fir + lane] : 1.0;
+          gt.x = fma(ar, al, gt.x);
+          gt.y = fma(ai, al, gt.y);
+        }
+      }
+      if (lane < n_fir) gsm[wib][lane] = gt;
+    }
+    // ---- transmitter: S symbols into the shared frame buffer (tx64_kernel) ----
+    for (int s = 0; s < S; ++s) {
+      tx64_symbol(bits, frame, s, nbits, D, sc_map, constellation, pilot, lane, tw, g, z);
+      for (int t = lane; t < T; t += 32) {
+        const double2 v = g[(t + K - CP) & (K - 1)];
+        fr[s * T + t] = make_float2((float)v.x, (float)v.y);
+      }
+      __syncwarp();
+    }
+    if (tx_out) {
+      float2* o = tx_out + (size_t)frame * n_samp;
+      for (int n = lane; n < n_samp; n += 32) o[n] = fr[n];
+    }
+    // ---- centred 'same' FIR with zero history, complex128 (chan_fir_kernel's accumulation order) ----
+    float2* rxf = rx + (size_t)frame * n_samp;
+    for (int n = lane; n < n_samp; n += 32) {
+      double accr = 0.0, acci = 0.0;
+      for (int j = 0; j < M; ++j) {
+        const int i = n + off - j;
+        const float2 xv = (i >= 0 && i < n_samp) ? fr[i] : make_float2(0.f, 0.f);
+        const double xr = xv.x, xi = xv.y;
+        fir_cmac(accr, acci, gsm[wib][j], xr, xi);
+      }
+      const float2 o = make_float2((float)accr, (float)acci);
+      rxf[n] = o;
+      pw += (double)o.x * o.x + (double)o.y * o.y;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+  if (lane == 0 && pw != 0.0) atomicAdd(power_sum, pw);
 }
 
 __global__ void bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint64_t seed) {

@@ -56,7 +56,9 @@ struct TrainLayer {
 struct TrainState {
   dccn_train_cfg cfg;
   int64_t maxB = 0;
-  int64_t step = 0;
+  int64_t step = 0;       // global_step: drives the learning-rate schedule on the host, can be set (resume)
+  int64_t adam_t = 0;     // updates applied to the CURRENT m / v slots: Adam's bias-correction exponent (beta^t); the
+                          // slots start at zero with the training state, so this never follows a set global_step
   std::vector<TrainParam> params;
   int mode = 0;            // DCCN_TRAIN_EQ / DCCN_TRAIN_RX
   int n_layers = 10;
@@ -1251,9 +1253,10 @@ int dccn_train_step(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t
   if (!apply_update) return 0;
   // ---- Adam (dev/py/ofdmreceiver_np_mp.py:345-347) ------------------------------------------------------------
   tr->step += 1;
+  tr->adam_t += 1;
   const double b1 = tr->cfg.beta1, b2 = tr->cfg.beta2;
-  const float lr_t = (float)((double)learning_rate * std::sqrt(1.0 - std::pow(b2, (double)tr->step)) /
-                             (1.0 - std::pow(b1, (double)tr->step)));
+  const float lr_t = (float)((double)learning_rate * std::sqrt(1.0 - std::pow(b2, (double)tr->adam_t)) /
+                             (1.0 - std::pow(b1, (double)tr->adam_t)));
   {
     LaunchScope ls(h, SLOT_T_ADAM, s, (int)tr->params.size());
     for (TrainParam& p : tr->params)

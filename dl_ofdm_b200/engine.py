@@ -285,20 +285,24 @@ class DCCN:
         return rx
 
     # -- transmitter ---------------------------------------------------------------------
-    def transmit(self, bits, ofdmobj, constellation):
-        """GPU OFDM transmitter: bits uint8 [B,D,nbits] -> float32 [B,S,T,2]."""
-        dev = bits.device
+    def _tx_tables(self, ofdmobj, constellation, dev):
         key = ('tx', id(ofdmobj))
         if key not in self._scratch:
             for sc in (ofdmobj.dataSc, ofdmobj.pilotSc):        # the device-side map builder ignores bad indices
                 sc = np.asarray(sc)
                 if sc.size and (sc.min() < 0 or sc.max() >= self.S * self.K):
                     raise DccnError('subcarrier index out of range [0, %d)' % (self.S * self.K))
+            # (the ofdm_tx object is kept in the entry: id() of a collected object may be handed out again)
             self._scratch[key] = (torch.as_tensor(np.asarray(ofdmobj.dataSc, dtype=np.int32), device=dev),
                                   torch.as_tensor(np.asarray(ofdmobj.pilotSc, dtype=np.int32), device=dev),
                                   torch.as_tensor(np.stack([constellation.real, constellation.imag], -1)
-                                                  .astype(np.float32), device=dev))
-        dsc, psc, const = self._scratch[key]
+                                                  .astype(np.float32), device=dev), ofdmobj)
+        return self._scratch[key][:3]
+
+    def transmit(self, bits, ofdmobj, constellation):
+        """GPU OFDM transmitter: bits uint8 [B,D,nbits] -> float32 [B,S,T,2]."""
+        dev = bits.device
+        dsc, psc, const = self._tx_tables(ofdmobj, constellation, dev)
         B = bits.shape[0]
         tx = torch.empty((B, self.S, self.T, 2), dtype=torch.float32, device=dev)
         pv = complex(ofdmobj.pilotValue)
@@ -306,6 +310,28 @@ class DCCN:
             _lib.check(self.lib.dccn_tx_frames(self._h, _ptr(bits), B, _ptr(dsc), dsc.numel(), _ptr(psc),
                                                psc.numel(), _ptr(const), pv.real, pv.imag, _ptr(tx), _stream()))
         return tx
+
+    def can_tx_fade(self):
+        return self.K == 64 and 0 < (self.T - self.K) <= 16 and self.S <= 8
+
+    def transmit_fade(self, bits, ofdmobj, constellation, alpha=None, coeff=None, z=None, seed=0, want_tx=False,
+                      reset_power=True):
+        """Fused feeder (nfft = 64): bits uint8 [B,D,nbits] -> faded float32 [B,S,T,2] (static Rayleigh FIR; alpha / coeff
+        None = no fading, i.e. the 'AWGN' channel) without the transmitted frames ever reaching HBM.  Bit-identical to
+        ``fading(transmit(bits))``.  Returns (faded, tx or None); the batch power is left for ``awgn``."""
+        dev = bits.device
+        dsc, psc, const = self._tx_tables(ofdmobj, constellation, dev)
+        B = bits.shape[0]
+        faded = torch.empty((B, self.S, self.T, 2), dtype=torch.float32, device=dev)
+        tx = torch.empty_like(faded) if want_tx else None
+        n_taps = 0 if coeff is None else int(coeff.numel())
+        n_fir = 1 if alpha is None else int(alpha.shape[1])
+        pv = complex(ofdmobj.pilotValue)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.dccn_tx_fade(self._h, _ptr(bits), B, _ptr(dsc), dsc.numel(), _ptr(psc), psc.numel(),
+                                             _ptr(const), pv.real, pv.imag, _ptr(alpha), _ptr(coeff), n_taps, n_fir,
+                                             _ptr(z), int(seed), int(bool(reset_power)), _ptr(tx), _ptr(faded), _stream()))
+        return faded, tx
 
 
 def launch_count():

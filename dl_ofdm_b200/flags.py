@@ -3,7 +3,9 @@
 Flag names, defaults and types are those of dev/py/ofdmreceiver_np_mp.py:33-58
 (a superset of dev/py/ofdmreceiver_np.py:30-53); ``parse_flags(argv)`` accepts the
 same ``--name=value`` strings that ``run_local_ofdm.py`` builds (dev/py/run_local_ofdm.py:74-78).
-Three extra flags select B200 execution: --precision, --gpus, --frames.
+The two drivers differ in four defaults (``parse_flags(argv, driver='np')`` applies ofdmreceiver_np.py's:
+SNR 3, max_epoch_num 1000, early_stop 100, load_model False -- ofdmreceiver_np.py:36-48).
+Two extra flags select B200 execution: --precision, --frames (0 = the driver's own test-set size).
 """
 from __future__ import annotations
 
@@ -18,8 +20,10 @@ _DEFS = [
     ('load_model', bool, True), ('split', float, 1.0), ('token', str, 'OFDM'), ('opt', int, 3),
     ('mobile', bool, False), ('init_learning', float, 0.001), ('test', bool, False),
     # B200 additions
-    ('precision', str, 'parity'), ('frames', int, 20000),
+    ('precision', str, 'parity'), ('frames', int, 0),
 ]
+# dev/py/ofdmreceiver_np.py:36-48 (the basic-receiver driver) where it differs from ofdmreceiver_np_mp.py
+_NP_DEFS = {'SNR': 3.0, 'max_epoch_num': 1000, 'early_stop': 100, 'load_model': False}
 
 
 def _to_bool(v):
@@ -47,9 +51,11 @@ class Flags:
         return f
 
 
-def parse_flags(argv=None):
+def parse_flags(argv=None, driver='mp'):
     p = argparse.ArgumentParser(allow_abbrev=False)
     for name, typ, default in _DEFS:
+        if driver == 'np' and name in _NP_DEFS:
+            default = _NP_DEFS[name]
         if typ is bool:
             p.add_argument('--' + name, type=_to_bool, default=default, nargs='?', const=True)
         else:

@@ -15,16 +15,27 @@ from . import _lib, tfbundle
 from .engine import DCCN
 from .init import detect_eq_opt
 
-_CACHE = {}
+_CACHE = []          # [(weights object, config key, engine)], newest last
+_CACHE_MAX = 8
 
 
 def _engine(FLAGS, ofdmobj, weights, equalizer, head, precision, eq_opt=0):
-    key = (id(weights), equalizer, head, precision, FLAGS.nbits, FLAGS.cp, torch.cuda.current_device(), eq_opt)
-    if key not in _CACHE:
-        m = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=equalizer, precision=precision, head=head, eq_opt=eq_opt)
-        m.load_weights(weights)
-        _CACHE[key] = m
-    return _CACHE[key]
+    """One engine per (weights dict, configuration).  The entry HOLDS the dict (a bare id() could be reused by a later
+    object after garbage collection and serve stale weights) and is matched by identity; the oldest engines are closed
+    when more than _CACHE_MAX are alive."""
+    if weights is None:
+        raise ValueError('weights: a dict of TF variable name -> array is required')
+    key = (equalizer, head, precision, FLAGS.nbits, FLAGS.cp, FLAGS.nfilter, ofdmobj.K, ofdmobj.CP, ofdmobj.nSymbol,
+           ofdmobj.frame_size, torch.cuda.current_device(), eq_opt)
+    for w, k, m in _CACHE:
+        if w is weights and k == key:
+            return m
+    m = DCCN.from_ofdm(FLAGS, ofdmobj, equalizer=equalizer, precision=precision, head=head, eq_opt=eq_opt)
+    m.load_weights(weights)
+    _CACHE.append((weights, key, m))
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.pop(0)[2].close()
+    return m
 
 
 def ofdm_dense_rx(inputs, FLAGS, ofdmobj, outshape=None, weights=None, head='dev', precision='parity'):
@@ -132,12 +143,15 @@ class Session:
 def load_model_np(path, session=None, FLAGS=None, ofdmobj=None, precision='parity'):
     """Restore ``path``.index/.data (TF bundle) -> Session (dev/py/model.py:51-72)."""
     weights = tfbundle.read_checkpoint(path)
-    weights.pop('global_step', None)
+    for n in ('global_step', 'optimizer/global_step'):
+        weights.pop(n, None)
     return Session(FLAGS, ofdmobj, weights, precision=precision)
 
 
-def save_model(path, weights, global_step=0):
-    """Write a checkpoint the reference's tf.train.Saver can restore (TF bundle v2)."""
+def save_model(path, weights, global_step=0, step_name='global_step'):
+    """Write a TF-bundle-v2 checkpoint with the reference's variable names.  The basic receiver's step counter is
+    ``global_step`` (dev/py/ofdmreceiver_np.py:185), the equalizer driver's lives in its 'optimizer' variable scope
+    (``optimizer/global_step``, dev/py/ofdmreceiver_np_mp.py:335-343)."""
     w = dict(weights)
-    w['global_step'] = np.asarray(global_step, dtype=np.float32).reshape(())
+    w[step_name] = np.asarray(global_step, dtype=np.float32).reshape(())
     tfbundle.write_checkpoint(path, w)

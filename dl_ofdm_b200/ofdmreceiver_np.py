@@ -60,7 +60,7 @@ def train_receiver(FLAGS, ofdmobj, weights=None, max_epoch_num=None, frame_cnt=N
         calls += 1
         bits = bit_source_gpu(frames * D * nb, seed=(int(seed) << 20) + calls, device=dev).view(frames, D, nb)
         snr = torch.full((frames,), float(FLAGS.SNR), dtype=torch.float32, device=dev)   # snr_seq is all zeros (:207)
-        return fading.run(eng.transmit(bits, ofdmobj, const), snr), bits
+        return fading.run_bits(bits, ofdmobj, const, snr), bits
 
     name = os.path.join(FLAGS.save_dir, FLAGS.token)
     test_loss_min, epoch_min_loss, history = 100.0, 0, []
@@ -116,19 +116,20 @@ def test_model(FLAGS, path_prefix_min, ofdmobj, session=None, frame_cnt=20000, s
 
 
 def main(argv=None):
-    FLAGS = parse_flags(argv)
+    FLAGS = parse_flags(argv, driver='np')
     ofdmobj = ofdm_tx(FLAGS)
-    if 'LOCAL_RANK' in os.environ and int(os.environ.get('WORLD_SIZE', 1)) > 1:
-        torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
-        dist.init_process_group('nccl')
+    rank, _ = sweep.init_distributed()
     path = os.path.join(FLAGS.save_dir, FLAGS.token)
-    if not FLAGS.test:
+    if not FLAGS.test and rank == 0:
+        # training is one sequential trajectory (the reference has no multi-GPU training): rank 0 trains and writes the
+        # checkpoint (atomically, tfbundle.write_checkpoint), the other ranks wait and then share the BER sweep
         os.makedirs(FLAGS.save_dir, exist_ok=True)
         session, _ = train_receiver(FLAGS, ofdmobj)
         session.close()
+    sweep.barrier()
     if not os.path.exists(path + '.index'):
         raise FileNotFoundError('%s.index: no checkpoint to evaluate' % path)
-    return test_model(FLAGS, path, ofdmobj, frame_cnt=FLAGS.frames)
+    return test_model(FLAGS, path, ofdmobj, frame_cnt=FLAGS.frames or 20000)      # :69
 
 
 if __name__ == '__main__':

@@ -65,9 +65,8 @@ class _DataGen:
         D, nb = self.ofdm.frame_size, self.fl.nbits
         bits = bit_source_gpu(frames * D * nb, seed=(self.seed << 20) + self.calls, device=dev).view(frames, D, nb)
         snr = torch.as_tensor(self.rng.choice(TRAIN_SNRS, frames, p=TRAIN_SNR_P), dtype=torch.float32, device=dev)
-        tx = self.eng.transmit(bits, self.ofdm, self.const)
         fading = self.fading1 if (phase2 and self.fading1 is not None) else self.fading0
-        return fading.run(tx, snr), bits
+        return fading.run_bits(bits, self.ofdm, self.const, snr), bits
 
 
 def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=None, frame_cnt=None, test_frames=1024,
@@ -116,7 +115,7 @@ def train_equalizer(FLAGS, ofdmobj, rx_weights, eq_weights=None, max_epoch_num=N
                 w = dict(weights)
                 for n in trainable:
                     w[n] = eng.get_weight(n).reshape(np.shape(weights[n]))
-                save_model(name, w, global_step=eng.global_step)
+                save_model(name, w, global_step=eng.global_step, step_name='optimizer/global_step')
         if epoch - FLAGS.early_stop > epoch_min_loss:                 # _mp.py:460-461
             break
     return session, history
@@ -136,7 +135,8 @@ def test_model_cross(FLAGS, path_prefix_min, ofdmobj, session=None, frame_cnt=30
     if rank == 0:
         for ch in channels:
             sub = [r for r in rows if r['channel'] == ch]
-            name = 'Test_DCCN_%s_test_chan_%s.csv' % (FLAGS.token + '_Equalizer%d_' % FLAGS.opt + FLAGS.channel, ch)
+            name = 'Test_DCCN_%s_test_chan_%s%s.csv' % (FLAGS.token + '_Equalizer%d_' % FLAGS.opt + FLAGS.channel, ch,
+                                                        '_mobile' if FLAGS.mobile else '')        # _mp.py:98-101
             sweep.write_csv(os.path.join(out_dir, name), sub)
     if own:
         session.close()
@@ -144,14 +144,12 @@ def test_model_cross(FLAGS, path_prefix_min, ofdmobj, session=None, frame_cnt=30
 
 
 def main(argv=None):
-    FLAGS = parse_flags(argv)
+    FLAGS = parse_flags(argv, driver='mp')
     ofdmobj = ofdm_tx(FLAGS)
-    if 'LOCAL_RANK' in os.environ and int(os.environ.get('WORLD_SIZE', 1)) > 1:
-        torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
-        dist.init_process_group('nccl')
+    rank, _ = sweep.init_distributed()
     name = FLAGS.token + ('_Equalizer_' if FLAGS.opt == 0 else '_Equalizer%d_' % FLAGS.opt) + FLAGS.channel
     path = os.path.join(FLAGS.save_dir, name)
-    if not FLAGS.test:
+    if not FLAGS.test and rank == 0:     # rank 0 trains and saves; every rank then takes its share of the test grid
         # transfer learning in front of the basic receiver saved by ofdmreceiver_np.py as save_dir/token (_mp.py:265-266)
         base = os.path.join(FLAGS.save_dir, FLAGS.token)
         if not os.path.exists(base + '.index'):
@@ -160,9 +158,10 @@ def main(argv=None):
               if k.startswith(('fft_like/', 'demodulation/')) and '/Adam' not in k}
         session, _ = train_equalizer(FLAGS, ofdmobj, rx)
         session.close()
+    sweep.barrier()
     if not os.path.exists(path + '.index'):
         raise FileNotFoundError('%s.index: no equalizer checkpoint to evaluate' % path)
-    return test_model_cross(FLAGS, path, ofdmobj, frame_cnt=FLAGS.frames)
+    return test_model_cross(FLAGS, path, ofdmobj, frame_cnt=FLAGS.frames or 30000)    # _mp.py:73
 
 
 if __name__ == '__main__':

@@ -132,3 +132,19 @@ class rayleigh_chan_lte:
         return self.engine.awgn(faded, snr_db, normals, seed=(self.seed << 20) + self._calls)
 
     __call__ = run
+
+    def run_bits(self, bits, ofdmobj, constellation, snr_db, z=None, normals=None):
+        """bits uint8 CUDA [B,D,nbits] -> received float32 [B,S,T,2]: the reference's chain
+        ``ofdm_tx_frame_np -> fading.run -> AWGN_channel_np`` (dev/py/ofdmreceiver_np.py:227-229).  For a single static
+        profile (or 'AWGN') on the nfft = 64 geometry the transmitter and the FIR run as ONE kernel (`dccn_tx_fade`: the
+        transmitted frames never reach HBM) with the same bits as the separate calls; otherwise it is
+        ``run(engine.transmit(bits))``."""
+        eng = self.engine
+        static = len(self.profiles) == 1 and doppler_hz(self.profiles[0], self.mobile) == 0.0
+        if not (static and eng.can_tx_fade()):
+            return self.run(eng.transmit(bits, ofdmobj, constellation), snr_db, z, normals)
+        self._calls += 1
+        alpha, coeff = self._profile(self.profiles[0], bits.device)
+        seed = (self.seed << 24) + (self._calls << 4)           # == fade()'s seed for profile index 0
+        faded, _ = eng.transmit_fade(bits, ofdmobj, constellation, alpha, coeff, z, seed)
+        return eng.awgn(faded, snr_db, normals, seed=(self.seed << 20) + self._calls)

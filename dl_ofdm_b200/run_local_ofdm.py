@@ -43,6 +43,9 @@ def job_list(awgn=True, token='OFDM_Dense3', batchsize=512, nfft=64, ebno=5.0, l
                      % ('mixRayleigh', save_dir, learning, nfft, batchsize, 4000 * nbits, cp, nfft, longcp, opt, mobile))
             tok = '%s_%dmod_snr%d_cp%s' % (token, nbits, int(snr), cp)
             flags += '--SNR=%.2f --nbits=%d --token=%s' % (snr, nbits, tok)
+            # the reference tests for ..._test_chan_Custom.csv (run_local_ofdm.py:107) although its mobile runs write
+            # ..._Custom_mobile.csv (_mp.py:98-99), so with --mobile=True its skip rule never fires; both names are
+            # accepted here
             jobs.append(('ofdmreceiver_np_mp', flags, 'Test_DCCN_%s_Equalizer%d_mixRayleigh_test_chan_Custom.csv' % (tok, opt)))
     return save_dir, result_dir, jobs
 
@@ -59,8 +62,11 @@ def main(argv=None):
     if not args.dry_run:
         for folder in (save_dir, result_dir):
             os.makedirs(folder, exist_ok=True)
+    from .sweep import init_distributed, barrier
+    rank, _ = init_distributed()
     for script, flags, csv in jobs:
-        if os.path.exists(csv) or os.path.exists(os.path.join(result_dir, csv)):   # resume rule (:82-86, :110-114)
+        alts = [csv, csv[:-4] + '_mobile.csv']
+        if any(os.path.exists(c) or os.path.exists(os.path.join(result_dir, c)) for c in alts):   # resume rule (:82-86, :110-114)
             print('skip (result exists):', csv)
             continue
         if args.max_epoch_num:
@@ -72,10 +78,13 @@ def main(argv=None):
             except FileNotFoundError as e:
                 print('  ->', e)
                 continue
+            barrier()                                  # every rank is past the job before its files move
             pre = csv.split('_test_chan_')[0] if '_test_chan_' in csv else csv[:-4]
-            for f in os.listdir('.'):
-                if f.startswith(pre) and f.endswith('.csv'):
-                    os.replace(f, os.path.join(result_dir, f))
+            if rank == 0:                              # rank 0 wrote the CSVs (test_model / test_model_cross)
+                for f in os.listdir('.'):
+                    if f.startswith(pre) and f.endswith('.csv'):
+                        os.replace(f, os.path.join(result_dir, f))
+            barrier()
 
 
 if __name__ == '__main__':

@@ -16,6 +16,23 @@ import torch
 import torch.distributed as dist
 
 
+def init_distributed():
+    """Join the torchrun job once (idempotent: the launcher calls the drivers' main() once per job in one process).
+    -> (rank, world)."""
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1 and 'LOCAL_RANK' in os.environ:
+        torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+        if not dist.is_initialized():
+            dist.init_process_group('nccl')
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 def make_cells(channels, snrs, nbits_list=(None,)):
     """Deterministic cell order: modulation-major, then channel, then SNR (the reference's loop nest)."""
     return [(nb, ch, float(s)) for nb in nbits_list for ch in channels for s in snrs]
@@ -86,9 +103,8 @@ class CellRunner:
         B, D, nb = self.frames, ofdm.frame_size, fl.nbits
         dev = eng.device
         bits = bit_source_gpu(B * D * nb, seed=(self.seed << 24) + index, device=dev).view(B, D, nb)
-        tx = eng.transmit(bits, ofdm, self.const)
         chan = rayleigh_chan_lte(fl.copy(channel=chan_name), ofdm.Fs, mobile=getattr(fl, 'mobile', False),
                                  engine=eng, seed=(self.seed << 12) + index)
-        x = chan.run(tx, torch.full((B,), snr, dtype=torch.float32, device=dev))
+        x = chan.run_bits(bits, ofdm, self.const, torch.full((B,), snr, dtype=torch.float32, device=dev))
         o = eng.forward(x, bits, want_soft=False, want_hard=False)
         return o['conf'].cpu().numpy(), float(o['ce_sum'].cpu()[0])

@@ -176,7 +176,23 @@ def _crc32c_table():
 _CRC_TBL = _crc32c_table()
 
 
+def _crc32c_native():
+    """dccn_crc32c of libdccn.so (host code, works without a GPU) or None when the library has not been built."""
+    try:
+        from . import _lib
+        return _lib.load().dccn_crc32c
+    except Exception:
+        return None
+
+
 def crc32c(data: bytes, crc: int = 0) -> int:
+    """CRC-32C.  Large buffers go through the library's slicing-by-8 routine (a checkpoint holds 12 MB of tensors and
+    is rewritten on every improving epoch); the pure-Python loop below is the small-input / no-library path."""
+    if len(data) >= 4096:
+        fn = _crc32c_native()
+        if fn is not None:
+            buf = bytes(data)
+            return int(fn(buf, len(buf), crc))
     crc ^= 0xFFFFFFFF
     for b in data:
         crc = _CRC_TBL[(crc ^ b) & 0xFF] ^ (crc >> 8)
@@ -237,7 +253,10 @@ def write_checkpoint(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
     # BundleHeaderProto{num_shards=1, endianness=LITTLE(0), version{producer=1}}
     header = _proto_field(1, 0, 1) + _proto_field(3, 2, _proto_field(1, 0, 1))
     entries.append((b'', header))
-    with open(prefix + '.data-00000-of-00001', 'wb') as f:
+    # both files are written under temporary names and renamed into place, so that a reader (another rank waiting to
+    # load the checkpoint, or a crash mid-write) never sees a truncated bundle
+    tmp_data, tmp_index = prefix + '.data-00000-of-00001.tmp%d' % os.getpid(), prefix + '.index.tmp%d' % os.getpid()
+    with open(tmp_data, 'wb') as f:
         for n in names:
             arr = np.asarray(tensors[n], order='C')
             entries.append((n.encode(), _entry_proto(arr, offset)))
@@ -258,5 +277,7 @@ def write_checkpoint(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
               _put_varint(index_off) + _put_varint(len(index_block)))
     footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', _MAGIC)
     out += footer
-    with open(prefix + '.index', 'wb') as f:
+    with open(tmp_index, 'wb') as f:
         f.write(bytes(out))
+    os.replace(tmp_data, prefix + '.data-00000-of-00001')
+    os.replace(tmp_index, prefix + '.index')

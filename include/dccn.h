@@ -198,6 +198,18 @@ int dccn_tx_frames(dccn_handle* h, const uint8_t* bits_dev, int64_t B,
                    const float* constellation_dev, float pilot_re, float pilot_im,
                    float* tx_dev, void* stream);
 
+/* Fused feeder for nfft = 64: dccn_tx_frames followed by the static branch of dccn_chan_fading on every frame, in ONE
+ * kernel -- the transmitted frame never touches HBM.  Replaces the call pair
+ *   iq_tx_cmpx, test_xs, _ = ofdmobj.ofdm_tx_frame_np(test_ys); test_xs, _ = fading.run(iq_tx_cmpx)
+ * (dev/py/ofdmreceiver_np.py:227-228, dev/py/ofdmreceiver_np_mp.py:84-87) for a single static profile.  Bit-identical to
+ * the two separate calls.  Accumulates the batch power for a following dccn_chan_awgn (reset_power != 0 zeroes it first).
+ * tx_dev: optional copy of the transmitted frames [B,S,T,2] (NULL = not wanted).  z_dev: optional injected path gains
+ * [B, n_taps, 2] float64 (NULL = Philox draws from `seed`, the same stream dccn_chan_fading uses). */
+int dccn_tx_fade(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int32_t* data_sc_dev, int n_data,
+                 const int32_t* pilot_sc_dev, int n_pilot, const float* constellation_dev, float pilot_re, float pilot_im,
+                 const double* alpha_dev, const double* coeff_dev, int n_taps, int n_fir, const double* z_dev,
+                 uint64_t seed, int reset_power, float* tx_dev, float* faded_dev, void* stream);
+
 /* -- BASELINE config 4: transfer learning of the equalizer in front of the frozen receiver.
  * Replaces `session.run([train_op, ce_mean, ...], {x, y})` (dev/py/ofdmreceiver_np_mp.py:419) with the graph of
  * dev/py/ofdmreceiver_np_mp.py:335-347:  total_loss = ce_mean + reg_coeff * sum(l2 * sum(w^2)) over kernel+bias of
@@ -252,6 +264,12 @@ int dccn_debug_mma_rate(int bn, int n_mma, int per_commit, int mode, int dep, in
 
 /* uniform random bits (util.bit_source, dev/py/util.py:25-34) from Philox */
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream);
+
+/* Host helper (no GPU involved): CRC-32C (Castagnoli) of `n` bytes continuing from `crc` (0 to start) -- the checksum of
+ * every tensor and table block in a TF-bundle checkpoint (`tf.train.Saver`, dev/py/ofdmreceiver_np.py:192,268-272).
+ * The Python writer (dl_ofdm_b200/tfbundle.py) saves a 12 MB equalizer checkpoint on every improving epoch; a
+ * byte-at-a-time Python loop made that save cost more than the epoch it follows. */
+uint32_t dccn_crc32c(const void* data_host, size_t n, uint32_t crc);
 
 #ifdef __cplusplus
 }

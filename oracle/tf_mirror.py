@@ -26,8 +26,8 @@ BN_EPS = 1e-9
 LN_EPS = 1e-12
 
 
-def _t(a):
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
 
 
 def conv2d_complex_tf(x, kernel, bias, padding):
@@ -56,8 +56,11 @@ class TFMirror:
     """Holds fp32 torch copies of the weights and runs the reference dataflow."""
 
     def __init__(self, w, nbits, nfft=64, cp_len=16, use_cp=True, head='dev', nfilter=64,
-                 equalizer=False):
-        self.w = {k: _t(v) for k, v in w.items()}
+                 equalizer=False, dtype=torch.float32):
+        """dtype float32 = the reference's arithmetic (the CPU baseline); float64 makes the mirror an independent
+        high-precision check of the NumPy restatement (tests/test_oracle_golden.py)."""
+        self.dtype = dtype
+        self.w = {k: _t(v, dtype) for k, v in w.items()}
         self.nbits, self.K, self.CP = nbits, nfft, cp_len
         self.use_cp, self.head, self.F, self.eq = use_cp, head, nfilter, equalizer
 
@@ -128,7 +131,7 @@ class TFMirror:
 
     @torch.no_grad()
     def forward(self, x):
-        z = self.norm(_t(x))
+        z = self.norm(_t(x, self.dtype))
         if self.eq:
             z = self.equalizer(z)
         return self.dense_rx(z)

@@ -25,13 +25,24 @@ def v1_weights(npz):
     """Expand a committed v1 fixture (live centre tap only) back to TF variable layout."""
     w = {}
     for k in npz.files:
-        w[k.replace('.', '/')] = npz[k]
+        if not k.startswith('meta_'):
+            w[k.replace('.', '/')] = npz[k]
     shape = tuple(int(v) for v in w.pop('fft_like/conv3d/kernel_shape'))
     centre = w.pop('fft_like/conv3d/kernel_center')
     full = np.zeros(shape, dtype=np.float32)
     full[0, (shape[1] - 1) // 2, 0] = centre
     w['fft_like/conv3d/kernel'] = full
     return w
+
+
+dev_weights = v1_weights        # same fixture format (tools/train_fixture.py): live centre tap of fft_like only
+
+
+@pytest.fixture(scope='session')
+def trained_dev():
+    """16-QAM receiver + equalizer_ofdm TRAINED on the GPU with the reference's two-phase schedule
+    (tools/train_fixture.py: AWGN 20 dB, then EPA transfer learning from TF's zero-bias init) -- TF variable names."""
+    return dev_weights(np.load(os.path.join(GOLDEN, 'dev_4mod_eq_trained.npz'), allow_pickle=False))
 
 
 @pytest.fixture(scope='session')

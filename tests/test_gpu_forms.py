@@ -180,3 +180,38 @@ def test_tx_v2_golden(libdccn, golden, monkeypatch, tag, nb, pilot, nsym):
         res[v2] = a
         m.close()
     assert np.abs(res['0'] - res['1']).max() < 1.2e-7          # both round an fp64 result: at most one fp32 ulp apart
+
+
+@pytest.mark.parametrize('chan', ['EPA', 'ETU', 'Flat', 'AWGN'])
+@pytest.mark.parametrize('nb', [4, 1])
+def test_tx_fade_equals_separate_kernels(libdccn, chan, nb):
+    """dccn_tx_fade (transmitter + static Rayleigh FIR in one kernel, frame kept in shared memory) == dccn_tx_frames followed
+    by dccn_chan_fading, bit for bit: faded frames, the optional copy of the transmitted frames, and (through the batch power)
+    the AWGN output; Philox path gains and injected ones; ragged batch."""
+    from dl_ofdm_b200.engine import DCCN, bit_source_gpu
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import const_map, ofdm_tx
+    from dl_ofdm_b200.radio import rayleigh_chan_lte
+    B = 1037
+    fl = Flags(nbits=nb, channel=chan)
+    o = ofdm_tx(fl)
+    m = DCCN(nbits=nb, n_data=o.frame_size, precision='exact')
+    bits = bit_source_gpu(B * o.frame_size * nb, seed=5, device=m.device).view(B, o.frame_size, nb)
+    snr = torch.full((B,), 12.0, device=m.device)
+    ch_a = rayleigh_chan_lte(fl, o.Fs, engine=m, seed=3)
+    ch_b = rayleigh_chan_lte(fl, o.Fs, engine=m, seed=3)
+    tx = m.transmit(bits, o, const_map(nb))
+    rx_sep = ch_a.run(tx, snr)
+    rx_fused = ch_b.run_bits(bits, o, const_map(nb), snr)
+    assert torch.equal(rx_sep, rx_fused)
+    alpha, coeff = ch_a._profile(ch_a.profiles[0], m.device)
+    n_taps = 0 if coeff is None else coeff.numel()
+    z = torch.randn((B, max(n_taps, 1), 2), dtype=torch.float64, device=m.device) * np.sqrt(0.5)
+    zz = z if n_taps else None
+    faded_sep = torch.empty_like(tx)
+    m.fading(tx, faded_sep, alpha, coeff, 0.0, o.Fs, zz, 0, 0, 1, True)
+    faded, tx2 = m.transmit_fade(bits, o, const_map(nb), alpha, coeff, zz, seed=0, want_tx=True)
+    assert torch.equal(tx2, tx) and torch.equal(faded, faded_sep)
+    if n_taps == 0:
+        assert torch.equal(faded, tx)
+    m.close()

@@ -206,6 +206,114 @@ def test_equalizer_seeded(libdccn, precision, cp):
     assert np.array_equal(out['hard'].cpu().numpy()[decided], hard_ref[decided])
 
 
+# ---------------------------------------------------------------------------------------------
+# a4 on TRAINED variables (tests/golden/dev_4mod_eq_trained.npz, tools/train_fixture.py): BASELINE config 3 frames
+# (16-QAM, LTE-EPA Rayleigh + AWGN) made by the GPU transmitter / channel kernels (golden-tested above), every frame
+# compared -- no conditioning mask: a trained channel estimate stays away from zero.
+# ---------------------------------------------------------------------------------------------
+def _config3_frames(m, B, snr_db, seed, nb=4, chan='EPA'):
+    from dl_ofdm_b200.engine import bit_source_gpu
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import const_map, ofdm_tx
+    from dl_ofdm_b200.radio import rayleigh_chan_lte
+    fl = Flags(nbits=nb, channel=chan)
+    o = ofdm_tx(fl)
+    bits = bit_source_gpu(B * o.frame_size * nb, seed=seed, device=m.device).view(B, o.frame_size, nb)
+    tx = m.transmit(bits, o, const_map(nb))
+    x = rayleigh_chan_lte(fl, o.Fs, engine=m, seed=seed + 1).run(tx, torch.full((B,), float(snr_db), device=m.device))
+    return x, bits
+
+
+@pytest.mark.parametrize('precision,f16', [('exact', '1'), ('parity', '1'), ('parity', '0')])
+@pytest.mark.parametrize('snr_db', [15.0, 30.0])
+def test_equalizer_trained(libdccn, trained_dev, monkeypatch, precision, f16, snr_db):
+    """eq + rx on trained variables against the fp64 oracle with the receiver tests' criterion (_check_soft: p99.9 <= 1e-5
+    or 1.5 x the oracle's own fp32 error, hard bits identical outside the 1e-4 margin), for the fp32 CUDA-core path and
+    both tensor-core forms (fp16 hi/lo = default, tf32 hi/lo)."""
+    monkeypatch.setenv('DCCN_F16X3', f16)
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle.dccn_oracle_lean import LeanModel
+    nb, B = 4, 900                                   # ragged: 900 frames / 6300 symbol rows are not multiples of 128
+    m = DCCN(nbits=nb, equalizer=True, precision=precision, chunk_frames=512)
+    m.load_weights(trained_dev)
+    x, bits = _config3_frames(m, B, snr_db, seed=31)
+    out = m.forward(x, bits, want_eq=True, want_chest=True)
+    torch.cuda.synchronize()
+    xs, bs = x.cpu().numpy(), bits.cpu().numpy()
+    z, _, _ = orc.batch_moment_norm(xs, np.float64)
+    soft_ref, eq_ref, chest_ref = LeanModel(trained_dev, nb).forward(z)
+    z32, _, _ = orc.batch_moment_norm(xs, np.float32)
+    soft_ref32, eq_ref32, _ = LeanModel(trained_dev, nb, dtype=np.float32).forward(z32)
+    chest = out['chest'].cpu().numpy()
+    chest = chest[..., 0] + 1j * chest[..., 1]
+    assert np.abs(chest_ref).min() > 1e-3, 'fixture: channel estimate came close to 0'
+    assert np.abs(chest - chest_ref).max() < 1e-5 * max(1.0, np.abs(chest_ref).max())
+    eq = out['eq'].cpu().numpy()
+    e32 = np.abs(eq_ref32 - eq_ref)
+    e = np.abs(eq - eq_ref)
+    assert np.quantile(e, 0.999) <= max(1e-5, 1.5 * np.quantile(e32, 0.999)), (np.quantile(e, 0.999), np.quantile(e32, 0.999))
+    assert e.max() <= max(5e-5, 2.0 * e32.max()), (e.max(), e32.max())
+    flips = _check_soft(out['soft'].cpu().numpy(), soft_ref, out['hard'].cpu().numpy(), soft_ref32)
+    _, conf_ref, ber_ref, ce_ref = orc.ber_head(soft_ref, bs)
+    conf = out['conf'].cpu().numpy()
+    assert conf.sum() == bs.size and np.abs(conf - conf_ref).sum() <= 2 * flips
+    assert abs(float(out['ce_sum'].cpu()[0]) / bs.size - ce_ref) < 1e-5
+    assert 1e-3 < ber_ref < 0.1                      # a working receiver, not the coin flip of random weights
+    m.close()
+
+
+def test_config3_full_batch_trained(libdccn, trained_dev):
+    """BASELINE config 3 at full size on trained variables: ALL 65 536 frames (8.4e7 bit decisions) of one batch against
+    the fp64 oracle, which runs in 4 096-frame chunks with the WHOLE batch's moments (a2 is a cross-batch reduction).
+    Hard bits must be identical wherever the oracle's margin |p1 - p0| >= 1e-4; the flips inside the margin are counted."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    from oracle.dccn_oracle_lean import LeanModel, batch_norm_with
+    nb, B, C = 4, 65536, 4096
+    m = DCCN(nbits=nb, equalizer=True, precision='parity')
+    m.load_weights(trained_dev)
+    x, bits = _config3_frames(m, B, 15.0, seed=77)
+    out = m.forward(x, bits)
+    torch.cuda.synchronize()
+    xd = x.double()
+    mean = xd.mean(dim=0).cpu().numpy()
+    var = xd.var(dim=0, unbiased=False).cpu().numpy()
+    del xd
+    inv = 1.0 / np.sqrt(var + 1e-9)
+    lean, lean32 = LeanModel(trained_dev, nb), LeanModel(trained_dev, nb, dtype=np.float32)
+    conf_ref = np.zeros((2, 2), dtype=np.int64)
+    flips = outside = 0
+    qs, mx, q32, mx32 = [], 0.0, [], 0.0
+    for b0 in range(0, B, C):
+        xs = x[b0:b0 + C].cpu().numpy()
+        soft_ref, _, chest = lean.forward(batch_norm_with(xs, mean, inv))
+        soft = out['soft'][b0:b0 + C].cpu().numpy()
+        hard = out['hard'][b0:b0 + C].cpu().numpy()
+        err = np.abs(soft - soft_ref)
+        qs.append(np.quantile(err, 0.999))
+        mx = max(mx, float(err.max()))
+        hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)
+        diff = hard != hard_ref
+        flips += int(diff.sum())
+        outside += int((diff & (np.abs(soft_ref[..., 1] - soft_ref[..., 0]) >= MARGIN)).sum())
+        np.add.at(conf_ref, (bits[b0:b0 + C].cpu().numpy().reshape(-1).astype(np.int64), hard_ref.reshape(-1).astype(np.int64)), 1)
+        if b0 < 2 * C:      # the oracle's own fp32 error on the first 8 192 frames (the bound's intrinsic term)
+            s32, _, _ = lean32.forward(batch_norm_with(xs, mean, inv, np.float32))
+            e32 = np.abs(s32 - soft_ref)
+            q32.append(np.quantile(e32, 0.999))
+            mx32 = max(mx32, float(e32.max()))
+    conf = out['conf'].cpu().numpy()
+    ber = (conf[0, 1] + conf[1, 0]) / conf.sum()
+    print('config 3 full batch: p99.9 |dsoft| %.3g (fp32 oracle %.3g)  max %.3g (%.3g)  flips %d / %d (outside the margin: %d)  BER %.5f'
+          % (max(qs), max(q32), mx, mx32, flips, bits.numel(), outside, ber))
+    assert outside == 0, 'hard-bit mismatch outside the tie margin'
+    assert max(qs) <= max(P999_TOL, 1.5 * max(q32)) and mx <= max(MAX_TOL, 2.0 * mx32)
+    assert conf.sum() == bits.numel() and np.abs(conf - conf_ref).sum() <= 2 * flips
+    assert 5e-3 < ber < 0.1
+    m.close()
+
+
 def test_subgraph_entry_points(libdccn):
     """ofdm_dense_rx(z) and equalizer_ofdm(z) as separate calls == the fused pass."""
     from dl_ofdm_b200 import _lib

@@ -196,7 +196,7 @@ def test_train_equalizer_driver(libdccn, tmp_path):
     if hist[1]['train_loss'] < hist[0]['train_loss']:
         a = session.engine.forward(x)['soft']
         b = s2.engine.forward(x)['soft']
-        assert torch.equal(a, b)
+        assert (a - b).abs().max().item() < 2e-6      # tf32 hi/lo form (training handle) vs fp16 hi/lo form (reloaded)
     s2.close()
     session.close()
 
@@ -314,7 +314,9 @@ def test_train_receiver_driver(libdccn, tmp_path):
             assert np.array_equal(ck[n].ravel(), session.engine.get_weight(n)), n
         s2 = load_model_np(path, FLAGS=FLAGS, ofdmobj=ofdmobj, precision='parity')
         x = torch.randn((64, 7, 80, 2), device='cuda') * 0.3
-        assert torch.equal(session.engine.forward(x)['soft'], s2.engine.forward(x)['soft'])
+        # (the training handle keeps the tf32 hi/lo GEMM form, the reloaded one runs the fp16 hi/lo form: the same
+        #  fp32-class results, not the same bits)
+        assert (session.engine.forward(x)['soft'] - s2.engine.forward(x)['soft']).abs().max().item() < 2e-6
         s2.close()
     session.close()
 

@@ -94,6 +94,74 @@ def test_oracle_equals_tf_mirror():
         assert np.quantile(np.abs(got[good] - ref[good]), 0.999) < 2e-4
 
 
+def test_oracle_equals_tf_mirror_fp64(trained_dev):
+    """The same cross-check in float64 on EVERY frame, on seeded and on the GPU-trained variables: the NumPy
+    restatement (tap loops, complex arithmetic) and the torch mirror (real zero-padded conv3d + reshape / subtract,
+    real arithmetic) share no code and agree to 1e-9 -- what is left unpinned is only TF's own kernels."""
+    torch = pytest.importorskip('torch')
+    from oracle.tf_mirror import TFMirror
+    rng = np.random.default_rng(14)
+    cases = [(4, True, trained_dev)]
+    for nb, cp in ((2, True), (3, False)):
+        cases.append((nb, cp, orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))))
+    for nb, cp, w in cases:
+        x = (rng.standard_normal((24, 7, 80, 2)) * 0.3).astype(np.float32)
+        ref, _, chest = orc.equalized_receiver(x, w, nb, 64, 16, use_cp=cp, dtype=np.float64)
+        got = TFMirror(w, nb, use_cp=cp, equalizer=True, dtype=torch.float64).forward(x).numpy()
+        # a frame whose channel estimate passes within 1e-6 of zero amplifies even fp64 rounding (no-epsilon divide)
+        scale = 1.0 / max(np.abs(chest).min(), 1e-6)
+        assert np.abs(got - ref).max() < 1e-12 * scale + 1e-10, (nb, cp, np.abs(got - ref).max())
+
+
+def test_lean_oracle_equals_literal(trained_dev):
+    """oracle/dccn_oracle_lean.py (dense-product form used for the full-size GPU parity run) == the literal op-by-op
+    restatement, float64, trained and seeded variables, with and without the cyclic prefix, receiver-only too."""
+    from oracle.dccn_oracle_lean import LeanModel, batch_norm_with
+    rng = np.random.default_rng(15)
+    x = (rng.standard_normal((40, 7, 80, 2)) * 0.3).astype(np.float32)
+    z, mean, inv = orc.batch_moment_norm(x, np.float64)
+    assert np.array_equal(batch_norm_with(x, mean, inv), z)
+    cases = [(4, True, trained_dev)]
+    for nb, cp in ((1, True), (2, False)):
+        cases.append((nb, cp, orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))))
+    for nb, cp, w in cases:
+        eq_ref, chest_ref = orc.equalizer_ofdm(z, w, 64, 16, use_cp=cp)
+        soft_ref = orc.ofdm_dense_rx(eq_ref, w, nb, 16, use_cp=cp)
+        soft, eq, chest = LeanModel(w, nb, use_cp=cp).forward(z)
+        scale = 1.0 / max(np.abs(chest_ref).min(), 1e-6)
+        assert np.abs(chest - chest_ref).max() < 1e-12
+        assert np.abs(eq - eq_ref).max() < 1e-12 * scale and np.abs(soft - soft_ref).max() < 1e-11 * scale
+        rx_ref = orc.ofdm_dense_rx(z, w, nb, 16, use_cp=cp)
+        rx, _, _ = LeanModel(w, nb, use_cp=cp, equalizer=False).forward(z)
+        assert np.abs(rx - rx_ref).max() < 1e-12
+
+
+def test_trained_fixture_is_a_working_receiver(trained_dev):
+    """The committed GPU-trained variables decode: the host transmitter + the oracle's EPA channel + AWGN at 25 dB
+    through the oracle give the BER the training run logged on the GPU (tests/golden/..., meta_curve_*)."""
+    import os
+    from conftest import GOLDEN
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from oracle.dccn_oracle_lean import LeanModel
+    meta = np.load(os.path.join(GOLDEN, 'dev_4mod_eq_trained.npz'))
+    curve = dict(zip(meta['meta_curve_snr'].tolist(), meta['meta_curve_ber'].tolist()))
+    rng = np.random.default_rng(16)
+    B, nb = 1500, 4
+    o = ofdm_tx(Flags(nbits=nb))
+    bits = rng.integers(0, 2, (B, o.frame_size, nb)).astype(np.uint8)
+    tx = o.ofdm_tx_frame_np(bits)[0]                                     # complex [B, S*T]
+    alpha = np.load(os.path.join(os.path.dirname(GOLDEN), '..', 'dl_ofdm_b200', 'data', 'lte_alpha.npz'))['epa']
+    zg = (rng.standard_normal((B, 7)) + 1j * rng.standard_normal((B, 7))) * np.sqrt(0.5)
+    faded, _ = orc.rayleigh_static(tx.reshape(B, -1), zg, orc.channel_coeff('epa'), alpha)
+    x, _, _ = orc.awgn(faded.reshape(B, 7, 80, 2), np.full((B, 1), 25.0), rng.standard_normal((B, 7, 80, 2)))
+    z, _, _ = orc.batch_moment_norm(x.astype(np.float32), np.float64)
+    soft, _, chest = LeanModel(trained_dev, nb).forward(z)
+    _, _, ber, _ = orc.ber_head(soft, bits)
+    assert 0.5 * curve[25.0] < ber < 2.0 * curve[25.0], (ber, curve[25.0])
+    assert np.abs(chest).mean() > 0.3                                    # a trained estimate, not one hovering at 0
+
+
 def test_ber_head_counts():
     soft = np.array([[[[0.7, 0.3]], [[0.5, 0.5]], [[0.2, 0.8]]]])      # [1,3,1,2]
     bits = np.array([[[0], [1], [1]]])

@@ -4,19 +4,24 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
   torchrun ... bench.py --gpus N ...           (one rank per GPU, NCCL)
 
-Workload (BASELINE.json config 3 / metric "OFDM frames/s (N=64, 16-QAM)"): 16-QAM, LTE-EPA
-Rayleigh + AWGN, B = 65536 frames of [7,80,2] fp32 per GPU, one *step* = one pass
+Workload (BASELINE.json config 3 / metric "OFDM frames/s (N=64, 16-QAM)"): 16-QAM, LTE-EPA Rayleigh + AWGN 15 dB,
+batches of B = 65536 frames of [7,80,2] fp32 per GPU; one *pass* =
   batch-moment norm -> equalizer_ofdm -> ofdm_dense_rx -> softmax/argmax -> confusion matrix
-over that batch (soft [B,320,4,2], hard [B,320,4] and the 2x2 confusion matrix are produced
-every step).  Synthetic frames: Philox bits -> GPU OFDM transmitter -> GPU EPA-FIR + AWGN, random
-glorot-initialised weights of the reference architecture (no trained dev checkpoint exists).
+over one batch (soft [B,320,4,2], hard [B,320,4] and the 2x2 confusion matrix are produced every pass), and one *step*
+= `passes_per_step` consecutive passes, chosen so that the K timed steps last >= 2 s (a 0.1 s window measures the
+boost clocks; the pass is power-limited under sustained load).  Synthetic frames: Philox bits -> GPU OFDM transmitter
++ EPA-FIR (one fused kernel) -> AWGN; weights: the receiver + equalizer TRAINED on the GPU with the reference's schedule
+(tests/golden/dev_4mod_eq_trained.npz, tools/train_fixture.py), so the BER is a receiver's, not a coin flip.
 `value`  : device-timed frames/s with inputs resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same pass through the host-buffer entry point (dccn_forward_host): pinned host
-           IQ + labels copied H2D and the confusion matrix / loss read back D2H EVERY step.
-`roofline`: dominant kernel's algorithmic FLOP/s from per-kernel CUDA events (library hook) vs
-           the measured tensor peak (MEASURED_PEAKS.json bf16 / 2 = tf32 rate).
-`cpu_baseline` / --impl reference: the restated reference (oracle/tf_mirror.py, torch-CPU fp32
-           mirror of the TF-1 graph incl. its zero-padded conv3d) on the host cores.
+`e2e`    : the same pass through the host-buffer entry point: pinned host IQ + labels (packed 8 per byte) copied H2D and
+           the confusion matrix / loss read back D2H EVERY pass; `e2e_variants` adds the one-byte-per-label call and
+           the call that also returns every hard decision.
+`roofline`: dominant kernel's algorithmic FLOP/s from per-kernel CUDA events (library hook) vs the measured tensor peak
+           of the instruction kind it issues (kind::f16 -> MEASURED_PEAKS.json bf16, sustained figure).
+`sweep_grid`: BASELINE config 5 -- the 40 SNR x 5 channel grid of 65536-frame cells sharded over the ranks, generation
+           included, ONE all-reduce (strong scaling; reported next to the weak-scaling `value`).
+`cpu_baseline` / --impl reference: the restated reference (oracle/tf_mirror.py, torch-CPU fp32 mirror of the TF-1 graph
+           incl. its zero-padded conv3d) on the host cores.
 """
 import argparse
 import json
@@ -38,9 +43,18 @@ MACS = {
     'eq_dense': 160 * 128 * 7, 'eq_dft': 128 * 128 * 7, 'eq_pilot': 896 * 32, 'eq_dense2': 32 * 896,
     'eq_dense3': 896 * 896, 'eq_dense4_tanh': 896 * 896, 'eq_conv7x64_phaseeq': 454656,
     'eq_corr_idft': 128 * 128 * 7, 'eq_idft': 128 * 128 * 7, 'eq_dense5': 256 * 160 * 7,
-    'rx_fft_like': 160 * 128 * 7, 'rx_demod_head': 896 * 640 + 320 * (2 * 16 + 18 * 8),
+    'rx_fft_like': 160 * 128 * 7, 'rx_demod_gemm': 896 * 640,
 }
-MFLOP_PER_FRAME = 2e-6 * sum(MACS.values())          # 7.330 for eq + rx at 16-QAM
+HEAD_MACS = 320 * (2 * 16 + 18 * 8)                  # per-subcarrier head, CUDA cores
+MFLOP_PER_FRAME = 2e-6 * (sum(MACS.values()) + HEAD_MACS)          # 7.330 for eq + rx at 16-QAM
+# MACs one tensor-core PASS actually executes per frame: K padded to the 64-wide k-block of the fp16 form, N to the
+# 128-wide tile, the real-only corr input (K = 64), the block band of the Toeplitz operand (37 of 49 blocks)
+EXEC_MACS = {
+    'eq_dense': 192 * 128 * 7, 'eq_dft': 128 * 128 * 7, 'eq_pilot': 896 * 32, 'eq_dense2': 64 * 896,
+    'eq_dense3': 896 * 896, 'eq_dense4_tanh': 896 * 896, 'eq_conv7x64_phaseeq': 37 * 128 * 128,
+    'eq_corr_idft': 64 * 128 * 7, 'eq_idft': 128 * 128 * 7, 'eq_dense5': 256 * 256 * 7,
+    'rx_fft_like': 192 * 128 * 7, 'rx_demod_gemm': 896 * 640,
+}
 
 
 def peaks():
@@ -117,11 +131,29 @@ def bind_to_gpu_numa(index):
     return None
 
 
+TRAINED = os.path.join(ROOT, 'tests', 'golden', 'dev_4mod_eq_trained.npz')
+WEIGHTS_DESC = None
+
+
 def make_weights(seed=2026):
+    """The 16-QAM receiver + equalizer trained on the GPU with the reference's schedule (tools/train_fixture.py; the
+    reference ships no dev-architecture checkpoint); glorot-initialised variables only if the fixture is missing."""
+    global WEIGHTS_DESC
+    if os.path.exists(TRAINED):
+        d = np.load(TRAINED, allow_pickle=False)
+        w = {k.replace('.', '/'): d[k] for k in d.files if not k.startswith('meta_')}
+        shape = tuple(int(v) for v in w.pop('fft_like/conv3d/kernel_shape'))
+        centre = w.pop('fft_like/conv3d/kernel_center')
+        full = np.zeros(shape, dtype=np.float32)
+        full[0, (shape[1] - 1) // 2, 0] = centre
+        w['fft_like/conv3d/kernel'] = full
+        WEIGHTS_DESC = 'trained on the GPU with the reference schedule (tests/golden/dev_4mod_eq_trained.npz)'
+        return w
     from dl_ofdm_b200 import init
     rng = np.random.default_rng(seed)
     w = init.receiver_variables(rng, NBITS, NFFT, CP, NSYM, NFILT, NDATA)
-    w.update(init.equalizer_variables(rng, NFFT, CP, NSYM, PILOT))
+    w.update(init.equalizer_variables(rng, NFFT, CP, NSYM, PILOT, chest_bias=(1.0, 0.0)))
+    WEIGHTS_DESC = 'glorot-initialised (trained fixture missing): BER ~ 0.5'
     return w
 
 
@@ -202,12 +234,14 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, frames_per_step):
+def workload_config(args, frames_per_step, passes_per_step=1):
     return {'workload': 'config3: 16-QAM, LTE-EPA Rayleigh + AWGN %.0f dB, N=64 CP=16 7-symbol frames; '
                         'norm -> equalizer_ofdm -> ofdm_dense_rx -> BER' % SNR_DB,
-            'frames_per_step_per_gpu': frames_per_step, 'nbits': NBITS, 'precision': args.precision,
-            'chunk_frames': args.chunk, 'parallelism': 'grid cells sharded, 1 all-reduce of the confusion matrix',
-            'l2': ('inputs per step (%.0f MB) exceed the 126 MB L2' % (frames_per_step * 4480 / 1e6)
+            'frames_per_step_per_gpu': frames_per_step * passes_per_step, 'frames_per_pass': frames_per_step,
+            'passes_per_step': passes_per_step, 'nbits': NBITS, 'precision': args.precision,
+            'chunk_frames': args.chunk, 'weights': WEIGHTS_DESC,
+            'parallelism': 'grid cells sharded, 1 all-reduce of the confusion matrix',
+            'l2': ('inputs per pass (%.0f MB) exceed the 126 MB L2' % (frames_per_step * 4480 / 1e6)
                    if args.impl == 'b200' else 'n/a (CPU arm: a bounded %d-frame sample of the workload per step)' % frames_per_step)}
 
 
@@ -225,7 +259,7 @@ def bench_train(args, dev, rank, B=4096, nbits=2):
     ofdm = ofdm_tx(fl)
     rng = np.random.default_rng(4)
     w = init.receiver_variables(rng, nbits, NFFT, CP, NSYM, NFILT, NDATA)
-    w.update(init.equalizer_variables(rng, NFFT, CP, NSYM, PILOT))
+    w.update(init.equalizer_variables(rng, NFFT, CP, NSYM, PILOT, chest_bias=(1.0, 0.0)))
     m = DCCN.from_ofdm(fl, ofdm, equalizer=True, precision=args.precision if args.precision != 'fast' else 'parity',
                        chunk_frames=B)
     m.load_weights(w)
@@ -318,6 +352,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-folded', action='store_true', help='skip the opt-in folded-schedule measurement')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary config-4 training measurement')
+    ap.add_argument('--no-grid', action='store_true', help='skip the config-5 sweep-grid measurement')
+    ap.add_argument('--grid-cells', type=int, default=0, help='limit the sweep grid to its first N cells (0 = all 200)')
+    ap.add_argument('--min-seconds', type=float, default=2.0, help='lower bound of the timed region (sets passes_per_step)')
+    ap.add_argument('--passes-per-step', type=int, default=0, help='override the automatic passes per step')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))
@@ -346,16 +384,16 @@ def main():
     w = make_weights()
     m = DCCN.from_ofdm(fl, ofdm, equalizer=True, precision=args.precision, chunk_frames=args.chunk)
     m.load_weights(w)
+    f16_form = args.precision == 'parity' and os.environ.get('DCCN_F16X3', '1') != '0'
 
     # ---- synthetic frames, generated on the GPU, resident in HBM -------------------------
     bits = bit_source_gpu(B * NDATA * NBITS, seed=1000 + rank, device=dev).view(B, NDATA, NBITS)
-    tx = m.transmit(bits, ofdm, const_map(NBITS))
     chan = rayleigh_chan_lte(fl, ofdm.Fs, engine=m, seed=77 + rank)
     snr_t = torch.full((B,), SNR_DB, dtype=torch.float32, device=dev)
-    x = chan.run(tx, snr_t)
+    x = chan.run_bits(bits, ofdm, const_map(NBITS), snr_t)
     torch.cuda.synchronize()
 
-    def step():
+    def one_pass():
         return m.forward(x, bits, want_soft=True, want_hard=True)
 
     def barrier():
@@ -364,28 +402,47 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        out = step()
+        out = one_pass()
     barrier()
+    # ---- step = passes_per_step passes, sized so that the K timed steps last >= --min-seconds ---------------------
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(5):
+        one_pass()
+    p1.record()
+    torch.cuda.synchronize()
+    pass_ms = torch.tensor([p0.elapsed_time(p1) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pass_ms, op=dist.ReduceOp.MAX)          # every rank must run the same number of passes
+    pps = args.passes_per_step or max(1, int(np.ceil(args.min_seconds * 1e3 / (args.steps * float(pass_ms[0])))))
+
+    def step():
+        o = None
+        for _ in range(pps):
+            o = one_pass()
+            conf_total.add_(o['conf'])
+        return o
+
     # ---- timed region (device events, max over ranks) -------------------------------------
     sampler = ClockSampler(list(range(world)) if world > 1 else local)    # rank 0 samples every GPU of the job
     if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
         sampler.start()
     # keep the GPU busy while nvidia-smi starts sampling: an idle gap here lets the clocks ramp down and the first
     # timed steps then pay the ramp-up (measured: +5 ms on the first step after a 150 ms sleep)
+    conf_total = torch.zeros((2, 2), dtype=torch.int64, device=dev)
     t_spin = time.perf_counter()
     while True:
-        step()
+        one_pass()
         torch.cuda.synchronize()
         if time.perf_counter() - t_spin > 0.6:      # same on every rank; nvidia-smi has printed its first rows by then
             break
     l0 = launch_count()
-    conf_total = torch.zeros((2, 2), dtype=torch.int64, device=dev)
+    conf_total.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
         out = step()
-        conf_total += out['conf']
     if world > 1:
         dist.all_reduce(conf_total)                  # the sweep's only collective: final BER all-reduce
     e1.record()
@@ -401,69 +458,112 @@ def main():
         ms_per_rank = [float(t[0]) / args.steps for t in allms]   # power capping differs from GPU to GPU
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms[0])
-    value = world * B * args.steps / (ms * 1e-3)
+    n_pass = args.steps * pps
+    value = world * B * n_pass / (ms * 1e-3)
+    conf = conf_total.cpu().numpy()
+    ber = float(conf[0, 1] + conf[1, 0]) / float(conf.sum())
+
+    # ---- a short burst (boost clocks, no sampler): what a 0.1 s window would have reported ----------------------
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    time.sleep(1.0)
+    for _ in range(2):
+        one_pass()
+    b0.record()
+    for _ in range(10):
+        one_pass()
+    b1.record()
+    torch.cuda.synchronize()
+    burst_ms = b0.elapsed_time(b1) / 10
 
     # ---- per-kernel CUDA events (library hook) -> dominant kernel + roofline ---------------
+    n_prof = max(args.steps, 10)
+    for _ in range(20):
+        one_pass()                                   # back under sustained load before the per-kernel pass
     m.profile(True)
-    for _ in range(args.steps):
-        step()
+    for _ in range(n_prof):
+        one_pass()
     prof = m.profile_collect()
     m.profile(False)
     tot_prof = sum(v[0] for v in prof.values())
     dom = max((k for k in prof if k in MACS), key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
-    frames_per_launch = B * args.steps / dom_n
+    frames_per_launch = B * n_prof / dom_n
     pk = peaks()
-    tf32_peak = pk['bf16'] / 2.0
-    achieved = 2.0 * MACS[dom] * frames_per_launch / (dom_ms / dom_n * 1e-3) / 1e12
+    # the parity GEMMs issue kind::f16 MMAs on fp16 (hi, lo) operand pairs (kind::tf32 with DCCN_F16X3=0 or in 'fast' mode):
+    # their pipe peak is the measured bf16/fp16 dense rate, the sustained figure since the kernel is timed inside a long
+    # back-to-back run; kind::tf32 runs at half of it
+    kind_peak = (pk['bf16_sustained'] or pk['bf16']) / (1.0 if f16_form else 2.0)
+    dom_s = dom_ms / dom_n * 1e-3
+    achieved = 2.0 * MACS[dom] * frames_per_launch / dom_s / 1e12
+    passes = 3 if args.precision == 'parity' else 1
+    exec_tf = 2.0 * passes * EXEC_MACS[dom] * frames_per_launch / dom_s / 1e12
+    gemm_ms = sum(prof[k][0] for k in prof if k in MACS) / n_prof
+    step_exec_tf = 2.0 * passes * sum(EXEC_MACS.values()) * B / (ms / n_pass * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom)
+            traffic = json.load(open(tp)).get(dom + ('' if f16_form else '_tf32'))
         except Exception:
             traffic = None
-    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved / tf32_peak, 'traffic': traffic,
-                'peak_note': 'kind::tf32 peak taken as %s bf16 %.0f TF/s / 2 (of %s)' % (pk['src'], pk['bf16'], pk['src']),
+    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': kind_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / kind_peak, 'traffic': traffic,
+                'peak_note': '%s dense peak = %s MEASURED_PEAKS bf16 sustained %.0f TF/s%s (burst %.0f); roofline.achieved '
+                             'counts ALGORITHMIC flops (live taps, one pass)' % (
+                                 'kind::f16' if f16_form else 'kind::tf32', pk['src'], pk['bf16_sustained'] or pk['bf16'],
+                                 '' if f16_form else ' / 2', pk['bf16']),
                 'kernel_share_of_step': dom_ms / tot_prof,
-                'mma_passes': 3 if args.precision == 'parity' else 1,
+                'mma_passes': passes,
+                'pipe_busy_frac_kernel': exec_tf / kind_peak,
+                'pipe_busy_frac_step': step_exec_tf / kind_peak,
+                'pipe_busy_note': 'executed MMA flops (3 hi/lo passes x tile-padded operands) / peak: the tensor-pipe utilisation '
+                                  'the north_star asks for; _step divides by the whole timed step incl. the non-GEMM kernels',
                 'whole_step_algorithmic_tflops': MFLOP_PER_FRAME * 1e6 * value / world / 1e12,
-                'kernel_ms': {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items())}}
+                'gemm_ms_per_pass': round(gemm_ms, 4),
+                'tf32_mma_rate_measured_tflops': 1048.0,     # profiles/mma_rate_r1c.txt: 72.7 clk per 128x128x8 kind::tf32 MMA at 1.965 GHz
+                'kernel_ms': {k: round(v[0] / n_prof, 4) for k, v in sorted(prof.items())}}
 
     # ---- the HBM-bound kernels of the path against the measured copy bandwidth ------------
     # algorithmic bytes per frame: the fp32 IQ record is 4 480 B; soft 10 240 B, hard / labels 1 280 B, out_iq 2 560 B
     m.profile(True)
-    for _ in range(3):
-        chan.run(tx, snr_t)                      # feeder: Rayleigh FIR + AWGN (timed apart from the receiver pass)
+    for _ in range(5):
+        chan.run_bits(bits, ofdm, const_map(NBITS), snr_t)    # feeder: fused transmitter + Rayleigh FIR, then AWGN
     cprof = m.profile_collect()
     m.profile(False)
-    tevt = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    tevt[0].record()
-    for _ in range(3):
-        m.transmit(bits, ofdm, const_map(NBITS))
-    tevt[1].record()
-    torch.cuda.synchronize()
     hbm_bytes = {'moments': 4480, 'prep_norm': 2 * 4480, 'rx_demod_head': 2560 + 1280 + 10240 + 1280,
-                 'chan_fir': 2 * 4480, 'chan_awgn': 2 * 4480}
+                 'chan_fir': 1280 + 4480, 'chan_awgn': 2 * 4480}
+    hbm_names = {'chan_fir': 'tx_fade (bits -> OFDM frame -> EPA FIR, fused; fp64 IDFT + complex128 FIR)'}
     hbm_kernels = {}
     for k, bpf in hbm_bytes.items():
-        src = prof if k in prof else cprof
+        src, n_k = (prof, n_prof) if k in prof else (cprof, 5)
         if k not in src:
             continue
-        ms_k = src[k][0] / (args.steps if src is prof else 3)
+        ms_k = src[k][0] / n_k
         gbs = bpf * B / (ms_k * 1e-3) / 1e9
         hbm_kernels[k] = {'ms': round(ms_k, 4), 'bytes_per_frame': bpf, 'achieved_gbs': round(gbs, 1),
                           'frac_of_hbm_peak': round(gbs / pk['hbm'], 3)}
-    ms_tx = tevt[0].elapsed_time(tevt[1]) / 3
-    hbm_kernels['tx_frame'] = {'ms': round(ms_tx, 4), 'bytes_per_frame': 1280 + 4480,
-                               'achieved_gbs': round((1280 + 4480) * B / (ms_tx * 1e-3) / 1e9, 1),
-                               'frac_of_hbm_peak': round((1280 + 4480) * B / (ms_tx * 1e-3) / 1e9 / pk['hbm'], 3)}
-    del tx
+        if k in hbm_names:
+            hbm_kernels[k]['what'] = hbm_names[k]
 
     # ---- the K-chunk knob (DCCN_KC): the headline drains the TMEM accumulator every k-block (kc = 1, the most accurate
     # setting, more accurate than fp32 FFMA); kc = 2 is still fp32-class (profiles/accuracy_r1.txt: same error as the
     # library's fp32 'exact' mode) and faster.  Reported next to the headline, never as it.
+    def timed(fn, n):
+        for _ in range(args.warmup):
+            o = fn()
+        barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(n):
+            o = fn()
+        k1.record()
+        barrier()
+        kms = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+        return float(kms[0]) / n, o
+
+    n_side = max(args.steps, 20)
     kc2 = None
     if not args.no_folded and args.precision == 'parity':
         os.environ['DCCN_KC'] = '2'
@@ -472,20 +572,8 @@ def main():
         finally:
             del os.environ['DCCN_KC']
         m2.load_weights(w)
-        for _ in range(args.warmup):
-            o2 = m2.forward(x, bits, want_soft=True, want_hard=True)
-        barrier()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(args.steps):
-            o2 = m2.forward(x, bits, want_soft=True, want_hard=True)
-        k1.record()
-        barrier()
-        kms = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(kms, op=dist.ReduceOp.MAX)
-        kc2 = {'value': world * B * args.steps / (float(kms[0]) * 1e-3), 'unit': 'frames/s',
-               'ms_per_step': float(kms[0]) / args.steps,
+        kms, o2 = timed(lambda: m2.forward(x, bits, want_soft=True, want_hard=True), n_side)
+        kc2 = {'value': world * B / (kms * 1e-3), 'unit': 'frames/s', 'ms_per_pass': kms,
                'what': 'same layer-by-layer pass with the TMEM accumulator drained every 2 k-blocks (DCCN_KC=2); opt-in',
                'hard_bits_equal_to_kc1': float((o2['hard'] == out['hard']).float().mean()),
                'max_abs_soft_diff_vs_kc1': float((o2['soft'] - out['soft']).abs().max())}
@@ -496,81 +584,121 @@ def main():
     folded = None
     if not args.no_folded:
         from dl_ofdm_b200 import _lib as _l
-        def fstep():
-            return m.forward(x, bits, want_soft=True, want_hard=True, flags=_l.FWD_FOLDED)
-        for _ in range(args.warmup):
-            fo = fstep()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            fo = fstep()
-        f1.record()
-        barrier()
-        fms = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
-        m.profile(True)
-        for _ in range(args.steps):
-            fstep()
-        fprof = m.profile_collect()
-        m.profile(False)
-        agree = float((fo['hard'] == out['hard']).float().mean())
-        folded = {'value': world * B * args.steps / (float(fms[0]) * 1e-3), 'unit': 'frames/s',
-                  'ms_per_step': float(fms[0]) / args.steps,
+        fms, fo = timed(lambda: m.forward(x, bits, want_soft=True, want_hard=True, flags=_l.FWD_FOLDED), n_side)
+        folded = {'value': world * B / (fms * 1e-3), 'unit': 'frames/s', 'ms_per_pass': fms,
                   'what': 'same pass with consecutive linear layers pre-multiplied at load time (12 GEMMs -> 5); '
                           'opt-in via DCCN_FWD_FOLDED, not the headline',
-                  'hard_bits_equal_to_layerwise': agree,
-                  'kernel_ms': {k: round(v[0] / args.steps, 4) for k, v in sorted(fprof.items())}}
+                  'hard_bits_equal_to_layerwise': float((fo['hard'] == out['hard']).float().mean())}
+        del fo
 
-    # ---- end to end through the host-buffer entry point ------------------------------------
+    # ---- end to end through the host-buffer entry points -----------------------------------
+    # every pass copies ITS inputs from pinned host memory (H2D) and reads ITS results back (D2H); the H2D copy of pass
+    # i+1 overlaps the pass over batch i (two slots), the D2H of pass i the pass over batch i+1 (own stream)
     xh = x.cpu().pin_memory()
     bh = bits.cpu().pin_memory()
-    for _ in range(2):
-        m.forward_host(xh, bh)
-    barrier()
-    # pipelined host entry point: the H2D copy of step i+1 overlaps the pass over step i; every step
-    # still copies its own inputs H2D and reads its own confusion matrix / loss back
-    t0 = time.perf_counter()
-    m.forward_host_begin(0, xh, bh)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            m.forward_host_begin((i + 1) & 1, xh, bh)
-        conf_h, ce_h = m.forward_host_end(i & 1)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {'value': world * B * args.steps / float(te[0]), 'unit': 'frames/s',
-           'h2d_bytes_per_step': int(xh.numel() * 4 + bh.numel()), 'd2h_bytes_per_step': 4 * 8 + 8,
-           'h2d_gbps': round(args.steps * (xh.numel() * 4 + bh.numel()) / float(te[0]) / 1e9, 1),
-           'numa_local_cpus': numa, 'pipelined': 'H2D of step i+1 overlaps the pass over step i (2 slots)'}
+    ph = torch.as_tensor(np.packbits(bh.numpy().reshape(-1), bitorder='little')).pin_memory()
+    hh = [torch.empty((B, NDATA, NBITS), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    n_e2e = max(args.steps, min(n_pass, 100))
 
-    # ---- staged (never run on a GPU yet, opt-in with BENCH_STAGED=1): the same end-to-end loop with the labels packed
-    # 8 per byte (dccn_forward_host_begin_packed): 4 640 instead of 5 760 B per frame over PCIe
-    e2e_packed = None
-    if os.environ.get('BENCH_STAGED'):
-        ph = torch.as_tensor(np.packbits(bh.numpy().reshape(-1), bitorder='little')).pin_memory()
-        m.forward_host_begin_packed(0, xh, ph)
-        conf_p, _ = m.forward_host_end(0)
+    def e2e_run(begin):
+        begin(0)
+        conf_e = m.forward_host_end(0)[0]
         barrier()
         t0 = time.perf_counter()
-        m.forward_host_begin_packed(0, xh, ph)
-        for i in range(args.steps):
-            if i + 1 < args.steps:
-                m.forward_host_begin_packed((i + 1) & 1, xh, ph)
-            conf_p, _ = m.forward_host_end(i & 1)
+        begin(0)
+        for i in range(n_e2e):
+            if i + 1 < n_e2e:
+                begin((i + 1) & 1)
+            conf_e, _ = m.forward_host_end(i & 1)
         barrier()
-        tp_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tp_, op=dist.ReduceOp.MAX)
-        e2e_packed = {'value': world * B * args.steps / float(tp_[0]), 'unit': 'frames/s',
-                      'h2d_bytes_per_step': int(xh.numel() * 4 + ph.numel()),
-                      'conf_equal_to_unpacked': bool(np.array_equal(conf_p, conf_h))}
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * B * n_e2e / float(te[0]), float(te[0]), conf_e
 
-    conf = conf_total.cpu().numpy()
-    ber = float(conf[0, 1] + conf[1, 0]) / float(conf.sum())
+    bytes_iq, bytes_lab, bytes_pack, bytes_res = int(xh.numel() * 4), int(bh.numel()), int(ph.numel()), 4 * 8 + 8
+    v_pack, t_pack, conf_p = e2e_run(lambda s_: m.forward_host_begin_packed(s_, xh, ph))
+    v_u8, t_u8, conf_u = e2e_run(lambda s_: m.forward_host_begin(s_, xh, bh))
+    v_hard, t_hard, conf_hd = e2e_run(lambda s_: m.forward_host_begin_packed(s_, xh, ph, hh[s_]))
+    hard_ok = bool(torch.equal(hh[(n_e2e - 1) & 1], out['hard'].cpu()))
+    # H2D alone (all ranks at once): the ceiling the host fabric puts on any end-to-end number
+    cs = torch.cuda.Stream()
+    xd = torch.empty_like(x)
+    with torch.cuda.stream(cs):
+        xd.copy_(xh, non_blocking=True)
+    cs.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(cs):
+        for _ in range(10):
+            xd.copy_(xh, non_blocking=True)
+    cs.synchronize()
+    th = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    h2d_only = 10 * bytes_iq / float(th[0]) / 1e9
+    del xd
+    e2e = {'value': v_pack, 'unit': 'frames/s', 'h2d_bytes_per_step': (bytes_iq + bytes_pack) * pps,
+           'd2h_bytes_per_step': bytes_res * pps, 'h2d_bytes_per_pass': bytes_iq + bytes_pack, 'passes_timed': n_e2e,
+           'h2d_gbps': round(n_e2e * (bytes_iq + bytes_pack) / t_pack / 1e9, 1),
+           'h2d_only_gbps_per_gpu': round(h2d_only, 1),
+           'h2d_bound_frames_per_s': round(world * h2d_only * 1e9 / (4480 + 160), 0),
+           'api': 'dccn_forward_host_begin_packed / _end: fp32 IQ + labels packed 8 per byte in, confusion matrix + loss out '
+                  '(the fetches of the reference\'s test_model: conf_matrix, linear_ber, ce_mean)',
+           'conf_equal_to_device_pass': bool(np.array_equal(conf_p, out['conf'].cpu().numpy())),
+           'numa_local_cpus': numa, 'pipelined': 'H2D of pass i+1 and D2H of pass i-1 overlap the pass over batch i (2 slots, 3 streams)'}
+    e2e_variants = {
+        'labels_one_byte_each': {'value': v_u8, 'unit': 'frames/s', 'h2d_bytes_per_pass': bytes_iq + bytes_lab,
+                                 'h2d_gbps': round(n_e2e * (bytes_iq + bytes_lab) / t_u8 / 1e9, 1),
+                                 'api': 'dccn_forward_host_begin (round-1 headline call)'},
+        'hard_bits_returned': {'value': v_hard, 'unit': 'frames/s', 'h2d_bytes_per_pass': bytes_iq + bytes_pack,
+                               'd2h_bytes_per_pass': bytes_lab + bytes_res, 'hard_bits_equal_to_device_pass': hard_ok,
+                               'api': 'dccn_forward_host_begin_packed(hard_host=...): every hard decision copied back '
+                                      '(D2H on the other copy engine)'}}
+    del xh, bh, ph, hh
+
+    # ---- BASELINE config 5: the SNR x channel grid sharded over the ranks, generation included ------------------
+    grid = None
+    if not args.no_grid:
+        import types
+        from dl_ofdm_b200 import sweep
+        chans = ['Flat', 'EPA', 'EVA', 'ETU', 'Custom']
+        cells = sweep.make_cells(chans, range(-10, 30), (NBITS,))
+        cells = cells[:args.grid_cells] if args.grid_cells else cells
+        runner = sweep.CellRunner(types.SimpleNamespace(engine=m, FLAGS=fl, ofdm=ofdm), B, seed=5)
+        mine = sweep.shard(cells, rank, world)
+        for i in mine[:2]:
+            runner(i, cells[i])                          # warm-up (allocator, first-use paths)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l1 = launch_count()
+        t0 = time.perf_counter()
+        g0.record()
+        gconf, gce = sweep.run_sweep(cells, runner, device=dev)      # includes the one all-reduce
+        g1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        gl = launch_count() - l1
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        per_rank = [float(gms[0])]
+        if world > 1:
+            allg = [torch.zeros_like(gms) for _ in range(world)]
+            dist.all_gather(allg, gms)
+            per_rank = [float(t[0]) for t in allg]
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        rows = sweep.ber_table(cells, gconf, gce)
+        pick = {(r['channel'], int(r['SNR'])): r['BER'] for r in rows}
+        grid = {'workload': 'config5: 16-QAM, %d cells = %d SNR x %s, %d frames per cell, bits -> OFDM TX -> Rayleigh FIR -> AWGN '
+                            '-> norm -> equalizer -> receiver -> BER per cell; cells dealt round-robin, ONE all-reduce' % (
+                                len(cells), len(cells) // len(chans) if len(cells) >= len(chans) else len(cells), '/'.join(chans), B),
+                'scaling': 'strong', 'cells': len(cells), 'frames': len(cells) * B,
+                'seconds': float(gms[0]) * 1e-3, 'wall_seconds_rank0': wall,
+                'frames_per_s': len(cells) * B / (float(gms[0]) * 1e-3), 'cells_per_s': len(cells) / (float(gms[0]) * 1e-3),
+                'ms_per_cell_per_gpu': float(gms[0]) / max(1, len(mine)),
+                'device_ms_per_rank': [round(t, 2) for t in per_rank], 'gpu_launches': int(gl),
+                'ber_samples': {'%s@%ddB' % k: pick[k] for k in [('EPA', 0), ('EPA', 15), ('EPA', 29), ('ETU', 15), ('Flat', 15)] if k in pick},
+                'bits_counted': int(gconf.sum())}
+
     train = train_rx = None
     if not args.no_train:
         try:
@@ -586,15 +714,22 @@ def main():
             'metric': 'ofdm_frames_per_s_n64_16qam', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'parity': 'tf32x3 (fp32-equivalent: 3-pass hi/lo split, fp32 accumulate)',
+            'dtype': {'parity': 'f16x3 (fp32-equivalent: fp16 hi/lo operand pairs, 3 kind::f16 MMA passes, fp32 accumulate '
+                                'drained every k-block)' if f16_form else
+                                'tf32x3 (fp32-equivalent: 3-pass hi/lo split, fp32 accumulate)',
                       'fast': 'tf32', 'exact': 'f32'}[args.precision],
-            'data': 'synthetic', 'config': workload_config(args, B),
-            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': sampler.summary(), 'ms_per_step_per_rank': [round(t, 4) for t in ms_per_rank],
+            'data': 'synthetic', 'config': workload_config(args, B, pps),
+            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'clocks': sampler.summary(),
+            'ms_per_pass': ms / n_pass, 'timed_region_s': ms * 1e-3,
+            'ms_per_step_per_rank': [round(t, 4) for t in ms_per_rank],
+            'burst': {'ms_per_pass': burst_ms, 'value': world * B / (burst_ms * 1e-3),
+                      'what': '10 passes after a 1 s pause (boost clocks, no sampler) -- the round-1 style 0.1 s window; '
+                              'the headline is the sustained figure'},
             'ber': ber, 'bits_counted': int(conf.sum()),
             'hbm_kernels': {'peak_gbs': pk['hbm'], 'kernels': hbm_kernels},
+            'e2e_variants': e2e_variants, 'sweep_grid': grid,
             'train_config4': train, 'train_receiver': train_rx, 'kc2_schedule': kc2, 'folded_schedule': folded,
-            'e2e_packed_labels': e2e_packed,
-            'target': {'frames_per_s_8gpu': 1e8, 'note': 'north_star target; random-init weights so BER ~ 0.5'},
+            'target': {'frames_per_s_8gpu': 1e8, 'tensor_pipe_frac': 0.4, 'note': 'north_star targets'},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

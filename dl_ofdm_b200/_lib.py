@@ -53,7 +53,7 @@ PROTOTYPES = {
     'dccn_forward_host': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     'dccn_forward_host_begin': (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     'dccn_forward_host_end': (C.c_int, [_vp, _i32, _vp, _vp]),
-    'dccn_forward_host_begin_packed': (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    'dccn_forward_host_begin_packed': (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     'dccn_cconv2d': (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'dccn_vconv2d': (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'dccn_chan_fir_awgn': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _u64,

@@ -810,11 +810,13 @@ static int run_head(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft
   int rc = run_gemm(h, SLOT_R2_GEMM, h->r2, h->r1o, 0, Bc, store_epi(h->r2, oiq, 0, Bc), s);
   if (rc) return rc;
   LaunchScope ls(h, SLOT_R2_HEAD, s);
-  const long long total = (long long)Bc * (h->r2.N >> 1);
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)h->num_sms * 16;
-  if (blocks > cap) blocks = cap;
-  head_kernel<NB, V1><<<(unsigned)blocks, 256, 0, s>>>(oiq.p0, e);
+  // one block per frame at a time (thread <-> data subcarrier), as many resident blocks as fit
+  const int D = h->r2.N >> 1;
+  int threads = ((D + 1) / 2 + 31) / 32 * 32;        // two subcarriers per thread
+  if (threads > 256) threads = 256;
+  long long blocks = (long long)h->num_sms * (1536 / threads);
+  if (blocks > Bc) blocks = Bc;
+  head_kernel<NB, V1><<<(unsigned)blocks, threads, 0, s>>>(oiq.p0, e);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1241,10 +1243,12 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
     if (cudaMallocHost((void**)&h->slot[i].h_conf, 4 * sizeof(int64_t)) != cudaSuccess ||
         cudaMallocHost((void**)&h->slot[i].h_ce, sizeof(double)) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->slot[i].copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->slot[i].computed, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming) != cudaSuccess)
       rc = set_error(-1, "host-slot allocation failed");
   }
-  if (!rc && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+  if (!rc && (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+              cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess))
     rc = set_error(-1, "cudaStreamCreate failed");
   if (rc) {
     dccn_destroy(h);
@@ -1262,9 +1266,11 @@ void dccn_destroy(dccn_handle* h) {
     if (h->slot[i].h_conf) cudaFreeHost(h->slot[i].h_conf);
     if (h->slot[i].h_ce) cudaFreeHost(h->slot[i].h_ce);
     if (h->slot[i].copied) cudaEventDestroy(h->slot[i].copied);
+    if (h->slot[i].computed) cudaEventDestroy(h->slot[i].computed);
     if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->ws_allocs) cudaFree(p);
   delete h;
@@ -1381,18 +1387,22 @@ int dccn_forward_host_begin(dccn_handle* h, int slot, const float* x_host, int64
   int rc = dccn_forward(h, S.d_x, B, bits_host ? S.d_bits : nullptr, nullptr, hard_host ? S.d_hard : nullptr, nullptr,
                         nullptr, S.d_conf, S.d_ce, 0, s);
   if (rc) return rc;
-  if (hard_host) DCCN_CUDA_OK(cudaMemcpyAsync(hard_host, S.d_hard, (size_t)B * nb, cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_conf, S.d_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_ce, S.d_ce, sizeof(double), cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaEventRecord(S.done, s));
+  // results leave on their own stream: the D2H copy of this batch's decisions (the other copy engine) overlaps the
+  // next batch's pass on the caller's stream and its H2D copy on the copy stream
+  DCCN_CUDA_OK(cudaEventRecord(S.computed, s));
+  DCCN_CUDA_OK(cudaStreamWaitEvent(h->d2h_stream, S.computed, 0));
+  if (hard_host) DCCN_CUDA_OK(cudaMemcpyAsync(hard_host, S.d_hard, (size_t)B * nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_conf, S.d_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_ce, S.d_ce, sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+  DCCN_CUDA_OK(cudaEventRecord(S.done, h->d2h_stream));
   S.busy = true;
   S.B = B;
   return 0;
 }
 
-// Same as dccn_forward_host_begin with the labels packed 8 per byte (staged: written without a GPU at hand).
+// Same as dccn_forward_host_begin with the labels packed 8 per byte.
 int dccn_forward_host_begin_packed(dccn_handle* h, int slot, const float* x_host, int64_t B,
-                                   const uint8_t* bits_packed_host, void* stream) {
+                                   const uint8_t* bits_packed_host, uint8_t* hard_host, void* stream) {
   DCCN_CHECK(h && x_host && bits_packed_host && B > 0 && (slot == 0 || slot == 1), "bad argument");
   dccn_handle::HostSlot& S = h->slot[slot];
   DCCN_CHECK(!S.busy, "slot %d still in flight: call dccn_forward_host_end first", slot);
@@ -1426,11 +1436,15 @@ int dccn_forward_host_begin_packed(dccn_handle* h, int slot, const float* x_host
   }
   DCCN_CUDA_OK(cudaMemsetAsync(S.d_conf, 0, 4 * sizeof(int64_t), s));
   DCCN_CUDA_OK(cudaMemsetAsync(S.d_ce, 0, sizeof(double), s));
-  int rc = dccn_forward(h, S.d_x, B, S.d_bits, nullptr, nullptr, nullptr, nullptr, S.d_conf, S.d_ce, 0, s);
+  int rc = dccn_forward(h, S.d_x, B, S.d_bits, nullptr, hard_host ? S.d_hard : nullptr, nullptr, nullptr, S.d_conf, S.d_ce,
+                        0, s);
   if (rc) return rc;
-  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_conf, S.d_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_ce, S.d_ce, sizeof(double), cudaMemcpyDeviceToHost, s));
-  DCCN_CUDA_OK(cudaEventRecord(S.done, s));
+  DCCN_CUDA_OK(cudaEventRecord(S.computed, s));
+  DCCN_CUDA_OK(cudaStreamWaitEvent(h->d2h_stream, S.computed, 0));
+  if (hard_host) DCCN_CUDA_OK(cudaMemcpyAsync(hard_host, S.d_hard, (size_t)B * nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_conf, S.d_conf, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+  DCCN_CUDA_OK(cudaMemcpyAsync(S.h_ce, S.d_ce, sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+  DCCN_CUDA_OK(cudaEventRecord(S.done, h->d2h_stream));
   S.busy = true;
   S.B = B;
   return 0;

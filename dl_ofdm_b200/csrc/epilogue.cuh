@@ -332,9 +332,85 @@ struct EpiHead {
   int M, N;
   static constexpr bool kWarpStore = false;
   struct State {   // per-thread accumulators (flushed once per thread)
+    // confusion counts as four 16-bit fields of one word: field (truth * 2 + decision); spilled into `big` before a
+    // field can overflow
+    unsigned long long packed = 0ull;
+    unsigned int n = 0;
     unsigned int c00 = 0, c01 = 0, c10 = 0, c11 = 0;
     float ce = 0.f;
   };
+  DCCN_DEVINL static void spill(State& st) {
+    st.c00 += (unsigned)(st.packed & 0xFFFFull);
+    st.c01 += (unsigned)((st.packed >> 16) & 0xFFFFull);
+    st.c10 += (unsigned)((st.packed >> 32) & 0xFFFFull);
+    st.c11 += (unsigned)(st.packed >> 48);
+    st.packed = 0ull;
+    st.n = 0;
+  }
+
+  // The head of ONE data subcarrier: (I, Q) = out_iq (bias already added) -> probabilities p[2*NB] (p0, p1 per bit) and
+  // the hard decisions as bit k of the return value.
+  DCCN_DEVINL unsigned subcarrier(float I, float Q, float (&p)[2 * NB]) const {
+    float h[MO];
+#pragma unroll
+    for (int m = 0; m < MO; ++m) h[m] = I * hw.Wc[0][m] + Q * hw.Wc[1][m] + hw.bc[m];
+    if constexpr (V1) {
+      float h2[MO];
+#pragma unroll
+      for (int n = 0; n < MO; ++n) {
+        float a = hw.bc1[n];
+#pragma unroll
+        for (int m = 0; m < MO; ++m) a += h[m] * hw.Wc1[m][n];
+        h2[n] = a;
+      }
+#pragma unroll
+      for (int m = 0; m < MO; ++m) h[m] = h2[m];
+    }
+#pragma unroll
+    for (int m = 0; m < MO; ++m) h[m] = fmaxf(0.2f * h[m], h[m]);
+    unsigned hbits = 0u;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      float l0 = hw.b1[2 * k], l1 = hw.b1[2 * k + 1];
+#pragma unroll
+      for (int m = 0; m < MO; ++m) {
+        l0 += h[m] * hw.W1[m][2 * k];
+        l1 += h[m] * hw.W1[m][2 * k + 1];
+      }
+      l0 += I * hw.W1[MO][2 * k] + Q * hw.W1[MO + 1][2 * k];
+      l1 += I * hw.W1[MO][2 * k + 1] + Q * hw.W1[MO + 1][2 * k + 1];
+      l0 = fmaxf(0.2f * l0, l0);
+      l1 = fmaxf(0.2f * l1, l1);
+      // softmax over the pair: exp(l - max) / sum  ==  {1, t} / (1 + t),  t = exp(-|l1 - l0|) in (0, 1].
+      // ex2.approx on -|d| * log2(e) is within 2 ulp of exp() for |d| < 1 and its absolute error only shrinks beyond;
+      // 1 / s is the correctly rounded reciprocal, t / s one more rounding: |dp| <= 1.5e-7, far inside the 1e-5 budget
+      // (the libm expf + two IEEE divides this replaces were a quarter of the kernel's instruction count)
+      const float t = __expf(-fabsf(l1 - l0));
+      const float pb = __frcp_rn(1.0f + t), ps = t * pb;       // probability of the larger / smaller logit
+      const bool one_big = l1 > l0;
+      const float p0 = one_big ? ps : pb, p1 = one_big ? pb : ps;
+      p[2 * k] = p0;
+      p[2 * k + 1] = p1;
+      hbits |= (p1 > p0 ? 1u : 0u) << k;                       // tf.argmax: first index on ties
+    }
+    return hbits;
+  }
+
+  // labels y (bit k = label of bit k), decisions hbits, probabilities p -> confusion counts + double-softmax CE
+  DCCN_DEVINL void account(State& st, unsigned y, unsigned hbits, const float (&p)[2 * NB]) const {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const unsigned yk = (y >> k) & 1u, hk = (hbits >> k) & 1u;
+      st.packed += 1ull << (16 * (2 * yk + hk));
+      // softmax-xent applied ON the softmax outputs (ofdmreceiver_np.py:155-159):
+      // logsumexp(p0,p1) - p_y = max(p) + log1p(exp(-|p1-p0|)) - p_y     (monitor only)
+      const float p0 = p[2 * k], p1 = p[2 * k + 1];
+      const float lse = fmaxf(p0, p1) + __logf(1.0f + __expf(-fabsf(p1 - p0)));
+      st.ce += lse - (yk ? p1 : p0);
+    }
+    st.n += NB;
+    if (st.n > 60000u) spill(st);
+  }
 
   template <int NC>
   DCCN_DEVINL void run(State& st, int row, int col0, float (&v)[NC]) const {
@@ -372,57 +448,26 @@ struct EpiHead {
     for (int i = 0; i < NC; i += 2) {
       const float I = v[i] + (bias ? __ldg(bias + col0 + i) : 0.f);
       const float Q = v[i + 1] + (bias ? __ldg(bias + col0 + i + 1) : 0.f);
-      float h[MO];
-#pragma unroll
-      for (int m = 0; m < MO; ++m) h[m] = I * hw.Wc[0][m] + Q * hw.Wc[1][m] + hw.bc[m];
-      if constexpr (V1) {
-        float h2[MO];
-#pragma unroll
-        for (int n = 0; n < MO; ++n) {
-          float a = hw.bc1[n];
-#pragma unroll
-          for (int m = 0; m < MO; ++m) a += h[m] * hw.Wc1[m][n];
-          h2[n] = a;
-        }
-#pragma unroll
-        for (int m = 0; m < MO; ++m) h[m] = h2[m];
-      }
-#pragma unroll
-      for (int m = 0; m < MO; ++m) h[m] = fmaxf(0.2f * h[m], h[m]);
+      float p[2 * NB];
+      const unsigned hbits = subcarrier(I, Q, p);
+      unsigned y = 0u;
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
-        float l0 = hw.b1[2 * k], l1 = hw.b1[2 * k + 1];
-#pragma unroll
-        for (int m = 0; m < MO; ++m) {
-          l0 += h[m] * hw.W1[m][2 * k];
-          l1 += h[m] * hw.W1[m][2 * k + 1];
-        }
-        l0 += I * hw.W1[MO][2 * k] + Q * hw.W1[MO + 1][2 * k];
-        l1 += I * hw.W1[MO][2 * k + 1] + Q * hw.W1[MO + 1][2 * k + 1];
-        l0 = fmaxf(0.2f * l0, l0);
-        l1 = fmaxf(0.2f * l1, l1);
-        // softmax over the pair: exp(l - max) / sum  ==  {1, t} / (1 + t),  t = exp(-|l1 - l0|)
-        const float t = expf(-fabsf(l1 - l0));
-        const float s = 1.0f + t;
-        const float pb = 1.0f / s, ps = t / s;       // probability of the larger / smaller logit
-        const bool one_big = l1 > l0;
-        const float p0 = one_big ? ps : pb, p1 = one_big ? pb : ps;
-        const unsigned hb = p1 > p0 ? 1u : 0u;           // tf.argmax: first index on ties
         const int bidx = (i >> 1) * NB + k;              // byte index inside this call
-        hw_out[bidx >> 2] |= hb << ((bidx & 3) * 8);
-        if (soft) *reinterpret_cast<float2*>(soft + (o0 + bidx) * 2) = make_float2(p0, p1);
-        if (bits) {
-          const unsigned y = (yw[bidx >> 2] >> ((bidx & 3) * 8)) & 1u;
-          st.c00 += (y == 0 && hb == 0);
-          st.c01 += (y == 0 && hb == 1);
-          st.c10 += (y == 1 && hb == 0);
-          st.c11 += (y == 1 && hb == 1);
-          // softmax-xent applied ON the softmax outputs (ofdmreceiver_np.py:155-159):
-          // logsumexp(p0,p1) - p_y = max(p) + log1p(exp(-|p1-p0|)) - p_y     (monitor only)
-          const float lse = fmaxf(p0, p1) + __logf(1.0f + __expf(-fabsf(p1 - p0)));
-          st.ce += lse - (y ? p1 : p0);
+        hw_out[bidx >> 2] |= ((hbits >> k) & 1u) << ((bidx & 3) * 8);
+        if (bits) y |= ((yw[bidx >> 2] >> ((bidx & 3) * 8)) & 1u) << k;
+      }
+      if (soft) {
+        float* sp = soft + (o0 + (size_t)(i >> 1) * NB) * 2;
+        if constexpr ((2 * NB) % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < 2 * NB; q += 4) *reinterpret_cast<float4*>(sp + q) = make_float4(p[q], p[q + 1], p[q + 2], p[q + 3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2 * NB; q += 2) *reinterpret_cast<float2*>(sp + q) = make_float2(p[q], p[q + 1]);
         }
       }
+      if (bits) account(st, y, hbits, p);
     }
     if (hard) {
       if constexpr (VEC) {
@@ -441,6 +486,7 @@ struct EpiHead {
   }
   DCCN_DEVINL void flush(State& st) const {
     if (!bits) return;
+    spill(st);
     unsigned a = __reduce_add_sync(0xffffffffu, st.c00);
     unsigned b = __reduce_add_sync(0xffffffffu, st.c01);
     unsigned c = __reduce_add_sync(0xffffffffu, st.c10);

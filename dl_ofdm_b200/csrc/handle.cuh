@@ -140,10 +140,11 @@ struct dccn_handle {
     int64_t* h_conf = nullptr;     // pinned host results
     double* h_ce = nullptr;
     uint8_t* hard_host = nullptr;  // caller's destination for hard bits (may be null)
-    cudaEvent_t copied = nullptr, done = nullptr;
+    cudaEvent_t copied = nullptr, computed = nullptr, done = nullptr;
     bool busy = false;
   } slot[2];
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // H2D of the host-buffer entry points
+  cudaStream_t d2h_stream = nullptr;       // their D2H (decisions, confusion matrix, loss)
   size_t ws_bytes = 0;
 };
 

@@ -676,16 +676,67 @@ __global__ void bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint6
 // out_iq [M, 2D] fp32 (bias already added by the GEMM epilogue).
 // =====================================================================================
 template <int NB, bool V1>
+DCCN_DEVINL void head_emit(const EpiHead<NB, V1>& epi, typename EpiHead<NB, V1>::State& st, size_t o0, unsigned hbits,
+                           const float (&p)[2 * NB]) {
+  if (epi.soft) {
+    float* sp = epi.soft + o0 * 2;
+    if constexpr ((2 * NB) % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < 2 * NB; q += 4) *reinterpret_cast<float4*>(sp + q) = make_float4(p[q], p[q + 1], p[q + 2], p[q + 3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2 * NB; q += 2) *reinterpret_cast<float2*>(sp + q) = make_float2(p[q], p[q + 1]);
+    }
+  }
+  unsigned y = 0u, hw = 0u;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) hw |= ((hbits >> k) & 1u) << (8 * k);
+  if constexpr (NB == 4) {
+    if (epi.hard) *reinterpret_cast<uint32_t*>(epi.hard + o0) = hw;
+    if (epi.bits) {
+      const uint32_t yw = __ldg(reinterpret_cast<const uint32_t*>(epi.bits + o0));
+#pragma unroll
+      for (int k = 0; k < NB; ++k) y |= ((yw >> (8 * k)) & 1u) << k;
+    }
+  } else if constexpr (NB == 2) {
+    if (epi.hard) *reinterpret_cast<uint16_t*>(epi.hard + o0) = (uint16_t)hw;
+    if (epi.bits) {
+      const uint32_t yw = __ldg(reinterpret_cast<const uint16_t*>(epi.bits + o0));
+#pragma unroll
+      for (int k = 0; k < NB; ++k) y |= ((yw >> (8 * k)) & 1u) << k;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      if (epi.hard) epi.hard[o0 + k] = (uint8_t)((hbits >> k) & 1u);
+      if (epi.bits) y |= (uint32_t)(__ldg(epi.bits + o0 + k) & 1u) << k;
+    }
+  }
+  if (epi.bits) epi.account(st, y, hbits, p);
+}
+
+template <int NB, bool V1>
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ out_iq, const __grid_constant__ EpiHead<NB, V1> epi) {
-  const long long total = (long long)epi.M * (epi.N >> 1);
+  // block <-> frame (grid-stride), thread <-> TWO data subcarriers (d, d + blockDim.x): no index division anywhere; a warp
+  // reads 32 adjacent (I, Q) pairs and writes 32 adjacent 8*NB-byte probability records (full 32-byte sectors) and NB-byte
+  // decision records; the two subcarriers share every weight fetch (the 200 head weights live in the constant bank and go
+  // through the uniform datapath) and give the scheduler two independent dependency chains.  The per-subcarrier arithmetic
+  // is EpiHead's (shared with the fused GEMM-epilogue form).
+  const int D = epi.N >> 1;
   typename EpiHead<NB, V1>::State st;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int D = epi.N >> 1;
-    const int row = (int)(i / D), d = (int)(i % D);
-    const float2 iq = __ldg(reinterpret_cast<const float2*>(out_iq + (size_t)row * epi.N) + d);
-    float v[2] = {iq.x, iq.y};
-    epi.template run<2>(st, row, 2 * d, v);
+  for (int row = blockIdx.x; row < epi.M; row += gridDim.x) {
+    const float2* iqp = reinterpret_cast<const float2*>(out_iq + (size_t)row * epi.N);
+    for (int d = threadIdx.x; d < D; d += 2 * blockDim.x) {
+      const int d2 = d + blockDim.x;
+      const bool two = d2 < D;
+      const float2 iq0 = __ldg(iqp + d);
+      const float2 iq1 = two ? __ldg(iqp + d2) : make_float2(0.f, 0.f);
+      float p0[2 * NB], p1[2 * NB];
+      const unsigned h0 = epi.subcarrier(iq0.x, iq0.y, p0);
+      const unsigned h1 = epi.subcarrier(iq1.x, iq1.y, p1);
+      head_emit<NB, V1>(epi, st, ((size_t)row * D + d) * NB, h0, p0);
+      if (two) head_emit<NB, V1>(epi, st, ((size_t)row * D + d2) * NB, h1, p1);
+    }
   }
   epi.flush(st);
 }

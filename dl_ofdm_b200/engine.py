@@ -157,21 +157,22 @@ class DCCN:
                                                   _ptr(conf), _ptr(ce), _stream()))
         return conf.numpy().reshape(2, 2).copy(), float(ce[0]), hard
 
-    def forward_host_begin(self, slot, x_host, bits_host=None):
-        """Queue H2D + pass + D2H for one batch on `slot` (0/1) and return immediately."""
+    def forward_host_begin(self, slot, x_host, bits_host=None, hard_host=None):
+        """Queue H2D + pass + D2H for one batch on `slot` (0/1) and return immediately.  ``hard_host``: optional pinned
+        uint8 [B,D,nbits] destination of the hard decisions (valid after ``forward_host_end(slot)``)."""
         assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dccn_forward_host_begin(self._h, int(slot), _ptr(x_host), x_host.shape[0],
-                                                        _ptr(bits_host), None, _stream()))
+                                                        _ptr(bits_host), _ptr(hard_host), _stream()))
 
-    def forward_host_begin_packed(self, slot, x_host, bits_packed_host):
+    def forward_host_begin_packed(self, slot, x_host, bits_packed_host, hard_host=None):
         """forward_host_begin with labels packed 8 per byte (``np.packbits(bits.reshape(-1), bitorder='little')``)."""
         assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
         assert not bits_packed_host.is_cuda and bits_packed_host.dtype == torch.uint8
         assert bits_packed_host.numel() * 8 == x_host.shape[0] * self.D * self.nbits
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dccn_forward_host_begin_packed(self._h, int(slot), _ptr(x_host), x_host.shape[0],
-                                                               _ptr(bits_packed_host), _stream()))
+                                                               _ptr(bits_packed_host), _ptr(hard_host), _stream()))
 
     def forward_host_end(self, slot):
         """Block until the batch on `slot` is done; -> (conf int64[2,2] numpy, ce_sum float)."""

@@ -54,17 +54,23 @@ def reduce_results(conf, ce, device=None):
 
 
 def run_sweep(cells, run_cell, device=None):
-    """Run the cells this rank owns with ``run_cell(index, cell) -> (conf int64[2,2], ce_sum float)``
-    and return the reduced (conf [n,2,2] numpy, ce_sum [n] numpy) on every rank."""
+    """Run the cells this rank owns with ``run_cell(index, cell) -> (conf int64[2,2], ce_sum)`` and return the reduced
+    (conf [n,2,2] numpy, ce_sum [n] numpy) on every rank.  A runner may return DEVICE tensors (CellRunner does): they are
+    gathered on the device without a host synchronisation per cell, so the cells of a rank run back to back, and the only
+    collective -- one all-reduce of the stacked matrices and loss sums -- runs on them directly."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     n = len(cells)
-    conf = torch.zeros((n, 2, 2), dtype=torch.int64)
-    ce = torch.zeros((n,), dtype=torch.float64)
+    conf = torch.zeros((n, 2, 2), dtype=torch.int64, device=device)
+    ce = torch.zeros((n,), dtype=torch.float64, device=device)
     for i in shard(cells, rank, world):
         c, l = run_cell(i, cells[i])
-        conf[i] = torch.as_tensor(np.asarray(c), dtype=torch.int64)
-        ce[i] = float(l)
+        if torch.is_tensor(c):
+            conf[i].copy_(c.reshape(2, 2), non_blocking=True)
+            ce[i:i + 1].copy_(l.reshape(1), non_blocking=True)
+        else:
+            conf[i] = torch.as_tensor(np.asarray(c), dtype=torch.int64)
+            ce[i] = float(l)
     conf, ce = reduce_results(conf, ce, device)
     return conf.cpu().numpy(), ce.cpu().numpy()
 
@@ -107,4 +113,4 @@ class CellRunner:
                                  engine=eng, seed=(self.seed << 12) + index)
         x = chan.run_bits(bits, ofdm, self.const, torch.full((B,), snr, dtype=torch.float32, device=dev))
         o = eng.forward(x, bits, want_soft=False, want_hard=False)
-        return o['conf'].cpu().numpy(), float(o['ce_sum'].cpu()[0])
+        return o['conf'], o['ce_sum']                      # device tensors: no host synchronisation per cell

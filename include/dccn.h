@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCCN_ABI_VERSION 2
+#define DCCN_ABI_VERSION 3
 
 /* arithmetic of the GEMM layers */
 enum {
@@ -137,9 +137,10 @@ int dccn_forward_host_end(dccn_handle* h, int slot, int64_t* conf_host, double* 
  * = label 8 i + j of the flattened [B, n_data, nbits] array (numpy.packbits(bitorder='little')); the device unpacks
  * them.  The reference feeds `bits_in` as int32 [B, D, nbits] (dev/py/ofdmreceiver_np.py:123) -- 5 120 B per 16-QAM
  * frame; this form moves 160 B, so the host-buffer call is bound by the fp32 IQ alone (4 480 B per frame).
- * STAGED: written without a GPU at hand, not yet run (tests/test_gpu_staged.py, DCCN_TEST_STAGED=1). */
+ * hard_host (optional, pinned): the hard decisions [B, n_data, nbits] uint8, copied back on the library's own D2H
+ * stream so that they overlap the next batch's pass and H2D copy. */
 int dccn_forward_host_begin_packed(dccn_handle* h, int slot, const float* x_host, int64_t B,
-                                   const uint8_t* bits_packed_host, void* stream);
+                                   const uint8_t* bits_packed_host, uint8_t* hard_host, void* stream);
 
 /* -- a1: layers_conv2d_complex(inputs, filters, kernal, strides=1, padding)
  * (dev/py/complex.py:140-196), op-level.  x_dev [B,L,W,C,2], kernel_dev

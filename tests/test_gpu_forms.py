@@ -215,3 +215,33 @@ def test_tx_fade_equals_separate_kernels(libdccn, chan, nb):
     if n_taps == 0:
         assert torch.equal(faded, tx)
     m.close()
+
+
+def test_host_entry_returns_hard_bits(libdccn, trained_dev):
+    """Both host-buffer entry points with a pinned destination for the hard decisions (copied back on the library's own
+    D2H stream): decisions == the device entry point's, through both slots, pipelined."""
+    from dl_ofdm_b200.engine import DCCN
+    rng = np.random.default_rng(19)
+    nb, B = 4, 517
+    m = DCCN(nbits=nb, equalizer=True, precision='parity')
+    m.load_weights(trained_dev)
+    xs = [torch.as_tensor((rng.standard_normal((B, 7, 80, 2)) * 0.4).astype(np.float32)).pin_memory() for _ in range(3)]
+    bits = rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)
+    bh = torch.as_tensor(bits).pin_memory()
+    packed = torch.as_tensor(np.packbits(bits.reshape(-1), bitorder='little')).pin_memory()
+    refs = []
+    for x in xs:
+        o = m.forward(x.cuda(), bh.cuda(), want_soft=False)
+        refs.append((o['hard'].cpu(), o['conf'].cpu().numpy()))
+    for packed_labels in (False, True):
+        hards = [torch.zeros((B, 320, nb), dtype=torch.uint8).pin_memory() for _ in range(3)]
+        begin = (lambda s, x, h: m.forward_host_begin_packed(s, x, packed, h)) if packed_labels else \
+                (lambda s, x, h: m.forward_host_begin(s, x, bh, h))
+        begin(0, xs[0], hards[0])
+        for i in range(3):
+            if i + 1 < 3:
+                begin((i + 1) & 1, xs[i + 1], hards[i + 1])
+            conf, _ = m.forward_host_end(i & 1)
+            assert np.array_equal(conf, refs[i][1])
+            assert torch.equal(hards[i], refs[i][0])
+    m.close()

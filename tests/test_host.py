@@ -83,7 +83,7 @@ def test_libdccn_exports_header_symbols(libdccn):
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     for name in declared:
         assert hasattr(libdccn, name)
-    assert libdccn.dccn_abi_version() == 2
+    assert libdccn.dccn_abi_version() == 3
 
 
 def test_no_gpu_fails_loudly(libdccn):

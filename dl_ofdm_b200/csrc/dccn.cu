@@ -743,17 +743,15 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
     if (split && h->f16x3 && L.f16_ok && !h->tr && !h->train_fwd && ks.ksplit <= 1) {
       op.b0 = L.tmH0;
       op.b1 = L.tmH1;
-      // short-K layers (the per-symbol maps, K <= 256 = 4 k-blocks): the dependent MMA chain the K-chunked accumulation
-      // exists for is short anyway, and with the whole K in one accumulator the epilogue warps leave the k-block loop
-      const int kc = (L.K <= h->kc_whole_k) ? 0 : h->kc;
+      const int kc = h->kc;
       if constexpr (std::is_same<Epi, EpiStore>::value) {
         if (L.BN == 32)
           return launch_gemm_tc<32, true, 1, true, false, Epi, true>(op, (int)M, L.N, L.K, kc, epi, s, h->num_sms, ks, 1.f,
-                                                                     L.w_scale_inv, A.amax);
+                                                                     L.w_scale_inv, A.amax, h->small_first);
       }
       if (L.BN == 128)
         return launch_gemm_tc<128, true, 2, true, false, Epi, true>(op, (int)M, L.N, L.K, kc, epi, s, h->num_sms, ks, 1.f,
-                                                                    L.w_scale_inv, A.amax);
+                                                                    L.w_scale_inv, A.amax, h->small_first);
       op.b0 = L.tmB0;
       op.b1 = L.tmB1;
     }
@@ -762,7 +760,7 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
 #define DCCN_TC_PAR(BNV, CGV)                                                                                \
   do {                                                                                                       \
     if (L.mc) return launch_gemm_tc<BNV, true, CGV, true, true, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks);  \
-    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks); \
+    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f, 1.f, nullptr, h->small_first); \
     return launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks);  \
   } while (0)
 #define DCCN_TC_SS(BNV, CGV)                                                                                 \
@@ -812,11 +810,13 @@ static int run_head(dccn_handle* h, int64_t Bc, const uint8_t* bits, float* soft
   LaunchScope ls(h, SLOT_R2_HEAD, s);
   // one block per frame at a time (thread <-> data subcarrier), as many resident blocks as fit
   const int D = h->r2.N >> 1;
-  int threads = ((D + 1) / 2 + 31) / 32 * 32;        // two subcarriers per thread
+  const int subs = h->head_subs == 2 ? 2 : 1;
+  int threads = ((D + subs - 1) / subs + 31) / 32 * 32;
   if (threads > 256) threads = 256;
-  long long blocks = (long long)h->num_sms * (1536 / threads);
+  long long blocks = (long long)h->num_sms * (h->head_blocks > 0 ? h->head_blocks : 2048 / threads);
   if (blocks > Bc) blocks = Bc;
-  head_kernel<NB, V1><<<(unsigned)blocks, threads, 0, s>>>(oiq.p0, e);
+  if (subs == 2) head_kernel<NB, V1, 2><<<(unsigned)blocks, threads, 0, s>>>(oiq.p0, e);
+  else head_kernel<NB, V1, 1><<<(unsigned)blocks, threads, 0, s>>>(oiq.p0, e);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1206,7 +1206,9 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   }
   h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 65536;   // per-launch overheads (~10 us x 15 kernels) amortise over the pass
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
-  if (const char* e = getenv("DCCN_KC_WHOLE_K")) h->kc_whole_k = atoi(e);
+  if (const char* e = getenv("DCCN_SMALL_FIRST")) h->small_first = atoi(e);
+  if (const char* e = getenv("DCCN_HEAD_SUBS")) h->head_subs = atoi(e);       // experiment knobs of the head kernel
+  if (const char* e = getenv("DCCN_HEAD_BLOCKS")) h->head_blocks = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);
   if (const char* e = getenv("DCCN_FUSED_HEAD")) h->fused_head = atoi(e);
   if (const char* e = getenv("DCCN_A_TMEM")) h->a_tmem = atoi(e);

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR), F16>
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                int M, int N, int K, int kc, int ksplit, int band, float a_scale, float out_scale,
-               const unsigned* __restrict__ amax_in, const __grid_constant__ Epi epi) {
+               const unsigned* __restrict__ amax_in, int small_first, const __grid_constant__ Epi epi) {
   constexpr bool DEC = ATM && !PAIR;
   using C = TcCfg<BN, SPLIT, CG, ATM, DEC, F16>;
   extern __shared__ uint8_t smem_raw[];
@@ -372,11 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 if constexpr (F16) {
                   umma_f16_ts(d, ka + 32, db_hi, idesc, accum);             // A_lo * B_hi
                   umma_f16_ts(d, ka, db_lo, idesc, 1u);                     // A_hi * B_lo
-                  umma_f16_ts(d, ka, db_hi, idesc, 1u);                     // A_hi * B_hi
+                  if (!small_first) umma_f16_ts(d, ka, db_hi, idesc, 1u);   // A_hi * B_hi
                 } else {
                   umma_tf32_ts(d, ka + 32, db_hi, idesc, accum);            // A_lo * B_hi
                   umma_tf32_ts(d, ka, db_lo, idesc, 1u);                    // A_hi * B_lo
-                  umma_tf32_ts(d, ka, db_hi, idesc, 1u);                    // A_hi * B_hi
+                  if (!small_first) umma_tf32_ts(d, ka, db_hi, idesc, 1u);  // A_hi * B_hi
                 }
               } else if (SPLIT) {
                 const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
@@ -386,6 +386,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 umma_tf32(d, da_hi, db_hi, idesc, 1u);
               } else {
                 umma_tf32(d, da_hi, db_hi, idesc, accum);
+              }
+            }
+            if constexpr (ATM && !PAIR) {
+              // small_first: the eight cross terms of the k-block (2^-11 of the result) went into the accumulator while
+              // it was still small; the four hi*hi MMAs follow.  The tensor core adds into its fp32 accumulator with
+              // truncation at the magnitude of the running sum, so the k-block now pays 4 truncations at full magnitude
+              // instead of 12 (measured, profiles/accuracy_r2.txt) -- same instructions, same operands, other order.
+              if (small_first) {
+#pragma unroll
+                for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+                  const uint64_t db_hi = umma_desc_sw128(b_hi + k * C::UMMA_K * 4);
+                  const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);
+                  if constexpr (F16) umma_f16_ts(d, ka, db_hi, idesc, 1u);
+                  else umma_tf32_ts(d, ka, db_hi, idesc, 1u);
+                }
               }
             }
             DCCN_TRACE_EV(9);
@@ -687,7 +702,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 template <int BN, bool SPLIT, int CG, bool ATM, bool PAIR, class Epi, bool F16 = false>
 inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, const Epi& epi, cudaStream_t s,
                           int num_sms, KSched ks = KSched(), float a_scale = 1.f, float out_scale = 1.f,
-                          const unsigned* amax_in = nullptr) {
+                          const unsigned* amax_in = nullptr, int small_first = 0) {
   using C = TcCfg<BN, SPLIT, CG, ATM, (ATM && !PAIR), F16>;
   if (M <= 0) return 0;
   auto kern = gemm_tc_kernel<BN, SPLIT, CG, ATM, PAIR, Epi, F16>;
@@ -725,7 +740,7 @@ inline int launch_gemm_tc(const TcOperands& op, int M, int N, int K, int kc, con
   cfg.stream = s;
   if (PAIR) ks = KSched();
   DCCN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, op.a0, op.b0, SPLIT ? op.b1 : op.b0, M, N, K, kc, ks.ksplit, ks.band, a_scale,
-                                  out_scale, amax_in, epi));
+                                  out_scale, amax_in, small_first, epi));
   return 0;
 }
 

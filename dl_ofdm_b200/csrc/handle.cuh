@@ -87,7 +87,9 @@ struct dccn_handle {
   bool ws_dirty = false;                   // an optional buffer was requested after the last build
   size_t ws_act_bytes = 0;
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
-  int kc_whole_k = 0;  // layers with K <= this keep their whole (short) K in one TMEM accumulator (DCCN_KC_WHOLE_K)
+  int small_first = 0; // parity GEMMs: per k-block the 8 cross-term MMAs first, then the 4 hi*hi MMAs (DCCN_SMALL_FIRST)
+  int head_subs = 2;   // data subcarriers per thread of the demod head kernel (1 or 2)
+  int head_blocks = 0; // resident head blocks per SM (0 = 2048 / threads)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers
   int a_tmem = 1;      // parity mode: A operand hi/lo staged in TMEM (TS-form MMA) instead of shared memory
   int multicast = 0;   // cta_group::2 CTA pairs (DCCN_PAIR=1 enables; measured slower than single-CTA tiles)

@@ -715,27 +715,36 @@ DCCN_DEVINL void head_emit(const EpiHead<NB, V1>& epi, typename EpiHead<NB, V1>:
   if (epi.bits) epi.account(st, y, hbits, p);
 }
 
-template <int NB, bool V1>
+template <int NB, bool V1, int SUBS>
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ out_iq, const __grid_constant__ EpiHead<NB, V1> epi) {
-  // block <-> frame (grid-stride), thread <-> TWO data subcarriers (d, d + blockDim.x): no index division anywhere; a warp
+  // block <-> frame (grid-stride), thread <-> SUBS data subcarriers (d, d + blockDim.x): no index division anywhere; a warp
   // reads 32 adjacent (I, Q) pairs and writes 32 adjacent 8*NB-byte probability records (full 32-byte sectors) and NB-byte
-  // decision records; the two subcarriers share every weight fetch (the 200 head weights live in the constant bank and go
-  // through the uniform datapath) and give the scheduler two independent dependency chains.  The per-subcarrier arithmetic
-  // is EpiHead's (shared with the fused GEMM-epilogue form).
+  // decision records.  SUBS = 2: the two subcarriers share every weight fetch (the 200 head weights live in the constant
+  // bank and go through the uniform datapath) and give the scheduler two independent dependency chains.  The
+  // per-subcarrier arithmetic is EpiHead's (shared with the fused GEMM-epilogue form).
   const int D = epi.N >> 1;
   typename EpiHead<NB, V1>::State st;
   for (int row = blockIdx.x; row < epi.M; row += gridDim.x) {
     const float2* iqp = reinterpret_cast<const float2*>(out_iq + (size_t)row * epi.N);
-    for (int d = threadIdx.x; d < D; d += 2 * blockDim.x) {
-      const int d2 = d + blockDim.x;
-      const bool two = d2 < D;
-      const float2 iq0 = __ldg(iqp + d);
-      const float2 iq1 = two ? __ldg(iqp + d2) : make_float2(0.f, 0.f);
-      float p0[2 * NB], p1[2 * NB];
-      const unsigned h0 = epi.subcarrier(iq0.x, iq0.y, p0);
-      const unsigned h1 = epi.subcarrier(iq1.x, iq1.y, p1);
-      head_emit<NB, V1>(epi, st, ((size_t)row * D + d) * NB, h0, p0);
-      if (two) head_emit<NB, V1>(epi, st, ((size_t)row * D + d2) * NB, h1, p1);
+    if constexpr (SUBS == 2) {
+      for (int d = threadIdx.x; d < D; d += 2 * blockDim.x) {
+        const int d2 = d + blockDim.x;
+        const bool two = d2 < D;
+        const float2 iq0 = __ldg(iqp + d);
+        const float2 iq1 = two ? __ldg(iqp + d2) : make_float2(0.f, 0.f);
+        float p0[2 * NB], p1[2 * NB];
+        const unsigned h0 = epi.subcarrier(iq0.x, iq0.y, p0);
+        const unsigned h1 = epi.subcarrier(iq1.x, iq1.y, p1);
+        head_emit<NB, V1>(epi, st, ((size_t)row * D + d) * NB, h0, p0);
+        if (two) head_emit<NB, V1>(epi, st, ((size_t)row * D + d2) * NB, h1, p1);
+      }
+    } else {
+      for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float2 iq0 = __ldg(iqp + d);
+        float p0[2 * NB];
+        const unsigned h0 = epi.subcarrier(iq0.x, iq0.y, p0);
+        head_emit<NB, V1>(epi, st, ((size_t)row * D + d) * NB, h0, p0);
+      }
     }
   }
   epi.flush(st);

@@ -1,0 +1,97 @@
+"""C2: BER-vs-SNR curves on the GPU against the known answers of the reference's shipped (TF-trained) v1 checkpoints.
+
+north_star: "BER-vs-SNR curve within +-0.1 dB of the reference across -10..29 dB".  The known answers
+(tests/golden/v1_curves.npz, = BASELINE.md section 2) are the fp64 oracle's bit errors on the seeded recipe frames
+(oracle/v1_recipe.py, 2000 frames per SNR point) for every shipped checkpoint.
+  * deterministic part: the SAME frames through the CUDA path -- error counts equal up to the handful of decisions that
+    sit inside fp32 rounding of a tie, i.e. a dB offset of ~0 at every point with BER >= 1e-4, and BER == 0 from 22 dB on;
+  * BASELINE config 2 as written (QPSK AWGN, -10..29 dB, batch 8192, frames made by the GPU transmitter / AWGN kernels
+    through sweep.run_sweep): an independent draw, so the offset to the known-answer curve is statistical -- <= 0.1 dB
+    wherever the reference BER >= 1e-3 (>= 6000 errors counted here), <= 0.25 dB down to 1e-4.
+"""
+import numpy as np
+import pytest
+
+from conftest import v1_weights
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+SNRS = np.arange(-10, 30)
+
+
+def db_offset(snr, ber, ref_snr, ref_ber):
+    """Horizontal distance (dB) from the point (snr, ber) to the reference curve: snr - s with ref_ber(s) = ber,
+    log-linear interpolation between the reference points (the curve falls monotonically)."""
+    lr = np.log10(np.maximum(ref_ber, 1e-12))
+    lb = np.log10(max(ber, 1e-12))
+    for i in range(len(ref_snr) - 1):
+        if lr[i] >= lb >= lr[i + 1] and lr[i] > lr[i + 1]:
+            s = ref_snr[i] + (lr[i] - lb) / (lr[i] - lr[i + 1]) * (ref_snr[i + 1] - ref_snr[i])
+            return float(snr - s)
+    return float('nan')
+
+
+def _v1_session(w, nb, cp, chunk=8192):
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.model import Session
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    fl = Flags(nbits=nb, pilot='scattered', nsymbol=8, npilot=8, nguard=8, channel='AWGN', cp=cp)
+    o = ofdm_tx(fl)
+    assert o.frame_size == 368
+    return Session(fl, o, w, precision='parity', head='v1', chunk_frames=chunk), fl, o
+
+
+@pytest.mark.parametrize('fixture,nb,cp', [('v1_2mod_cpTrue.npz', 2, True), ('v1_3mod_cpTrue.npz', 3, True),
+                                           ('v1_4mod_cpTrue.npz', 4, True), ('v1_1mod_cpFalse.npz', 1, False)])
+def test_ber_curve_known_answers(libdccn, golden, fixture, nb, cp):
+    from oracle.v1_recipe import v1_frames
+    cur = golden('v1_curves.npz')
+    ref_err = cur['%dmod_cp%s_errors' % (nb, cp)]
+    n_bits = int(cur['%dmod_cp%s_bits' % (nb, cp)])
+    s, _, _ = _v1_session(v1_weights(golden(fixture)), nb, cp)
+    errs = []
+    for snr in SNRS:
+        x, bits = v1_frames(nb, int(snr), 2000)
+        conf = s.run('conf_matrix', {'tx_ofdm': x, 'bits_in': bits})
+        assert conf.sum() == n_bits
+        errs.append(int(conf[0, 1] + conf[1, 0]))
+    s.close()
+    errs = np.array(errs)
+    ref_ber, ber = ref_err / n_bits, errs / n_bits
+    # (1) the same decisions: a tie inside fp32 rounding may fall the other way, nothing else
+    assert np.abs(errs - ref_err).max() <= 3, (errs - ref_err).tolist()
+    # (2) +-0.1 dB at every point of the waterfall (BER >= 1e-4), floor reached where the reference reaches it
+    worst = 0.0
+    for snr, b, rb in zip(SNRS, ber, ref_ber):
+        if rb >= 1e-4:
+            off = db_offset(snr, b, SNRS, ref_ber)
+            assert abs(off) <= 0.1, (int(snr), b, rb, off)
+            worst = max(worst, abs(off))
+    assert (ber[SNRS >= 22] == 0).all() and (ref_ber[SNRS >= 22] == 0).all()
+    print('%s: max |dB offset| %.4f over BER >= 1e-4, max |d errors| %d' % (fixture, worst, np.abs(errs - ref_err).max()))
+
+
+def test_config2_qpsk_awgn_sweep(libdccn, golden, tmp_path):
+    """BASELINE config 2: QPSK AWGN, SNR -10..29 dB, batch 8192 frames per point, frames generated ON THE GPU (Philox bits
+    -> transmitter -> AWGN) and swept through sweep.run_sweep, against the known-answer curve of the reference's own
+    QPSK checkpoint.  Also writes the CSV the reference's test_model writes."""
+    from dl_ofdm_b200 import sweep
+    cur = golden('v1_curves.npz')
+    ref_ber = cur['2mod_cpTrue_errors'] / float(cur['2mod_cpTrue_bits'])
+    s, fl, o = _v1_session(v1_weights(golden('v1_2mod_cpTrue.npz')), 2, True)
+    cells = sweep.make_cells(['AWGN'], SNRS, (2,))
+    conf, ce = sweep.run_sweep(cells, sweep.CellRunner(s, 8192, seed=3), device=s.engine.device)
+    rows = sweep.ber_table(cells, conf, ce)
+    sweep.write_csv(str(tmp_path / 'Test_DCCN_v1_2mod_AWGN.csv'), rows)
+    s.close()
+    ber = np.array([r['BER'] for r in rows])
+    assert all(r['bits'] == 8192 * 368 * 2 for r in rows)
+    offs = {}
+    for snr, b, rb in zip(SNRS, ber, ref_ber):
+        if rb >= 1e-4:
+            offs[int(snr)] = db_offset(snr, b, SNRS, ref_ber)
+            assert abs(offs[int(snr)]) <= (0.1 if rb >= 1e-3 else 0.25), (int(snr), b, rb, offs[int(snr)])
+    assert (ber[SNRS >= 22] == 0).all()
+    assert np.all(np.diff(ber[ber > 0]) < 0)                         # a waterfall: strictly falling while non-zero
+    print('config 2 sweep: dB offsets', {k: round(v, 3) for k, v in offs.items()})

@@ -26,7 +26,7 @@ def _cuda(a, dtype=None):
     return t.cuda().contiguous()
 
 
-def _check_soft(soft, soft_ref, hard, soft_ref32=None, p999=P999_TOL, mx=MAX_TOL):
+def _check_soft(soft, soft_ref, hard, soft_ref32=None, p999=P999_TOL, mx=MAX_TOL, k_intrinsic=1.5):
     """soft_ref: fp64 oracle.  soft_ref32: the same oracle evaluated in fp32 -- the error an fp32
     CPU implementation (like the reference's TF kernels) makes against fp64 on THIS input; a
     trained network with steep logits can exceed the nominal 1e-5 in any fp32 arithmetic, so
@@ -35,8 +35,8 @@ def _check_soft(soft, soft_ref, hard, soft_ref32=None, p999=P999_TOL, mx=MAX_TOL
     q = np.quantile(err, 0.999)
     if soft_ref32 is not None:
         e32 = np.abs(soft_ref32.astype(np.float64) - soft_ref)
-        p999 = max(p999, 1.5 * np.quantile(e32, 0.999))
-        mx = max(mx, 2.0 * e32.max())
+        p999 = max(p999, k_intrinsic * np.quantile(e32, 0.999))
+        mx = max(mx, (k_intrinsic + 0.5) * e32.max())
     assert q <= p999, 'p99.9 |dsoft| = %.3g (bound %.3g)' % (q, p999)
     assert err.max() <= mx, 'max |dsoft| = %.3g (bound %.3g)' % (err.max(), mx)
     hard_ref = (soft_ref[..., 1] > soft_ref[..., 0]).astype(np.uint8)

@@ -236,3 +236,25 @@ def test_fp16_split_operand_error_matches_tf32_split():
     assert f16[0] < 1.5 * tf32[0] and f16[1] < 2.0 * tf32[1]
     assert f16[1] < 1e-5                                      # the north-star tolerance on soft outputs
     assert r['fp16x3 unscaled'][0] > 2.0 * f16[0]            # the weight scale is what keeps the lo plane normal
+
+
+def test_v1_curves_match_baseline_table(golden):
+    """tests/golden/v1_curves.npz (bit errors of the 8 shipped checkpoints on the seeded recipe frames, -10..29 dB; the
+    known answers of tests/test_gpu_curves.py) reproduces every entry of the table in BASELINE.md section 2."""
+    import os
+    import re
+    cur = golden('v1_curves.npz')
+    cols = ['%dmod_cp%s' % (nb, cp) for nb in (1, 2, 3, 4) for cp in (True, False)]
+    rows = {}
+    for line in open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'BASELINE.md')):
+        m = re.match(r'\| (-?\d+) \|(.*)\|', line)
+        if m:
+            rows[int(m.group(1))] = [float(v) for v in m.group(2).split('|')]
+    assert len(rows) == 32
+    for snr, vals in rows.items():
+        i = int(np.where(cur['snr'] == snr)[0][0])
+        for c, v in zip(cols, vals):
+            b = cur[c + '_errors'][i] / float(cur[c + '_bits'])
+            assert abs(b - v) <= 5.1e-4 * v + 1e-12, (snr, c, b, v)       # the table prints 4 significant digits
+    for c in cols:
+        assert (cur[c + '_errors'][cur['snr'] >= 22] == 0).all()

@@ -29,51 +29,55 @@ x1, b1 = v1_frames(4, 10, 700)
 ref1 = orc.basic_receiver(x1, w1, 4, 16, head='v1', dtype=np.float64)
 wt = dev_weights(np.load(os.path.join(GOLDEN, 'dev_4mod_eq_trained.npz')))
 rng = np.random.default_rng(0)
-for whole in ('0', '256'):
-    os.environ['DCCN_KC_WHOLE_K'] = whole
+def run_variant(tag, env, timing=True):
+    for k, v in env.items():
+        os.environ[k] = v
+    import test_gpu_parity as tp
     m = DCCN(nbits=4, nsymbol=8, n_data=368, head='v1', precision='parity')
     m.load_weights(w1)
     o = m.forward(torch.as_tensor(x1).cuda(), torch.as_tensor(b1).cuda())
-    report('v1 receiver   WHOLE_K=%s' % whole, o['soft'].cpu().numpy(), o['hard'].cpu().numpy(), ref1)
+    report('v1 receiver   %s' % tag, o['soft'].cpu().numpy(), o['hard'].cpu().numpy(), ref1)
     m.close()
     m = DCCN(nbits=4, equalizer=True, precision='parity')
     m.load_weights(wt)
-    import test_gpu_parity as tp
-    x, bits = tp._config3_frames(m, 2000, 15.0, seed=3)
-    o = m.forward(x, bits)
-    z, _, _ = orc.batch_moment_norm(x.cpu().numpy(), np.float64)
-    ref, _, _ = LeanModel(wt, 4).forward(z)
-    report('trained eq+rx WHOLE_K=%s' % whole, o['soft'].cpu().numpy(), o['hard'].cpu().numpy(), ref)
-    xg, bg = tp._config3_frames(m, 65536, 15.0, seed=4)
-    for _ in range(3):
-        m.forward(xg, bg)
-    torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(10):
-        m.forward(xg, bg)
-    t1.record()
-    torch.cuda.synchronize()
-    m.profile(True)
-    for _ in range(5):
-        m.forward(xg, bg)
-    prof = m.profile_collect()
-    m.profile(False)
-    print('WHOLE_K=%s: burst %.3f ms / pass   %s' % (whole, t0.elapsed_time(t1) / 10,
-                                                    {k: round(v[0] / 5, 3) for k, v in sorted(prof.items())}), flush=True)
-    if whole == '0':
-        # sustained run: events every 25 passes, host enqueue time alongside
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(33)]
+    for snr in (15.0, 30.0):
+        x, bits = tp._config3_frames(m, 2000, snr, seed=3)
+        o = m.forward(x, bits)
+        z, _, _ = orc.batch_moment_norm(x.cpu().numpy(), np.float64)
+        ref, _, _ = LeanModel(wt, 4).forward(z)
+        report('trained eq+rx %g dB %s' % (snr, tag), o['soft'].cpu().numpy(), o['hard'].cpu().numpy(), ref)
+        if tag == 'base':
+            z32, _, _ = orc.batch_moment_norm(x.cpu().numpy(), np.float32)
+            r32, _, _ = LeanModel(wt, 4, dtype=np.float32).forward(z32)
+            report('   (numpy fp32 oracle itself, %g dB)' % snr, r32, (r32[..., 1] > r32[..., 0]), ref)
+    if timing:
+        xg, bg = tp._config3_frames(m, 65536, 15.0, seed=4)
+        for _ in range(3):
+            m.forward(xg, bg)
         torch.cuda.synchronize()
-        time.sleep(1.0)
-        th0 = time.perf_counter()
-        ev[0].record()
-        for i in range(32):
-            for _ in range(25):
-                m.forward(xg, bg)
-            ev[i + 1].record()
-        host = time.perf_counter() - th0
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            m.forward(xg, bg)
+        t1.record()
         torch.cuda.synchronize()
-        print('sustained: ms/pass per 25-pass window:', [round(ev[i].elapsed_time(ev[i + 1]) / 25, 3) for i in range(32)],
-              ' host enqueue %.3f ms/pass' % (host / 800 * 1e3), flush=True)
+        m.profile(True)
+        for _ in range(5):
+            m.forward(xg, bg)
+        prof = m.profile_collect()
+        m.profile(False)
+        print('%s: burst %.3f ms / pass   %s' % (tag, t0.elapsed_time(t1) / 10,
+                                                  {k: round(v[0] / 5, 3) for k, v in sorted(prof.items())}), flush=True)
     m.close()
+    for k in env:
+        del os.environ[k]
+
+
+run_variant('base', {})
+run_variant('small_first', {'DCCN_SMALL_FIRST': '1'})
+run_variant('small_first kc=2', {'DCCN_SMALL_FIRST': '1', 'DCCN_KC': '2'})
+run_variant('kc=2', {'DCCN_KC': '2'}, timing=False)
+run_variant('exact', {}, timing=False) if False else None
+run_variant('head subs=1', {'DCCN_HEAD_SUBS': '1'})
+run_variant('head subs=1 blocks=8', {'DCCN_HEAD_SUBS': '1', 'DCCN_HEAD_BLOCKS': '8'})
+run_variant('head subs=2 blocks=5', {'DCCN_HEAD_SUBS': '2', 'DCCN_HEAD_BLOCKS': '5'})

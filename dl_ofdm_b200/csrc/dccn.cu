@@ -737,6 +737,9 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
   if (split) op.b1 = L.tmB1;
+  // MMA order inside a k-block (gemm_tc.cuh `small_first`): cross terms first for every forward / dgrad GEMM; the
+  // split-K weight-gradient GEMMs (contraction over the batch, heavy cancellation) measured better interleaved
+  const int small_first = (h->small_first && ks.ksplit <= 1) ? 1 : 0;
   // DCCN_F16X3 (staged, inference only: the training step re-derives only the tf32 planes on the device)
   if constexpr (std::is_same<Epi, EpiStore>::value || std::is_same<Epi, EpiPhaseEq>::value ||
                 std::is_same<Epi, EpiPhaseEqSym>::value) {
@@ -747,11 +750,11 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
       if constexpr (std::is_same<Epi, EpiStore>::value) {
         if (L.BN == 32)
           return launch_gemm_tc<32, true, 1, true, false, Epi, true>(op, (int)M, L.N, L.K, kc, epi, s, h->num_sms, ks, 1.f,
-                                                                     L.w_scale_inv, A.amax, h->small_first);
+                                                                     L.w_scale_inv, A.amax, small_first);
       }
       if (L.BN == 128)
         return launch_gemm_tc<128, true, 2, true, false, Epi, true>(op, (int)M, L.N, L.K, kc, epi, s, h->num_sms, ks, 1.f,
-                                                                    L.w_scale_inv, A.amax, h->small_first);
+                                                                    L.w_scale_inv, A.amax, small_first);
       op.b0 = L.tmB0;
       op.b1 = L.tmB1;
     }
@@ -760,7 +763,7 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
 #define DCCN_TC_PAR(BNV, CGV)                                                                                \
   do {                                                                                                       \
     if (L.mc) return launch_gemm_tc<BNV, true, CGV, true, true, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks);  \
-    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f, 1.f, nullptr, h->small_first); \
+    if (h->a_tmem) return launch_gemm_tc<BNV, true, CGV, true, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks, 1.f, 1.f, nullptr, small_first); \
     return launch_gemm_tc<BNV, true, CGV, false, false, Epi>(op, (int)M, L.N, L.K, h->kc, epi, s, h->num_sms, ks);  \
   } while (0)
 #define DCCN_TC_SS(BNV, CGV)                                                                                 \

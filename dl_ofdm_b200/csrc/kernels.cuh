@@ -457,104 +457,118 @@ __global__ void txmap_kernel(const int* __restrict__ data_sc, int n_data, const 
   }
 }
 
-// ---- shared by tx64_kernel and tx_fade_kernel: one OFDM symbol of K = 64 subcarriers by one warp ------------------------
-struct Tx64Twiddles {
-  double2 w8[8];     // W8^(a j), j = 0..7      (a = lane & 7)
-  double2 w64[2];    // W64^(a (b + 4 h))       (b = lane >> 3)
-};
-DCCN_DEVINL void tx64_twiddles(int lane, Tx64Twiddles& tw) {
-  const int a = lane & 7, b = lane >> 3;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    double sn, cs;
-    sincospi(0.25 * (double)((a * j) & 7), &sn, &cs);
-    tw.w8[j] = make_double2(cs, sn);
-  }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    double sn, cs;
-    sincospi((double)((a * (b + 4 * h)) & 63) / 32.0, &sn, &cs);
-    tw.w64[h] = make_double2(cs, sn);
-  }
-}
-// acc += x * w (complex128, fixed contraction)
-DCCN_DEVINL void cmac64(double& ar, double& ai, const double2 x, const double2 w) {
-  ar = fma(-x.y, w.y, fma(x.x, w.x, ar));
-  ai = fma(x.y, w.x, fma(x.x, w.y, ai));
-}
-// frequency grid of symbol s of `frame` -> g[0..63]; 8 x 8 IDFT through z; time-domain symbol (no CP, scaled 1/64) left
-// in g[n].  Ends with a __syncwarp, so the caller may read g at once.
-DCCN_DEVINL void tx64_symbol(const uint8_t* __restrict__ bits, long long frame, int s, int nbits, int D,
-                             const int* __restrict__ sc_map, const float2* __restrict__ constellation, float2 pilot,
-                             int lane, const Tx64Twiddles& tw, double2* g, double2* z) {
-  constexpr int K = 64;
-  const int a = lane & 7, b = lane >> 3;
-#pragma unroll
-  for (int k = lane; k < K; k += 32) {
-    const int m = sc_map[s * K + k];
-    float2 v = make_float2(0.f, 0.f);
-    if (m == -2) v = pilot;
-    else if (m >= 0) {
-      int idx = 0;
-      const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
-      for (int q = 0; q < nbits; ++q) idx = (idx << 1) | bp[q];
-      v = constellation[idx];
-    }
-    g[k] = make_double2(v.x, v.y);
-  }
-  __syncwarp();
-  // pass 1 (+ twiddle): outputs (k1 = b + 4 h, n2 = a)
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int k1 = b + 4 * h;
-    double yr = 0.0, yi = 0.0;
-#pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) cmac64(yr, yi, g[k1 + 8 * k2], tw.w8[k2]);
-    z[k1 * 8 + a] = make_double2(fma(-yi, tw.w64[h].y, yr * tw.w64[h].x), fma(yi, tw.w64[h].x, yr * tw.w64[h].y));
-  }
-  __syncwarp();
-  // pass 2: outputs n = 8 n1 + n2 with n1 = a, n2 = b + 4 h (g is free: every lane finished pass 1)
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int n2 = b + 4 * h;
-    double xr = 0.0, xi = 0.0;
-#pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) cmac64(xr, xi, z[k1 * 8 + n2], tw.w8[k1]);
-    g[8 * a + n2] = make_double2(xr * (1.0 / K), xi * (1.0 / K));
-  }
-  __syncwarp();
+// ---- shared by tx64_kernel and tx_fade_kernel: FOUR OFDM symbols of K = 64 subcarriers per warp ------------------------
+// 64-point inverse DFT as 8 x 8 (n = 8 n1 + n2, k = k1 + 8 k2):
+//   Y[k1][n2] = sum_k2 X[k1 + 8 k2] W8^(n2 k2),   Z = Y * W64^(n2 k1),   x[8 n1 + n2] = sum_k1 Z[k1][n2] W8^(n1 k1) / 64
+// with each 8-point transform done by ONE lane as radix-2 butterflies in registers (48 complex additions and two
+// multiplications by (+-1 + j)/sqrt(2) instead of the 64 complex MACs of the matrix form -- the transmitter is fp64-bound),
+// lane = 8 * slot + q: slot = which of the warp's four symbols, q = k1 in the first pass and n2 in the second.  The
+// frequency grid never touches shared memory (a lane maps the 8 subcarriers q + 8 k2 itself); Z goes through a padded
+// [8][9] tile per slot (conflict-free both ways).  fp64 like NumPy's pocketfft; results are rounded to fp32 by the caller.
+constexpr int kTxZ = 72;                       // double2 per slot: Z[k1 * 9 + n2]
+
+// inverse 8-point DFT in place: a[n] <- sum_k a[k] exp(+2 pi j n k / 8)
+DCCN_DEVINL void idft8(double2 (&a)[8]) {
+  const double r = 0.70710678118654752440;
+  const double2 b0 = make_double2(a[0].x + a[4].x, a[0].y + a[4].y), b1 = make_double2(a[0].x - a[4].x, a[0].y - a[4].y);
+  const double2 b2 = make_double2(a[2].x + a[6].x, a[2].y + a[6].y), b3 = make_double2(a[2].x - a[6].x, a[2].y - a[6].y);
+  const double2 b4 = make_double2(a[1].x + a[5].x, a[1].y + a[5].y), b5 = make_double2(a[1].x - a[5].x, a[1].y - a[5].y);
+  const double2 b6 = make_double2(a[3].x + a[7].x, a[3].y + a[7].y), b7 = make_double2(a[3].x - a[7].x, a[3].y - a[7].y);
+  // j * (x + j y) = -y + j x
+  const double2 c0 = make_double2(b0.x + b2.x, b0.y + b2.y), c2 = make_double2(b0.x - b2.x, b0.y - b2.y);
+  const double2 c1 = make_double2(b1.x - b3.y, b1.y + b3.x), c3 = make_double2(b1.x + b3.y, b1.y - b3.x);
+  const double2 c4 = make_double2(b4.x + b6.x, b4.y + b6.y), c6 = make_double2(b4.x - b6.x, b4.y - b6.y);
+  const double2 c5 = make_double2(b5.x - b7.y, b5.y + b7.x), c7 = make_double2(b5.x + b7.y, b5.y - b7.x);
+  // W8 c5 = (1 + j)/sqrt2 (x + j y) = ((x - y) + j (x + y)) r ;  W8^3 c7 = (-1 + j)/sqrt2 (x + j y) = ((-x - y) + j (x - y)) r
+  const double2 w5 = make_double2((c5.x - c5.y) * r, (c5.x + c5.y) * r);
+  const double2 w7 = make_double2((-c7.x - c7.y) * r, (c7.x - c7.y) * r);
+  a[0] = make_double2(c0.x + c4.x, c0.y + c4.y);
+  a[4] = make_double2(c0.x - c4.x, c0.y - c4.y);
+  a[1] = make_double2(c1.x + w5.x, c1.y + w5.y);
+  a[5] = make_double2(c1.x - w5.x, c1.y - w5.y);
+  a[2] = make_double2(c2.x - c6.y, c2.y + c6.x);
+  a[6] = make_double2(c2.x + c6.y, c2.y - c6.x);
+  a[3] = make_double2(c3.x + w7.x, c3.y + w7.y);
+  a[7] = make_double2(c3.x - w7.x, c3.y - w7.y);
 }
 
-// The same transmitter for K = 64 (the default since round 2; DCCN_TX_V2=0 selects tx_kernel) with the IDFT as
-// 8 x 8 (n = 8 n1 + n2, k = k1 + 8 k2):  Y[k1][n2] = sum_k2 X[k1 + 8 k2] W8^(n2 k2),  Z = Y * W64^(n2 k1),
-// x[8 n1 + n2] = sum_k1 Z[k1][n2] W8^(n1 k1) / 64  -- 1 024 + 64 complex fp64 MACs per symbol instead of 4 096, the
-// eight W8 powers a lane needs held in registers (lane & 7 selects n2 in the first pass and n1 in the second, so one
-// set serves both), warps loop over symbols (twiddles computed once per thread), output staged in shared memory and
-// written with the cyclic prefix as 80 consecutive float2.
+// W64^i = exp(+2 pi j i / 64), i = 0..63, once per block
+DCCN_DEVINL void tx64_twiddle_table(double2* tw64) {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    double sn, cs;
+    sincospi((double)i / 32.0, &sn, &cs);
+    tw64[i] = make_double2(cs, sn);
+  }
+}
+
+// Symbol `s` of `frame` (this lane's slot; `active` = the slot holds a symbol) -> x[n1] = time sample 8 n1 + q of the
+// symbol, scaled by 1/64, no cyclic prefix.  Whole warp must call (two __syncwarp inside).
+DCCN_DEVINL void tx64_group(const uint8_t* __restrict__ bits, long long frame, int s, bool active, int nbits, int D,
+                            const int* __restrict__ sc_map, const float2* __restrict__ constellation, float2 pilot,
+                            int lane, const double2* tw64, double2* z_slot, double2 (&x)[8]) {
+  constexpr int K = 64;
+  const int q = lane & 7;
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) {
+    float2 v = make_float2(0.f, 0.f);
+    if (active) {
+      const int m = sc_map[s * K + q + 8 * k2];
+      if (m == -2) v = pilot;
+      else if (m >= 0) {
+        int idx = 0;
+        const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
+        for (int b = 0; b < nbits; ++b) idx = (idx << 1) | bp[b];
+        v = constellation[idx];
+      }
+    }
+    x[k2] = make_double2(v.x, v.y);
+  }
+  idft8(x);                                            // x[n2] = Y[k1 = q][n2]
+#pragma unroll
+  for (int n2 = 0; n2 < 8; ++n2) {
+    const double2 w = tw64[(n2 * q) & 63];
+    z_slot[q * 9 + n2] = make_double2(fma(-x[n2].y, w.y, x[n2].x * w.x), fma(x[n2].y, w.x, x[n2].x * w.y));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) x[k1] = z_slot[k1 * 9 + q];      // Z[k1][n2 = q]
+  __syncwarp();
+  idft8(x);                                            // x[n1] = 64 * sample 8 n1 + q
+#pragma unroll
+  for (int n1 = 0; n1 < 8; ++n1) x[n1] = make_double2(x[n1].x * (1.0 / K), x[n1].y * (1.0 / K));
+}
+
+// The same transmitter for K = 64 (the default since round 2; DCCN_TX_V2=0 selects tx_kernel).
 __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ bits, long long B, int S, int CP, int nbits,
                                                    int D, const int* __restrict__ sc_map,
                                                    const float2* __restrict__ constellation, float2 pilot,
                                                    float2* __restrict__ tx) {
   constexpr int K = 64;
-  __shared__ double2 sm_g[8][K];      // per warp: frequency grid, later the time-domain symbol
-  __shared__ double2 sm_z[8][K];      // per warp: Z[k1 * 8 + n2]
+  __shared__ double2 sm_tw[64];
+  __shared__ double2 sm_z[8][4][kTxZ];
+  tx64_twiddle_table(sm_tw);
+  __syncthreads();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Tx64Twiddles tw;
-  tx64_twiddles(lane, tw);
-  double2* g = sm_g[wib];
-  double2* z = sm_z[wib];
+  const int slot = lane >> 3, q = lane & 7;
   const int T = K + CP;
   const long long total = B * S;
-  for (long long sym = (long long)blockIdx.x * 8 + wib; sym < total; sym += (long long)gridDim.x * 8) {
-    const long long frame = sym / S;
-    const int s = (int)(sym - frame * S);
-    tx64_symbol(bits, frame, s, nbits, D, sc_map, constellation, pilot, lane, tw, g, z);
-    float2* o = tx + (size_t)sym * T;
-    for (int t = lane; t < T; t += 32) {
-      const double2 v = g[(t + K - CP) & (K - 1)];     // cyclic prefix = the last CP samples, then the symbol
-      o[t] = make_float2((float)v.x, (float)v.y);
+  for (long long sym0 = ((long long)blockIdx.x * 8 + wib) * 4; sym0 < total; sym0 += (long long)gridDim.x * 32) {
+    const long long sym = sym0 + slot;
+    const bool active = sym < total;
+    const long long frame = active ? sym / S : 0;
+    const int s = active ? (int)(sym - frame * S) : 0;
+    double2 x[8];
+    tx64_group(bits, frame, s, active, nbits, D, sc_map, constellation, pilot, lane, sm_tw, sm_z[wib][slot], x);
+    if (active) {
+      float2* o = tx + (size_t)sym * T;
+#pragma unroll
+      for (int n1 = 0; n1 < 8; ++n1) {
+        const int n = 8 * n1 + q;
+        const float2 v = make_float2((float)x[n1].x, (float)x[n1].y);
+        o[CP + n] = v;
+        if (n >= K - CP) o[n - (K - CP)] = v;           // cyclic prefix = the last CP samples
+      }
     }
-    __syncwarp();
   }
 }
 
@@ -576,15 +590,14 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
     const double* __restrict__ coeff, int n_taps, int n_fir, const double* __restrict__ z_in, uint64_t seed,
     float2* __restrict__ tx_out, float2* __restrict__ rx, double* __restrict__ power_sum) {
   constexpr int K = 64;
-  __shared__ double2 sm_g[kGenWarps][K];
-  __shared__ double2 sm_z[kGenWarps][K];
+  __shared__ double2 sm_tw[64];
+  __shared__ double2 sm_z[kGenWarps][4][kTxZ];
   __shared__ double2 gsm[kGenWarps][kMaxFir];
   __shared__ float2 sm_fr[kGenWarps][kGenMaxSamp];
+  tx64_twiddle_table(sm_tw);
+  __syncthreads();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Tx64Twiddles tw;
-  tx64_twiddles(lane, tw);
-  double2* g = sm_g[wib];
-  double2* z = sm_z[wib];
+  const int slot = lane >> 3, q = lane & 7;
   float2* fr = sm_fr[wib];
   const int T = K + CP, n_samp = S * T;
   const int M = n_taps == 0 ? 1 : n_fir;
@@ -624,15 +637,23 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
       }
       if (lane < n_fir) gsm[wib][lane] = gt;
     }
-    // ---- transmitter: S symbols into the shared frame buffer (tx64_kernel) ----
-    for (int s = 0; s < S; ++s) {
-      tx64_symbol(bits, frame, s, nbits, D, sc_map, constellation, pilot, lane, tw, g, z);
-      for (int t = lane; t < T; t += 32) {
-        const double2 v = g[(t + K - CP) & (K - 1)];
-        fr[s * T + t] = make_float2((float)v.x, (float)v.y);
+    // ---- transmitter: the S symbols, four at a time, into the shared frame buffer as fp32 (tx64_kernel's values) ----
+    for (int s0 = 0; s0 < S; s0 += 4) {
+      const int s = s0 + slot;
+      const bool active = s < S;
+      double2 x[8];
+      tx64_group(bits, frame, active ? s : 0, active, nbits, D, sc_map, constellation, pilot, lane, sm_tw, sm_z[wib][slot], x);
+      if (active) {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int n = 8 * n1 + q;
+          const float2 v = make_float2((float)x[n1].x, (float)x[n1].y);
+          fr[s * T + CP + n] = v;
+          if (n >= K - CP) fr[s * T + n - (K - CP)] = v;
+        }
       }
-      __syncwarp();
     }
+    __syncwarp();
     if (tx_out) {
       float2* o = tx_out + (size_t)frame * n_samp;
       for (int n = lane; n < n_samp; n += 32) o[n] = fr[n];

@@ -148,10 +148,18 @@ def load_model_np(path, session=None, FLAGS=None, ofdmobj=None, precision='parit
     return Session(FLAGS, ofdmobj, weights, precision=precision)
 
 
-def save_model(path, weights, global_step=0, step_name='global_step'):
+def save_model(path, weights, global_step=0, step_name='global_step', FLAGS=None, ofdmobj=None):
     """Write a TF-bundle-v2 checkpoint with the reference's variable names.  The basic receiver's step counter is
     ``global_step`` (dev/py/ofdmreceiver_np.py:185), the equalizer driver's lives in its 'optimizer' variable scope
-    (``optimizer/global_step``, dev/py/ofdmreceiver_np_mp.py:335-343)."""
+    (``optimizer/global_step``, dev/py/ofdmreceiver_np_mp.py:335-343).
+    With ``FLAGS`` / ``ofdmobj`` a ``.meta`` graph is written next to a BASIC-RECEIVER bundle (tfmeta.write_meta: the
+    graph of ofdmreceiver_np.py with the named tensors the reference's ``load_model_np`` fetches after
+    ``import_meta_graph``, dev/py/model.py:51-72).  Equalizer bundles get no ``.meta``: the spliced graph of
+    ofdmreceiver_np_mp.py:264-320 is not emitted."""
     w = dict(weights)
     w[step_name] = np.asarray(global_step, dtype=np.float32).reshape(())
     tfbundle.write_checkpoint(path, w)
+    if FLAGS is not None and ofdmobj is not None and not any(k.startswith('Equalizer/') for k in w):
+        from . import tfmeta
+        head = 'v1' if 'demodulation/conv2d_1/kernel' in w else 'dev'
+        tfmeta.write_meta(path, FLAGS.nbits, ofdmobj, nfilter=FLAGS.nfilter, cp=FLAGS.cp, head=head)

@@ -91,7 +91,7 @@ def train_receiver(FLAGS, ofdmobj, weights=None, max_epoch_num=None, frame_cnt=N
                 w = dict(weights)
                 for n in RX_TRAINABLE:
                     w[n] = eng.get_weight(n).reshape(np.shape(weights[n]))
-                save_model(name, w, global_step=eng.global_step)
+                save_model(name, w, global_step=eng.global_step, FLAGS=FLAGS, ofdmobj=ofdmobj)
         if epoch - FLAGS.early_stop > epoch_min_loss:                           # :271-272
             break
     return session, history

@@ -53,8 +53,14 @@ def _shape_proto(shape):
     return p
 
 
-def _tensor_proto(value, dtype):
+def _tensor_proto(value, dtype, splat_shape=None):
+    """splat_shape: `tf.constant(scalar, shape=...)` -- the shape with ONE typed value entry (how TF stores zeros(...))."""
     t = tensor_pb2.TensorProto(dtype=dtype)
+    if splat_shape is not None:
+        t.tensor_shape.CopyFrom(_shape_proto(splat_shape))
+        field = {FLOAT: t.float_val, INT32: t.int_val, INT64: t.int64_val, BOOL: t.bool_val}[dtype]
+        field.append(np.asarray(value, dtype=_NP[dtype]).item())
+        return t, list(splat_shape)
     if dtype == STRING:
         vals = value if isinstance(value, (list, tuple)) else [value]
         shape = [len(vals)] if isinstance(value, (list, tuple)) else []
@@ -187,14 +193,14 @@ def a_strs(vs):
     return attr_value_pb2.AttrValue(list=attr_value_pb2.AttrValue.ListValue(s=[v.encode() for v in vs]))
 
 
-def a_tensor(value, dtype):
-    t, shape = _tensor_proto(value, dtype)
+def a_tensor(value, dtype, splat_shape=None):
+    t, shape = _tensor_proto(value, dtype, splat_shape)
     return attr_value_pb2.AttrValue(tensor=t), shape
 
 
 # ---- the subset of tf.* used by the reference graph ----------------------------------------------
-def const(g, value, dtype, name='Const'):
-    av, shape = a_tensor(value, dtype)
+def const(g, value, dtype, name='Const', splat_shape=None):
+    av, shape = a_tensor(value, dtype, splat_shape)
     return g.add('Const', name, [], {'value': av, 'dtype': a_type(dtype)}, [(dtype, shape)])
 
 

@@ -205,12 +205,25 @@ def test_train_equalizer_driver(libdccn, tmp_path):
 # training of the basic receiver itself (DCCN_TRAIN_RX; dev/py/ofdmreceiver_np.py:154-189)
 # ---------------------------------------------------------------------------------------------
 def _rx_case(seed, B, nbits, use_cp=True):
+    """Seeded receiver case whose leaky-ReLU inputs all stay away from the kink: a pre-activation within fp32 rounding of 0
+    (1.5 M units per case; the first draw of one case had |v| = 1.2e-8) takes slope 0.2 or 1 depending on the last bit of
+    the forward arithmetic, which changes the GRADIENT by a finite amount in any fp32 implementation -- such a draw tests
+    the coin, not the kernels, so the next seed is taken instead."""
     from oracle import dccn_oracle as orc
-    rng = np.random.default_rng(seed)
-    w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=False, bias_scale=0.05)
-    x = (rng.standard_normal((B, 7, 80, 2)) * 0.3).astype(np.float32)
-    bits = rng.integers(0, 2, (B, 320, nbits)).astype(np.uint8)
-    return w, x, bits
+    for attempt in range(20):
+        rng = np.random.default_rng(seed + 1000 * attempt)
+        w = orc.glorot_weights(rng, nbits, use_cp=use_cp, equalizer=False, bias_scale=0.05)
+        x = (rng.standard_normal((B, 7, 80, 2)) * 0.3).astype(np.float32)
+        bits = rng.integers(0, 2, (B, 320, nbits)).astype(np.uint8)
+        z, _, _ = orc.batch_moment_norm(x, np.float64)
+        _, inter = orc.ofdm_dense_rx(z, w, nbits, 16, use_cp=use_cp, return_intermediate=True)
+        oiq = inter['out_iq']
+        h = oiq @ w['demodulation/conv2d/kernel'].reshape(2, -1).astype(np.float64) + w['demodulation/conv2d/bias']
+        lg = np.concatenate([np.maximum(0.2 * h, h), oiq], -1) @ w['demodulation/dense_1/kernel'].astype(np.float64) + \
+            w['demodulation/dense_1/bias']
+        if min(np.abs(h).min(), np.abs(lg).min()) > 4e-8:     # these values are O(0.1): fp32 forward error ~1e-8
+            return w, x, bits
+    raise AssertionError('no kink-free draw')
 
 
 def _rx_engine(w, nbits, precision, max_batch, use_cp=True):

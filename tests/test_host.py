@@ -125,3 +125,102 @@ def test_equalizer_graph_tables_agree():
     # dense_8 only exists in equalizer_dnnE (dense, dense_1, ..., dense_8; no conv3d)
     assert [n for _, n in init.eq_layer_roles(3)][-1] == 'dense_8'
     assert [n for _, n in init.eq_layer_roles(2)] == ['dense', 'conv3d', 'dense_1', 'dense_2', 'dense_3']
+
+
+def _meta_digest_helpers():
+    import hashlib
+
+    def node_key(n):
+        attrs = ''.join('%s=%s;' % (k, n.attr[k].SerializeToString(deterministic=True).hex()) for k in sorted(n.attr.keys()))
+        return '%s|%s|%s|%s|%s' % (n.name, n.op, ','.join(n.input), n.device, attrs)
+
+    def needed(nodes, fetches):
+        st = list(fetches) + [n for n in nodes if n.endswith('/Assign') and 'Adam' not in n and '_power' not in n
+                              and not n.startswith('save/')]
+        seen = set()
+        while st:
+            n = st.pop().lstrip('^').split(':')[0]
+            if n not in seen:
+                seen.add(n)
+                st.extend(nodes[n].input)
+        return sorted(seen)
+
+    def digest(nodes, names):
+        h = hashlib.sha256()
+        for n in names:
+            h.update(node_key(nodes[n]).encode())
+            h.update(b'\n')
+        return h.hexdigest()
+    return node_key, needed, digest
+
+
+@pytest.mark.parametrize('nb', [1, 2, 3, 4])
+@pytest.mark.parametrize('cp', [True, False])
+def test_meta_graph_matches_shipped_v1(nb, cp):
+    """The `.meta` emitter (tfmeta / tfgraph, no TensorFlow) rebuilds the graph of every checkpoint the reference ships
+    (test_v1/model/*.meta, written by TF 1.10.1): all 452 / 455 nodes reachable from the named fetches of
+    dev/py/model.py:51-72 and from the model variables' initializers are identical in name, op, inputs, device and
+    EVERY attribute (tests/golden/v1_meta_digest.json, made by oracle/make_meta_digest.py from the shipped files)."""
+    import hashlib
+    import json
+    from dl_ofdm_b200 import tfmeta
+    node_key, needed, digest = _meta_digest_helpers()
+    gold = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'v1_meta_digest.json')))
+    name = 'OFDM_Dense3_%dmod_snr%d_cp%s' % (nb, 3 * nb, cp)
+    g = tfmeta.build_receiver_graph(nb, 8, 80, 64, 8 * 46, 64, cp, 'v1')
+    m = tfmeta.meta_graph(g, '1.10.1', 'v1.10.1-0-g4dcfddc5d1')
+    nodes = {n.name: n for n in m.graph_def.node}
+    names = needed(nodes, tfmeta.FETCHES)
+    assert len(names) == gold[name]['nodes']
+    assert hashlib.sha256('\n'.join(names).encode()).hexdigest() == gold[name]['names_sha256']
+    if 'per_node' in gold[name]:
+        bad = [n for n in names if hashlib.sha1(node_key(nodes[n]).encode()).hexdigest()[:12] != gold[name]['per_node'][n]]
+        assert not bad, bad[:10]
+    assert digest(nodes, names) == gold[name]['sha256']
+    # saver + collections the reference's import_meta_graph / restore use
+    assert m.saver_def.filename_tensor_name == 'save/Const:0' and m.saver_def.restore_op_name == 'save/restore_all'
+    assert m.saver_def.save_tensor_name == 'save/control_dependency:0' and m.saver_def.version == 2
+    from tensorboard.compat.proto import variable_pb2
+    vs = []
+    for b in m.collection_def['variables'].bytes_list.value:
+        v = variable_pb2.VariableDef()
+        v.ParseFromString(b)
+        vs.append(v)
+    assert [v.variable_name for v in vs] == ['fft_like/conv3d/kernel:0', 'fft_like/conv3d/bias:0', 'demodulation/dense/kernel:0',
+                                             'demodulation/dense/bias:0', 'demodulation/conv2d/kernel:0', 'demodulation/conv2d/bias:0',
+                                             'demodulation/conv2d_1/kernel:0', 'demodulation/conv2d_1/bias:0',
+                                             'demodulation/dense_1/kernel:0', 'demodulation/dense_1/bias:0', 'global_step:0']
+    assert all(v.snapshot_name == v.variable_name[:-2] + '/read:0' and v.initializer_name == v.variable_name[:-2] + '/Assign' for v in vs)
+    assert len(m.collection_def['trainable_variables'].bytes_list.value) == 10
+    assert list(m.collection_def['regularization_losses'].node_list.value) == [
+        'receiver/demodulation/%s/Regularizer/l2_regularizer:0' % t for t in ('dense/kernel', 'dense/bias', 'dense_1/kernel', 'dense_1/bias')]
+
+
+def test_save_model_writes_meta_for_the_bundle(tmp_path):
+    """save_model on a basic receiver writes .index / .data AND a .meta whose saver covers exactly the bundle's tensors and
+    whose graph holds every tensor name dev/py/model.py:51-72 fetches after import_meta_graph (dev architecture)."""
+    from tensorboard.compat.proto import meta_graph_pb2
+    from dl_ofdm_b200 import init, tfbundle
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.model import save_model
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    for nb, cp in ((4, True), (1, False)):
+        fl = Flags(nbits=nb, cp=cp)
+        o = ofdm_tx(fl)
+        w = init.receiver_variables(np.random.default_rng(0), nb, use_cp=cp)
+        prefix = str(tmp_path / ('rx%d' % nb))
+        save_model(prefix, w, global_step=123, FLAGS=fl, ofdmobj=o)
+        m = meta_graph_pb2.MetaGraphDef()
+        m.ParseFromString(open(prefix + '.meta', 'rb').read())
+        nodes = {n.name: n for n in m.graph_def.node}
+        for t in ('bits_in', 'tx_ofdm', 'input', 'output', 'cost', 'log_ber', 'linear_ber', 'conf_matrix', 'tx_power',
+                  'noise_power', 'iq_rx', 'iq_tx', 'ce_mean', 'SNR'):
+            assert t in nodes, t
+        saved = [s.decode() for s in nodes['save/SaveV2/tensor_names'].attr['value'].tensor.string_val]
+        assert saved == sorted(tfbundle.read_checkpoint(prefix).keys())
+        assert list(nodes['save/SaveV2'].input[3:]) == saved
+        shp = lambda n: [d.size for d in nodes[n].attr['_output_shapes'].list.shape[0].dim]      # noqa: E731
+        assert shp('tx_ofdm') == [-1, 7, 80, 2] and shp('output') == [-1, 320, nb, 2] and shp('bits_in') == [-1, 320, nb]
+        T = 80 if cp else 64
+        assert shp('fft_like/conv3d/kernel') == [1, T, 1, T, 128] == list(w['fft_like/conv3d/kernel'].shape)
+        assert shp('demodulation/dense/kernel') == [896, 640]

@@ -1641,11 +1641,23 @@ int dccn_tx_fade(dccn_handle* h, const uint8_t* bits_dev, int64_t B, const int32
   long long blocks = (B + kGenWarps - 1) / kGenWarps;
   const long long cap = (long long)h->num_sms * 8;
   if (blocks > cap) blocks = cap;
-  tx_fade_kernel<<<(unsigned)blocks, 32 * kGenWarps, 0, s>>>(bits_dev, (long long)B, h->S, h->cfg.cp_len, h->NB, h->D,
-                                                           h->d_txmap, (const float2*)constellation_dev,
-                                                           make_float2(pilot_re, pilot_im), alpha_dev, coeff_dev, n_taps,
-                                                           n_fir, z_dev, seed, (float2*)tx_dev, (float2*)faded_dev,
-                                                           h->d_power);
+  const int n_samp = h->S * h->T;
+  auto launch = [&](auto kern, size_t smem) -> int {
+    static bool attr_set[2] = {false, false};
+    const int which = smem == tx_fade_smem<18>() ? 0 : 1;
+    if (!attr_set[which]) {
+      DCCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[which] = true;
+    }
+    kern<<<(unsigned)blocks, 32 * kGenWarps, smem, s>>>(bits_dev, (long long)B, h->S, h->cfg.cp_len, h->NB, h->D, h->d_txmap,
+                                                       (const float2*)constellation_dev, make_float2(pilot_re, pilot_im),
+                                                       alpha_dev, coeff_dev, n_taps, n_fir, z_dev, seed, (float2*)tx_dev,
+                                                       (float2*)faded_dev, h->d_power);
+    return 0;
+  };
+  // L = output samples per lane of the FIR's blocked mapping: 18 covers the 560-sample LTE frame, 20 the 640-sample v1 frame
+  int rc = n_samp <= 32 * 18 ? launch(tx_fade_kernel<18>, tx_fade_smem<18>()) : launch(tx_fade_kernel<20>, tx_fade_smem<20>());
+  if (rc) return rc;
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1757,7 +1769,8 @@ uint32_t dccn_crc32c(const void* data_host, size_t n, uint32_t crc) {
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream) {
   DCCN_CHECK(bits_dev && n >= 0, "bad argument");
   if (n == 0) return 0;
-  const long long threads = (n + 15) / 16;
+  const long long threads = (n + 127) / 128;
+  g_launches += 1;
   bit_source_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits_dev, (long long)n, seed);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;

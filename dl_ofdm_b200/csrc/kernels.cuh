@@ -584,21 +584,71 @@ __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ b
 constexpr int kGenWarps = 4;
 constexpr int kGenMaxSamp = 8 * 80;     // S <= 8 symbols of K + CP <= 80 samples
 
+// Shared-memory frame buffers of the fused feeder use a padded layout: sample n of a frame sits at n + n / L (L = samples
+// per lane in the FIR's blocked mapping), i.e. lane l's run starts at (L + 1) l -- an odd stride in 8-byte words, so the
+// 32 lanes of a warp hit 32 different bank pairs when each reads "its" i-th sample.
+template <int L>
+DCCN_DEVINL int fr_pos(int n) { return n + n / L; }
+
+// FIR of one frame, blocked mapping: lane l produces outputs [L l, L l + L) from a register window that slides over
+// fr[] (each input sample is loaded from shared memory and converted to double ONCE per lane instead of once per tap),
+// taps in registers (MT >= M of them, zero-padded).  out[n] = sum_j g[j] x[n + off - j], zero outside the frame
+// (np.convolve(tx, g, 'same'), radio.py:436), complex128, same accumulation order as chan_fir_kernel (fir_cmac, j ascending).
+template <int L, int MT>
+DCCN_DEVINL double fir_blocked(const float2* fr, float2* fo, const double2* gs, int M, int off, int n_samp, int lane) {
+  double2 g[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j) g[j] = j < M ? gs[j] : make_double2(0.0, 0.0);
+  // window w[t] = x[n0 + t - (MT - 1)] for the current output n0 + i; element for tap j of output i: x[n0 + i + off - j]
+  const int n0 = L * lane;
+  double2 win[MT];                                   // win[j] = x[n + off - j] for the current n
+  auto load = [&](int n) -> double2 {
+    if (n < 0 || n >= n_samp) return make_double2(0.0, 0.0);
+    const float2 v = fr[fr_pos<L>(n)];
+    return make_double2((double)v.x, (double)v.y);
+  };
+#pragma unroll
+  for (int j = 1; j < MT; ++j) win[j] = load(n0 + off - j);      // history of the first output (j = 0 is loaded in the loop)
+  double pw = 0.0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const int n = n0 + i;
+    win[0] = load(n + off);
+    double accr = 0.0, acci = 0.0;
+#pragma unroll
+    for (int j = 0; j < MT; ++j) fir_cmac(accr, acci, g[j], win[j].x, win[j].y);
+    if (n < n_samp) {
+      const float2 o = make_float2((float)accr, (float)acci);
+      fo[fr_pos<L>(n)] = o;
+      pw += (double)o.x * o.x + (double)o.y * o.y;
+    }
+#pragma unroll
+    for (int j = MT - 1; j > 0; --j) win[j] = win[j - 1];       // renaming only: the loops are fully unrolled
+  }
+  return pw;
+}
+
+template <int L>
 __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
     const uint8_t* __restrict__ bits, long long B, int S, int CP, int nbits, int D, const int* __restrict__ sc_map,
     const float2* __restrict__ constellation, float2 pilot, const double* __restrict__ alpha,
     const double* __restrict__ coeff, int n_taps, int n_fir, const double* __restrict__ z_in, uint64_t seed,
     float2* __restrict__ tx_out, float2* __restrict__ rx, double* __restrict__ power_sum) {
   constexpr int K = 64;
-  __shared__ double2 sm_tw[64];
-  __shared__ double2 sm_z[kGenWarps][4][kTxZ];
-  __shared__ double2 gsm[kGenWarps][kMaxFir];
-  __shared__ float2 sm_fr[kGenWarps][kGenMaxSamp];
+  constexpr int FR = 32 * (L + 1);                   // padded frame buffer (float2)
+  extern __shared__ __align__(16) uint8_t gen_smem[];
+  double2* sm_tw = reinterpret_cast<double2*>(gen_smem);                                  // [64]
+  double2* sm_z_all = sm_tw + 64;                                                          // [warps][4][kTxZ]
+  double2* gsm_all = sm_z_all + kGenWarps * 4 * kTxZ;                                      // [warps][kMaxFir]
+  float2* sm_fr_all = reinterpret_cast<float2*>(gsm_all + kGenWarps * kMaxFir);            // [warps][FR]
+  float2* sm_fo_all = sm_fr_all + kGenWarps * FR;                                          // [warps][FR]
   tx64_twiddle_table(sm_tw);
   __syncthreads();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = lane >> 3, q = lane & 7;
-  float2* fr = sm_fr[wib];
+  double2* gs = gsm_all + wib * kMaxFir;
+  float2* fr = sm_fr_all + wib * FR;
+  float2* fo = sm_fo_all + wib * FR;
   const int T = K + CP, n_samp = S * T;
   const int M = n_taps == 0 ? 1 : n_fir;
   const int off = (M - 1) - (M >> 1);
@@ -606,7 +656,7 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
   for (long long frame = (long long)blockIdx.x * kGenWarps + wib; frame < B; frame += (long long)gridDim.x * kGenWarps) {
     // ---- path gains -> sample-spaced FIR (chan_fir_kernel) ----
     if (n_taps == 0) {
-      if (lane == 0) gsm[wib][0] = make_double2(1.0, 0.0);
+      if (lane == 0) gs[0] = make_double2(1.0, 0.0);
     } else {
       double2 pa = make_double2(0.0, 0.0);
       if (lane < n_taps) {
@@ -635,43 +685,49 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
           gt.y = fma(ai, al, gt.y);
         }
       }
-      if (lane < n_fir) gsm[wib][lane] = gt;
+      if (lane < n_fir) gs[lane] = gt;
     }
     // ---- transmitter: the S symbols, four at a time, into the shared frame buffer as fp32 (tx64_kernel's values) ----
     for (int s0 = 0; s0 < S; s0 += 4) {
       const int s = s0 + slot;
       const bool active = s < S;
       double2 x[8];
-      tx64_group(bits, frame, active ? s : 0, active, nbits, D, sc_map, constellation, pilot, lane, sm_tw, sm_z[wib][slot], x);
+      tx64_group(bits, frame, active ? s : 0, active, nbits, D, sc_map, constellation, pilot, lane, sm_tw,
+                 sm_z_all + (wib * 4 + slot) * kTxZ, x);
       if (active) {
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
           const int n = 8 * n1 + q;
           const float2 v = make_float2((float)x[n1].x, (float)x[n1].y);
-          fr[s * T + CP + n] = v;
-          if (n >= K - CP) fr[s * T + n - (K - CP)] = v;
+          fr[fr_pos<L>(s * T + CP + n)] = v;
+          if (n >= K - CP) fr[fr_pos<L>(s * T + n - (K - CP))] = v;
         }
       }
     }
     __syncwarp();
     if (tx_out) {
       float2* o = tx_out + (size_t)frame * n_samp;
-      for (int n = lane; n < n_samp; n += 32) o[n] = fr[n];
+      for (int n = lane; n < n_samp; n += 32) o[n] = fr[fr_pos<L>(n)];
     }
-    // ---- centred 'same' FIR with zero history, complex128 (chan_fir_kernel's accumulation order) ----
-    float2* rxf = rx + (size_t)frame * n_samp;
-    for (int n = lane; n < n_samp; n += 32) {
-      double accr = 0.0, acci = 0.0;
-      for (int j = 0; j < M; ++j) {
-        const int i = n + off - j;
-        const float2 xv = (i >= 0 && i < n_samp) ? fr[i] : make_float2(0.f, 0.f);
-        const double xr = xv.x, xi = xv.y;
-        fir_cmac(accr, acci, gsm[wib][j], xr, xi);
+    // ---- centred 'same' FIR with zero history, complex128 ----
+    if (M <= 9) pw += fir_blocked<L, 9>(fr, fo, gs, M, off, n_samp, lane);
+    else if (M <= 13) pw += fir_blocked<L, 13>(fr, fo, gs, M, off, n_samp, lane);
+    else {                                             // long filters: interleaved mapping, taps and samples from shared memory
+      for (int n = lane; n < n_samp; n += 32) {
+        double accr = 0.0, acci = 0.0;
+        for (int j = 0; j < M; ++j) {
+          const int i = n + off - j;
+          const float2 xv = (i >= 0 && i < n_samp) ? fr[fr_pos<L>(i)] : make_float2(0.f, 0.f);
+          fir_cmac(accr, acci, gs[j], (double)xv.x, (double)xv.y);
+        }
+        const float2 o = make_float2((float)accr, (float)acci);
+        fo[fr_pos<L>(n)] = o;
+        pw += (double)o.x * o.x + (double)o.y * o.y;
       }
-      const float2 o = make_float2((float)accr, (float)acci);
-      rxf[n] = o;
-      pw += (double)o.x * o.x + (double)o.y * o.y;
     }
+    __syncwarp();
+    float2* rxf = rx + (size_t)frame * n_samp;
+    for (int n = lane; n < n_samp; n += 32) rxf[n] = fo[fr_pos<L>(n)];     // coalesced copy-out
     __syncwarp();
   }
 #pragma unroll
@@ -679,15 +735,35 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
   if (lane == 0 && pw != 0.0) atomicAdd(power_sum, pw);
 }
 
-__global__ void bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint64_t seed) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x);   // 16 bytes per thread
-  if (i * 16 >= n) return;
+template <int L>
+constexpr size_t tx_fade_smem() {
+  return (64 + kGenWarps * 4 * kTxZ + kGenWarps * kMaxFir) * sizeof(double2) + 2 * kGenWarps * 32 * (L + 1) * sizeof(float2);
+}
+
+// util.bit_source (dev/py/util.py:25-34): n uniform bits, one per byte.  A thread expands ONE Philox-4x32 call (128 random
+// bits) into 128 bytes with eight 16-byte stores (round 1 drew one call per 16 bytes and stored them a byte at a time:
+// 0.22 ms per 65 536-frame cell, now store-bound).
+__global__ void __launch_bounds__(256) bit_source_kernel(uint8_t* __restrict__ bits, long long n, uint64_t seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // 128 bytes per thread
+  if (i * 128 >= n) return;
   uint32_t r[4];
   Philox{seed}((uint64_t)i, 0xB175u, r);
-  const uint32_t w = r[0];
+  auto spread = [](uint32_t v) {      // 4 bits -> 4 bytes of 0 / 1
+    return (v & 1u) | ((v & 2u) << 7) | ((v & 4u) << 14) | ((v & 8u) << 21);
+  };
+  if (i * 128 + 128 <= n && (reinterpret_cast<uintptr_t>(bits) & 15) == 0) {
+    uint4* o = reinterpret_cast<uint4*>(bits + i * 128);
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (i * 16 + j < n) bits[i * 16 + j] = (uint8_t)((w >> j) & 1u);
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t v = r[w] >> (16 * h);
+        o[2 * w + h] = make_uint4(spread(v), spread(v >> 4), spread(v >> 8), spread(v >> 12));
+      }
+    }
+  } else {
+    for (int j = 0; j < 128 && i * 128 + j < n; ++j) bits[i * 128 + j] = (uint8_t)((r[j >> 5] >> (j & 31)) & 1u);
+  }
 }
 
 // =====================================================================================

@@ -67,6 +67,8 @@ PROTOTYPES = {
                                _u64, _i32, _vp, _vp, _vp]),
     'dccn_bit_source': (C.c_int, [_vp, _i64, _u64, _vp]),
     'dccn_crc32c': (C.c_uint32, [_vp, C.c_size_t, C.c_uint32]),
+    'dccn_monitors': (C.c_int, [_vp, _vp, _i64, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    'dccn_forward_monitors': (C.c_int, [_vp, _vp, _vp, _i32]),
     'dccn_debug_tma_rate': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'dccn_debug_mma_rate': (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'dccn_train_init': (C.c_int, [_vp, C.POINTER(dccn_train_cfg), _vp]),

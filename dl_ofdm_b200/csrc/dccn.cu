@@ -733,6 +733,9 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
     if ((rc = make_tmap(&epi.tm_eq, epi.eq.p0 + epi.eq.col_off, epi.M, epi.eq.ld - epi.eq.col_off, epi.eq.ld, 32)))
       return rc;
     if (epi.chest_out && (rc = make_tmap(&epi.tm_chest, epi.chest_out, epi.M, epi.N, epi.N, 32))) return rc;
+    if (epi.corr.p0 && (rc = make_tmap(&epi.tm_corr, epi.corr.p0 + epi.corr.col_off, epi.M, epi.corr.ld - epi.corr.col_off,
+                                       epi.corr.ld, 32)))
+      return rc;
   }
   op.b0 = L.tmB0;
   const bool split = prec == DCCN_PREC_PARITY;
@@ -998,6 +1001,13 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       KSched ks;
       if (h->band_skip && h->g7.BN == 2 * K && (2 * K) % 32 == 0) ks.band = ((S - 1) / 2) * (2 * K / 32);
       if ((rc = run_gemm(h, SLOT_G7_PHASEEQ, h->g7, c4, 0, Bc, e, s, ks))) return rc;
+    }
+    if (h->mon_snr_db) {      // snr_db monitor of this pass (reads the phase-equalised frame the epilogue just wrote)
+      g_launches += 1;
+      snr_monitor_kernel<<<(unsigned)((Bc + 7) / 8), 256, 0, s>>>((const float2*)h->eq.p0, (long long)Bc, S, K,
+                                                                 h->mon_pilot_carriers, h->mon_n_pilot,
+                                                                 h->mon_snr_db + h->mon_frame0);
+      DCCN_CUDA_OK(cudaGetLastError());
     }
     // corr / eq (1,K) 'valid' complex convs -> [eq_out | corr_out]  model.py:437-448
     if ((rc = run_gemm(h, SLOT_G8, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
@@ -1348,8 +1358,11 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
   const int64_t per = ((B + n_pass - 1) / n_pass + 127) / 128 * 128;
   if ((flags & DCCN_FWD_FOLDED) && h->cfg.equalizer && !h->ws_eqc) h->ws_eqc = h->ws_dirty = true;
   if ((rc = ensure_workspace(h, per))) return rc;
+  DCCN_CHECK(!h->mon_snr_db || (h->cfg.equalizer && h->eq_opt == 0 && !(flags & (DCCN_FWD_SKIP_EQ | DCCN_FWD_FOLDED))),
+             "the snr_db monitor belongs to equalizer_ofdm's layer-by-layer schedule");
   for (int64_t b0 = 0; b0 < B; b0 += per) {
     const int64_t Bc = (B - b0) < per ? (B - b0) : per;
+    h->mon_frame0 = b0;
     rc = run_chunk(h, x_dev + (size_t)b0 * h->P, Bc, bits_dev ? bits_dev + (size_t)b0 * D * NB : nullptr,
                    soft_dev ? soft_dev + (size_t)b0 * D * NB * 2 : nullptr,
                    hard_dev ? hard_dev + (size_t)b0 * D * NB : nullptr,
@@ -1358,11 +1371,38 @@ int dccn_forward(dccn_handle* h, const float* x_dev, int64_t B, const uint8_t* b
                    want_conf ? h->d_conf : nullptr, (bits_dev && ce_sum_dev) ? ce_sum_dev : nullptr, flags, s);
     if (rc) return rc;
   }
+  h->mon_snr_db = nullptr;       // one-shot request
   if (want_conf) {
     g_launches += 1;
     conf_copy_kernel<<<1, 32, 0, s>>>(h->d_conf, (long long*)conf_dev);
     DCCN_CUDA_OK(cudaGetLastError());
   }
+  return 0;
+}
+
+int dccn_forward_monitors(dccn_handle* h, float* snr_db_dev, const int32_t* pilot_carriers_dev, int n_pilot_carriers) {
+  DCCN_CHECK(h, "null handle");
+  DCCN_CHECK(!snr_db_dev || (pilot_carriers_dev && n_pilot_carriers > 0), "pilot carrier list missing");
+  h->mon_snr_db = snr_db_dev;
+  h->mon_pilot_carriers = pilot_carriers_dev;
+  h->mon_n_pilot = n_pilot_carriers;
+  return 0;
+}
+
+int dccn_monitors(dccn_handle* h, const float* x_dev, int64_t B, const float* snr_db_dev, uint64_t seed, double* sums_dev,
+                  float* input_dev, void* iq_tx_dev, void* iq_rx_dev, void* stream) {
+  DCCN_CHECK(h && x_dev && sums_dev && B > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = run_moments(h, x_dev, B, h->d_mean, h->d_rstd, s);
+  if (rc) return rc;
+  DCCN_CUDA_OK(cudaMemsetAsync(sums_dev, 0, 2 * sizeof(double), s));
+  long long blocks = (B + 7) / 8;
+  if (blocks > (long long)h->num_sms * 8) blocks = (long long)h->num_sms * 8;
+  g_launches += 1;
+  monitor_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float2*)x_dev, (long long)B, h->S * h->T, (const float2*)h->d_mean,
+                                                  (const float2*)h->d_rstd, snr_db_dev, seed, sums_dev, (float2*)input_dev,
+                                                  (__half2*)iq_tx_dev, (__half2*)iq_rx_dev);
+  DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

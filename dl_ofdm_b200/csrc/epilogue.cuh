@@ -205,7 +205,10 @@ struct EpiPhaseEqT {
   unsigned* amax_corr = nullptr;
   CUtensorMap tm_eq;    // tensor-core path: view of eq.p0 + eq.col_off, box 32 x 32 (set by run_gemm)
   CUtensorMap tm_chest; // same for chest_out
-  struct State {};
+  CUtensorMap tm_corr;  // view of corr.p0 + corr.col_off, box 32 x 32
+  struct State {
+    float c_even[16];   // corr values of the even 32-column chunk, kept until the odd chunk completes a 32 x 32 block
+  };
   static constexpr bool kWarpStore = true;
   DCCN_DEVINL int eq_col(int c) const {
     if constexpr (SYM) return (c / sym_cols) * sym_stride + c % sym_cols;
@@ -217,7 +220,7 @@ struct EpiPhaseEqT {
   }
 
   // tensor-core path: rows row0 + lane; eq goes out through the coalescing transpose
-  DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
+  DCCN_DEVINL void run_warp(State& st, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
     if (col0 >= N || row0 >= M) return;          // warp-uniform
     const int row = row0 + lane;
     const bool ok = row < M;
@@ -252,7 +255,25 @@ struct EpiPhaseEqT {
     if (amax_corr && corr.p0) amax_update_warp<16>(amax_corr, c, ok);
     store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch);
     if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch);
-    if (ok && corr.p0) store_act<16>(corr, row, corr_col(col0 / 2), c);
+    if (corr.p0) {
+      // corr is half as wide as eq: the 16 values of an even 32-column chunk wait in registers for the 16 of the odd
+      // chunk (a warp owns both: its column group is 64 wide), then leave as ONE 32 x 32 block through the TMA engine --
+      // 64-byte per-thread st.global pieces from the epilogue warps backed the LSU up (the round-1 finding for eq itself)
+      if (((col0 >> 5) & 1) == 0 && col0 + 32 < N) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st.c_even[i] = c[i];
+      } else if ((col0 >> 5) & 1) {
+        float blk[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          blk[i] = st.c_even[i];
+          blk[16 + i] = c[i];
+        }
+        store_block_tma(&tm_corr, corr_col((col0 - 32) / 2), nullptr, 0, row0, lane, blk, patch);
+      } else if (ok) {
+        store_act<16>(corr, row, corr_col(col0 / 2), c);      // lone even chunk at the ragged edge
+      }
+    }
   }
 
   template <int NC>

@@ -318,23 +318,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (crank == 0) {   // whole warp, warp-uniform control flow; one elected lane issues
-      constexpr uint32_t idesc_full = F16 ? umma_idesc_f16(BN, 128) : umma_idesc_tf32(BN, PAIR ? 256 : 128);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(BN, 128) : umma_idesc_tf32(BN, PAIR ? 256 : 128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const TileK tk = decode(tile);
-        // ragged last n-tile (N = 160 -> 128 + 32, N = 736 -> 5 x 128 + 96): the MMAs only span the valid columns
-        // rounded up to 16 -- the weight rows beyond N are TMA zero-fill, their products are never read
-        uint32_t idesc = idesc_full;
-        if constexpr (!PAIR) {
-          const int n_left = N - tk.n_blk * BN;
-          if (n_left < BN) {
-            const int nv = (n_left + 15) & ~15;
-            idesc = F16 ? umma_idesc_f16(nv, 128) : umma_idesc_tf32(nv, 128);
-          }
-        }
         for (int kb0 = tk.kb0; kb0 < tk.kb1; kb0 += kb_per_chunk) {
           const int kb1 = kb0 + kb_per_chunk < tk.kb1 ? kb0 + kb_per_chunk : tk.kb1;
           if (lane == 0) DCCN_TRACE_EV(2);
@@ -658,7 +648,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * C::COLS_PER_GROUP);
 #pragma unroll
         for (int j = 0; j < C::NCH; ++j) {
-          if (n_blk * BN + cg * C::COLS_PER_GROUP + j * 32 >= N) continue;   // warp-uniform: chunk beyond the ragged edge
           float v[32];
           if (DCCN_ABL(4)) {
 #pragma unroll
@@ -687,7 +676,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int j = 0; j < C::NCH; ++j) {
         if (warp == C::EPI_WARP0 && lane == 0 && j > 0) DCCN_TRACE_EV(1);
         const int col = n_blk * BN + cg * C::COLS_PER_GROUP + j * 32;
-        if (col >= N) continue;
         if constexpr (F16) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[j][i] *= out_scale;

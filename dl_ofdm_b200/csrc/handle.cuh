@@ -100,6 +100,11 @@ struct dccn_handle {
   int tx_v2 = 1;       // 8 x 8 IDFT transmitter kernel for nfft = 64 (DCCN_TX_V2=0: the generic K-point DFT kernel)
   int32_t* d_txmap = nullptr;           // [S*K] subcarrier role map, rebuilt on the device by every dccn_tx_frames call
   int f16x3 = 1;       // inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (DCCN_F16X3=0: tf32 pairs)
+  // monitor outputs requested for the NEXT forward (dccn_forward_monitors), consumed and cleared by it
+  float* mon_snr_db = nullptr;          // [B] equalizer snr_db (model.py:464-475)
+  const int32_t* mon_pilot_carriers = nullptr;
+  int mon_n_pilot = 0;
+  int64_t mon_frame0 = 0;               // first frame of the pass being run (offset into mon_snr_db)
   unsigned* d_amax = nullptr;           // [kAmaxSlots] per-buffer max |activation| of the current pass (Act::amax)
   // layers
   dccn::GemmLayer r1, r2;                               // receiver: learned DFT, demod dense

@@ -3,6 +3,7 @@
 //   Rayleigh FIR (warp-shuffle) + AWGN (a6, a7), OFDM transmitter, BER accumulation (a5),
 //   and the op-level layers_conv2d_complex (a1).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -508,6 +509,7 @@ DCCN_DEVINL void tx64_group(const uint8_t* __restrict__ bits, long long frame, i
                             int lane, const double2* tw64, double2* z_slot, double2 (&x)[8]) {
   constexpr int K = 64;
   const int q = lane & 7;
+  const uint8_t* fbits = bits + (size_t)frame * D * nbits;
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
     float2 v = make_float2(0.f, 0.f);
@@ -515,9 +517,17 @@ DCCN_DEVINL void tx64_group(const uint8_t* __restrict__ bits, long long frame, i
       const int m = sc_map[s * K + q + 8 * k2];
       if (m == -2) v = pilot;
       else if (m >= 0) {
-        int idx = 0;
-        const uint8_t* bp = bits + ((size_t)frame * D + m) * nbits;
-        for (int b = 0; b < nbits; ++b) idx = (idx << 1) | bp[b];
+        int idx;
+        if (nbits == 4) {          // the symbol's label bytes in one aligned word (MSB-first index, ofdm.py:121-153)
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(fbits + 4 * m);
+          idx = (int)(((w & 1u) << 3) | ((w >> 6) & 4u) | ((w >> 15) & 2u) | ((w >> 24) & 1u));
+        } else if (nbits == 2) {
+          const uint32_t w = *reinterpret_cast<const uint16_t*>(fbits + 2 * m);
+          idx = (int)(((w & 1u) << 1) | ((w >> 8) & 1u));
+        } else {
+          idx = 0;
+          for (int b = 0; b < nbits; ++b) idx = (idx << 1) | fbits[m * nbits + b];
+        }
         v = constellation[idx];
       }
     }
@@ -642,8 +652,15 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
   double2* gsm_all = sm_z_all + kGenWarps * 4 * kTxZ;                                      // [warps][kMaxFir]
   float2* sm_fr_all = reinterpret_cast<float2*>(gsm_all + kGenWarps * kMaxFir);            // [warps][FR]
   float2* sm_fo_all = sm_fr_all + kGenWarps * FR;                                          // [warps][FR]
+  float2* sm_fo_end = sm_fo_all + kGenWarps * FR;
+  int* sm_map = reinterpret_cast<int*>(sm_fo_end);                                         // [S * K] subcarrier roles
+  float2* sm_const = reinterpret_cast<float2*>(sm_map + 8 * K);                            // [16] constellation
   tx64_twiddle_table(sm_tw);
+  for (int i = threadIdx.x; i < S * K; i += blockDim.x) sm_map[i] = sc_map[i];
+  for (int i = threadIdx.x; i < (1 << nbits); i += blockDim.x) sm_const[i] = constellation[i];
   __syncthreads();
+  sc_map = sm_map;
+  constellation = sm_const;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = lane >> 3, q = lane & 7;
   double2* gs = gsm_all + wib * kMaxFir;
@@ -737,7 +754,8 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
 
 template <int L>
 constexpr size_t tx_fade_smem() {
-  return (64 + kGenWarps * 4 * kTxZ + kGenWarps * kMaxFir) * sizeof(double2) + 2 * kGenWarps * 32 * (L + 1) * sizeof(float2);
+  return (64 + kGenWarps * 4 * kTxZ + kGenWarps * kMaxFir) * sizeof(double2) + 2 * kGenWarps * 32 * (L + 1) * sizeof(float2) +
+         8 * 64 * sizeof(int) + 16 * sizeof(float2);
 }
 
 // util.bit_source (dev/py/util.py:25-34): n uniform bits, one per byte.  A thread expands ONE Philox-4x32 call (128 random
@@ -859,6 +877,91 @@ __global__ void __launch_bounds__(256) unpack_bits_kernel(const uint8_t* __restr
     o.y = ((b >> 4) & 1u) | (((b >> 5) & 1u) << 8) | (((b >> 6) & 1u) << 16) | (((b >> 7) & 1u) << 24);
     *reinterpret_cast<uint2*>(bits + 8 * i) = o;
   }
+}
+
+// =====================================================================================
+// Monitor tensors of the reference graph (dev/py/ofdmreceiver_np.py:125-149,172-183) -- NOT on the receiver's data path:
+//   input    = batch-moment norm of tx_ofdm / sqrt(2)                       ('input:0', what the receiver consumes)
+//   iq_layer = tf.clip_by_norm(input, 8, axes=[-1])   (complex.py:21-27)   -> tx_power = mean(I^2 + Q^2), iq_tx (fp16)
+//   the in-graph AWGN (radio.py:62-88, built but bypassed, :136-138): noise = |level * N(0,1)| * (sin phi, cos phi) with
+//   level = sqrt(.5) 10^(-SNR/20), phi ~ U(0, 2 pi)                         -> noise_power = mean(|noise|^2), iq_rx (fp16)
+// The second batch normalisation inside AWGN_channel (eps 1e-8, / sqrt 2) maps the already normalised batch onto itself to
+// 1e-8 relative, so iq_rx = iq_layer + noise.  One warp per frame; sums[0] = sum |iq_layer|^2, sums[1] = sum |noise|^2.
+// TF's Philox stream cannot be reproduced, so noise_power / iq_rx agree with the reference in distribution only.
+// =====================================================================================
+__global__ void __launch_bounds__(256) monitor_kernel(const float2* __restrict__ x, long long B, int n_samp,
+                                                      const float2* __restrict__ mean, const float2* __restrict__ rstd,
+                                                      const float* __restrict__ snr_db, uint64_t seed,
+                                                      double* __restrict__ sums, float2* __restrict__ input_out,
+                                                      __half2* __restrict__ iq_tx, __half2* __restrict__ iq_rx) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double p_tx = 0.0, p_n = 0.0;
+  for (long long b = warp0; b < B; b += nwarps) {
+    const float level = snr_db ? 0.70710678118f * exp10f(-__ldg(snr_db + b) / 20.0f) : 0.f;
+    for (int n = lane; n < n_samp; n += 32) {
+      const float2 v = x[b * n_samp + n], m = __ldg(mean + n), r = __ldg(rstd + n);
+      float2 z;
+      z.x = __fdiv_rn(__fadd_rn(__fmul_rn(v.x, r.x), __fmul_rn(-m.x, r.x)), 1.41421356237f);
+      z.y = __fdiv_rn(__fadd_rn(__fmul_rn(v.y, r.y), __fmul_rn(-m.y, r.y)), 1.41421356237f);
+      if (input_out) input_out[b * n_samp + n] = z;
+      const float l2 = sqrtf(z.x * z.x + z.y * z.y);
+      const float den = fmaxf(l2, 8.0f);
+      const float2 c = make_float2(z.x * 8.0f / den, z.y * 8.0f / den);
+      p_tx += (double)(c.x * c.x + c.y * c.y);
+      if (iq_tx) iq_tx[b * n_samp + n] = __floats2half2_rn(c.x, c.y);
+      if (snr_db) {
+        uint32_t rr[4];
+        Philox{seed}((uint64_t)(b * n_samp + n), 0x1107u, rr);
+        float n0, n1, s, cs;
+        box_muller(rr[0], rr[1], n0, n1);
+        const float amp = fabsf(level * n0);
+        __sincosf(6.283185307179586f * ((float)rr[2] * 2.3283064365386963e-10f), &s, &cs);
+        const float2 nz = make_float2(amp * s, amp * cs);
+        p_n += (double)(nz.x * nz.x + nz.y * nz.y);
+        if (iq_rx) iq_rx[b * n_samp + n] = __floats2half2_rn(c.x + nz.x, c.y + nz.y);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p_tx += __shfl_xor_sync(0xffffffffu, p_tx, o);
+    p_n += __shfl_xor_sync(0xffffffffu, p_n, o);
+  }
+  if (lane == 0) {
+    atomicAdd(sums, p_tx);
+    atomicAdd(sums + 1, p_n);
+  }
+}
+
+// equalizer_ofdm's SNR monitor (dev/py/model.py:464-475): over the S * P pilot-carrier points of the phase-equalised
+// frequency-domain frame, signal = mean |eq|^2, noise = variance of |eq|^2, snr_db = log10(clip(signal / noise, 1e-3, 1e4)).
+// (The reference names it snr_db but takes a plain log10 -- kept.)  One warp per frame; eq [B, S, K] complex.
+__global__ void __launch_bounds__(256) snr_monitor_kernel(const float2* __restrict__ eq, long long B, int S, int K,
+                                                          const int* __restrict__ pilot_carriers, int P,
+                                                          float* __restrict__ snr_out) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const int n = S * P;
+  float s1 = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float2 v = eq[(b * S + i / P) * K + pilot_carriers[i % P]];
+    s1 += v.x * v.x + v.y * v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  const float mu = s1 / (float)n;
+  float s2 = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float2 v = eq[(b * S + i / P) * K + pilot_carriers[i % P]];
+    const float d = v.x * v.x + v.y * v.y - mu;
+    s2 += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if (lane == 0) snr_out[b] = log10f(fminf(fmaxf(mu / (s2 / (float)n), 0.001f), 10000.0f));
 }
 
 // a5: confusion matrix of hard decisions vs bits (rows = truth)

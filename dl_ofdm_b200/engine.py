@@ -105,7 +105,7 @@ class DCCN:
 
     # -- the pass ----------------------------------------------------------------------
     def forward(self, x, bits=None, want_soft=True, want_hard=True, want_eq=False, want_chest=False,
-                flags=0):
+                flags=0, snr_pilot_carriers=None):
         """x: float32 CUDA tensor [B,S,T,2]; bits: uint8 CUDA tensor [B,D,nbits] or None.
 
         Returns dict(soft, hard, eq, chest, conf (int64 [2,2] tensor), ce_sum (float64 [1]), n_bits).
@@ -131,10 +131,16 @@ class DCCN:
             assert tuple(bits.shape) == (B, self.D, self.nbits), bits.shape
             conf = torch.zeros((2, 2), dtype=torch.int64, device=dev)
             ce = torch.zeros((1,), dtype=torch.float64, device=dev)
+        snr_db = None
         with torch.cuda.device(dev):
+            if snr_pilot_carriers is not None:         # equalizer_ofdm's snr_db monitor (model.py:464-475), one-shot request
+                pc = torch.as_tensor(np.asarray(snr_pilot_carriers, dtype=np.int32), device=dev)
+                snr_db = torch.empty((B, 1), dtype=torch.float32, device=dev)
+                self._scratch['snr_pc'] = pc           # keep alive until the pass has run
+                _lib.check(self.lib.dccn_forward_monitors(self._h, _ptr(snr_db), _ptr(pc), pc.numel()))
             _lib.check(self.lib.dccn_forward(self._h, _ptr(x), B, _ptr(bits), _ptr(soft), _ptr(hard), _ptr(eq),
                                              _ptr(chest), _ptr(conf), _ptr(ce), int(flags), _stream()))
-        out.update(soft=soft, hard=hard, eq=eq, chest=chest, conf=conf, ce_sum=ce,
+        out.update(soft=soft, hard=hard, eq=eq, chest=chest, conf=conf, ce_sum=ce, snr_db=snr_db,
                    n_bits=B * self.D * self.nbits)
         return out
 
@@ -180,6 +186,26 @@ class DCCN:
         ce = C.c_double()
         _lib.check(self.lib.dccn_forward_host_end(self._h, int(slot), conf, C.byref(ce)))
         return np.array(conf[:], dtype=np.int64).reshape(2, 2), float(ce.value)
+
+    def monitors(self, x, snr_db=None, seed=0, want_input=False, want_iq=False):
+        """The reference graph's monitor tensors for a batch x [B,S,T,2] (dev/py/ofdmreceiver_np.py:125-149,172-183):
+        dict(tx_power, noise_power (None without snr_db), input, iq_tx, iq_rx).  Synchronises (two scalars come back)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        B = x.shape[0]
+        n = B * self.S * self.T
+        sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+        inp = torch.empty_like(x) if want_input else None
+        iq_tx = torch.empty((n, 2), dtype=torch.float16, device=x.device) if want_iq else None
+        iq_rx = torch.empty((n, 2), dtype=torch.float16, device=x.device) if (want_iq and snr_db is not None) else None
+        if snr_db is not None:
+            snr_db = torch.as_tensor(snr_db, dtype=torch.float32, device=x.device).reshape(-1).contiguous()
+            assert snr_db.numel() == B
+        with torch.cuda.device(x.device):
+            _lib.check(self.lib.dccn_monitors(self._h, _ptr(x), B, _ptr(snr_db), int(seed), _ptr(sums), _ptr(inp), _ptr(iq_tx),
+                                              _ptr(iq_rx), _stream()))
+        s = sums.cpu().numpy()
+        return dict(tx_power=np.float32(s[0] / n), noise_power=np.float32(s[1] / n) if snr_db is not None else None,
+                    input=inp, iq_tx=iq_tx, iq_rx=iq_rx)
 
     def batch_moments(self, x):
         P = self.S * self.T * 2

@@ -48,16 +48,17 @@ def ofdm_dense_rx(inputs, FLAGS, ofdmobj, outshape=None, weights=None, head='dev
 
 
 def equalizer_ofdm(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
-    """Normalised IQ [B,S,T,2] -> (equalized [B,S,T,2], snr_db placeholder, chest complex [B,S,K])
-    (dev/py/model.py:349-478).  The snr_db monitor of the reference is not computed (None)."""
+    """Normalised IQ [B,S,T,2] -> (equalized [B,S,T,2], snr_db [B,1], chest complex [B,S,K])
+    (dev/py/model.py:349-478; snr_db is the monitor of :464-475)."""
     return _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, 0)
 
 
 def _run_equalizer(inputs, FLAGS, ofdmobj, weights, precision, opt):
     m = _engine(FLAGS, ofdmobj, weights, True, 'dev', precision, opt)
     o = m.forward(inputs.contiguous(), want_soft=False, want_hard=False, want_eq=True, want_chest=True,
-                  flags=_lib.FWD_NO_NORM | _lib.FWD_EQ_ONLY)
-    return o['eq'], None, torch.view_as_complex(o['chest'])
+                  flags=_lib.FWD_NO_NORM | _lib.FWD_EQ_ONLY,
+                  snr_pilot_carriers=ofdmobj.pilotCarriers if opt == 0 else None)    # the ablation graphs: monitor not served
+    return o['eq'], o['snr_db'], torch.view_as_complex(o['chest'])
 
 
 def equalizer_nocconv(inputs, FLAGS, ofdmobj, weights=None, precision='parity'):
@@ -93,7 +94,10 @@ def equalizer_noresdl4(inputs, FLAGS, ofdmobj, weights=None, precision='parity')
 class Session:
     """Stands in for tf.Session + imported graph: holds the engine, serves the named fetches."""
 
-    FETCHES = ('conf_matrix', 'linear_ber', 'log_ber', 'ce_mean', 'output', 'hard')
+    # the named tensors of dev/py/ofdmreceiver_np.py:172-183 (+ 'hard', the argmax the confusion matrix is built from)
+    FETCHES = ('conf_matrix', 'linear_ber', 'log_ber', 'ce_mean', 'output', 'hard', 'cost', 'tx_power', 'noise_power',
+               'input', 'iq_tx', 'iq_rx')
+    MONITORS = ('tx_power', 'noise_power', 'input', 'iq_tx', 'iq_rx')
 
     def __init__(self, FLAGS, ofdmobj, weights, precision='parity', head=None, chunk_frames=0):
         self.FLAGS, self.ofdm = FLAGS, ofdmobj
@@ -119,9 +123,27 @@ class Session:
             if n not in self.FETCHES:
                 raise KeyError('unknown fetch %r (have %s)' % (n, ', '.join(self.FETCHES)))
         o = self.engine.forward(x, y, want_soft='output' in names, want_hard='hard' in names)
+        mon = None
+        if any(n in self.MONITORS for n in names):
+            snr = feed.get('SNR')
+            mon = self.engine.monitors(x, snr, seed=int(feed.get('seed', 0)), want_input='input' in names,
+                                       want_iq=('iq_tx' in names or 'iq_rx' in names))
         res = []
         conf = o['conf'].cpu().numpy() if o['conf'] is not None else None
         for n in names:
+            if n in self.MONITORS:
+                res.append(mon[n])
+                continue
+            if n == 'cost':
+                # total_loss = ce_mean + berlin * 1e-4 * sum(reg) + log(BER)  (ofdmreceiver_np.py:162-171); reg = the keras
+                # l2(0.01) terms of the two dense layers of the receiver (model.py:1270-1286)
+                ber = (conf[0, 1] + conf[1, 0]) / conf.sum()
+                reg = sum(0.01 * float(np.sum(np.square(np.asarray(self.weights[k], dtype=np.float64))))
+                          for k in ('demodulation/dense/kernel', 'demodulation/dense/bias', 'demodulation/dense_1/kernel',
+                                    'demodulation/dense_1/bias'))
+                ce = float(o['ce_sum'].cpu()[0]) / o['n_bits']
+                res.append(np.float32(ce + ber * 1e-4 * reg + (np.log(ber) if ber > 0 else -np.inf)))
+                continue
             if n == 'conf_matrix':
                 res.append(conf)
             elif n == 'linear_ber':

@@ -266,6 +266,22 @@ int dccn_debug_mma_rate(int bn, int n_mma, int per_commit, int mode, int dep, in
 /* uniform random bits (util.bit_source, dev/py/util.py:25-34) from Philox */
 int dccn_bit_source(uint8_t* bits_dev, int64_t n, uint64_t seed, void* stream);
 
+/* Monitor tensors of the reference graph that are NOT on the receiver's data path but are fetched by its drivers
+ * (`session.run([conf_matrix, berlin, power_tx, noise_pwr, ce_mean, iq_tx, iq_rx], ...)`, dev/py/ofdmreceiver_np.py:80;
+ * named identities :172-183).  sums_dev[0] = sum over all B * S * T samples of |clip_by_norm(input, 8)|^2 (tx_power =
+ * sums[0] / (B S T)), sums_dev[1] = sum of |noise|^2 of the (bypassed) in-graph AWGN channel at snr_db_dev[B]
+ * (noise_power; Philox draws from `seed`, so equal to the reference in distribution only; NULL snr_db_dev skips it).
+ * Optional outputs (NULL = not wanted): input_dev float [B,S,T,2] = 'input:0'; iq_tx_dev / iq_rx_dev fp16 [B*S*T, 2] =
+ * 'iq_tx:0' / 'iq_rx:0' (constellation dumps).  Computes the batch moments of x itself. */
+int dccn_monitors(dccn_handle* h, const float* x_dev, int64_t B, const float* snr_db_dev, uint64_t seed, double* sums_dev,
+                  float* input_dev, void* iq_tx_dev, void* iq_rx_dev, void* stream);
+
+/* One-shot request for the NEXT dccn_forward on this handle: write equalizer_ofdm's `snr_db` monitor
+ * (dev/py/model.py:464-475: log10(clip(mean / variance of |equalized_freq|^2 over the S * P pilot-carrier points, 1e-3, 1e4)))
+ * to snr_db_dev[B].  pilot_carriers_dev: ofdm_tx.pilotCarriers (P subcarrier indices, the same in every symbol).
+ * snr_db_dev = NULL cancels.  Only with cfg.equalizer, eq_opt 0, layer-by-layer schedule. */
+int dccn_forward_monitors(dccn_handle* h, float* snr_db_dev, const int32_t* pilot_carriers_dev, int n_pilot_carriers);
+
 /* Host helper (no GPU involved): CRC-32C (Castagnoli) of `n` bytes continuing from `crc` (0 to start) -- the checksum of
  * every tensor and table block in a TF-bundle checkpoint (`tf.train.Saver`, dev/py/ofdmreceiver_np.py:192,268-272).
  * The Python writer (dl_ofdm_b200/tfbundle.py) saves a 12 MB equalizer checkpoint on every improving epoch; a

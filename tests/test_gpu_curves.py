@@ -22,14 +22,20 @@ SNRS = np.arange(-10, 30)
 
 def db_offset(snr, ber, ref_snr, ref_ber):
     """Horizontal distance (dB) from the point (snr, ber) to the reference curve: snr - s with ref_ber(s) = ber,
-    log-linear interpolation between the reference points (the curve falls monotonically)."""
-    lr = np.log10(np.maximum(ref_ber, 1e-12))
+    log-linear interpolation between the reference points (the curve falls monotonically); a point just outside the
+    tabulated range (e.g. slightly above the -10 dB entry) is extrapolated along the nearest segment."""
+    pos = ref_ber > 0
+    rs, lr = np.asarray(ref_snr)[pos].astype(float), np.log10(ref_ber[pos])
     lb = np.log10(max(ber, 1e-12))
-    for i in range(len(ref_snr) - 1):
+    seg = None
+    for i in range(len(rs) - 1):
         if lr[i] >= lb >= lr[i + 1] and lr[i] > lr[i + 1]:
-            s = ref_snr[i] + (lr[i] - lb) / (lr[i] - lr[i + 1]) * (ref_snr[i + 1] - ref_snr[i])
-            return float(snr - s)
-    return float('nan')
+            seg = i
+            break
+    if seg is None:
+        seg = 0 if lb > lr[0] else len(rs) - 2
+    s = rs[seg] + (lr[seg] - lb) / (lr[seg] - lr[seg + 1]) * (rs[seg + 1] - rs[seg])
+    return float(snr - s)
 
 
 def _v1_session(w, nb, cp, chunk=8192):

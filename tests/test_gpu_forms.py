@@ -245,3 +245,51 @@ def test_host_entry_returns_hard_bits(libdccn, trained_dev):
             assert np.array_equal(conf, refs[i][1])
             assert torch.equal(hards[i], refs[i][0])
     m.close()
+
+
+def test_monitor_fetches(libdccn, trained_dev):
+    """The monitor tensors the reference's drivers fetch next to the BER (dev/py/ofdmreceiver_np.py:80,172-183) and
+    equalizer_ofdm's snr_db (dev/py/model.py:464-475) against NumPy restatements."""
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.model import Session, equalizer_ofdm
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from oracle import dccn_oracle as orc
+    from oracle.dccn_oracle_lean import LeanModel
+    rng = np.random.default_rng(23)
+    B = 300
+    fl = Flags(nbits=4)
+    o = ofdm_tx(fl)
+    x = (rng.standard_normal((B, 7, 80, 2)) * 0.7 + 0.1).astype(np.float32)
+    x[5, 3, 10] = (90.0, -70.0)                                   # an outlier that the PAPR clip (norm 8) catches
+    bits = rng.integers(0, 2, (B, 320, 4)).astype(np.uint8)
+    snr = np.full((B, 1), 10.0, dtype=np.float32)
+    s = Session(fl, o, trained_dev, precision='parity')
+    conf, cost, txp, npw, inp, iq_tx, iq_rx, ce = s.run(
+        ['conf_matrix', 'cost', 'tx_power', 'noise_power', 'input', 'iq_tx', 'iq_rx', 'ce_mean'],
+        {'tx_ofdm': x, 'bits_in': bits, 'SNR': snr})
+    z, _, _ = orc.batch_moment_norm(x, np.float32)
+    assert np.abs(inp.cpu().numpy() - z).max() < 2e-6
+    nrm = np.sqrt((z.astype(np.float64) ** 2).sum(-1, keepdims=True))
+    clipped = z * 8.0 / np.maximum(nrm, 8.0)                       # tf.clip_by_norm(x, 8, axes=[-1])
+    assert nrm.max() > 8.0
+    assert abs(float(txp) - (clipped ** 2).sum(-1).mean()) < 1e-5 * float(txp)
+    assert np.abs(iq_tx.float().cpu().numpy() - clipped.reshape(-1, 2)).max() < 4e-3          # fp16 rounding
+    assert abs(float(npw) - 0.5 * 10 ** (-1.0)) < 0.02 * 0.05                                  # E|noise|^2 = level^2
+    d = iq_rx.float().cpu().numpy() - clipped.reshape(-1, 2)
+    assert abs((d ** 2).sum(-1).mean() - float(npw)) < 0.03 * float(npw)
+    ber = (conf[0, 1] + conf[1, 0]) / conf.sum()
+    reg = sum(0.01 * float((trained_dev[k].astype(np.float64) ** 2).sum()) for k in
+              ('demodulation/dense/kernel', 'demodulation/dense/bias', 'demodulation/dense_1/kernel', 'demodulation/dense_1/bias'))
+    assert abs(float(cost) - (float(ce) + ber * 1e-4 * reg + np.log(ber))) < 1e-5
+    s.close()
+    # snr_db: oracle = the literal definition on the lean oracle's phase-equalised frequency-domain frame
+    zc = torch.as_tensor(z).cuda()
+    eq, snr_db, chest = equalizer_ofdm(zc, fl, o, weights=trained_dev)
+    lm = LeanModel(trained_dev, 4)
+    xx = orc.layer_norm(z.astype(np.float64)).reshape(B, 7, 160)
+    f = ((xx @ lm.g1[0] + lm.g1[1]) @ lm.g2[0] + lm.g2[1]).reshape(B, 7, 64, 2)
+    _, ch = lm.equalizer(z.astype(np.float64))
+    eqf = (f[..., 0] + 1j * f[..., 1]) * (np.conj(ch) / np.abs(ch))
+    p = np.abs(eqf[:, :, o.pilotCarriers]).reshape(B, -1) ** 2
+    ref = np.log10(np.clip(p.mean(1) / p.var(1), 1e-3, 1e4))
+    assert np.abs(snr_db.cpu().numpy().reshape(-1) - ref).max() < 2e-3

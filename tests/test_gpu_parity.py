@@ -252,9 +252,13 @@ def test_equalizer_trained(libdccn, trained_dev, monkeypatch, precision, f16, sn
     eq = out['eq'].cpu().numpy()
     e32 = np.abs(eq_ref32 - eq_ref)
     e = np.abs(eq - eq_ref)
-    assert np.quantile(e, 0.999) <= max(1e-5, 1.5 * np.quantile(e32, 0.999)), (np.quantile(e, 0.999), np.quantile(e32, 0.999))
-    assert e.max() <= max(5e-5, 2.0 * e32.max()), (e.max(), e32.max())
-    flips = _check_soft(out['soft'].cpu().numpy(), soft_ref, out['hard'].cpu().numpy(), soft_ref32)
+    ki = 3.0 if precision == 'exact' else 1.5
+    assert np.quantile(e, 0.999) <= max(1e-5, ki * np.quantile(e32, 0.999)), (np.quantile(e, 0.999), np.quantile(e32, 0.999))
+    assert e.max() <= max(5e-5, (ki + 0.5) * e32.max()), (e.max(), e32.max())
+    # 'exact' adds 896 products in sequence in fp32 (error ~ K ulp), NumPy's blocked BLAS sums pairwise-ish (~ sqrt K): the
+    # CUDA-core mode gets 3 x the fp32 oracle's own error, the tensor-core modes (fp32 adds of 64-wide chunks) 1.5 x
+    flips = _check_soft(out['soft'].cpu().numpy(), soft_ref, out['hard'].cpu().numpy(), soft_ref32,
+                        k_intrinsic=3.0 if precision == 'exact' else 1.5)
     _, conf_ref, ber_ref, ce_ref = orc.ber_head(soft_ref, bs)
     conf = out['conf'].cpu().numpy()
     assert conf.sum() == bs.size and np.abs(conf - conf_ref).sum() <= 2 * flips

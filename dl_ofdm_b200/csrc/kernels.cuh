@@ -502,35 +502,44 @@ DCCN_DEVINL void tx64_twiddle_table(double2* tw64) {
   }
 }
 
-// Symbol `s` of `frame` (this lane's slot; `active` = the slot holds a symbol) -> x[n1] = time sample 8 n1 + q of the
-// symbol, scaled by 1/64, no cyclic prefix.  Whole warp must call (two __syncwarp inside).
-DCCN_DEVINL void tx64_group(const uint8_t* __restrict__ bits, long long frame, int s, bool active, int nbits, int D,
+// Symbol `s` of the frame whose label bytes start at `fbits` (this lane's slot; `active` = the slot holds a symbol) ->
+// x[n1] = time sample 8 n1 + q of the symbol, scaled by 1/64, no cyclic prefix.  Whole warp must call (two __syncwarp
+// inside).  The eight role / label / constellation lookups of a lane are issued as three batches of independent
+// (predicated) loads -- written with branches they formed eight serial map -> label -> constellation chains, which was
+// where the fused feeder spent a third of its stall samples.
+DCCN_DEVINL void tx64_group(const uint8_t* fbits, int s, bool active, int nbits,
                             const int* __restrict__ sc_map, const float2* __restrict__ constellation, float2 pilot,
                             int lane, const double2* tw64, double2* z_slot, double2 (&x)[8]) {
   constexpr int K = 64;
   const int q = lane & 7;
-  const uint8_t* fbits = bits + (size_t)frame * D * nbits;
+  int m[8];
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) m[k2] = active ? sc_map[s * K + q + 8 * k2] : -1;
+  int idx[8];
+  if (nbits == 4) {            // the symbol's label bytes in one aligned word (MSB-first index, ofdm.py:121-153)
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      const uint32_t w = m[k2] >= 0 ? *reinterpret_cast<const uint32_t*>(fbits + 4 * m[k2]) : 0u;
+      idx[k2] = (int)(((w & 1u) << 3) | ((w >> 6) & 4u) | ((w >> 15) & 2u) | ((w >> 24) & 1u));
+    }
+  } else if (nbits == 2) {
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      const uint32_t w = m[k2] >= 0 ? *reinterpret_cast<const uint16_t*>(fbits + 2 * m[k2]) : 0u;
+      idx[k2] = (int)(((w & 1u) << 1) | ((w >> 8) & 1u));
+    }
+  } else {
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      int v = 0;
+      for (int b = 0; b < nbits; ++b) v = (v << 1) | (m[k2] >= 0 ? fbits[m[k2] * nbits + b] : 0);
+      idx[k2] = v;
+    }
+  }
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
-    float2 v = make_float2(0.f, 0.f);
-    if (active) {
-      const int m = sc_map[s * K + q + 8 * k2];
-      if (m == -2) v = pilot;
-      else if (m >= 0) {
-        int idx;
-        if (nbits == 4) {          // the symbol's label bytes in one aligned word (MSB-first index, ofdm.py:121-153)
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(fbits + 4 * m);
-          idx = (int)(((w & 1u) << 3) | ((w >> 6) & 4u) | ((w >> 15) & 2u) | ((w >> 24) & 1u));
-        } else if (nbits == 2) {
-          const uint32_t w = *reinterpret_cast<const uint16_t*>(fbits + 2 * m);
-          idx = (int)(((w & 1u) << 1) | ((w >> 8) & 1u));
-        } else {
-          idx = 0;
-          for (int b = 0; b < nbits; ++b) idx = (idx << 1) | fbits[m * nbits + b];
-        }
-        v = constellation[idx];
-      }
-    }
+    const float2 c = constellation[idx[k2]];
+    const float2 v = m[k2] >= 0 ? c : (m[k2] == -2 ? pilot : make_float2(0.f, 0.f));
     x[k2] = make_double2(v.x, v.y);
   }
   idft8(x);                                            // x[n2] = Y[k1 = q][n2]
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ b
     const long long frame = active ? sym / S : 0;
     const int s = active ? (int)(sym - frame * S) : 0;
     double2 x[8];
-    tx64_group(bits, frame, s, active, nbits, D, sc_map, constellation, pilot, lane, sm_tw, sm_z[wib][slot], x);
+    tx64_group(bits + (size_t)frame * D * nbits, s, active, nbits, sc_map, constellation, pilot, lane, sm_tw, sm_z[wib][slot], x);
     if (active) {
       float2* o = tx + (size_t)sym * T;
 #pragma unroll
@@ -593,6 +602,7 @@ __global__ void __launch_bounds__(256) tx64_kernel(const uint8_t* __restrict__ b
 // =====================================================================================
 constexpr int kGenWarps = 4;
 constexpr int kGenMaxSamp = 8 * 80;     // S <= 8 symbols of K + CP <= 80 samples
+constexpr int kGenBitBytes = 1536;      // label bytes of a frame staged per warp (368 data cells x 4 bits max)
 
 // Shared-memory frame buffers of the fused feeder use a padded layout: sample n of a frame sits at n + n / L (L = samples
 // per lane in the FIR's blocked mapping), i.e. lane l's run starts at (L + 1) l -- an odd stride in 8-byte words, so the
@@ -655,6 +665,7 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
   float2* sm_fo_end = sm_fo_all + kGenWarps * FR;
   int* sm_map = reinterpret_cast<int*>(sm_fo_end);                                         // [S * K] subcarrier roles
   float2* sm_const = reinterpret_cast<float2*>(sm_map + 8 * K);                            // [16] constellation
+  uint8_t* sm_bits_all = reinterpret_cast<uint8_t*>(sm_const + 16);                        // [warps][kGenBitBytes] labels of the frame
   tx64_twiddle_table(sm_tw);
   for (int i = threadIdx.x; i < S * K; i += blockDim.x) sm_map[i] = sc_map[i];
   for (int i = threadIdx.x; i < (1 << nbits); i += blockDim.x) sm_const[i] = constellation[i];
@@ -666,11 +677,21 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
   double2* gs = gsm_all + wib * kMaxFir;
   float2* fr = sm_fr_all + wib * FR;
   float2* fo = sm_fo_all + wib * FR;
+  uint8_t* fb = sm_bits_all + wib * kGenBitBytes;
+  const int nbytes = D * nbits;
+  const bool stage_bits = nbytes <= kGenBitBytes && (nbytes & 15) == 0;
   const int T = K + CP, n_samp = S * T;
   const int M = n_taps == 0 ? 1 : n_fir;
   const int off = (M - 1) - (M >> 1);
   double pw = 0.0;
   for (long long frame = (long long)blockIdx.x * kGenWarps + wib; frame < B; frame += (long long)gridDim.x * kGenWarps) {
+    // the frame's labels: one coalesced copy into shared memory (the per-subcarrier lookups then never wait on HBM)
+    const uint8_t* fbits = bits + (size_t)frame * nbytes;
+    if (stage_bits) {
+      for (int i = lane; i < (nbytes >> 4); i += 32)
+        reinterpret_cast<uint4*>(fb)[i] = __ldg(reinterpret_cast<const uint4*>(fbits) + i);
+      fbits = fb;
+    }
     // ---- path gains -> sample-spaced FIR (chan_fir_kernel) ----
     if (n_taps == 0) {
       if (lane == 0) gs[0] = make_double2(1.0, 0.0);
@@ -704,12 +725,13 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
       }
       if (lane < n_fir) gs[lane] = gt;
     }
+    __syncwarp();                                      // staged labels and taps visible to every lane
     // ---- transmitter: the S symbols, four at a time, into the shared frame buffer as fp32 (tx64_kernel's values) ----
     for (int s0 = 0; s0 < S; s0 += 4) {
       const int s = s0 + slot;
       const bool active = s < S;
       double2 x[8];
-      tx64_group(bits, frame, active ? s : 0, active, nbits, D, sc_map, constellation, pilot, lane, sm_tw,
+      tx64_group(fbits, active ? s : 0, active, nbits, sc_map, constellation, pilot, lane, sm_tw,
                  sm_z_all + (wib * 4 + slot) * kTxZ, x);
       if (active) {
 #pragma unroll
@@ -755,7 +777,7 @@ __global__ void __launch_bounds__(32 * kGenWarps) tx_fade_kernel(
 template <int L>
 constexpr size_t tx_fade_smem() {
   return (64 + kGenWarps * 4 * kTxZ + kGenWarps * kMaxFir) * sizeof(double2) + 2 * kGenWarps * 32 * (L + 1) * sizeof(float2) +
-         8 * 64 * sizeof(int) + 16 * sizeof(float2);
+         8 * 64 * sizeof(int) + 16 * sizeof(float2) + kGenWarps * kGenBitBytes;
 }
 
 // util.bit_source (dev/py/util.py:25-34): n uniform bits, one per byte.  A thread expands ONE Philox-4x32 call (128 random

@@ -203,7 +203,10 @@ def test_tx_fade_equals_separate_kernels(libdccn, chan, nb):
     tx = m.transmit(bits, o, const_map(nb))
     rx_sep = ch_a.run(tx, snr)
     rx_fused = ch_b.run_bits(bits, o, const_map(nb), snr)
-    assert torch.equal(rx_sep, rx_fused)
+    # (after AWGN: the batch power is an fp64 sum of per-warp partials added with atomics, in an order that differs between
+    #  the two kernels and from run to run -- the scale can differ in its last bit, i.e. single fp32 ulps in rx)
+    assert (rx_sep - rx_fused).abs().max().item() <= 2.5e-7 * rx_sep.abs().max().item()
+    assert (rx_sep != rx_fused).float().mean().item() < 0.05
     alpha, coeff = ch_a._profile(ch_a.profiles[0], m.device)
     n_taps = 0 if coeff is None else coeff.numel()
     z = torch.randn((B, max(n_taps, 1), 2), dtype=torch.float64, device=m.device) * np.sqrt(0.5)
@@ -268,7 +271,7 @@ def test_monitor_fetches(libdccn, trained_dev):
         ['conf_matrix', 'cost', 'tx_power', 'noise_power', 'input', 'iq_tx', 'iq_rx', 'ce_mean'],
         {'tx_ofdm': x, 'bits_in': bits, 'SNR': snr})
     z, _, _ = orc.batch_moment_norm(x, np.float32)
-    assert np.abs(inp.cpu().numpy() - z).max() < 2e-6
+    assert np.abs(inp.cpu().numpy() - z).max() < 2e-7 * np.abs(z).max()            # fp32 op order as TF's; z holds a ~90 outlier
     nrm = np.sqrt((z.astype(np.float64) ** 2).sum(-1, keepdims=True))
     clipped = z * 8.0 / np.maximum(nrm, 8.0)                       # tf.clip_by_norm(x, 8, axes=[-1])
     assert nrm.max() > 8.0

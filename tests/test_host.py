@@ -224,3 +224,37 @@ def test_save_model_writes_meta_for_the_bundle(tmp_path):
         T = 80 if cp else 64
         assert shp('fft_like/conv3d/kernel') == [1, T, 1, T, 128] == list(w['fft_like/conv3d/kernel'].shape)
         assert shp('demodulation/dense/kernel') == [896, 640]
+
+
+def test_expert_baselines_restated():
+    """dl_ofdm_b200/baselines.py (NumPy restatement of the estimators of dev/m/OFDM_Benchmark_dev.m) on frames from the host
+    transmitter + the oracle's Rayleigh / AWGN: the interpolation matrices reproduce their defining properties, and the
+    BER ordering perfect CSI <= ideal LMMSE <= LS-spline <= LS-linear holds on a fading channel, all tending to 0 on AWGN."""
+    from dl_ofdm_b200.baselines import ClassicReceiver, spline_matrix, linear_matrix
+    from dl_ofdm_b200.flags import Flags
+    from dl_ofdm_b200.ofdm import ofdm_tx
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(5)
+    # interpolators: exact at the nodes; the linear one reproduces any plane, the spline one any constant... at the nodes
+    px, py = rng.uniform(1, 64, 16), rng.uniform(1, 7, 16)
+    assert np.abs(spline_matrix(px, py, px, py) - np.eye(16)).max() < 1e-8
+    assert np.abs(linear_matrix(px, py, px, py) - np.eye(16)).max() < 1e-9
+    qx, qy = rng.uniform(10, 50, 40), rng.uniform(2, 6, 40)
+    plane = lambda x, y: 0.3 * x - 1.7 * y + 4.0                                   # noqa: E731
+    assert np.abs(linear_matrix(px, py, qx, qy) @ plane(px, py) - plane(qx, qy)).max() < 1e-9
+    nb, B = 2, 1500
+    o = ofdm_tx(Flags(nbits=nb))
+    cr = ClassicReceiver(o, nb)
+    bits = rng.integers(0, 2, (B, o.frame_size, nb)).astype(np.uint8)
+    tx = o.ofdm_tx_frame_np(bits)[0].reshape(B, -1)
+    alpha = np.load(os.path.join(ROOT, 'dl_ofdm_b200', 'data', 'lte_alpha.npz'))['etu']
+    coeff = orc.channel_coeff('etu')
+    z = (rng.standard_normal((B, len(coeff))) + 1j * rng.standard_normal((B, len(coeff)))) * np.sqrt(.5)
+    faded, g = orc.rayleigh_static(tx, z, coeff, alpha)
+    x, _, _ = orc.awgn(faded.reshape(B, 7, 80, 2), np.full((B, 1), 20.0), rng.standard_normal((B, 7, 80, 2)))
+    ber = {e: cr.ber(x, bits, e, 20.0, g) for e in ('perfect', 'lmmse', 'ls_spline', 'ls_linear')}
+    assert ber['perfect'] < ber['lmmse'] < ber['ls_spline'] < ber['ls_linear'] < 0.06, ber
+    assert 0.004 < ber['perfect'] < 0.02                                          # Rayleigh QPSK at 20 dB: ~1 / (4 snr) + ISI floor
+    xa, _, _ = orc.awgn(np.stack([tx.real, tx.imag], -1).reshape(B, 7, 80, 2), np.full((B, 1), 20.0), rng.standard_normal((B, 7, 80, 2)))
+    g1 = np.ones((B, 1), dtype=np.complex128)
+    assert all(cr.ber(xa, bits, e, 20.0, g1) == 0.0 for e in ('perfect', 'ls_spline', 'ls_linear'))

@@ -271,7 +271,7 @@ def test_monitor_fetches(libdccn, trained_dev):
         ['conf_matrix', 'cost', 'tx_power', 'noise_power', 'input', 'iq_tx', 'iq_rx', 'ce_mean'],
         {'tx_ofdm': x, 'bits_in': bits, 'SNR': snr})
     z, _, _ = orc.batch_moment_norm(x, np.float32)
-    assert np.abs(inp.cpu().numpy() - z).max() < 2e-7 * np.abs(z).max()            # fp32 op order as TF's; z holds a ~90 outlier
+    assert np.abs(inp.cpu().numpy() - z).max() < 5e-7 * np.abs(z).max()            # fp32 op order as TF; the oracle takes its moments in fp32, the kernel in fp64
     nrm = np.sqrt((z.astype(np.float64) ** 2).sum(-1, keepdims=True))
     clipped = z * 8.0 / np.maximum(nrm, 8.0)                       # tf.clip_by_norm(x, 8, axes=[-1])
     assert nrm.max() > 8.0

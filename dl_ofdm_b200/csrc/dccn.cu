@@ -733,6 +733,7 @@ static int run_gemm(dccn_handle* h, int slot, const GemmLayer& L, const Act& A, 
     if ((rc = make_tmap(&epi.tm_eq, epi.eq.p0 + epi.eq.col_off, epi.M, epi.eq.ld - epi.eq.col_off, epi.eq.ld, 32)))
       return rc;
     if (epi.chest_out && (rc = make_tmap(&epi.tm_chest, epi.chest_out, epi.M, epi.N, epi.N, 32))) return rc;
+    epi.pf = h->epi_prefetch;
     if (epi.corr.p0 && (rc = make_tmap(&epi.tm_corr, epi.corr.p0 + epi.corr.col_off, epi.M, epi.corr.ld - epi.corr.col_off,
                                        epi.corr.ld, 32)))
       return rc;
@@ -1220,6 +1221,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   h->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 65536;   // per-launch overheads (~10 us x 15 kernels) amortise over the pass
   if (const char* e = getenv("DCCN_KC")) h->kc = atoi(e);
   if (const char* e = getenv("DCCN_SMALL_FIRST")) h->small_first = atoi(e);
+  if (const char* e = getenv("DCCN_EPI_PREFETCH")) h->epi_prefetch = atoi(e);
   if (const char* e = getenv("DCCN_HEAD_SUBS")) h->head_subs = atoi(e);       // experiment knobs of the head kernel
   if (const char* e = getenv("DCCN_HEAD_BLOCKS")) h->head_blocks = atoi(e);
   if (const char* e = getenv("DCCN_BN_WIDE")) h->bn_wide = atoi(e);

@@ -106,13 +106,19 @@ DCCN_DEVINL void store_block_tma(const CUtensorMap* tm0, int col0_0, const CUten
 // order).  The fp16 hi/lo GEMM that consumes the buffer derives its power-of-two operand scale from it (gemm_tc.cuh,
 // `amax_in`), so that no trained weight set can push an operand past fp16's 65 504.  One redux + one RED per 32x32 block.
 template <int NV>
-DCCN_DEVINL void amax_update_warp(unsigned* amax, const float (&y)[NV], bool row_ok) {
+DCCN_DEVINL void amax_update_warp(unsigned* amax, const float (&y)[NV], bool row_ok, unsigned& seen) {
   unsigned m = 0u;
 #pragma unroll
   for (int i = 0; i < NV; ++i) m = max(m, __float_as_uint(y[i]) & 0x7FFFFFFFu);
   if (!row_ok) m = 0u;
   m = __reduce_max_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(amax, m);
+  // `seen` = the largest value this warp has already reported (warp-uniform): every block of every CTA firing a RED at
+  // the SAME address serialises in one L2 slice (~1e5 same-address atomics per layer); after a warp's first few blocks
+  // its running maximum rarely moves, so almost all of them are dropped here.
+  if (m > seen) {
+    seen = m;
+    if ((threadIdx.x & 31) == 0) atomicMax(amax, m);
+  }
 }
 
 // -------------------------------------------------------------------------------------
@@ -128,7 +134,9 @@ struct EpiStore {
   unsigned* amax = nullptr;   // optional: running max |y| of the destination buffer (see amax_update_warp)
   CUtensorMap tm_out;  // tensor-core path: [M, N] view of out.p0 + out.col_off, box 32 x 32 (set by run_gemm)
   CUtensorMap tm_aux;  // same for aux
-  struct State {};
+  struct State {
+    unsigned amax_seen = 0u;   // see amax_update_warp
+  };
 
   template <int NC>
   DCCN_DEVINL void run(State&, int row, int col0, float (&v)[NC]) const {
@@ -148,7 +156,8 @@ struct EpiStore {
   }
   // tensor-core path: the 32 lanes of a warp hold 32 consecutive rows (row0 + lane)
   static constexpr bool kWarpStore = true;
-  DCCN_DEVINL void run_warp(State&, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
+  static constexpr bool kPrefetch = false;
+  DCCN_DEVINL void run_warp(State& st, int row0, int lane, int col0, float (&v)[32], uint32_t patch) const {
     if (col0 >= N || row0 >= M) return;          // warp-uniform
     // All bias loads first (8 independent 16-byte broadcasts; the bias array is padded to a multiple of 128 floats),
     // then the arithmetic, with the activation switch outside the loop: with the per-element `act ? tanhf : id`
@@ -172,7 +181,7 @@ struct EpiStore {
     }
     if (amax) {
       // columns >= N of a ragged tile hold bias-padding zeros + accumulated zeros (TMA zero-fills the weight rows)
-      amax_update_warp<32>(amax, v, row0 + lane < M);
+      amax_update_warp<32>(amax, v, row0 + lane < M, st.amax_seen);
     }
     store_block_tma(&tm_out, col0, aux ? &tm_aux : nullptr, col0, row0, lane, v, patch);
   }
@@ -208,8 +217,20 @@ struct EpiPhaseEqT {
   CUtensorMap tm_corr;  // view of corr.p0 + corr.col_off, box 32 x 32
   struct State {
     float c_even[16];   // corr values of the even 32-column chunk, kept until the odd chunk completes a 32 x 32 block
+    unsigned seen_eq = 0u, seen_corr = 0u;   // see amax_update_warp
   };
   static constexpr bool kWarpStore = true;
+  static constexpr bool kPrefetch = true;
+  int pf = 1;           // pull the tile's f rows into L2 while the tile is still accumulating (DCCN_EPI_PREFETCH=0 disables)
+  // The tail below reads f with per-lane row loads that nothing else has touched since the learned-DFT layer wrote it
+  // ~1 ms earlier: from DRAM that latency sits between the last K chunk and the first store of every tile, while the
+  // MMA warp has only two accumulators of head start on the next tile.
+  DCCN_DEVINL void prefetch(int row0, int lane, int col0, int cols) const {
+    const int row = row0 + lane;
+    if (!pf || row >= M || col0 >= N) return;
+    const float* p = f0 + (size_t)row * ld_f + col0;
+    for (int c = 0; c < cols && col0 + c < N; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
+  }
   DCCN_DEVINL int eq_col(int c) const {
     if constexpr (SYM) return (c / sym_cols) * sym_stride + c % sym_cols;
     else return c;
@@ -232,15 +253,22 @@ struct EpiPhaseEqT {
 #pragma unroll
     for (int i = 0; i < 8; ++i) f4[i] = fp0[i];
     float e[32], c[16];
+    // the activation switch stays OUTSIDE the arithmetic loop (a per-element runtime branch makes the compiler serialise
+    // load -> wait -> tanh per column, the EpiStore finding)
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float4 bq = b4[i >> 2], fq = f4[i >> 2];
-      float cr = v[i] + ((i & 2) ? bq.z : bq.x);
-      float ci = v[i + 1] + ((i & 2) ? bq.w : bq.y);
-      if (act == 1) {
-        cr = tanhf(cr);
-        ci = tanhf(ci);
-      }
+      const float4 bq = b4[i >> 2];
+      v[i] += (i & 2) ? bq.z : bq.x;
+      v[i + 1] += (i & 2) ? bq.w : bq.y;
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float4 fq = f4[i >> 2];
+      const float cr = v[i], ci = v[i + 1];
       const float2 f = (i & 2) ? make_float2(fq.z, fq.w) : make_float2(fq.x, fq.y);
       const float inv = rsqrtf(cr * cr + ci * ci);
       const float nr = cr * inv, ni = (-ci) * inv;
@@ -248,11 +276,9 @@ struct EpiPhaseEqT {
       e[i] = er;
       e[i + 1] = ei;
       c[i / 2] = er * er + ei * ei;
-      v[i] = cr;
-      v[i + 1] = ci;
     }
-    if (amax_eq) amax_update_warp<32>(amax_eq, e, ok);
-    if (amax_corr && corr.p0) amax_update_warp<16>(amax_corr, c, ok);
+    if (amax_eq) amax_update_warp<32>(amax_eq, e, ok, st.seen_eq);
+    if (amax_corr && corr.p0) amax_update_warp<16>(amax_corr, c, ok, st.seen_corr);
     store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch);
     if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch);
     if (corr.p0) {
@@ -352,6 +378,7 @@ struct EpiHead {
   double* ce_sum;             // [1] or nullptr
   int M, N;
   static constexpr bool kWarpStore = false;
+  static constexpr bool kPrefetch = false;
   struct State {   // per-thread accumulators (flushed once per thread)
     // confusion counts as four 16-bit fields of one word: field (truth * 2 + decision); spilled into `big` before a
     // field can overflow

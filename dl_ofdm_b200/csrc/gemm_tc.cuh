@@ -395,7 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
               // instead of 12 (measured, profiles/accuracy_r2.txt) -- same instructions, same operands, other order.
               if (small_first) {
 #pragma unroll
-                for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+                for (int k = 0; k < (DCCN_ABL(32) ? 0 : C::BK / C::UMMA_K); ++k) {
                   const uint64_t db_hi = umma_desc_sw128(b_hi + k * C::UMMA_K * 4);
                   const uint32_t ka = ta_hi + (uint32_t)(k * C::UMMA_K);
                   if constexpr (F16) umma_f16_ts(d, ka, db_hi, idesc, 1u);
@@ -471,6 +471,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
             const uint32_t rowp = smem_u32(a_ring + sa * C::A_BYTES + r * 128);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+              if (DCCN_ABL(1)) {
+                hi[16 * bx + 2 * c] = hi[16 * bx + 2 * c + 1] = lo[16 * bx + 2 * c] = lo[16 * bx + 2 * c + 1] = 0.f;
+                continue;
+              }
               const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
               f16_split_pack(v.x * a_scale, v.y * a_scale, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
               f16_split_pack(v.z * a_scale, v.w * a_scale, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
@@ -623,6 +627,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int row_base = (tk.kslice * m_tiles + tk.m_blk) * C::BM + q * 32;   // split-K slices stack along the rows
       const int row = row_base + lane;
       const int num_chunks = (tk.kb1 - tk.kb0 + kb_per_chunk - 1) / kb_per_chunk;
+      if constexpr (Epi::kPrefetch) epi.prefetch(row_base, lane, n_blk * BN + cg * C::COLS_PER_GROUP, C::COLS_PER_GROUP);
       for (int ch = 0; ch < num_chunks; ++ch) {
         if (stage_signal) {
           // (estage, ephase) = ring position of the chunk's FIRST k-block; wait for its last one, then step over the chunk

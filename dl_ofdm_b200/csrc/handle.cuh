@@ -88,6 +88,7 @@ struct dccn_handle {
   size_t ws_act_bytes = 0;
   int kc = 1;          // k-blocks accumulated inside TMEM before the fp32 register add (parity mode)
   int small_first = 1; // parity GEMMs: per k-block the 8 cross-term MMAs first, then the 4 hi*hi MMAs (DCCN_SMALL_FIRST=0: interleaved)
+  int epi_prefetch = 1; // phase-equaliser epilogue: L2-prefetch the tile's f rows at tile start (DCCN_EPI_PREFETCH=0 disables)
   int head_subs = 2;   // data subcarriers per thread of the demod head kernel (1 or 2)
   int head_blocks = 0; // resident head blocks per SM (0 = 2048 / threads)
   int bn_wide = 0;     // use 256-wide tiles for the 896-wide layers

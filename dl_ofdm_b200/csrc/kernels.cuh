@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ x, 
   }
   if (amax) {   // max |y| of the pass: operand scale of the fp16 hi/lo GEMM that reads this buffer (amax_update_warp)
     mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0 && mx) atomicMax(amax, mx);
+    // one RED per row at ONE address would serialise in its L2 slice (4.6e5 rows per pass): look first (an L2 read that
+    // any number of warps share), fire only when this row raises the maximum -- a handful of times per pass
+    if (lane == 0 && mx > *reinterpret_cast<volatile unsigned*>(amax)) atomicMax(amax, mx);
   }
 }
 

@@ -47,6 +47,8 @@ MACS = {
 }
 HEAD_MACS = 320 * (2 * 16 + 18 * 8)                  # per-subcarrier head, CUDA cores
 MFLOP_PER_FRAME = 2e-6 * (sum(MACS.values()) + HEAD_MACS)          # 7.330 for eq + rx at 16-QAM
+# chained per-symbol kernels (csrc/chain.cu): one launch runs several of the layers above
+CHAINS = {'eq_chain_front': ('eq_dense', 'eq_dft'), 'eq_chain_tail': ('eq_idft', 'eq_corr_idft', 'eq_dense5')}
 # MACs one tensor-core PASS actually executes per frame: K padded to the 64-wide k-block of the fp16 form, N to the
 # 128-wide tile, the real-only corr input (K = 64), the block band of the Toeplitz operand (37 of 49 blocks)
 EXEC_MACS = {
@@ -55,6 +57,10 @@ EXEC_MACS = {
     'eq_corr_idft': 64 * 128 * 7, 'eq_idft': 128 * 128 * 7, 'eq_dense5': 256 * 256 * 7,
     'rx_fft_like': 192 * 128 * 7, 'rx_demod_gemm': 896 * 640,
 }
+STEP_EXEC_MACS = sum(EXEC_MACS.values())             # per frame and MMA pass, whichever way the layers are launched
+for _c, _ls in CHAINS.items():
+    MACS[_c] = sum(MACS[_l] for _l in _ls)
+    EXEC_MACS[_c] = sum(EXEC_MACS[_l] for _l in _ls)
 
 
 def peaks():
@@ -498,7 +504,7 @@ def main():
     passes = 3 if args.precision == 'parity' else 1
     exec_tf = 2.0 * passes * EXEC_MACS[dom] * frames_per_launch / dom_s / 1e12
     gemm_ms = sum(prof[k][0] for k in prof if k in MACS) / n_prof
-    step_exec_tf = 2.0 * passes * sum(EXEC_MACS.values()) * B / (ms / n_pass * 1e-3) / 1e12
+    step_exec_tf = 2.0 * passes * STEP_EXEC_MACS * B / (ms / n_pass * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
     if os.path.exists(tp):

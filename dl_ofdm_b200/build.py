@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ_DIR = os.path.join(HERE, 'build')
 OUT = os.path.join(HERE, 'libdccn.so')
-UNITS = ['dccn.cu', 'train.cu']
+UNITS = ['dccn.cu', 'train.cu', 'chain.cu']
 HEADERS = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))] + \
           [os.path.join(os.path.dirname(HERE), 'include', 'dccn.h')]
 FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC']

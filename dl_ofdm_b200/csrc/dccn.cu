@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "handle.cuh"
+#include "chain.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -96,7 +97,8 @@ const char* kSlotNames[SLOT_COUNT] = {
     "moments", "prep_norm", "eq_dense", "eq_dft", "eq_pilot", "eq_dense2", "eq_dense3", "eq_dense4_tanh",
     "eq_conv7x64_phaseeq", "eq_corr_idft", "eq_idft", "eq_dense5", "rx_fft_like", "rx_demod_head",
     "chan_fir", "chan_awgn", "rx_demod_gemm", "train_head_bwd", "train_dgrad", "train_wgrad", "train_pointwise",
-    "train_reduce_adam", "train_repack", "fold_dense_dft", "fold_mlp_tanh", "fold_tail_fft"};
+    "train_reduce_adam", "train_repack", "fold_dense_dft", "fold_mlp_tanh", "fold_tail_fft", "eq_chain_front",
+    "eq_chain_tail"};
 
 }  // namespace dccn
 
@@ -854,6 +856,76 @@ int run_moments(dccn_handle* h, const float* x, int64_t B, float* mean, float* r
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// chained per-symbol runs of equalizer_ofdm (chain.cu): same layers, same fp32 rounding per layer, intermediates in TMEM
+// ---------------------------------------------------------------------------------------
+static bool chain_layer_ok(const GemmLayer& L) { return L.f16_ok && L.BN == 128; }
+
+static bool chain_enabled(const dccn_handle* h) {
+  return h->chain && h->cfg.precision == DCCN_PREC_PARITY && h->f16x3 && h->a_tmem && h->kc == 1 && !h->tr &&
+         !h->train_fwd && (h->eq_opt == 0 || h->eq_opt == 7);
+}
+
+static long long* g_chain_trace[2] = {nullptr, nullptr};   // tools/chain_trace.py: timeline buffers of the front / tail chain
+
+static int chain_finish(dccn_handle* h, int slot, ChainParams& p, cudaStream_t s) {
+  int rc;
+  p.trace = g_chain_trace[slot == SLOT_CH_TAIL ? 1 : 0];
+  EpiStore& e = p.epi;
+  if ((rc = make_tmap(&e.tm_out, e.out.p0 + e.out.col_off, e.M, e.N, e.out.ld, 32))) return rc;
+  if (e.aux && (rc = make_tmap(&e.tm_aux, e.aux, e.M, e.N, e.aux_ld, 32))) return rc;
+  p.small_first = h->small_first ? 1 : 0;
+  LaunchScope ls(h, slot, s);
+  return launch_chain(p, s, h->num_sms);
+}
+
+// dense (2 Tin -> 2K) -> learned DFT (1,K) complex conv, per symbol                       model.py:370-379
+static bool chain_front_ok(const dccn_handle* h) {
+  return chain_enabled(h) && chain_layer_ok(h->g1) && chain_layer_ok(h->g2) && h->g1.N == 128 && h->g1.K <= 192 &&
+         h->g2.K == 128 && h->g2.N <= 128;
+}
+static int run_chain_front(dccn_handle* h, const Act& a0v, int cp_off, int64_t MS, const Act& fv, cudaStream_t s) {
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_tmap(&p.tmA[0], a0v.p0 + cp_off, MS, h->g1.K, a0v.ld, 128))) return rc;
+  p.tmA[1] = p.tmA[0];
+  p.tmW[0][0] = h->g1.tmH0;  p.tmW[0][1] = h->g1.tmH1;
+  p.tmW[1][0] = h->g2.tmH0;  p.tmW[1][1] = h->g2.tmH1;
+  p.st[0] = ChainStage{0, (h->g1.K + 63) / 64, 0, 1, 0, h->g1.w_scale_inv, h->g1.dBias, a0v.amax};
+  p.st[1] = ChainStage{-1, 2, 0, 1, -1, h->g2.w_scale_inv, nullptr, nullptr};
+  p.nst = 2;
+  p.M = (int)MS;
+  p.epi = store_epi(h->g2, fv, 0, MS);
+  return chain_finish(h, SLOT_CH_FRONT, p, s);
+}
+
+// (1,K) conv(eq) | (1,K) conv(corr) -> concat -> dense_5 (4K -> 2T), per symbol             model.py:437-462
+static bool chain_tail_ok(const dccn_handle* h) {
+  return chain_enabled(h) && chain_layer_ok(h->g8) && chain_layer_ok(h->g9) && chain_layer_ok(h->g10) &&
+         h->g9.K == 128 && h->g9.N == 128 && h->g8.K == 64 && h->g8.N == 128 && h->g10.K == 256 && h->g10.N <= 256;
+}
+static int run_chain_tail(dccn_handle* h, const Act& eqv, const Act& corrv, int64_t MS, const Act& oeqv, float* eq_out,
+                          int eq_out_ld, cudaStream_t s) {
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_tmap(&p.tmA[0], eqv.p0, MS, h->g9.K, eqv.ld, 128))) return rc;
+  if ((rc = make_tmap(&p.tmA[1], corrv.p0, MS, h->g8.K, corrv.ld, 128))) return rc;
+  p.tmW[0][0] = h->g9.tmH0;   p.tmW[0][1] = h->g9.tmH1;
+  p.tmW[1][0] = h->g8.tmH0;   p.tmW[1][1] = h->g8.tmH1;
+  p.tmW[2][0] = h->g10.tmH0;  p.tmW[2][1] = h->g10.tmH1;
+  // slots: eq staged in 0,1 -> conv3d_3 output (cat columns 0..2K) back into 0,1; corr staged in 2 -> conv3d_2 output
+  // (cat columns 2K..4K) into 2,3; dense_5 contracts slots 0..3
+  p.st[0] = ChainStage{0, 2, 0, 1, 0, h->g9.w_scale_inv, h->g9.dBias, eqv.amax};
+  p.st[1] = ChainStage{1, 1, 2, 1, 2, h->g8.w_scale_inv, h->g8.dBias, corrv.amax};
+  p.st[2] = ChainStage{-1, 4, 0, (h->g10.N + 127) / 128, -1, h->g10.w_scale_inv, nullptr, nullptr};
+  p.nst = 3;
+  p.M = (int)MS;
+  p.epi = store_epi(h->g10, oeqv, 0, MS, 0, eq_out, eq_out_ld);
+  return chain_finish(h, SLOT_CH_TAIL, p, s);
+}
+
 // one chunk of Bc frames through [equalizer ->] receiver
 int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, float* soft, uint8_t* hard,
                      float* eq_out, float* chest_out, unsigned long long* conf, double* ce, int flags,
@@ -972,9 +1044,14 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
     Act catv = h->cat;   // [Bc*S, 4K]
     Act oeqv = h->oeq; oeqv.ld = 2 * T;
     // dense: per-symbol 2*Tin -> 2K                               model.py:370
-    if ((rc = run_gemm(h, SLOT_G1, h->g1, a0v, cp_off, MS, store_epi(h->g1, t1v, 0, MS), s))) return rc;
-    // learned DFT (1,K) 'valid' complex conv                       model.py:377-379
-    if ((rc = run_gemm(h, SLOT_G2, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
+    if (chain_front_ok(h)) {
+      // both layers in one kernel, the [MS, 2K] intermediate stays in tensor memory (chain.cu)
+      if ((rc = run_chain_front(h, a0v, cp_off, MS, fv, s))) return rc;
+    } else {
+      if ((rc = run_gemm(h, SLOT_G1, h->g1, a0v, cp_off, MS, store_epi(h->g1, t1v, 0, MS), s))) return rc;
+      // learned DFT (1,K) 'valid' complex conv                       model.py:377-379
+      if ((rc = run_gemm(h, SLOT_G2, h->g2, t1v, 0, MS, store_epi(h->g2, fv, 0, MS), s))) return rc;
+    }
     // pilot bottleneck and channel-estimate MLP                    model.py:393-424
     if ((rc = run_gemm(h, SLOT_G3, h->g3, h->f, 0, Bc, store_epi(h->g3, h->p32, 0, Bc), s))) return rc;
     // (chain activations: linear, linear, tanh for equalizer_ofdm; tanh x3 for equalizer_separateIQ, model.py:1140-1162)
@@ -1011,10 +1088,15 @@ int run_chunk(dccn_handle* h, const float* x, int64_t Bc, const uint8_t* bits, f
       DCCN_CUDA_OK(cudaGetLastError());
     }
     // corr / eq (1,K) 'valid' complex convs -> [eq_out | corr_out]  model.py:437-448
-    if ((rc = run_gemm(h, SLOT_G8, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
-    if ((rc = run_gemm(h, SLOT_G9, h->g9, eqv, 0, MS, store_epi(h->g9, catv, 0, MS), s))) return rc;
-    // dense_5: 4K -> 2T per symbol                                  model.py:457-462
-    if ((rc = run_gemm(h, SLOT_G10, h->g10, catv, 0, MS, store_epi(h->g10, oeqv, 0, MS, 0, eq_out, 2 * T), s))) return rc;
+    if (chain_tail_ok(h)) {
+      // the three layers in one kernel: the concatenated [MS, 4K] tile goes to dense_5 through tensor memory (chain.cu)
+      if ((rc = run_chain_tail(h, eqv, corrv, MS, oeqv, eq_out, 2 * T, s))) return rc;
+    } else {
+      if ((rc = run_gemm(h, SLOT_G8, h->g8, corrv, 0, MS, store_epi(h->g8, catv, 2 * K, MS), s))) return rc;
+      if ((rc = run_gemm(h, SLOT_G9, h->g9, eqv, 0, MS, store_epi(h->g9, catv, 0, MS), s))) return rc;
+      // dense_5: 4K -> 2T per symbol                                  model.py:457-462
+      if ((rc = run_gemm(h, SLOT_G10, h->g10, catv, 0, MS, store_epi(h->g10, oeqv, 0, MS, 0, eq_out, 2 * T), s))) return rc;
+    }
     rx_in = &h->oeq;
     if (flags & DCCN_FWD_EQ_ONLY) return 0;
   }
@@ -1232,6 +1314,7 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_MC_MIN_K")) h->mc_min_k = atoi(e);
   if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
   if (const char* e = getenv("DCCN_F16X3")) h->f16x3 = atoi(e);   // 0: tf32 hi/lo pairs (the round-1 form)
+  if (const char* e = getenv("DCCN_CHAIN")) h->chain = atoi(e);   // 0: every per-symbol layer through HBM
   if (const char* e = getenv("DCCN_TX_V2")) h->tx_v2 = atoi(e);
   if (const char* e = getenv("DCCN_BN192")) h->bn192 = atoi(e);
   if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;
@@ -1716,6 +1799,14 @@ int dccn_debug_abl(int mask) {
   return 0;
 }
 #endif
+
+/* measurement aid (tools/chain_trace.py, not part of include/dccn.h): CTA 0 of the next chained kernels (which = 0 front,
+   1 tail) writes 5 x 1024 clock64() samples into buf_dev; nullptr switches it off */
+int dccn_debug_chain_trace(int which, long long* buf_dev) {
+  if (which < 0 || which > 1) return -2;
+  g_chain_trace[which] = buf_dev;
+  return 0;
+}
 
 int64_t dccn_launch_count(void) { return (int64_t)g_launches.load(); }
 

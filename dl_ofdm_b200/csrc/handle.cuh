@@ -64,7 +64,7 @@ struct HostTensor {
 
 extern std::atomic<long long> g_launches;   // kernels launched by this library (dccn_launch_count)
 enum { SLOT_MOMENTS = 0, SLOT_PREP, SLOT_G1, SLOT_G2, SLOT_G3, SLOT_G4, SLOT_G5, SLOT_G6, SLOT_G7_PHASEEQ,
-       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_T_HEAD, SLOT_T_DGRAD, SLOT_T_WGRAD, SLOT_T_POINT, SLOT_T_ADAM, SLOT_T_REPACK, SLOT_F1, SLOT_F4, SLOT_F9, SLOT_COUNT };
+       SLOT_G8, SLOT_G9, SLOT_G10, SLOT_R1, SLOT_R2_HEAD, SLOT_CHAN_FIR, SLOT_AWGN, SLOT_R2_GEMM, SLOT_T_HEAD, SLOT_T_DGRAD, SLOT_T_WGRAD, SLOT_T_POINT, SLOT_T_ADAM, SLOT_T_REPACK, SLOT_F1, SLOT_F4, SLOT_F9, SLOT_CH_FRONT, SLOT_CH_TAIL, SLOT_COUNT };
 extern const char* kSlotNames[SLOT_COUNT];
 struct ProfRec { int slot; cudaEvent_t a, b; };
 struct TrainState;
@@ -100,6 +100,7 @@ struct dccn_handle {
   int band_skip = 1;   // skip the structurally-zero k-blocks of the Toeplitz ((S,K) 'same' conv) operand
   int tx_v2 = 1;       // 8 x 8 IDFT transmitter kernel for nfft = 64 (DCCN_TX_V2=0: the generic K-point DFT kernel)
   int32_t* d_txmap = nullptr;           // [S*K] subcarrier role map, rebuilt on the device by every dccn_tx_frames call
+  int chain = 1;       // per-symbol layer runs of equalizer_ofdm as chained kernels (chain.cu; DCCN_CHAIN=0: layer by layer through HBM)
   int f16x3 = 1;       // inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (DCCN_F16X3=0: tf32 pairs)
   // monitor outputs requested for the NEXT forward (dccn_forward_monitors), consumed and cleared by it
   float* mon_snr_db = nullptr;          // [B] equalizer snr_db (model.py:464-475)

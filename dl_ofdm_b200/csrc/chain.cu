@@ -8,9 +8,9 @@
 //               128-column accumulators, ONE tcgen05.commit per k-block (kc = 1: the accumulator is drained every k-block and
 //               the partial sums are added in fp32 round-to-nearest by the epilogue warps -- the tensor core's own
 //               accumulator truncates)
-//   warps 2..5  splitters: raw fp32 A boxes of the HBM-fed stages -> fp16 (hi, lo) -> tcgen05.st into an operand slot
-//   warp 6      producer of the raw-A ring (4 x [128 x 32 fp32])
-//   warps 7..14 epilogue: drain every k-block, add; at the end of a stage either (intermediate) add the bias, pick a
+//   warp 2      producer of the raw-A ring (4 x [128 x 32 fp32])
+//   warps 4..7  splitters: raw fp32 A boxes of the HBM-fed stages -> fp16 (hi, lo) -> tcgen05.st into an operand slot
+//   warps 8..15 epilogue: drain every k-block, add; at the end of a stage either (intermediate) add the bias, pick a
 //               power-of-two scale per ROW and k-block (exact; recorded in shared memory and undone when the next stage's
 //               partial sums are drained), split to fp16 hi/lo and tcgen05.st the result into the operand slots, or
 //               (last stage) EpiStore: bias / amax / swizzled patch / bulk tensor store.
@@ -25,13 +25,20 @@ namespace dccn {
 namespace {
 
 constexpr int CH_BM = 128, CH_BN = 128, CH_KB = 64;
-constexpr int CH_STAGES = 4;                       // weight ring
+// weight ring: 3 stages, not 4 -- with 4 the kernel held 226 KB of shared memory, which leaves NO L1 data cache (228 KB
+// unified): every bias load and every register spill of the epilogue warps then pays the L2 latency
+constexpr int CH_STAGES = 3;
 constexpr int CH_W_PLANE = CH_BN * CH_KB * 2;      // 16 KB: one fp16 plane of a weight stage
 constexpr int CH_W_STAGE = 2 * CH_W_PLANE;         // 32 KB
 constexpr int CH_SA = 4;                           // raw-A ring slots
 constexpr int CH_A_BYTES = CH_BM * 32 * 4;         // 16 KB: [128 x 32 fp32]
-constexpr int CH_EPI_WARP0 = 7;
-constexpr int CH_THREADS = 32 * CH_EPI_WARP0 + 256;   // 480
+// 16 warps = 4 warpgroups, so that setmaxnreg can move registers between the roles: warps 0..3 = weight producer, MMA issuer,
+// raw-A producer, (idle); warps 4..7 = splitters; warps 8..15 = epilogue.  An SM sub-partition holds 16 K registers, i.e.
+// 128 per thread at 4 warps each; the epilogue warps (64 accumulators + 32 freshly loaded values + the stage state) spilled
+// their ACCUMULATORS at 128 -- the two producer-side warpgroups hand them 48 registers per thread.
+constexpr int CH_EPI_WARP0 = 8;
+constexpr int CH_THREADS = 512;
+constexpr int CH_REGS_CTRL = 80, CH_REGS_SPLIT = 112, CH_REGS_EPI = 160;   // 128 * (56 + 104 + 2 * 176) = 65 536
 constexpr int CH_PATCH_BYTES = 8 * 4096;
 constexpr int CH_SMALL_BYTES = 1024;               // row-scale exponents (4 x 128 int8) + barriers + TMEM pointer
 constexpr int CH_SMEM_BYTES = CH_STAGES * CH_W_STAGE + CH_SA * CH_A_BYTES + CH_PATCH_BYTES + CH_SMALL_BYTES + 1024;
@@ -48,7 +55,83 @@ DCCN_DEVINL int scale_exp_from_amax(unsigned bits) {
 }
 DCCN_DEVINL float pow2f(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
 
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams p) {
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot, each lane rounded exactly
+// like its scalar form).  The epilogue warps are issue-bound (two of them share a scheduler with a splitter warp), so
+// the per-k-block partial-sum adds and the stage finalisation run on pairs.
+typedef unsigned long long f32x2;
+DCCN_DEVINL f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+DCCN_DEVINL void unpack2(f32x2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+DCCN_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+DCCN_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+DCCN_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// The (stage, n-subtile, k-block) nest of one tile, flattened on the host (launch_chain): every role walks the same list.
+struct ChainStep {
+  uint8_t stage, kb, sub, slot;
+  uint8_t flags;       // see CS_*
+  uint8_t pad[3];
+};
+enum { CS_FIRST = 1,   // first k-block of its (stage, n-subtile): the partial sum starts here
+       CS_LAST = 2,    // last k-block of its (stage, n-subtile): the stage output is complete after this drain
+       CS_READY = 4,   // the MMA warp has to wait for the operand slot (first pass of the stage over its slots)
+       CS_TILE_END = 8,   // last step of the tile: operand slots are free for the next tile's staging afterwards
+       CS_HBM = 16 };     // the slot is staged from HBM by the splitter warps (first pass of an HBM-fed stage)
+constexpr int kChainMaxSteps = 24;
+struct ChainSched {
+  int nsteps;
+  ChainStep steps[kChainMaxSteps];
+};
+
+// 32 lanes x 32 columns block of the last stage: bias, running max |y| of the destination buffer, then out through the
+// warp's 4 KB patch -- as bulk tensor stores (store_mode 0, EpiStore's path without the activation switch: the chains end in
+// linear layers) or as coalesced st.global (store_mode 1; measured slower, kept as the comparison)
+template <bool STG>
+DCCN_DEVINL void final_block(const EpiStore& e, EpiStore::State& st, int row0, int lane, int col0, float (&v)[32],
+                             uint32_t patch) {
+  if (col0 >= e.N || row0 >= e.M) return;
+  if (e.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = __ldg(bp + 4 * h + i);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[16 * h + 4 * i + 0] += b[i].x;
+        v[16 * h + 4 * i + 1] += b[i].y;
+        v[16 * h + 4 * i + 2] += b[i].z;
+        v[16 * h + 4 * i + 3] += b[i].w;
+      }
+    }
+  }
+  if (e.amax) amax_update_warp<32>(e.amax, v, row0 + lane < e.M, st.amax_seen);
+  if (STG) {
+    store_block_warp(e.out.p0 + e.out.col_off + col0, e.out.ld, row0, e.M, lane, v, patch);
+    if (e.aux) store_block_warp(e.aux + col0, e.aux_ld, row0, e.M, lane, v, patch);
+  } else {
+    store_block_tma(&e.tm_out, col0, e.aux ? &e.tm_aux : nullptr, col0, row0, lane, v, patch);
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams p,
+                                                                  const __grid_constant__ ChainSched sc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem + CH_STAGES * CH_W_STAGE;
@@ -64,16 +147,24 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // timeline of CTA 0 (role r: trace[r * 1024 + i]); 0 MMA step issued, 1 drain starts, 2 drain done, 3 stage finalised,
-  // 4 splitter k-block staged
+  // timeline of CTA 0 (role r: trace[r * 1024 + i], i = k-block step counted from the kernel's start): 0 MMAs issued,
+  // 1 drain starts (7: the epilogue warp reached the drain's wait), 2 drain done, 3 stage output finished,
+  // 4 splitter k-block staged, 5 / 6 intermediate stage: bias + amax done / fp16 pairs packed
+#ifdef DCCN_CHAIN_TRACE   // tools/build_chain_trace.sh -> libdccn_chtrace.so; the product build carries no trace code
   long long* const trc = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr;
   int trn = 0;
-#define CH_TRACE(role)                                              \
-  do {                                                              \
-    if (trc && trn < 1024) trc[(role) * 1024 + trn++] = clock64();  \
+#define CH_TRACE_AT(role, idx)                                       \
+  do {                                                               \
+    if (trc && (idx) < 1024) trc[(role) * 1024 + (idx)] = clock64(); \
   } while (0)
+#define CH_TRACE_NEXT() ++trn
+#else
+#define CH_TRACE_AT(role, idx)
+#define CH_TRACE_NEXT()
+#endif
   const int m_tiles = (p.M + CH_BM - 1) / CH_BM;
   const int tile0 = (int)blockIdx.x, tile_step = (int)gridDim.x;
+  const int nsteps = sc.nsteps;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) tma_prefetch_desc(&p.tmA[i]);
@@ -106,28 +197,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_CTRL));
   if (warp == 0) {
     // =============================== weight producer ===============================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < m_tiles; tile += tile_step) {
-      for (int s = 0; s < p.nst; ++s) {
-        const ChainStage& cs = p.st[s];
-        for (int sub = 0; sub < cs.nsub; ++sub) {
-          for (int kb = 0; kb < cs.nkb; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&full[stage], CH_W_STAGE);
-              uint8_t* st = smem + stage * CH_W_STAGE;
-              tma_load_2d(st, &p.tmW[s][0], &full[stage], kb * CH_KB, sub * CH_BN);
-              tma_load_2d(st + CH_W_PLANE, &p.tmW[s][1], &full[stage], kb * CH_KB, sub * CH_BN);
-            }
-            __syncwarp();
-            if (++stage == CH_STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
+      for (int i = 0; i < nsteps; ++i) {
+        const ChainStep stp = sc.steps[i];
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], CH_W_STAGE);
+          uint8_t* st = smem + stage * CH_W_STAGE;
+          tma_load_2d(st, &p.tmW[stp.stage][0], &full[stage], stp.kb * CH_KB, stp.sub * CH_BN);
+          tma_load_2d(st + CH_W_PLANE, &p.tmW[stp.stage][1], &full[stage], stp.kb * CH_KB, stp.sub * CH_BN);
+        }
+        __syncwarp();
+        if (++stage == CH_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -140,87 +229,85 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     uint32_t acc_phase = 0;
     uint32_t arph = 0;                          // phase bit of every operand-slot barrier
     for (int tile = tile0; tile < m_tiles; tile += tile_step) {
-      for (int s = 0; s < p.nst; ++s) {
-        const ChainStage& cs = p.st[s];
-        for (int sub = 0; sub < cs.nsub; ++sub) {
-          for (int kb = 0; kb < cs.nkb; ++kb) {
-            const int slot = cs.slot0 + kb;
-            // weight planes landed + accumulator drained + (first pass over the slots of this stage) operand slot written
-            mbar_wait_multi(&full[stage], phase, &tempty[acc], acc_phase ^ 1, sub == 0 ? &aready[slot] : nullptr,
-                            (arph >> slot) & 1u);
-            if (sub == 0) arph ^= 1u << slot;
-            CH_TRACE(0);
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(smem + stage * CH_W_STAGE);
-            const uint32_t b_lo = b_hi + CH_W_PLANE;
-            const uint32_t d = tmem_base + (uint32_t)(acc * CH_BN);
-            const uint32_t ta_hi = tmem_base + (uint32_t)(CH_ACT_COL0 + slot * 64);
-            const bool last_of_tile = (s == p.nst - 1) && (sub == cs.nsub - 1) && (kb == cs.nkb - 1);
-            if (elect_one()) {
-              if (p.small_first) {
-                // the 8 cross-term MMAs of the k-block while the accumulator is small, then the 4 hi*hi MMAs (gemm_tc.cuh)
+      for (int i = 0; i < nsteps; ++i) {
+        const ChainStep stp = sc.steps[i];
+        const int slot = stp.slot;
+        const bool wait_ready = (stp.flags & CS_READY) != 0;
+        // weight planes landed + accumulator drained + (first pass over the slots of this stage) operand slot written
+        mbar_wait_multi(&full[stage], phase, &tempty[acc], acc_phase ^ 1, wait_ready ? &aready[slot] : nullptr,
+                        (arph >> slot) & 1u);
+        if (wait_ready) arph ^= 1u << slot;
+        CH_TRACE_AT(0, trn);
+        CH_TRACE_NEXT();
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(smem + stage * CH_W_STAGE);
+        const uint32_t b_lo = b_hi + CH_W_PLANE;
+        const uint32_t d = tmem_base + (uint32_t)(acc * CH_BN);
+        const uint32_t ta_hi = tmem_base + (uint32_t)(CH_ACT_COL0 + slot * 64);
+        if (elect_one()) {
+          if (p.small_first) {
+            // the 8 cross-term MMAs of the k-block while the accumulator is small, then the 4 hi*hi MMAs (gemm_tc.cuh)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t db_hi = umma_desc_sw128(b_hi + k * 32);
-                  const uint64_t db_lo = umma_desc_sw128(b_lo + k * 32);
-                  const uint32_t ka = ta_hi + (uint32_t)(k * 8);
-                  umma_f16_ts(d, ka + 32, db_hi, idesc, k != 0 ? 1u : 0u);   // A_lo * B_hi
-                  umma_f16_ts(d, ka, db_lo, idesc, 1u);                      // A_hi * B_lo
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16_ts(d, ta_hi + (uint32_t)(k * 8), umma_desc_sw128(b_hi + k * 32), idesc, 1u);   // A_hi * B_hi
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t db_hi = umma_desc_sw128(b_hi + k * 32);
-                  const uint64_t db_lo = umma_desc_sw128(b_lo + k * 32);
-                  const uint32_t ka = ta_hi + (uint32_t)(k * 8);
-                  umma_f16_ts(d, ka + 32, db_hi, idesc, k != 0 ? 1u : 0u);
-                  umma_f16_ts(d, ka, db_lo, idesc, 1u);
-                  umma_f16_ts(d, ka, db_hi, idesc, 1u);
-                }
-              }
-              umma_commit(&empty[stage]);          // weight stage reusable + accumulator ready (the epilogue waits on it too)
-              if (last_of_tile) umma_commit(sfree);   // operand slots reusable by the next tile's staging
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t db_hi = umma_desc_sw128(b_hi + k * 32);
+              const uint64_t db_lo = umma_desc_sw128(b_lo + k * 32);
+              const uint32_t ka = ta_hi + (uint32_t)(k * 8);
+              umma_f16_ts(d, ka + 32, db_hi, idesc, k != 0 ? 1u : 0u);   // A_lo * B_hi
+              umma_f16_ts(d, ka, db_lo, idesc, 1u);                      // A_hi * B_lo
             }
-            __syncwarp();
-            if (++stage == CH_STAGES) {
-              stage = 0;
-              phase ^= 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(d, ta_hi + (uint32_t)(k * 8), umma_desc_sw128(b_hi + k * 32), idesc, 1u);   // A_hi * B_hi
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t db_hi = umma_desc_sw128(b_hi + k * 32);
+              const uint64_t db_lo = umma_desc_sw128(b_lo + k * 32);
+              const uint32_t ka = ta_hi + (uint32_t)(k * 8);
+              umma_f16_ts(d, ka + 32, db_hi, idesc, k != 0 ? 1u : 0u);
+              umma_f16_ts(d, ka, db_lo, idesc, 1u);
+              umma_f16_ts(d, ka, db_hi, idesc, 1u);
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
           }
+          umma_commit(&empty[stage]);          // weight stage reusable + accumulator ready (the epilogue waits on it too)
+          if (stp.flags & CS_TILE_END) umma_commit(sfree);   // operand slots reusable by the next tile's staging
         }
+        __syncwarp();
+        if (++stage == CH_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // =============================== raw-A producer =================================
     int sa = 0;
     uint32_t pa = 0;
     for (int tile = tile0; tile < m_tiles; tile += tile_step) {
-      for (int s = 0; s < p.nst; ++s) {
-        const ChainStage& cs = p.st[s];
-        if (cs.src < 0) continue;
-        for (int kb = 0; kb < cs.nkb; ++kb) {
+      for (int i = 0; i < nsteps; ++i) {
+        const ChainStep stp = sc.steps[i];
+        if (!(stp.flags & CS_HBM)) continue;
+        const int src = p.st[stp.stage].src;
 #pragma unroll
-          for (int bx = 0; bx < 2; ++bx) {
-            mbar_wait(&emptyA[sa], pa ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&fullA[sa], CH_A_BYTES);
-              tma_load_2d(a_ring + sa * CH_A_BYTES, &p.tmA[cs.src], &fullA[sa], kb * CH_KB + bx * 32, tile * CH_BM);
-            }
-            __syncwarp();
-            if (++sa == CH_SA) {
-              sa = 0;
-              pa ^= 1;
-            }
+        for (int bx = 0; bx < 2; ++bx) {
+          mbar_wait(&emptyA[sa], pa ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&fullA[sa], CH_A_BYTES);
+            tma_load_2d(a_ring + sa * CH_A_BYTES, &p.tmA[src], &fullA[sa], stp.kb * CH_KB + bx * 32, tile * CH_BM);
+          }
+          __syncwarp();
+          if (++sa == CH_SA) {
+            sa = 0;
+            pa ^= 1;
           }
         }
       }
     }
-  } else if (warp < 6) {
+  }   // (warp 3 idles: it only fills the control warpgroup)
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_SPLIT));
     // =============================== splitters ======================================
     int sa = 0;
     uint32_t pa = 0;
@@ -228,138 +315,173 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     int iter = 0;
     for (int tile = tile0; tile < m_tiles; tile += tile_step, ++iter) {
       bool gated = (iter == 0);                 // the previous tile's MMAs no longer read the slots
-      for (int s = 0; s < p.nst; ++s) {
-        const ChainStage& cs = p.st[s];
-        if (cs.src < 0) continue;
+      for (int i = 0; i < nsteps; ++i) {
+        const ChainStep stp = sc.steps[i];
+        if (!(stp.flags & CS_HBM)) continue;
+        const unsigned* amax_in = p.st[stp.stage].amax_in;
         float a_scale = 1.f;
-        if (cs.amax_in) a_scale = pow2f(-scale_exp_from_amax(__ldg(cs.amax_in)));
-        for (int kb = 0; kb < cs.nkb; ++kb) {
-          float hi[32], lo[32];
+        if (amax_in) a_scale = pow2f(-scale_exp_from_amax(__ldg(amax_in)));
+        float hi[32], lo[32];
 #pragma unroll
-          for (int bx = 0; bx < 2; ++bx) {
-            mbar_wait(&fullA[sa], pa);
-            const uint32_t rowp = smem_u32(a_ring + sa * CH_A_BYTES + r * 128);
+        for (int bx = 0; bx < 2; ++bx) {
+          mbar_wait(&fullA[sa], pa);
+          const uint32_t rowp = smem_u32(a_ring + sa * CH_A_BYTES + r * 128);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
-              f16_split_pack(v.x * a_scale, v.y * a_scale, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
-              f16_split_pack(v.z * a_scale, v.w * a_scale, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
-            }
-            // the release must not overtake the loads still queued in the LSU (gemm_tc.cuh)
-#pragma unroll
-            for (int c = 0; c < 16; ++c) asm volatile("" : "+f"(hi[16 * bx + c]));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&emptyA[sa]);
-            if (++sa == CH_SA) {
-              sa = 0;
-              pa ^= 1;
-            }
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
+            f16_split_pack(v.x * a_scale, v.y * a_scale, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
+            f16_split_pack(v.z * a_scale, v.w * a_scale, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
           }
-          if (!gated) {
-            mbar_wait(sfree, (uint32_t)((iter - 1) & 1));
-            gated = true;
-          }
-          tc_fence_after();
-          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(CH_ACT_COL0 + (cs.slot0 + kb) * 64);
-          tmem_st_32x32(ta, hi);
-          tmem_st_32x32(ta + 32, lo);
-          tmem_st_wait();
-          tc_fence_before();
+          // the release must not overtake the loads still queued in the LSU (gemm_tc.cuh)
+#pragma unroll
+          for (int c = 0; c < 16; ++c) asm volatile("" : "+f"(hi[16 * bx + c]));
           __syncwarp();
-          if (lane == 0) mbar_arrive(&aready[cs.slot0 + kb]);
-          if (warp == 2) CH_TRACE(4);
+          if (lane == 0) mbar_arrive(&emptyA[sa]);
+          if (++sa == CH_SA) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        if (!gated) {
+          mbar_wait(sfree, (uint32_t)((iter - 1) & 1));
+          gated = true;
+        }
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(CH_ACT_COL0 + stp.slot * 64);
+        tmem_st_32x32(ta, hi);
+        tmem_st_32x32(ta + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aready[stp.slot]);
+        if (warp == 4) {
+          CH_TRACE_AT(4, trn);
+          CH_TRACE_NEXT();
         }
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CH_REGS_EPI));
     // =============================== epilogue warps =================================
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int cg = (warp - CH_EPI_WARP0) >> 2;       // column group: accumulator columns cg * 64 .. + 63
     const int rrow = q * 32 + lane;                  // row of the tile this thread owns
+#ifdef DCCN_CHAIN_TRACE
+    const bool tr_w = warp == CH_EPI_WARP0;
+#else
+    constexpr bool tr_w = false;
+#endif
+    const uint32_t patch = smem_u32(patches + (warp - CH_EPI_WARP0) * 4096);
     EpiStore::State est;
     int acc = 0;
     int estage = 0;
     uint32_t ephase = 0;
-    float r[2][32];
+    f32x2 r[2][16];                                  // this row's 64 output columns of the current stage, as fp32 pairs
     for (int tile = tile0; tile < m_tiles; tile += tile_step) {
-      const int row_base = tile * CH_BM + q * 32;
-      for (int s = 0; s < p.nst; ++s) {
-        const ChainStage& cs = p.st[s];
-        // scale that undoes the operand scales of this stage: weights always; HBM operand: the uniform activation scale
-        float o_sc = cs.w_scale_inv;
-        if (cs.src >= 0 && cs.amax_in) o_sc *= pow2f(scale_exp_from_amax(__ldg(cs.amax_in)));
-        for (int sub = 0; sub < cs.nsub; ++sub) {
-          for (int kb = 0; kb < cs.nkb; ++kb) {
-            mbar_wait(&empty[estage], ephase);
-            if (++estage == CH_STAGES) {
-              estage = 0;
-              ephase ^= 1;
-            }
-            if (warp == CH_EPI_WARP0) CH_TRACE(1);
-            tc_fence_after();
-            // slot-fed stage: the operand of this k-block carried a per-row power-of-two scale; undo it here (exact)
-            float rs = 1.f;
-            if (cs.src < 0) rs = pow2f((int)rsexp[(cs.slot0 + kb) * 128 + rrow]);
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CH_BN + cg * 64);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float v[32];
-              tmem_ld_32x32(t0 + j * 32, v);
-              if (kb == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[j][i] = v[i] * rs;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[j][i] = __fadd_rn(r[j][i], v[i] * rs);
-              }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (warp == CH_EPI_WARP0 && trc && trn < 1024) trc[2 * 1024 + trn - 1] = clock64();
-            acc ^= 1;
-          }
-          // ---- end of a (stage, n-subtile): r = the layer's pre-bias output columns sub*128 + cg*64 .. +63 of row rrow ----
+      for (int i = 0; i < nsteps; ++i) {
+        const ChainStep stp = sc.steps[i];
+        const ChainStage& cs = p.st[stp.stage];
+        if (tr_w) CH_TRACE_AT(7, trn);
+        mbar_wait(&empty[estage], ephase);
+        if (++estage == CH_STAGES) {
+          estage = 0;
+          ephase ^= 1;
+        }
+        if (tr_w) CH_TRACE_AT(1, trn);
+        tc_fence_after();
+        // slot-fed stage: the operand of this k-block carried a per-row power-of-two scale; undo it here (exact)
+        float rs = 1.f;
+        if (cs.src < 0) rs = pow2f((int)rsexp[stp.slot * 128 + rrow]);
+        const f32x2 rs2 = pack2(rs, rs);
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CH_BN + cg * 64);
+        if (stp.flags & CS_FIRST) {                    // the partial sum of a (stage, n-subtile) starts at +0
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[j][i] *= o_sc;
-          if (cs.dst_slot0 < 0) {
+            for (int c = 0; c < 16; ++c) r[j][c] = 0ull;
+        }
+        // partial sums of the k-blocks are added in fp32 round-to-nearest, in k order (v * rs is exact); one code path for
+        // the first and the later k-blocks keeps the 64 accumulators in place (no register shuffling between the paths)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              p.epi.run_warp(est, row_base, lane, sub * CH_BN + cg * 64 + j * 32, r[j],
-                             smem_u32(patches + (warp - CH_EPI_WARP0) * 4096));
-          } else {
-            // intermediate layer: y = r + bias (fp32, what the layer-by-layer schedule stored), then the fp16 (hi, lo) pair of
-            // y * 2^-k with k chosen from this row's 64 values -- the next stage's k-block `cg`
-            const float4* bp = reinterpret_cast<const float4*>(cs.bias + cg * 64);
-            unsigned am = 0u;
+        for (int j = 0; j < 2; ++j) {
+          float v[32];
+          tmem_ld_32x32(t0 + j * 32, v);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) r[j][c] = fma2(pack2(v[2 * c], v[2 * c + 1]), rs2, r[j][c]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (tr_w) CH_TRACE_AT(2, trn);
+        acc ^= 1;
+        if (stp.flags & CS_LAST) {
+          // ---- r = the layer's pre-bias output columns sub*128 + cg*64 .. +63 of row rrow, up to the operand scales:
+          // weights always; HBM operand: the uniform activation scale (slot operands were unscaled per k-block above)
+          float o_sc = cs.w_scale_inv;
+          if (cs.src >= 0 && cs.amax_in) o_sc *= pow2f(scale_exp_from_amax(__ldg(cs.amax_in)));
+          const f32x2 o2 = pack2(o_sc, o_sc);
+          if (cs.dst_slot0 < 0) {
+            const int row_base = tile * CH_BM + q * 32;
+            const int col = stp.sub * CH_BN + cg * 64;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              float4 b[8];
+              float v[32];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + j * 8 + i);
+              for (int c = 0; c < 16; ++c) unpack2(mul2(r[j][c], o2), v[2 * c], v[2 * c + 1]);
+              if (p.store_mode == 1) final_block<true>(p.epi, est, row_base, lane, col + 32 * j, v, patch);
+              else final_block<false>(p.epi, est, row_base, lane, col + 32 * j, v, patch);
+            }
+          } else {
+            // intermediate layer: y = r * o_sc + bias (one fp32 rounding: the product with the power-of-two scale is exact --
+            // the value the layer-by-layer schedule stored), then the fp16 (hi, lo) pair of y * 2^-k with k chosen from this
+            // row's 64 values -- the next stage's k-block `cg`
+            const float4* bp = reinterpret_cast<const float4*>(cs.bias + cg * 64);
+            float am = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                r[j][4 * i + 0] += b[i].x;
-                r[j][4 * i + 1] += b[i].y;
-                r[j][4 * i + 2] += b[i].z;
-                r[j][4 * i + 3] += b[i].w;
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float4 b[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) b[c] = __ldg(bp + j * 8 + h * 4 + c);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  r[j][8 * h + 2 * c] = fma2(r[j][8 * h + 2 * c], o2, pack2(b[c].x, b[c].y));
+                  r[j][8 * h + 2 * c + 1] = fma2(r[j][8 * h + 2 * c + 1], o2, pack2(b[c].z, b[c].w));
+                }
               }
 #pragma unroll
-              for (int i = 0; i < 32; ++i) am = max(am, __float_as_uint(r[j][i]) & 0x7FFFFFFFu);
+              for (int c = 0; c < 16; ++c) {
+                float y0, y1;
+                unpack2(r[j][c], y0, y1);
+                am = fmaxf(am, fmaxf(fabsf(y0), fabsf(y1)));
+              }
             }
-            const int k = scale_exp_from_amax(am);
+            if (tr_w) CH_TRACE_AT(5, trn);
+            const int k = scale_exp_from_amax(__float_as_uint(am));
             const int dslot = cs.dst_slot0 + cg;
             rsexp[dslot * 128 + rrow] = (int8_t)k;
             const float as = pow2f(-k);
+            const f32x2 as2 = pack2(as, as);
             float hi[32], lo[32];
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
-              for (int c = 0; c < 16; ++c)
-                f16_split_pack(r[j][2 * c] * as, r[j][2 * c + 1] * as, hi[16 * j + c], lo[16 * j + c]);
+              for (int c = 0; c < 16; ++c) {
+                // (y0, y1) * 2^-k -> packed fp16 pair hi, and lo = fp16(y * 2^-k - hi)   (f16_split_pack on pairs)
+                const f32x2 ys = mul2(r[j][c], as2);
+                float y0, y1;
+                unpack2(ys, y0, y1);
+                const __half2 hh = __floats2half2_rn(y0, y1);
+                const float2 hf = __half22float2(hh);
+                float l0, l1;
+                unpack2(sub2(ys, pack2(hf.x, hf.y)), l0, l1);
+                const __half2 ll = __floats2half2_rn(l0, l1);
+                hi[16 * j + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
+                lo[16 * j + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&ll));
+              }
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(CH_ACT_COL0 + dslot * 64);
+            if (tr_w) CH_TRACE_AT(6, trn);
             tmem_st_32x32(ta, hi);
             tmem_st_32x32(ta + 32, lo);
             tmem_st_wait();
@@ -367,11 +489,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&aready[dslot]);
           }
-          if (warp == CH_EPI_WARP0 && trc && trn < 1024) trc[3 * 1024 + trn - 1] = clock64();
+          if (tr_w) CH_TRACE_AT(3, trn);
         }
+        CH_TRACE_NEXT();
       }
     }
-    p.epi.flush(est);
+    if (p.store_mode != 1) p.epi.flush(est);
   }
 
   tc_fence_before();
@@ -388,8 +511,31 @@ int launch_chain(const ChainParams& p, cudaStream_t s, int num_sms) {
     DCCN_CUDA_OK(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
     attr_set = true;
   }
+  // flatten the (stage, n-subtile, k-block) nest of one tile
+  ChainSched sc;
+  memset(&sc, 0, sizeof(sc));
+  for (int st = 0; st < p.nst; ++st) {
+    const ChainStage& cs = p.st[st];
+    DCCN_CHECK(cs.nkb >= 1 && cs.slot0 >= 0 && cs.slot0 + cs.nkb <= kChainSlots, "chain stage %d: k-blocks do not fit the slots", st);
+    DCCN_CHECK(cs.dst_slot0 < 0 || (cs.nsub == 1 && cs.dst_slot0 + 2 <= kChainSlots && cs.bias), "chain stage %d: bad destination", st);
+    for (int sub = 0; sub < cs.nsub; ++sub)
+      for (int kb = 0; kb < cs.nkb; ++kb) {
+        DCCN_CHECK(sc.nsteps < kChainMaxSteps, "chain has more than %d k-block steps", kChainMaxSteps);
+        ChainStep& t = sc.steps[sc.nsteps++];
+        t.stage = (uint8_t)st;
+        t.kb = (uint8_t)kb;
+        t.sub = (uint8_t)sub;
+        t.slot = (uint8_t)(cs.slot0 + kb);
+        t.flags = (uint8_t)((kb == 0 ? CS_FIRST : 0) | (kb == cs.nkb - 1 ? CS_LAST : 0) | (sub == 0 ? CS_READY : 0) |
+                            (sub == 0 && cs.src >= 0 ? CS_HBM : 0));
+      }
+  }
+  DCCN_CHECK(sc.nsteps >= 1 && p.st[p.nst - 1].dst_slot0 < 0 && p.st[p.nst - 1].src < 0,
+             "the last chain stage reads the operand slots and writes to HBM");
+  DCCN_CHECK(p.epi.act == 0, "chained kernels end in a linear layer");
+  sc.steps[sc.nsteps - 1].flags |= CS_TILE_END;
   const int m_tiles = (p.M + CH_BM - 1) / CH_BM;
-  chain_tc_kernel<<<m_tiles < num_sms ? m_tiles : num_sms, CH_THREADS, CH_SMEM_BYTES, s>>>(p);
+  chain_tc_kernel<<<m_tiles < num_sms ? m_tiles : num_sms, CH_THREADS, CH_SMEM_BYTES, s>>>(p, sc);
   DCCN_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -106,7 +106,10 @@ struct TcCfg {
   static constexpr int PLANES = SPLIT ? 2 : 1;
   static constexpr int STAGE_BYTES = (DEC ? 0 : (ATM ? A_BYTES : PLANES * A_BYTES)) + PLANES * B_BYTES;
   static constexpr int B_OFF = DEC ? 0 : (ATM ? A_BYTES : PLANES * A_BYTES);   // offset of B_hi inside a stage
-  static constexpr int SA = DEC ? 4 : 0;                           // slots of the separate raw-A ring
+#ifndef DCCN_TC_SA
+#define DCCN_TC_SA 4             // experiment knob: slots of the raw-A ring (2 = one fp16-form k-block)
+#endif
+  static constexpr int SA = DEC ? DCCN_TC_SA : 0;                  // slots of the separate raw-A ring
   static constexpr int A_RING_BYTES = SA * A_BYTES;
   static constexpr int A_TMEM_COLS = ATM ? 64 : 0;                 // per stage: 32 hi + 32 lo columns
   static constexpr int TX_BYTES = A_BYTES + PLANES * B_BYTES;   // bytes TMA delivers per stage
@@ -117,7 +120,11 @@ struct TcCfg {
   static constexpr int PATCH_BYTES = 4 * CG * 4096;                // store-transpose patches of the epilogue warps
   static constexpr int STAGES_RAW = (SMEM_BUDGET - A_RING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 8;
-  static constexpr int STAGES = imin(imin(STAGES_RAW, STAGES_TM), 8);
+#ifndef DCCN_TC_STAGE_CAP
+#define DCCN_TC_STAGE_CAP 3      // 4 stages of the fp16 form = 226 KB of shared memory = NO L1 data cache left (228 KB unified): bias loads, the
+                                 // phase equaliser's f rows and register spills of the epilogue warps then pay L2 latency (measured: 3.31 -> 2.99 ms per pass)
+#endif
+  static constexpr int STAGES = imin(imin(STAGES_RAW, STAGES_TM), DCCN_TC_STAGE_CAP);
   static constexpr int A_TMEM_COL0 = 2 * BN;                       // A staging columns follow the accumulators
   static constexpr int TMEM_COLS = pow2_at_least(2 * BN + STAGES * A_TMEM_COLS);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + A_RING_BYTES + PATCH_BYTES + 1024 /*align*/ + 512 /*barriers*/;

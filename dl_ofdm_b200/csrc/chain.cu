@@ -30,7 +30,7 @@ constexpr int CH_BM = 128, CH_BN = 128, CH_KB = 64;
 constexpr int CH_STAGES = 3;
 constexpr int CH_W_PLANE = CH_BN * CH_KB * 2;      // 16 KB: one fp16 plane of a weight stage
 constexpr int CH_W_STAGE = 2 * CH_W_PLANE;         // 32 KB
-constexpr int CH_SA = 4;                           // raw-A ring slots
+constexpr int CH_SA = 3;                           // raw-A ring slots (a k-block is two boxes; 3 leaves room for 8 KB patches)
 constexpr int CH_A_BYTES = CH_BM * 32 * 4;         // 16 KB: [128 x 32 fp32]
 // 16 warps = 4 warpgroups, so that setmaxnreg can move registers between the roles: warps 0..3 = weight producer, MMA issuer,
 // raw-A producer, (idle); warps 4..7 = splitters; warps 8..15 = epilogue.  An SM sub-partition holds 16 K registers, i.e.
@@ -39,8 +39,9 @@ constexpr int CH_A_BYTES = CH_BM * 32 * 4;         // 16 KB: [128 x 32 fp32]
 constexpr int CH_EPI_WARP0 = 8;
 constexpr int CH_THREADS = 512;
 constexpr int CH_REGS_CTRL = 80, CH_REGS_SPLIT = 112, CH_REGS_EPI = 160;   // 128 * (56 + 104 + 2 * 176) = 65 536
-constexpr int CH_PATCH_BYTES = 8 * 4096;
-constexpr int CH_SMALL_BYTES = 1024;               // row-scale exponents (4 x 128 int8) + barriers + TMEM pointer
+constexpr int CH_PATCH_BYTES = 8 * 8192;           // per epilogue warp: both [32 x 32] fp32 blocks of its 64 columns
+constexpr int CH_BIAS_FLOATS = 128 * (kChainMaxStages - 1) + 256;   // intermediate stages: 128 each; last stage: up to 256
+constexpr int CH_SMALL_BYTES = CH_BIAS_FLOATS * 4 + 1024;   // biases, row-scale exponents (4 x 128 int8), barriers, TMEM pointer
 constexpr int CH_SMEM_BYTES = CH_STAGES * CH_W_STAGE + CH_SA * CH_A_BYTES + CH_PATCH_BYTES + CH_SMALL_BYTES + 1024;
 constexpr int CH_ACT_COL0 = 2 * CH_BN;             // first operand-slot column
 constexpr int CH_TMEM_COLS = 512;
@@ -55,31 +56,8 @@ DCCN_DEVINL int scale_exp_from_amax(unsigned bits) {
 }
 DCCN_DEVINL float pow2f(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
 
-// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot, each lane rounded exactly
-// like its scalar form).  The epilogue warps are issue-bound (two of them share a scheduler with a splitter warp), so
-// the per-k-block partial-sum adds and the stage finalisation run on pairs.
-typedef unsigned long long f32x2;
-DCCN_DEVINL f32x2 pack2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-DCCN_DEVINL void unpack2(f32x2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-DCCN_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-DCCN_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-DCCN_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
+// (the epilogue warps are issue-bound -- two of them share a scheduler with a splitter warp -- so the per-k-block partial-sum
+// adds and the stage finalisation run on packed fp32 pairs: pack2 / fma2 / mul2 / sub2, common.cuh)
 
 // The (stage, n-subtile, k-block) nest of one tile, flattened on the host (launch_chain): every role walks the same list.
 struct ChainStep {
@@ -98,45 +76,14 @@ struct ChainSched {
   ChainStep steps[kChainMaxSteps];
 };
 
-// 32 lanes x 32 columns block of the last stage: bias, running max |y| of the destination buffer, then out through the
-// warp's 4 KB patch -- as bulk tensor stores (store_mode 0, EpiStore's path without the activation switch: the chains end in
-// linear layers) or as coalesced st.global (store_mode 1; measured slower, kept as the comparison)
-template <bool STG>
-DCCN_DEVINL void final_block(const EpiStore& e, EpiStore::State& st, int row0, int lane, int col0, float (&v)[32],
-                             uint32_t patch) {
-  if (col0 >= e.N || row0 >= e.M) return;
-  if (e.bias) {
-    const float4* bp = reinterpret_cast<const float4*>(e.bias + col0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float4 b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = __ldg(bp + 4 * h + i);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[16 * h + 4 * i + 0] += b[i].x;
-        v[16 * h + 4 * i + 1] += b[i].y;
-        v[16 * h + 4 * i + 2] += b[i].z;
-        v[16 * h + 4 * i + 3] += b[i].w;
-      }
-    }
-  }
-  if (e.amax) amax_update_warp<32>(e.amax, v, row0 + lane < e.M, st.amax_seen);
-  if (STG) {
-    store_block_warp(e.out.p0 + e.out.col_off + col0, e.out.ld, row0, e.M, lane, v, patch);
-    if (e.aux) store_block_warp(e.aux + col0, e.aux_ld, row0, e.M, lane, v, patch);
-  } else {
-    store_block_tma(&e.tm_out, col0, e.aux ? &e.tm_aux : nullptr, col0, row0, lane, v, patch);
-  }
-}
-
 __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_constant__ ChainParams p,
                                                                   const __grid_constant__ ChainSched sc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem + CH_STAGES * CH_W_STAGE;
   uint8_t* patches = a_ring + CH_SA * CH_A_BYTES;
-  int8_t* rsexp = reinterpret_cast<int8_t*>(patches + CH_PATCH_BYTES);       // [kChainSlots][128]
+  float* sbias = reinterpret_cast<float*>(patches + CH_PATCH_BYTES);         // stage s < last: [128] at s * 128; last: [256]
+  int8_t* rsexp = reinterpret_cast<int8_t*>(sbias + CH_BIAS_FLOATS);         // [kChainSlots][128]
   uint64_t* full = reinterpret_cast<uint64_t*>(rsexp + kChainSlots * 128);   // [STAGES] weight planes landed
   uint64_t* empty = full + CH_STAGES;     // [STAGES] MMAs of the k-block retired: weight stage free + accumulator ready
   uint64_t* aready = empty + CH_STAGES;   // [kChainSlots] operand slot written (4 warps: splitters or one column group)
@@ -172,6 +119,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
       tma_prefetch_desc(&p.tmW[i][0]);
       tma_prefetch_desc(&p.tmW[i][1]);
     }
+  }
+  // the biases of every stage, once per CTA (the epilogue warps read them every tile: broadcast ld.shared instead of 16
+  // global loads per thread and stage)
+  for (int i = threadIdx.x; i < CH_BIAS_FLOATS; i += CH_THREADS) {
+    const int st = i < 128 * (kChainMaxStages - 1) ? i >> 7 : p.nst - 1;
+    const int c = i < 128 * (kChainMaxStages - 1) ? i & 127 : i - 128 * (kChainMaxStages - 1);
+    float b = 0.f;
+    if (st < p.nst - 1) {
+      if (p.st[st].bias) b = __ldg(p.st[st].bias + c);
+    } else if (i >= 128 * (kChainMaxStages - 1) && p.epi.bias && c < ((p.epi.N + 127) & ~127)) {
+      b = __ldg(p.epi.bias + c);
+    }
+    sbias[i] = b;
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -371,7 +331,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
 #else
     constexpr bool tr_w = false;
 #endif
-    const uint32_t patch = smem_u32(patches + (warp - CH_EPI_WARP0) * 4096);
+    const uint32_t patch = smem_u32(patches + (warp - CH_EPI_WARP0) * 8192);
     EpiStore::State est;
     int acc = 0;
     int estage = 0;
@@ -423,19 +383,50 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
           if (cs.dst_slot0 < 0) {
             const int row_base = tile * CH_BM + q * 32;
             const int col = stp.sub * CH_BN + cg * 64;
+            if (col < p.epi.N && row_base < p.epi.M) {          // warp-uniform
+              const float4* bp = reinterpret_cast<const float4*>(sbias + 128 * (kChainMaxStages - 1) + col);
+              // both [32 x 32] blocks go into the warp's 8 KB patch (128B-swizzle pattern, conflict-free), ONE proxy fence, then
+              // the bulk tensor stores (plain coalesced st.global from the patch measured slower: 0.26 vs 0.22 ms front chain)
+              if (lane == 0) tma_store_wait_read();              // the previous tile's blocks have left the patch
+              __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float v[32];
+              for (int j = 0; j < 2; ++j) {
+                float v[32];
 #pragma unroll
-              for (int c = 0; c < 16; ++c) unpack2(mul2(r[j][c], o2), v[2 * c], v[2 * c + 1]);
-              if (p.store_mode == 1) final_block<true>(p.epi, est, row_base, lane, col + 32 * j, v, patch);
-              else final_block<false>(p.epi, est, row_base, lane, col + 32 * j, v, patch);
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b = bp[j * 8 + c];
+                  unpack2(fma2(r[j][2 * c], o2, pack2(b.x, b.y)), v[4 * c], v[4 * c + 1]);
+                  unpack2(fma2(r[j][2 * c + 1], o2, pack2(b.z, b.w)), v[4 * c + 2], v[4 * c + 3]);
+                }
+                // (N = 160: the second block of the last column group is past N -- not recorded, not stored)
+                if (p.epi.amax && col + 32 * j < p.epi.N)
+                  amax_update_warp<32>(p.epi.amax, v, row_base + lane < p.epi.M, est.amax_seen);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const uint32_t a = patch + (uint32_t)(j * 4096) + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4);
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                               "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                               : "memory");
+                }
+              }
+              fence_proxy_async();                               // generic-proxy writes -> visible to the TMA engine
+              __syncwarp();
+              if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  if (col + 32 * j < p.epi.N) {                  // (columns past N inside a block are clipped by the tensor map)
+                    tma_store_2d(&p.epi.tm_out, patch + j * 4096, col + 32 * j, row_base);
+                    if (p.epi.aux) tma_store_2d(&p.epi.tm_aux, patch + j * 4096, col + 32 * j, row_base);
+                  }
+                }
+                tma_store_commit();
+              }
             }
           } else {
             // intermediate layer: y = r * o_sc + bias (one fp32 rounding: the product with the power-of-two scale is exact --
             // the value the layer-by-layer schedule stored), then the fp16 (hi, lo) pair of y * 2^-k with k chosen from this
             // row's 64 values -- the next stage's k-block `cg`
-            const float4* bp = reinterpret_cast<const float4*>(cs.bias + cg * 64);
+            const float4* bp = reinterpret_cast<const float4*>(sbias + stp.stage * 128 + cg * 64);
             float am = 0.f;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -443,7 +434,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
               for (int h = 0; h < 2; ++h) {
                 float4 b[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) b[c] = __ldg(bp + j * 8 + h * 4 + c);
+                for (int c = 0; c < 4; ++c) b[c] = bp[j * 8 + h * 4 + c];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   r[j][8 * h + 2 * c] = fma2(r[j][8 * h + 2 * c], o2, pack2(b[c].x, b[c].y));
@@ -494,7 +485,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         CH_TRACE_NEXT();
       }
     }
-    if (p.store_mode != 1) p.epi.flush(est);
+    p.epi.flush(est);
   }
 
   tc_fence_before();

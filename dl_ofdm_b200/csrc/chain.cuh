@@ -34,7 +34,6 @@ struct alignas(64) ChainParams {
   int nst;
   int M;
   int small_first;
-  int store_mode;     // last stage: 0 = bulk tensor stores from the patch (EpiStore::run_warp), 1 = coalesced st.global from the patch
   long long* trace;   // measurement aid (tools/chain_trace.py): CTA 0 records clock64() at its hand-off points, or nullptr
 };
 

@@ -364,6 +364,32 @@ DCCN_DEVINL void f16_split_pack(float v0, float v1, float& hi, float& lo) {
   lo = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2: two IEEE fp32 operations per issue slot, each lane rounded exactly like its
+// scalar form).  A pair is a 64-bit register; a scalar operand built as pack2(x, x) is folded into the instruction's
+// broadcast form, a pair of adjacent kernel-parameter words into its uniform-register form.
+typedef unsigned long long f32x2;
+DCCN_DEVINL f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+DCCN_DEVINL void unpack2(f32x2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+DCCN_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+DCCN_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+DCCN_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 DCCN_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile(

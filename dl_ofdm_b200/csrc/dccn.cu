@@ -875,7 +875,6 @@ static int chain_finish(dccn_handle* h, int slot, ChainParams& p, cudaStream_t s
   if ((rc = make_tmap(&e.tm_out, e.out.p0 + e.out.col_off, e.M, e.N, e.out.ld, 32))) return rc;
   if (e.aux && (rc = make_tmap(&e.tm_aux, e.aux, e.M, e.N, e.aux_ld, 32))) return rc;
   p.small_first = h->small_first ? 1 : 0;
-  p.store_mode = (h->chain_stg && e.N % 32 == 0) ? 1 : 0;
   LaunchScope ls(h, slot, s);
   return launch_chain(p, s, h->num_sms);
 }
@@ -1316,7 +1315,6 @@ int dccn_create(const dccn_cfg* cfg, dccn_handle** out) {
   if (const char* e = getenv("DCCN_BAND")) h->band_skip = atoi(e);
   if (const char* e = getenv("DCCN_F16X3")) h->f16x3 = atoi(e);   // 0: tf32 hi/lo pairs (the round-1 form)
   if (const char* e = getenv("DCCN_CHAIN")) h->chain = atoi(e);   // 0: every per-symbol layer through HBM
-  if (const char* e = getenv("DCCN_CHAIN_STG")) h->chain_stg = atoi(e);
   if (const char* e = getenv("DCCN_TX_V2")) h->tx_v2 = atoi(e);
   if (const char* e = getenv("DCCN_BN192")) h->bn192 = atoi(e);
   if (const char* e = getenv("DCCN_FOLD")) if (atoi(e)) h->default_flags |= DCCN_FWD_FOLDED;

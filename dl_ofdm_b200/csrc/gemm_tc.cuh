@@ -114,8 +114,18 @@ struct TcCfg {
   static constexpr int A_TMEM_COLS = ATM ? 64 : 0;                 // per stage: 32 hi + 32 lo columns
   static constexpr int TX_BYTES = A_BYTES + PLANES * B_BYTES;   // bytes TMA delivers per stage
   static constexpr int SPLIT_WARPS = SPLIT ? 4 : 0;
-  static constexpr int APROD_WARP = 2 + SPLIT_WARPS;               // DEC: producer warp of the A ring
-  static constexpr int EPI_WARP0 = 2 + SPLIT_WARPS + (DEC ? 1 : 0);
+  // REGBAL (DEC with 8 epilogue warps): 16 warps in four role-pure warpgroups -- 0..3 = producer, MMA issuer, A-ring producer,
+  // (idle); 4..7 = splitters; 8..15 = epilogue -- so that setmaxnreg can move registers to the epilogue warps
+#ifndef DCCN_TC_REGBAL
+#define DCCN_TC_REGBAL 0      // OFF: see below
+#endif
+  static constexpr bool REGBAL = DCCN_TC_REGBAL && DEC && CG == 2;
+#ifndef DCCN_TC_REGS_EPI
+#define DCCN_TC_REGS_EPI 168
+#endif
+  static constexpr int REGS_CTRL = 72, REGS_SPLIT = 104, REGS_EPI = DCCN_TC_REGS_EPI;   // 128 * (72 + 104 + 2 * 168) = 65 536
+  static constexpr int APROD_WARP = REGBAL ? 2 : 2 + SPLIT_WARPS;  // DEC: producer warp of the A ring
+  static constexpr int EPI_WARP0 = REGBAL ? 8 : 2 + SPLIT_WARPS + (DEC ? 1 : 0);
   static constexpr int SMEM_BUDGET = 193 * 1024;                   // operand rings; + 4 KB per epilogue warp below
   static constexpr int PATCH_BYTES = 4 * CG * 4096;                // store-transpose patches of the epilogue warps
   static constexpr int STAGES_RAW = (SMEM_BUDGET - A_RING_BYTES) / STAGE_BYTES;
@@ -290,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   };
 
-  if (warp == 0) {
+  auto role_producer = [&]() {
     // =============================== TMA producer ===============================
     // The WHOLE warp runs the loop so that addresses / coordinates stay warp-uniform (uniform
     // registers feed UTMALDG directly); one elected lane issues.  A single-lane branch makes the
@@ -322,7 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-  } else if (warp == 1) {
+  };
+  auto role_mma = [&]() {
     // =============================== MMA issuer =================================
     if (crank == 0) {   // whole warp, warp-uniform control flow; one elected lane issues
       constexpr uint32_t idesc = F16 ? umma_idesc_f16(BN, 128) : umma_idesc_tf32(BN, PAIR ? 256 : 128);
@@ -434,7 +445,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-  } else if (DEC && warp == C::APROD_WARP) {
+  };
+  auto role_aprod = [&]() {
     // =============================== A-ring producer (DEC) ======================
     int sa = 0;
     uint32_t pa = 0;
@@ -459,7 +471,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-  } else if (DEC && warp < C::APROD_WARP) {
+  };
+  auto role_split_dec = [&]() {
     // =============================== A-operand splitters (DEC) ==================
     // read the raw tile early (frees the A slot at once), keep hi/lo in registers, and write
     // them to the TMEM staging slot the moment the MMAs that used it have retired.
@@ -552,7 +565,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-  } else if (SPLIT && warp < C::EPI_WARP0) {
+  };
+  auto role_split_smem = [&]() {
     // =============================== A-operand splitters ========================
     // fp32 tile (as landed by TMA, swizzled) -> hi in place, lo at the same offsets of the
     // second buffer.  Elementwise, so the swizzle pattern needs no decoding.
@@ -617,7 +631,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-  } else {
+  };
+  auto role_epilogue = [&]() {
     // =============================== epilogue warps =============================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int cg = (warp - C::EPI_WARP0) >> 2; // column group
@@ -700,6 +715,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(1);
     }
     epi.flush(st);
+  };
+  // No load may still be in flight when a warp gives registers away (setmaxnreg.dec below): the prologue's amax load is issued
+  // by every warp, also by those whose role never reads the scale; its late write-back would land in a register that by then
+  // belongs to an epilogue warp (seen as run-to-run differences in ~0.03 % of the outputs, 20 x more without an L1).
+  asm volatile("" ::"f"(a_scale), "f"(out_scale), "r"(tmem_base) : "memory");
+  if constexpr (C::REGBAL) {
+    // warpgroup-aligned roles + setmaxnreg: the epilogue warps (64 accumulators + 32 loaded values + epilogue arithmetic) spilled
+    // at the 128 registers a 16-warp CTA gets per thread; the producer-side warpgroups hand theirs over (csrc/chain.cu)
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
+      if (warp == 0) role_producer();
+      else if (warp == 1) role_mma();
+      else if (warp == C::APROD_WARP) role_aprod();
+    } else if (warp < 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
+      role_split_dec();
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));
+      role_epilogue();
+    }
+  } else {
+    if (warp == 0) role_producer();
+    else if (warp == 1) role_mma();
+    else if (DEC && warp == C::APROD_WARP) role_aprod();
+    else if (DEC && warp < C::APROD_WARP) role_split_dec();
+    else if (SPLIT && warp < C::EPI_WARP0) role_split_smem();
+    else role_epilogue();
   }
 
   tc_fence_before();

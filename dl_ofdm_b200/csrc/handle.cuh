@@ -101,7 +101,6 @@ struct dccn_handle {
   int tx_v2 = 1;       // 8 x 8 IDFT transmitter kernel for nfft = 64 (DCCN_TX_V2=0: the generic K-point DFT kernel)
   int32_t* d_txmap = nullptr;           // [S*K] subcarrier role map, rebuilt on the device by every dccn_tx_frames call
   int chain = 1;       // per-symbol layer runs of equalizer_ofdm as chained kernels (chain.cu; DCCN_CHAIN=0: layer by layer through HBM)
-  int chain_stg = 0;   // chained kernels: last stage stores with st.global from the patch instead of bulk tensor stores
   int f16x3 = 1;       // inference GEMMs of the parity mode through the fp16 hi/lo kind::f16 form (DCCN_F16X3=0: tf32 pairs)
   // monitor outputs requested for the NEXT forward (dccn_forward_monitors), consumed and cleared by it
   float* mon_snr_db = nullptr;          // [B] equalizer snr_db (model.py:464-475)

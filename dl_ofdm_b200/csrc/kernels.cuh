@@ -827,23 +827,16 @@ DCCN_DEVINL void head_emit(const EpiHead<NB, V1>& epi, typename EpiHead<NB, V1>:
       for (int q = 0; q < 2 * NB; q += 2) *reinterpret_cast<float2*>(sp + q) = make_float2(p[q], p[q + 1]);
     }
   }
-  unsigned y = 0u, hw = 0u;
-#pragma unroll
-  for (int k = 0; k < NB; ++k) hw |= ((hbits >> k) & 1u) << (8 * k);
+  // decision bit k -> byte k (0 / 1) and label byte k -> bit k, each with one multiply: bit k times (1 + 2^7 + 2^14 + 2^21) lands
+  // on bit 8k of byte k (every other copy falls between the byte LSBs); byte j's LSB times 2^(24 - 7j) lands on bit 24 + j
+  unsigned y = 0u;
+  const unsigned hw = (hbits * 0x00204081u) & 0x01010101u;
   if constexpr (NB == 4) {
     if (epi.hard) *reinterpret_cast<uint32_t*>(epi.hard + o0) = hw;
-    if (epi.bits) {
-      const uint32_t yw = __ldg(reinterpret_cast<const uint32_t*>(epi.bits + o0));
-#pragma unroll
-      for (int k = 0; k < NB; ++k) y |= ((yw >> (8 * k)) & 1u) << k;
-    }
+    if (epi.bits) y = ((__ldg(reinterpret_cast<const uint32_t*>(epi.bits + o0)) & 0x01010101u) * 0x01020408u) >> 24;
   } else if constexpr (NB == 2) {
     if (epi.hard) *reinterpret_cast<uint16_t*>(epi.hard + o0) = (uint16_t)hw;
-    if (epi.bits) {
-      const uint32_t yw = __ldg(reinterpret_cast<const uint16_t*>(epi.bits + o0));
-#pragma unroll
-      for (int k = 0; k < NB; ++k) y |= ((yw >> (8 * k)) & 1u) << k;
-    }
+    if (epi.bits) y = (((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(epi.bits + o0)) & 0x0101u) * 0x01020408u) >> 24;
   } else {
 #pragma unroll
     for (int k = 0; k < NB; ++k) {

@@ -133,6 +133,33 @@ def test_f16_form_chunk_invariance_full_size(libdccn, monkeypatch):
     assert np.array_equal(res[0][1], res[1][1])
 
 
+def test_run_to_run_determinism_full_size(libdccn, monkeypatch):
+    """The same 65 536-frame pass twice (persistent multi-tile kernels, every pipeline ring wrapping hundreds of times):
+    soft outputs, channel estimate and equaliser output must be bit-identical, with the chained per-symbol kernels and with
+    the layer-by-layer schedule.  (Regression test: a register-rebalancing experiment in the GEMM kernel -- setmaxnreg, see
+    gemm_tc.cuh DCCN_TC_REGBAL -- passed every parity test at small sizes and differed from run to run in 0.03 % of the
+    channel estimates at this size.)"""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(11)
+    nb, B = 4, 65536
+    w = orc.glorot_weights(rng, nb, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+    g = torch.Generator(device='cuda').manual_seed(12)
+    x = torch.randn((B, 7, 80, 2), generator=g, device='cuda') * 0.2
+    for chain in ('1', '0'):
+        monkeypatch.setenv('DCCN_CHAIN', chain)
+        m = DCCN(nbits=nb, equalizer=True, precision='parity')
+        m.load_weights(w)
+        outs = []
+        for _ in range(2):
+            o = m.forward(x, None, want_eq=True, want_chest=True)
+            torch.cuda.synchronize()
+            outs.append({k: o[k].clone() for k in ('soft', 'hard', 'eq', 'chest')})
+        for k in ('chest', 'eq', 'soft', 'hard'):
+            assert torch.equal(outs[0][k], outs[1][k]), (chain, k, int((outs[0][k] != outs[1][k]).sum()))
+        m.close()
+
+
 def test_packed_labels_host_entry(libdccn):
     """dccn_forward_host_begin_packed (labels 8 per byte) == dccn_forward_host_begin (one uint8 per label): same
     confusion matrix and loss, through both slots; ragged batch."""

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
         const unsigned* amax_in = p.st[stp.stage].amax_in;
         float a_scale = 1.f;
         if (amax_in) a_scale = pow2f(-scale_exp_from_amax(__ldg(amax_in)));
+        const f32x2 a_scale2 = pack2(a_scale, a_scale);
         float hi[32], lo[32];
 #pragma unroll
         for (int bx = 0; bx < 2; ++bx) {
@@ -289,8 +290,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
-            f16_split_pack(v.x * a_scale, v.y * a_scale, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
-            f16_split_pack(v.z * a_scale, v.w * a_scale, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
+            f16_split_pack_scaled(v.x, v.y, a_scale2, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
+            f16_split_pack_scaled(v.z, v.w, a_scale2, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
           }
           // the release must not overtake the loads still queued in the LSU (gemm_tc.cuh)
 #pragma unroll
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
                 const __half2 hh = __floats2half2_rn(y0, y1);
                 const float2 hf = __half22float2(hh);
                 float l0, l1;
-                unpack2(sub2(ys, pack2(hf.x, hf.y)), l0, l1);
+                unpack2(fma2(pack2(hf.x, hf.y), pack2(-1.f, -1.f), ys), l0, l1);   // y - hi, one rounding
                 const __half2 ll = __floats2half2_rn(l0, l1);
                 hi[16 * j + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
                 lo[16 * j + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&ll));

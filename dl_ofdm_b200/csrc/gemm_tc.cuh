@@ -38,6 +38,7 @@
 //   the tensor core already fills the other accumulator.  kc = 0 keeps the whole K in TMEM
 //   (DCCN_PREC_FAST, where operand rounding dominates anyway).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -479,6 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     int stage = 0, sa = 0;
     uint32_t phase = 0, pa = 0;
     const int r = (warp & 3) * 32 + lane;
+    const f32x2 a_scale2 = pack2(a_scale, a_scale);
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
       for (int kb = tk.kb0; kb < tk.kb1; ++kb) {
@@ -496,8 +498,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                 continue;
               }
               const float4 v = lds128(rowp + ((c ^ (r & 7)) << 4));   // undo the 128B swizzle: chunk c of row r
-              f16_split_pack(v.x * a_scale, v.y * a_scale, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
-              f16_split_pack(v.z * a_scale, v.w * a_scale, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
+              f16_split_pack_scaled(v.x, v.y, a_scale2, hi[16 * bx + 2 * c], lo[16 * bx + 2 * c]);
+              f16_split_pack_scaled(v.z, v.w, a_scale2, hi[16 * bx + 2 * c + 1], lo[16 * bx + 2 * c + 1]);
             }
 #pragma unroll
             for (int c = 0; c < 16; ++c) asm volatile("" : "+f"(hi[16 * bx + c]));   // loads done before the release (below)
@@ -642,7 +644,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     int estage = 0;                            // kc = 1: the smem-stage ring position of the chunk being drained
     uint32_t ephase = 0;
     const bool stage_signal = !PAIR && 2 * kb_per_chunk <= C::STAGES;
-    float r[C::NCH][32];
+    // plain-store epilogue: the accumulator columns live as fp32 PAIRS (FFMA2: the per-chunk adds take half the issue slots);
+    // the arithmetic-heavy fused epilogues keep the scalar form (the pair form cost them registers: 1.5 KB of spills)
+    constexpr bool kPairs = std::is_same<Epi, EpiStore>::value;
+    f32x2 r[kPairs ? C::NCH : 1][16];
+    float rf[kPairs ? 1 : C::NCH][32];
+    const f32x2 one2 = pack2(1.f, 1.f);
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileK tk = decode(tile);
       const int n_blk = tk.n_blk;
@@ -673,19 +680,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
         tc_fence_after();
         const uint32_t t0 =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * C::COLS_PER_GROUP);
+        if constexpr (kPairs) {
+          if (ch == 0) {                           // the tile's sum starts at +0 (one code path for every chunk below)
 #pragma unroll
-        for (int j = 0; j < C::NCH; ++j) {
-          float v[32];
-          if (DCCN_ABL(4)) {
+            for (int j = 0; j < C::NCH; ++j)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 1.f;
-          } else tmem_ld_32x32(t0 + j * 32, v);
-          if (ch == 0) {
+              for (int i = 0; i < 16; ++i) r[j][i] = 0ull;
+          }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[j][i] = v[i];
-          } else {
+          for (int j = 0; j < C::NCH; ++j) {
+            float v[32];
+            tmem_ld_32x32(t0 + j * 32, v);
+            // fp32 round-to-nearest adds of the K chunks, two per issue slot (v * 1 + r: one rounding, the value of the add)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[j][i] = __fadd_rn(r[j][i], v[i]);
+            for (int i = 0; i < 16; ++i) r[j][i] = fma2(pack2(v[2 * i], v[2 * i + 1]), one2, r[j][i]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < C::NCH; ++j) {
+            float v[32];
+            if (DCCN_ABL(4)) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 1.f;
+            } else tmem_ld_32x32(t0 + j * 32, v);
+            if (ch == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rf[j][i] = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rf[j][i] = __fadd_rn(rf[j][i], v[i]);
+            }
           }
         }
         tc_fence_before();
@@ -703,14 +727,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int j = 0; j < C::NCH; ++j) {
         if (warp == C::EPI_WARP0 && lane == 0 && j > 0) DCCN_TRACE_EV(1);
         const int col = n_blk * BN + cg * C::COLS_PER_GROUP + j * 32;
-        if constexpr (F16) {
+        if constexpr (kPairs) {
+          float y[32];
+          if constexpr (F16) {
+            const f32x2 os2 = pack2(out_scale, out_scale);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[j][i] *= out_scale;
+            for (int i = 0; i < 16; ++i) unpack2(mul2(r[j][i], os2), y[2 * i], y[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) unpack2(r[j][i], y[2 * i], y[2 * i + 1]);
+          }
+          epi.run_warp(st, row_base, lane, col, y, smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
+        } else {
+          if constexpr (F16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rf[j][i] *= out_scale;
+          }
+          if constexpr (Epi::kWarpStore)
+            epi.run_warp(st, row_base, lane, col, rf[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
+          else
+            epi.template run<32>(st, row, col, rf[j]);
         }
-        if constexpr (Epi::kWarpStore)
-          epi.run_warp(st, row_base, lane, col, r[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
-        else
-          epi.template run<32>(st, row, col, r[j]);
       }
       if (warp == C::EPI_WARP0 && lane == 0) DCCN_TRACE_EV(1);
     }

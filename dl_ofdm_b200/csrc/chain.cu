@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // timeline of CTA 0 (role r: trace[r * 1024 + i], i = k-block step counted from the kernel's start): 0 MMAs issued,
   // 1 drain starts (7: the epilogue warp reached the drain's wait), 2 drain done, 3 stage output finished,
-  // 4 splitter k-block staged, 5 / 6 intermediate stage: bias + amax done / fp16 pairs packed
+  // 4 splitter k-block staged, 5 / 6 intermediate stage: bias + amax done / fp16 pairs packed, 8 / 9 / 10 last stage: patch free /
+  // blocks written to the patch / proxy fence done
 #ifdef DCCN_CHAIN_TRACE   // tools/build_chain_trace.sh -> libdccn_chtrace.so; the product build carries no trace code
   long long* const trc = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr;
   int trn = 0;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
               // the bulk tensor stores (plain coalesced st.global from the patch measured slower: 0.26 vs 0.22 ms front chain)
               if (lane == 0) tma_store_wait_read();              // the previous tile's blocks have left the patch
               __syncwarp();
+              if (tr_w) CH_TRACE_AT(8, trn);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 float v[32];
@@ -410,8 +412,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
                                : "memory");
                 }
               }
+              if (tr_w) CH_TRACE_AT(9, trn);
               fence_proxy_async();                               // generic-proxy writes -> visible to the TMA engine
               __syncwarp();
+              if (tr_w) CH_TRACE_AT(10, trn);
               if (lane == 0) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {

@@ -760,16 +760,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   if constexpr (C::REGBAL) {
     // warpgroup-aligned roles + setmaxnreg: the epilogue warps (64 accumulators + 32 loaded values + epilogue arithmetic) spilled
     // at the 128 registers a 16-warp CTA gets per thread; the producer-side warpgroups hand theirs over (csrc/chain.cu)
+    // DCCN_TC_REGBAL_MODE (experiments on the non-determinism): 1 = dec + inc, 2 = role layout only (no setmaxnreg),
+    // 3 = dec only (epilogue warps stay at 128)
+#ifndef DCCN_TC_REGBAL_MODE
+#define DCCN_TC_REGBAL_MODE 1
+#endif
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
+      if (DCCN_TC_REGBAL_MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
       if (warp == 0) role_producer();
       else if (warp == 1) role_mma();
       else if (warp == C::APROD_WARP) role_aprod();
     } else if (warp < 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
+      if (DCCN_TC_REGBAL_MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
       role_split_dec();
     } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));
+      if (DCCN_TC_REGBAL_MODE == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));
       role_epilogue();
     }
   } else {

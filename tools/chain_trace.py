@@ -25,7 +25,7 @@ x, bits = tp._config3_frames(m, 65536, 15.0, seed=4)
 for _ in range(2):
     m.forward(x, bits)
 torch.cuda.synchronize()
-bufs = [torch.zeros(8 * 1024, dtype=torch.int64, device='cuda') for _ in range(2)]
+bufs = [torch.zeros(11 * 1024, dtype=torch.int64, device='cuda') for _ in range(2)]
 for i in range(2):
     lib.dccn_debug_chain_trace(i, C.c_void_p(bufs[i].data_ptr()))
 m.forward(x, bits)
@@ -33,17 +33,18 @@ torch.cuda.synchronize()
 for i in range(2):
     lib.dccn_debug_chain_trace(i, None)
 for name, buf, steps in (('front', bufs[0], 5), ('tail', bufs[1], 11)):
-    t = buf.cpu().numpy().reshape(8, 1024)
+    t = buf.cpu().numpy().reshape(11, 1024)
     t0 = t[0, 0]
     print('== %s chain, CTA 0: cycles since the first MMA issue; %d k-block steps per tile' % (name, steps))
-    print('%5s %9s %9s %9s %9s %9s %9s %9s   %s' % ('step', 'mma', 'at_wait', 'drain0', 'drain1', 'bias', 'pack', 'final', 'd(mma)'))
+    print('%5s %9s %9s %9s %9s %9s %9s %9s   %s' % ('step', 'mma', 'at_wait', 'drain0', 'drain1', 'bias', 'pack', 'final', 'd(mma)') + '   last stage: patch free / written / fenced')
     for k in range(3 * steps + 2):
         if t[0, k] == 0:
             break
         fin = t[3, k] - t0 if t[3, k] else -1
         print('%5d %9d %9d %9d %9d %9d %9d %9d   %6d%s' % (k, t[0, k] - t0, t[7, k] - t0, t[1, k] - t0, t[2, k] - t0,
                                                      t[5, k] - t0 if t[5, k] else -1, t[6, k] - t0 if t[6, k] else -1, fin,
-                                               t[0, k] - t[0, k - 1] if k else 0, '   <- tile' if k % steps == 0 else ''))
+                                               t[0, k] - t[0, k - 1] if k else 0, '   <- tile' if k % steps == 0 else '') +
+              ('   %d / %d / %d' % (t[8, k] - t0, t[9, k] - t0, t[10, k] - t0) if t[8, k] else ''))
     sp = t[4][t[4] > 0][:12] - t0
     print('splitter k-blocks staged at', sp.tolist())
 m.close()

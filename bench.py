@@ -246,6 +246,9 @@ def workload_config(args, frames_per_step, passes_per_step=1):
             'frames_per_step_per_gpu': frames_per_step * passes_per_step, 'frames_per_pass': frames_per_step,
             'passes_per_step': passes_per_step, 'nbits': NBITS, 'precision': args.precision,
             'chunk_frames': args.chunk, 'weights': WEIGHTS_DESC,
+            'schedule': ('layer by layer; the per-symbol runs dense -> conv3d and conv3d_3 | conv3d_2 -> dense_5 of equalizer_ofdm '
+                         'as one chained kernel each (same per-layer fp32 rounding, bit-identical outputs; DCCN_CHAIN=0 disables)'
+                         if os.environ.get('DCCN_CHAIN', '1') != '0' else 'layer by layer, every layer through HBM'),
             'parallelism': 'grid cells sharded, 1 all-reduce of the confusion matrix',
             'l2': ('inputs per pass (%.0f MB) exceed the 126 MB L2' % (frames_per_step * 4480 / 1e6)
                    if args.impl == 'b200' else 'n/a (CPU arm: a bounded %d-frame sample of the workload per step)' % frames_per_step)}

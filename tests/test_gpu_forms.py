@@ -133,6 +133,45 @@ def test_f16_form_chunk_invariance_full_size(libdccn, monkeypatch):
     assert np.array_equal(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize('cp,nb,B,want_eq', [(True, 4, 900, True), (False, 2, 333, True), (True, 1, 128, False), (True, 4, 4099, False)])
+def test_chained_kernels_equal_layer_by_layer(libdccn, trained_dev, monkeypatch, cp, nb, B, want_eq):
+    """csrc/chain.cu keeps the layer-by-layer arithmetic (same fp32 sums, same order, bias in fp32, then the fp16 split): the
+    chained schedule must reproduce the layer-by-layer one -- soft outputs to 2e-7 (in practice bit for bit; the per-row
+    operand scale can only differ from the per-pass one below fp16's normal range), identical hard bits, and the dense_5
+    side output (`eq`, the aux store of the tail chain) -- on ragged batches, both CP modes, several passes per call."""
+    from dl_ofdm_b200.engine import DCCN
+    from oracle import dccn_oracle as orc
+    rng = np.random.default_rng(21)
+    if cp and nb == 4:
+        w = trained_dev
+        from test_gpu_parity import _config3_frames
+        m0 = DCCN(nbits=nb, equalizer=True, precision='parity', chunk_frames=2048)
+        x, bits = _config3_frames(m0, B, 15.0, seed=5)
+        m0.close()
+    else:
+        w = orc.glorot_weights(rng, nb, use_cp=cp, equalizer=True, bias_scale=0.05, chest_bias=(0.6, -0.4))
+        x = torch.as_tensor((rng.standard_normal((B, 7, 80, 2)) * 0.2).astype(np.float32)).cuda()
+        bits = torch.as_tensor(rng.integers(0, 2, (B, 320, nb)).astype(np.uint8)).cuda()
+    outs = {}
+    for chain in ('0', '1'):
+        monkeypatch.setenv('DCCN_CHAIN', chain)
+        m = DCCN(nbits=nb, use_cp=cp, equalizer=True, precision='parity', chunk_frames=2048)
+        m.load_weights(w)
+        m.profile(True)
+        o = m.forward(x, bits, want_eq=want_eq)
+        torch.cuda.synchronize()
+        slots = set(m.profile_collect())
+        m.profile(False)
+        assert ('eq_chain_tail' in slots) == (chain == '1') and ('eq_dense5' in slots) == (chain == '0'), slots
+        outs[chain] = {k: o[k].clone() for k in (('soft', 'hard', 'conf', 'eq') if want_eq else ('soft', 'hard', 'conf'))}
+        m.close()
+    assert (outs['0']['soft'] - outs['1']['soft']).abs().max().item() <= 2e-7
+    assert torch.equal(outs['0']['hard'], outs['1']['hard']) and torch.equal(outs['0']['conf'], outs['1']['conf'])
+    if want_eq:
+        scale = max(1.0, outs['0']['eq'].abs().max().item())
+        assert (outs['0']['eq'] - outs['1']['eq']).abs().max().item() <= 2e-7 * scale
+
+
 def test_run_to_run_determinism_full_size(libdccn, monkeypatch):
     """The same 65 536-frame pass twice (persistent multi-tile kernels, every pipeline ring wrapping hundreds of times):
     soft outputs, channel estimate and equaliser output must be bit-identical, with the chained per-symbol kernels and with

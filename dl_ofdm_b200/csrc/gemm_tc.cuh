@@ -124,7 +124,10 @@ struct TcCfg {
 #ifndef DCCN_TC_REGS_EPI
 #define DCCN_TC_REGS_EPI 168
 #endif
-  static constexpr int REGS_CTRL = 72, REGS_SPLIT = 104, REGS_EPI = DCCN_TC_REGS_EPI;   // 128 * (72 + 104 + 2 * 168) = 65 536
+#ifndef DCCN_TC_REGS_CTRL
+#define DCCN_TC_REGS_CTRL 72
+#endif
+  static constexpr int REGS_CTRL = DCCN_TC_REGS_CTRL, REGS_SPLIT = 104, REGS_EPI = DCCN_TC_REGS_EPI;   // 128 * (72 + 104 + 2 * 168) = 65 536
   static constexpr int APROD_WARP = REGBAL ? 2 : 2 + SPLIT_WARPS;  // DEC: producer warp of the A ring
   static constexpr int EPI_WARP0 = REGBAL ? 8 : 2 + SPLIT_WARPS + (DEC ? 1 : 0);
   static constexpr int SMEM_BUDGET = 193 * 1024;                   // operand rings; + 4 KB per epilogue warp below
@@ -218,6 +221,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(emptyA + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifndef DCCN_TC_REGBAL_MODE
+#define DCCN_TC_REGBAL_MODE 1
+#endif
+  if constexpr (C::REGBAL && DCCN_TC_REGBAL_MODE == 4) {   // experiment: rebalance before anything else happens
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
+    else if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));
+  }
   DCCN_TRACE_DECL;
   DCCN_ABL_DECL;
   if constexpr (F16) {
@@ -762,16 +773,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     // at the 128 registers a 16-warp CTA gets per thread; the producer-side warpgroups hand theirs over (csrc/chain.cu)
     // DCCN_TC_REGBAL_MODE (experiments on the non-determinism): 1 = dec + inc, 2 = role layout only (no setmaxnreg),
     // 3 = dec only (epilogue warps stay at 128)
-#ifndef DCCN_TC_REGBAL_MODE
-#define DCCN_TC_REGBAL_MODE 1
-#endif
     if (warp < 4) {
-      if (DCCN_TC_REGBAL_MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
+      if (DCCN_TC_REGBAL_MODE != 2 && DCCN_TC_REGBAL_MODE != 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
       if (warp == 0) role_producer();
       else if (warp == 1) role_mma();
       else if (warp == C::APROD_WARP) role_aprod();
     } else if (warp < 8) {
-      if (DCCN_TC_REGBAL_MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
+      if (DCCN_TC_REGBAL_MODE != 2 && DCCN_TC_REGBAL_MODE != 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
       role_split_dec();
     } else {
       if (DCCN_TC_REGBAL_MODE == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));

@@ -521,6 +521,7 @@ def main():
                              'counts ALGORITHMIC flops (live taps, one pass)' % (
                                  'kind::f16' if f16_form else 'kind::tf32', pk['src'], pk['bf16_sustained'] or pk['bf16'],
                                  '' if f16_form else ' / 2', pk['bf16']),
+                'frac_vs_round1_peak': achieved / ((pk['bf16_sustained'] or pk['bf16']) / 2.0),   # round 1 quoted kind::tf32 = bf16 / 2
                 'kernel_share_of_step': dom_ms / tot_prof,
                 'mma_passes': passes,
                 'pipe_busy_frac_kernel': exec_tf / kind_peak,

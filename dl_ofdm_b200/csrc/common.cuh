@@ -171,6 +171,8 @@ DCCN_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, i
 DCCN_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING shared memory (the source may be reused)
 DCCN_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent bulk store group (two alternating source patches: the latest store reads the OTHER one)
+DCCN_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // multicast variant: the box is written to the same shared-memory offset of every CTA in
 // cta_mask and completes bytes on the mbarrier at the same offset in each of them

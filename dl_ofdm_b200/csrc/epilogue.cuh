@@ -82,9 +82,22 @@ DCCN_DEVINL void store_block_warp(float* base, int ld, int row0, int M, int lane
 // waits for global-store credits (measured: ~3.5 k clk per block with st.global while all 148 SMs drain their tiles at
 // once, during which the K-chunk drains of the next tile were stalled); rows >= M and columns >= N are clipped by
 // the tensor map.  `tm1` is an optional second destination of the same block (API side outputs).
+// DCCN_TC_PATCH_KB = 8: a warp owns TWO 4 KB patches and alternates between them (`tog`), so a block only waits for the
+// store issued two blocks ago.  Why: a 4 KB store queues in the TMA unit behind whatever loads the producer warps have in
+// flight (~160 KB in the ingress-bound layers = ~4 k clk), and with one patch every block of the tile epilogue sat out that
+// latency before it could overwrite the patch.
+#ifndef DCCN_TC_PATCH_KB
+#define DCCN_TC_PATCH_KB 4
+#endif
 DCCN_DEVINL void store_block_tma(const CUtensorMap* tm0, int col0_0, const CUtensorMap* tm1, int col0_1, int row0,
-                                 int lane, const float (&y)[32], uint32_t patch) {
-  if (lane == 0) tma_store_wait_read();        // the previous block has left the patch
+                                 int lane, const float (&y)[32], uint32_t patch, unsigned& tog) {
+  if (tog & 2u) {                              // bit 1: the kernel gave this warp two patches; bit 0: which one is next
+    patch += (tog & 1u) * 4096u;
+    tog ^= 1u;
+    if (lane == 0) tma_store_wait_read1();     // the store before last (same patch) has been read
+  } else {
+    if (lane == 0) tma_store_wait_read();      // the previous block has left the patch
+  }
   __syncwarp();
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -136,6 +149,7 @@ struct EpiStore {
   CUtensorMap tm_aux;  // same for aux
   struct State {
     unsigned amax_seen = 0u;   // see amax_update_warp
+    unsigned tog = 0u;         // store patches of this warp: bit 1 = two of them, bit 0 = which is next (store_block_tma)
   };
 
   template <int NC>
@@ -183,7 +197,7 @@ struct EpiStore {
       // columns >= N of a ragged tile hold bias-padding zeros + accumulated zeros (TMA zero-fills the weight rows)
       amax_update_warp<32>(amax, v, row0 + lane < M, st.amax_seen);
     }
-    store_block_tma(&tm_out, col0, aux ? &tm_aux : nullptr, col0, row0, lane, v, patch);
+    store_block_tma(&tm_out, col0, aux ? &tm_aux : nullptr, col0, row0, lane, v, patch, st.tog);
   }
   DCCN_DEVINL void flush(State&) const { tma_store_wait_read(); }   // shared memory outlives the last bulk store
 };
@@ -218,6 +232,7 @@ struct EpiPhaseEqT {
   struct State {
     float c_even[16];   // corr values of the even 32-column chunk, kept until the odd chunk completes a 32 x 32 block
     unsigned seen_eq = 0u, seen_corr = 0u;   // see amax_update_warp
+    unsigned tog = 0u;                       // store patches of this warp (store_block_tma)
   };
   static constexpr bool kWarpStore = true;
   static constexpr bool kPrefetch = true;
@@ -250,8 +265,11 @@ struct EpiPhaseEqT {
     float4 b4[8], f4[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) b4[i] = __ldg(bp + i);   // all loads in flight before the arithmetic
+#ifndef DCCN_PE_ABL
+#define DCCN_PE_ABL 0      // timing experiments only (results are garbage when != 0): 1 no f loads, 2 no corr store, 4 no amax, 8 no eq store
+#endif
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f4[i] = fp0[i];
+    for (int i = 0; i < 8; ++i) f4[i] = (DCCN_PE_ABL & 1) ? make_float4(1.f, 2.f, 3.f, 4.f) : fp0[i];
     float e[32], c[16];
     // the activation switch stays OUTSIDE the arithmetic loop (a per-element runtime branch makes the compiler serialise
     // load -> wait -> tanh per column, the EpiStore finding)
@@ -277,11 +295,11 @@ struct EpiPhaseEqT {
       e[i + 1] = ei;
       c[i / 2] = er * er + ei * ei;
     }
-    if (amax_eq) amax_update_warp<32>(amax_eq, e, ok, st.seen_eq);
-    if (amax_corr && corr.p0) amax_update_warp<16>(amax_corr, c, ok, st.seen_corr);
-    store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch);
-    if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch);
-    if (corr.p0) {
+    if (amax_eq && !(DCCN_PE_ABL & 4)) amax_update_warp<32>(amax_eq, e, ok, st.seen_eq);
+    if (amax_corr && corr.p0 && !(DCCN_PE_ABL & 4)) amax_update_warp<16>(amax_corr, c, ok, st.seen_corr);
+    if (!(DCCN_PE_ABL & 8)) store_block_tma(&tm_eq, eq_col(col0), nullptr, 0, row0, lane, e, patch, st.tog);
+    if (chest_out) store_block_tma(&tm_chest, col0, nullptr, 0, row0, lane, v, patch, st.tog);
+    if (corr.p0 && !(DCCN_PE_ABL & 2)) {
       // corr is half as wide as eq: the 16 values of an even 32-column chunk wait in registers for the 16 of the odd
       // chunk (a warp owns both: its column group is 64 wide), then leave as ONE 32 x 32 block through the TMA engine --
       // 64-byte per-thread st.global pieces from the epilogue warps backed the LSU up (the round-1 finding for eq itself)
@@ -295,7 +313,7 @@ struct EpiPhaseEqT {
           blk[i] = st.c_even[i];
           blk[16 + i] = c[i];
         }
-        store_block_tma(&tm_corr, corr_col((col0 - 32) / 2), nullptr, 0, row0, lane, blk, patch);
+        store_block_tma(&tm_corr, corr_col((col0 - 32) / 2), nullptr, 0, row0, lane, blk, patch, st.tog);
       } else if (ok) {
         store_act<16>(corr, row, corr_col(col0 / 2), c);      // lone even chunk at the ragged edge
       }

@@ -130,8 +130,9 @@ struct TcCfg {
   static constexpr int REGS_CTRL = DCCN_TC_REGS_CTRL, REGS_SPLIT = 104, REGS_EPI = DCCN_TC_REGS_EPI;   // 128 * (72 + 104 + 2 * 168) = 65 536
   static constexpr int APROD_WARP = REGBAL ? 2 : 2 + SPLIT_WARPS;  // DEC: producer warp of the A ring
   static constexpr int EPI_WARP0 = REGBAL ? 8 : 2 + SPLIT_WARPS + (DEC ? 1 : 0);
-  static constexpr int SMEM_BUDGET = 193 * 1024;                   // operand rings; + 4 KB per epilogue warp below
-  static constexpr int PATCH_BYTES = 4 * CG * 4096;                // store-transpose patches of the epilogue warps
+  static constexpr int PATCH_KB = (DCCN_TC_PATCH_KB == 8 && BN <= 128) ? 8 : 4;   // per epilogue warp: one or two 4 KB patches
+  static constexpr int PATCH_BYTES = 4 * CG * 1024 * PATCH_KB;     // store-transpose patches of the epilogue warps
+  static constexpr int SMEM_BUDGET = 225 * 1024 - PATCH_BYTES;     // operand rings (227 KB minus patches, alignment, barriers)
   static constexpr int STAGES_RAW = (SMEM_BUDGET - A_RING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_TM = ATM ? (512 - 2 * BN) / 64 : 8;
 #ifndef DCCN_TC_STAGE_CAP
@@ -650,6 +651,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int cg = (warp - C::EPI_WARP0) >> 2; // column group
     typename Epi::State st;
+    if constexpr (Epi::kWarpStore && C::PATCH_KB == 8) st.tog = 2u;   // two store patches per warp (store_block_tma)
     int acc = 0;
     uint32_t acc_phase = 0;
     int estage = 0;                            // kc = 1: the smem-stage ring position of the chunk being drained
@@ -748,14 +750,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll
             for (int i = 0; i < 16; ++i) unpack2(r[j][i], y[2 * i], y[2 * i + 1]);
           }
-          epi.run_warp(st, row_base, lane, col, y, smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
+          epi.run_warp(st, row_base, lane, col, y, smem_u32(patches + (warp - C::EPI_WARP0) * 1024 * C::PATCH_KB));
         } else {
           if constexpr (F16) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) rf[j][i] *= out_scale;
           }
           if constexpr (Epi::kWarpStore)
-            epi.run_warp(st, row_base, lane, col, rf[j], smem_u32(patches + (warp - C::EPI_WARP0) * 4096));
+            epi.run_warp(st, row_base, lane, col, rf[j], smem_u32(patches + (warp - C::EPI_WARP0) * 1024 * C::PATCH_KB));
           else
             epi.template run<32>(st, row, col, rf[j]);
         }

@@ -35,10 +35,10 @@ constexpr int CH_A_BYTES = CH_BM * 32 * 4;         // 16 KB: [128 x 32 fp32]
 // 16 warps = 4 warpgroups, so that setmaxnreg can move registers between the roles: warps 0..3 = weight producer, MMA issuer,
 // raw-A producer, (idle); warps 4..7 = splitters; warps 8..15 = epilogue.  An SM sub-partition holds 16 K registers, i.e.
 // 128 per thread at 4 warps each; the epilogue warps (64 accumulators + 32 freshly loaded values + the stage state) spilled
-// their ACCUMULATORS at 128 -- the two producer-side warpgroups hand them 48 registers per thread.
+// their ACCUMULATORS at 128 -- the control warpgroup (three busy warps that need < 56 registers) hands them 32 per thread.
 constexpr int CH_EPI_WARP0 = 8;
 constexpr int CH_THREADS = 512;
-constexpr int CH_REGS_CTRL = 80, CH_REGS_SPLIT = 112, CH_REGS_EPI = 160;   // 128 * (56 + 104 + 2 * 176) = 65 536
+constexpr int CH_REGS_CTRL = 56, CH_REGS_SPLIT = 128, CH_REGS_EPI = 160;   // 128 * (56 + 128 + 2 * 160) = 64 512 of 65 536
 constexpr int CH_PATCH_BYTES = 8 * 8192;           // per epilogue warp: both [32 x 32] fp32 blocks of its 64 columns
 constexpr int CH_BIAS_FLOATS = 128 * (kChainMaxStages - 1) + 256;   // intermediate stages: 128 each; last stage: up to 256
 constexpr int CH_SMALL_BYTES = CH_BIAS_FLOATS * 4 + 1024;   // biases, row-scale exponents (4 x 128 int8), barriers, TMEM pointer
@@ -268,7 +268,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(const __grid_co
     }
   }   // (warp 3 idles: it only fills the control warpgroup)
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_SPLIT));
+    // (the splitters keep their 128 registers: in gemm_tc_kernel a setmaxnreg.dec of the SPLITTER warpgroup -- and only that one --
+    // made full-size passes differ from run to run; here it never showed, but nothing is gained by it either)
+    static_assert(CH_REGS_SPLIT == 128, "splitter warpgroup keeps its launch-time registers");
     // =============================== splitters ======================================
     int sa = 0;
     uint32_t pa = 0;

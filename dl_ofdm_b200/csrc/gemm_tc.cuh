@@ -118,16 +118,16 @@ struct TcCfg {
   // REGBAL (DEC with 8 epilogue warps): 16 warps in four role-pure warpgroups -- 0..3 = producer, MMA issuer, A-ring producer,
   // (idle); 4..7 = splitters; 8..15 = epilogue -- so that setmaxnreg can move registers to the epilogue warps
 #ifndef DCCN_TC_REGBAL
-#define DCCN_TC_REGBAL 0      // OFF: see below
+#define DCCN_TC_REGBAL 1      // ON in mode 5 (only the control warpgroup gives registers away), see below
 #endif
   static constexpr bool REGBAL = DCCN_TC_REGBAL && DEC && CG == 2;
 #ifndef DCCN_TC_REGS_EPI
-#define DCCN_TC_REGS_EPI 168
+#define DCCN_TC_REGS_EPI 160
 #endif
 #ifndef DCCN_TC_REGS_CTRL
-#define DCCN_TC_REGS_CTRL 72
+#define DCCN_TC_REGS_CTRL 56
 #endif
-  static constexpr int REGS_CTRL = DCCN_TC_REGS_CTRL, REGS_SPLIT = 104, REGS_EPI = DCCN_TC_REGS_EPI;   // 128 * (72 + 104 + 2 * 168) = 65 536
+  static constexpr int REGS_CTRL = DCCN_TC_REGS_CTRL, REGS_SPLIT = 104, REGS_EPI = DCCN_TC_REGS_EPI;   // mode 5: 128 * (56 + 128 + 2 * 160) = 64 512
   static constexpr int APROD_WARP = REGBAL ? 2 : 2 + SPLIT_WARPS;  // DEC: producer warp of the A ring
   static constexpr int EPI_WARP0 = REGBAL ? 8 : 2 + SPLIT_WARPS + (DEC ? 1 : 0);
   static constexpr int PATCH_KB = (DCCN_TC_PATCH_KB == 8 && BN <= 128) ? 8 : 4;   // per epilogue warp: one or two 4 KB patches
@@ -223,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifndef DCCN_TC_REGBAL_MODE
-#define DCCN_TC_REGBAL_MODE 1
+#define DCCN_TC_REGBAL_MODE 5    // 5 = control warpgroup 128 -> 56, splitters untouched, epilogue warps 128 -> 160 (the deterministic one)
 #endif
   if constexpr (C::REGBAL && DCCN_TC_REGBAL_MODE == 4) {   // experiment: rebalance before anything else happens
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
@@ -776,15 +776,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
     // DCCN_TC_REGBAL_MODE (experiments on the non-determinism): 1 = dec + inc, 2 = role layout only (no setmaxnreg),
     // 3 = dec only (epilogue warps stay at 128)
     if (warp < 4) {
-      if (DCCN_TC_REGBAL_MODE != 2 && DCCN_TC_REGBAL_MODE != 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
+      if (DCCN_TC_REGBAL_MODE != 2 && DCCN_TC_REGBAL_MODE != 4 && DCCN_TC_REGBAL_MODE != 6) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_CTRL));
       if (warp == 0) role_producer();
       else if (warp == 1) role_mma();
       else if (warp == C::APROD_WARP) role_aprod();
     } else if (warp < 8) {
-      if (DCCN_TC_REGBAL_MODE != 2 && DCCN_TC_REGBAL_MODE != 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
+      if (DCCN_TC_REGBAL_MODE != 2 && DCCN_TC_REGBAL_MODE != 4 && DCCN_TC_REGBAL_MODE != 5) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_SPLIT));
       role_split_dec();
     } else {
-      if (DCCN_TC_REGBAL_MODE == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));
+      if (DCCN_TC_REGBAL_MODE == 1 || DCCN_TC_REGBAL_MODE == 5 || DCCN_TC_REGBAL_MODE == 6) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));   // 5: only the control warpgroup gives registers away, 6: only the splitters
       role_epilogue();
     }
   } else {
